@@ -1,0 +1,751 @@
+// Host front-end: reads the reference's scene.json (+ buffers) and method JSON and produces the
+// plain-array AkrSceneDesc.  Re-implements, for the formats the hot path needs, what the Rust
+// host does in:
+//   crates/akari_scenegraph/src/scene.rs:598-668   (MmapScene::open, buffer views)
+//   crates/akari_render/src/load.rs:129-237,457-535 (transforms, camera, instances, mesh slices)
+//   crates/akari_render/src/svm/compiler.rs:25-347  (shader graph -> bytecode + constant blob)
+//   crates/akari_integrator/src/lib.rs:57-109        (RenderTask JSON)
+// Written from the behaviour of those files; no code is shared with them.
+#include "../../../include/akari_b200_host.h"
+#include "json.hpp"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <sstream>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int set_error(int code, const std::string &msg) {
+    g_last_error = msg;
+    return code;
+}
+
+std::string read_file(const std::string &path) {
+    std::ifstream f(path, std::ios::binary);
+    if (!f) throw std::runtime_error("cannot open '" + path + "'");
+    std::ostringstream ss;
+    ss << f.rdbuf();
+    return ss.str();
+}
+
+bool file_exists(const std::string &path) {
+    std::ifstream f(path, std::ios::binary);
+    return static_cast<bool>(f);
+}
+
+std::string dirname_of(const std::string &p) {
+    size_t i = p.find_last_of('/');
+    if (i == std::string::npos) return ".";
+    if (i == 0) return "/";
+    return p.substr(0, i);
+}
+
+std::string basename_any(const std::string &p) {
+    size_t i = p.find_last_of("/\\");
+    return i == std::string::npos ? p : p.substr(i + 1);
+}
+
+// ---- column-major 4x4, following glam::Mat4's scalar formulas --------------------------------
+struct Mat4 {
+    float c[4][4];  // c[col][row]
+    static Mat4 identity() {
+        Mat4 m{};
+        for (int i = 0; i < 4; ++i) m.c[i][i] = 1.0f;
+        return m;
+    }
+    static Mat4 from_scale(float x, float y, float z) {
+        Mat4 m = identity();
+        m.c[0][0] = x;
+        m.c[1][1] = y;
+        m.c[2][2] = z;
+        return m;
+    }
+    static Mat4 from_translation(float x, float y, float z) {
+        Mat4 m = identity();
+        m.c[3][0] = x;
+        m.c[3][1] = y;
+        m.c[3][2] = z;
+        return m;
+    }
+    // glam::Mat4::from_axis_angle
+    static Mat4 from_axis_angle(float ax, float ay, float az, float angle) {
+        float s = std::sin(angle), co = std::cos(angle);
+        float axs = ax * s, ays = ay * s, azs = az * s;
+        float axq = ax * ax, ayq = ay * ay, azq = az * az;
+        float omc = 1.0f - co;
+        float xyomc = ax * ay * omc, xzomc = ax * az * omc, yzomc = ay * az * omc;
+        Mat4 m{};
+        m.c[0][0] = axq * omc + co;
+        m.c[0][1] = xyomc + azs;
+        m.c[0][2] = xzomc - ays;
+        m.c[1][0] = xyomc - azs;
+        m.c[1][1] = ayq * omc + co;
+        m.c[1][2] = yzomc + axs;
+        m.c[2][0] = xzomc + ays;
+        m.c[2][1] = yzomc - axs;
+        m.c[2][2] = azq * omc + co;
+        m.c[3][3] = 1.0f;
+        return m;
+    }
+    // glam mul_mat4: result.col_j = a.col0*b[j].x + a.col1*b[j].y + a.col2*b[j].z + a.col3*b[j].w
+    Mat4 operator*(const Mat4 &b) const {
+        Mat4 r{};
+        for (int j = 0; j < 4; ++j)
+            for (int i = 0; i < 4; ++i) {
+                float v = c[0][i] * b.c[j][0];
+                v = v + c[1][i] * b.c[j][1];
+                v = v + c[2][i] * b.c[j][2];
+                v = v + c[3][i] * b.c[j][3];
+                r.c[j][i] = v;
+            }
+        return r;
+    }
+    Mat4 transpose() const {
+        Mat4 r{};
+        for (int j = 0; j < 4; ++j)
+            for (int i = 0; i < 4; ++i) r.c[j][i] = c[i][j];
+        return r;
+    }
+    void store(float out[16]) const { std::memcpy(out, c, sizeof(float) * 16); }
+};
+
+constexpr float kPi = 3.14159265358979323846f;
+
+// load.rs:129-171
+Mat4 load_transform(const akr::json::Value &t, bool is_camera) {
+    const std::string &type = t.at("type").string();
+    const akr::json::Value &data = t.at("data");
+    if (type == "trs") {
+        const std::string &cs = data.at("coordinate_system").string();
+        float tr[3], r[3], s[3];
+        for (int i = 0; i < 3; ++i) {
+            tr[i] = data.at("translation").at(i).f32();
+            r[i] = data.at("rotation").at(i).f32();
+            s[i] = data.at("scale").at(i).f32();
+        }
+        Mat4 m = Mat4::identity();
+        if (!is_camera) m = Mat4::from_scale(s[0], s[1], s[2]) * m;
+        if (cs == "Akari") {
+            m = Mat4::from_axis_angle(0, 0, 1, r[2]) * m;
+            m = Mat4::from_axis_angle(1, 0, 0, r[0]) * m;
+            m = Mat4::from_axis_angle(0, 1, 0, r[1]) * m;
+            m = Mat4::from_translation(tr[0], tr[1], tr[2]) * m;
+        } else if (cs == "Blender") {
+            if (is_camera) m = Mat4::from_axis_angle(1, 0, 0, -kPi / 2.0f) * m;
+            m = Mat4::from_axis_angle(1, 0, 0, r[0]) * m;
+            m = Mat4::from_axis_angle(0, 0, 1, -r[1]) * m;
+            m = Mat4::from_axis_angle(0, 1, 0, r[2]) * m;
+            m = Mat4::from_translation(tr[0], tr[2], -tr[1]) * m;
+        } else {
+            throw std::runtime_error("unknown coordinate_system '" + cs + "'");
+        }
+        return m;
+    }
+    if (type == "matrix") {
+        // Mat4::from_cols_array_2d(m).transpose(): the JSON rows are matrix rows.
+        Mat4 m{};
+        for (int row = 0; row < 4; ++row)
+            for (int col = 0; col < 4; ++col) m.c[col][row] = data.at(row).at(col).f32();
+        return m;
+    }
+    throw std::runtime_error("unknown transform type '" + type + "'");
+}
+
+// ---- base64 (Buffer::EmbeddedBase64) -----------------------------------------------------------
+std::vector<uint8_t> base64_decode(const std::string &in) {
+    static int8_t lut[256];
+    static bool init = false;
+    if (!init) {
+        std::memset(lut, -1, sizeof(lut));
+        const char *abc = "ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789+/";
+        for (int i = 0; i < 64; ++i) lut[static_cast<uint8_t>(abc[i])] = static_cast<int8_t>(i);
+        init = true;
+    }
+    std::vector<uint8_t> out;
+    uint32_t acc = 0;
+    int bits = 0;
+    for (unsigned char ch : in) {
+        if (ch == '=') break;
+        int8_t v = lut[ch];
+        if (v < 0) continue;
+        acc = (acc << 6) | static_cast<uint32_t>(v);
+        bits += 6;
+        if (bits >= 8) {
+            bits -= 8;
+            out.push_back(static_cast<uint8_t>((acc >> bits) & 0xFF));
+        }
+    }
+    return out;
+}
+
+// ---- SVM compiler (svm/compiler.rs) --------------------------------------------------------------
+struct CompiledShader {
+    std::vector<AkrSvmNode> nodes;
+    std::vector<uint8_t> data;
+};
+
+bool same_bytecode(const std::vector<AkrSvmNode> &a, const std::vector<AkrSvmNode> &b) {
+    if (a.size() != b.size()) return false;
+    for (size_t i = 0; i < a.size(); ++i) {
+        if (a[i].op != b[i].op || a[i].n_args != b[i].n_args) return false;
+        for (uint32_t k = 0; k < a[i].n_args; ++k)
+            if (a[i].a[k] != b[i].a[k]) return false;
+    }
+    return true;
+}
+
+class ShaderCompiler {
+  public:
+    explicit ShaderCompiler(const akr::json::Value &graph) : graph_(graph), nodes_(graph.at("nodes")) {}
+    CompiledShader compile() {
+        const std::string &kind = graph_.at("kind").string();
+        if (kind != "surface") throw std::runtime_error("shader kind '" + kind + "' is not supported (compiler.rs:277-286)");
+        compile_node(graph_.at("output").at("id").string());
+        CompiledShader out;
+        out.nodes = std::move(bytecode_);
+        out.data = std::move(data_);
+        return out;
+    }
+
+  private:
+    const akr::json::Value &graph_;
+    const akr::json::Value &nodes_;
+    std::map<std::string, uint32_t> env_;
+    std::vector<AkrSvmNode> bytecode_;
+    std::vector<uint8_t> data_;
+
+    // util::ByteVecBuilder::push (util/mod.rs:481-494): offset rounded up to align_of::<T>().
+    uint32_t push_bytes(const void *p, size_t size, size_t align) {
+        size_t off = (data_.size() + align - 1) / align * align;
+        data_.resize(off + size, 0);
+        std::memcpy(data_.data() + off, p, size);
+        return static_cast<uint32_t>(off);
+    }
+    uint32_t push_f32(float v) { return push_bytes(&v, 4, 4); }
+    uint32_t push_float3(const float v[3]) {
+        // luisa Float3: 16-byte size and alignment; the pad lane is zero.
+        float q[4] = {v[0], v[1], v[2], 0.0f};
+        return push_bytes(q, 16, 16);
+    }
+    uint32_t push(uint32_t op, std::initializer_list<uint32_t> args) {
+        AkrSvmNode n{};
+        n.op = op;
+        n.n_args = static_cast<uint32_t>(args.size());
+        uint32_t k = 0;
+        for (uint32_t a : args) n.a[k++] = a;
+        bytecode_.push_back(n);
+        return static_cast<uint32_t>(bytecode_.size() - 1);
+    }
+    uint32_t ref(const akr::json::Value &node, const char *field) {
+        return compile_node(node.at(field).at("id").string());
+    }
+    uint32_t compile_node(const std::string &id) {
+        auto it = env_.find(id);
+        if (it != env_.end()) return it->second;
+        const akr::json::Value &node = nodes_.at(id);
+        const std::string &type = node.at("type").string();
+        uint32_t idx;
+        if (type == "float") {
+            idx = push(AKR_SVM_FLOAT, {push_f32(node.at("value").f32())});
+        } else if (type == "float3") {
+            float v[3] = {node.at("value").at(0).f32(), node.at("value").at(1).f32(), node.at("value").at(2).f32()};
+            idx = push(AKR_SVM_FLOAT3, {push_float3(v)});
+        } else if (type == "rgb") {
+            float v[3] = {node.at("value").at(0).f32(), node.at("value").at(1).f32(), node.at("value").at(2).f32()};
+            const std::string &cs = node.at("colorspace").string();
+            uint32_t cs_id;
+            if (cs == "srgb") cs_id = 1;          // ColorSpaceId::SRGB (color.rs:29-47)
+            else if (cs == "aces") cs_id = 2;
+            else throw std::runtime_error("rgb node: unknown colorspace '" + cs + "'");
+            uint32_t data = push(AKR_SVM_FLOAT3, {push_float3(v)});
+            idx = push(AKR_SVM_RGB_TEX, {data, cs_id});
+        } else if (type == "spectral_uplift") {
+            idx = push(AKR_SVM_SPECTRAL_UPLIFT, {ref(node, "rgb")});
+        } else if (type == "diffuse") {
+            idx = push(AKR_SVM_DIFFUSE_BSDF, {ref(node, "color")});
+        } else if (type == "emission") {
+            uint32_t c = ref(node, "color");
+            uint32_t s = ref(node, "strength");
+            idx = push(AKR_SVM_EMISSION, {c, s});
+        } else if (type == "glass") {
+            uint32_t c = ref(node, "color");
+            uint32_t ior = ref(node, "ior");
+            uint32_t rough = ref(node, "roughness");
+            idx = push(AKR_SVM_GLASS_BSDF, {c, c, rough, ior});
+        } else if (type == "principled") {
+            // compile order = field order in compiler.rs:181-205 (subsurface_ior is skipped)
+            static const char *fields[25] = {
+                "base_color", "metallic", "roughness", "ior", "alpha", "normal", "subsurface_weight",
+                "subsurface_radius", "subsurface_scale", "subsurface_anisotropy", "specular_ior_level",
+                "specular_tint", "anisotropic", "anisotropic_rotation", "tangent", "transmission_weight",
+                "sheen_weight", "sheen_tint", "coat_weight", "coat_roughness", "coat_ior", "coat_tint",
+                "coat_normal", "emission_color", "emission_strength"};
+            AkrSvmNode n{};
+            n.op = AKR_SVM_PRINCIPLED_BSDF;
+            n.n_args = 25;
+            for (int k = 0; k < 25; ++k) n.a[k] = ref(node, fields[k]);
+            bytecode_.push_back(n);
+            idx = static_cast<uint32_t>(bytecode_.size() - 1);
+        } else if (type == "output") {
+            idx = push(AKR_SVM_MATERIAL_OUTPUT, {ref(node, "node")});
+        } else {
+            // image / checkerboard / mapping / normal_map / texcoords / extract / separate_color are
+            // SURVEY 8(f) rank 2 ("next"); float4 / noise / mix / math are todo!() in the reference.
+            throw std::runtime_error("shader node type '" + type + "' is outside the implemented hot-path scope");
+        }
+        env_[id] = idx;
+        return idx;
+    }
+};
+
+}  // namespace
+
+// ---- AkrHostScene ----------------------------------------------------------------------------
+struct AkrHostScene {
+    std::map<std::string, std::vector<uint8_t>> buffers;
+    struct MeshStore {
+        std::vector<float> vertices, normals, uvs, tangents;
+        std::vector<uint32_t> indices, material_slots;
+        bool has_normals = false, has_uvs = false, has_tangents = false;
+    };
+    std::vector<MeshStore> mesh_store;
+    std::vector<AkrMesh> meshes;
+    std::vector<std::vector<AkrSvmNode>> kind_nodes;
+    std::vector<AkrShaderKind> kinds;
+    std::vector<uint8_t> shader_data;
+    std::vector<std::vector<AkrShaderRef>> instance_materials;
+    std::vector<AkrInstance> instances;
+    std::vector<std::string> instance_names, geometry_names, material_names;
+    AkrSceneDesc desc{};
+
+    void refresh_desc() {
+        meshes.resize(mesh_store.size());
+        for (size_t i = 0; i < mesh_store.size(); ++i) {
+            MeshStore &m = mesh_store[i];
+            AkrMesh &d = meshes[i];
+            d.vertices = m.vertices.data();
+            d.indices = m.indices.data();
+            d.normals = m.has_normals ? m.normals.data() : nullptr;
+            d.uvs = m.has_uvs ? m.uvs.data() : nullptr;
+            d.tangents = m.has_tangents ? m.tangents.data() : nullptr;
+            d.material_slots = m.material_slots.data();
+            d.n_vertices = static_cast<uint32_t>(m.vertices.size() / 3);
+            d.n_triangles = static_cast<uint32_t>(m.indices.size() / 3);
+            d.n_material_slots = static_cast<uint32_t>(m.material_slots.size());
+            d._pad = 0;
+        }
+        kinds.resize(kind_nodes.size());
+        for (size_t i = 0; i < kind_nodes.size(); ++i) {
+            kinds[i].nodes = kind_nodes[i].data();
+            kinds[i].n_nodes = static_cast<uint32_t>(kind_nodes[i].size());
+        }
+        for (size_t i = 0; i < instances.size(); ++i) {
+            instances[i].materials = instance_materials[i].data();
+            instances[i].n_materials = static_cast<uint32_t>(instance_materials[i].size());
+        }
+        desc.abi_version = AKR_B200_ABI_VERSION;
+        desc.n_meshes = static_cast<uint32_t>(meshes.size());
+        desc.n_instances = static_cast<uint32_t>(instances.size());
+        desc.n_shader_kinds = static_cast<uint32_t>(kinds.size());
+        desc.meshes = meshes.data();
+        desc.instances = instances.data();
+        desc.shader_kinds = kinds.data();
+        desc.shader_data = shader_data.data();
+        desc.shader_data_size = shader_data.size();
+    }
+};
+
+namespace {
+
+void load_scene_impl(const std::string &path, AkrHostScene &hs) {
+    using akr::json::Value;
+    const std::string dir = dirname_of(path);
+    Value root = akr::json::parse(read_file(path));
+
+    // ---- buffers (scene.rs:604-647) ----
+    for (const auto &[name, b] : root.at("buffers").object()) {
+        const std::string &type = b.at("type").string();
+        std::vector<uint8_t> bytes;
+        if (type == "path") {
+            std::string p = b.at("path").string();
+            std::string resolved;
+            if (!p.empty() && p[0] == '/' && file_exists(p)) resolved = p;
+            else if (file_exists(dir + "/" + p)) resolved = dir + "/" + p;
+            else if (file_exists(dir + "/" + basename_any(p))) resolved = dir + "/" + basename_any(p);
+            else throw std::runtime_error("buffer '" + name + "': cannot resolve path '" + p + "'");
+            std::string s = read_file(resolved);
+            bytes.assign(s.begin(), s.end());
+            uint64_t expect = b.at("length").u64();
+            if (expect != bytes.size())
+                throw std::runtime_error("buffer size mismatch: expected " + std::to_string(expect) + ", got " +
+                                         std::to_string(bytes.size()));
+        } else if (type == "base64") {
+            bytes = base64_decode(b.at("data").string());
+        } else if (type == "binary") {
+            for (const Value &v : b.at("data").array()) bytes.push_back(static_cast<uint8_t>(v.u32()));
+        } else {
+            throw std::runtime_error("buffer '" + name + "': unsupported type '" + type + "'");
+        }
+        hs.buffers[name] = std::move(bytes);
+    }
+    const Value &views = root.at("buffer_views");
+    auto view_bytes = [&](const Value &ref, size_t elem, const char *what) -> std::pair<const uint8_t *, size_t> {
+        const Value &v = views.at(ref.at("id").string());
+        const std::vector<uint8_t> &buf = hs.buffers.at(v.at("buffer").at("id").string());
+        size_t off = static_cast<size_t>(v.at("offset").u64());
+        size_t len = static_cast<size_t>(v.at("length").u64());
+        if (off + len > buf.size()) throw std::runtime_error(std::string("buffer view out of range for ") + what);
+        if (len % elem != 0) throw std::runtime_error(std::string("Invalid slice length for ") + what);
+        return {buf.data() + off, len};
+    };
+
+    // ---- geometries (load.rs:494-529); geom_id = BTreeMap order ----
+    std::map<std::string, uint32_t> geom_ids;
+    for (const auto &[name, g] : root.at("geometries").object()) {
+        if (g.at("type").string() != "mesh") throw std::runtime_error("geometry '" + name + "': only meshes are supported");
+        AkrHostScene::MeshStore m;
+        auto copy_f = [&](const Value &ref, size_t elem, std::vector<float> &dst, const char *what) {
+            auto [p, len] = view_bytes(ref, elem, what);
+            dst.resize(len / 4);
+            std::memcpy(dst.data(), p, len);
+        };
+        auto copy_u = [&](const Value &ref, size_t elem, std::vector<uint32_t> &dst, const char *what) {
+            auto [p, len] = view_bytes(ref, elem, what);
+            dst.resize(len / 4);
+            std::memcpy(dst.data(), p, len);
+        };
+        copy_f(g.at("vertices"), 12, m.vertices, "vertices");
+        copy_u(g.at("indices"), 12, m.indices, "indices");
+        if (g.has("normals") && !g.at("normals").is_null()) {
+            copy_f(g.at("normals"), 12, m.normals, "normals");
+            m.has_normals = true;
+        }
+        if (g.has("uvs") && !g.at("uvs").is_null()) {
+            copy_f(g.at("uvs"), 8, m.uvs, "uvs");
+            m.has_uvs = true;
+        }
+        if (g.has("tangents") && !g.at("tangents").is_null()) {
+            copy_f(g.at("tangents"), 12, m.tangents, "tangents");
+            m.has_tangents = true;
+        }
+        copy_u(g.at("materials"), 4, m.material_slots, "materials");
+        size_t ntri = m.indices.size() / 3;
+        if (m.has_normals && m.normals.size() != ntri * 9) throw std::runtime_error("mesh '" + name + "': normals are not per-corner");
+        if (m.has_uvs && m.uvs.size() != ntri * 6) throw std::runtime_error("mesh '" + name + "': uvs are not per-corner");
+        if (m.has_tangents && m.tangents.size() != ntri * 9) throw std::runtime_error("mesh '" + name + "': tangents are not per-corner");
+        geom_ids[name] = static_cast<uint32_t>(hs.mesh_store.size());
+        hs.geometry_names.push_back(name);
+        hs.mesh_store.push_back(std::move(m));
+    }
+
+    // ---- materials -> SVM (load.rs:242-253; compiler.rs:25-46) ----
+    std::map<std::string, AkrShaderRef> mat_refs;
+    for (const auto &[name, mat] : root.at("materials").object()) {
+        CompiledShader cs = ShaderCompiler(mat.at("shader")).compile();
+        uint32_t kind = UINT32_MAX;
+        for (size_t k = 0; k < hs.kind_nodes.size(); ++k)
+            if (same_bytecode(hs.kind_nodes[k], cs.nodes)) {
+                kind = static_cast<uint32_t>(k);
+                break;
+            }
+        if (kind == UINT32_MAX) {
+            kind = static_cast<uint32_t>(hs.kind_nodes.size());
+            hs.kind_nodes.push_back(cs.nodes);
+        }
+        AkrShaderRef r{kind, static_cast<uint32_t>(hs.shader_data.size())};
+        hs.shader_data.insert(hs.shader_data.end(), cs.data.begin(), cs.data.end());
+        size_t padding = 16 - (hs.shader_data.size() % 16);  // compiler.rs:38-41 (adds 16 when already aligned)
+        hs.shader_data.insert(hs.shader_data.end(), padding, 0);
+        mat_refs[name] = r;
+        hs.material_names.push_back(name);
+    }
+
+    // ---- camera (load.rs:172-194) ----
+    {
+        const Value &cam = root.at("camera");
+        if (cam.is_null()) throw std::runtime_error("scene has no camera");
+        if (cam.at("type").string() != "perspective") throw std::runtime_error("only perspective cameras are supported");
+        const Value &d = cam.at("data");
+        Mat4 c2w = load_transform(d.at("transform"), true);
+        c2w.store(hs.desc.camera.c2w);
+        float fov_deg = d.at("fov").f32();
+        hs.desc.camera.fov = fov_deg * (kPi / 180.0f);  // f32::to_radians
+        float focal_distance = d.at("focal_distance").f32();
+        float fstop = d.at("fstop").f32();
+        hs.desc.camera.lens_radius = focal_distance / (2.0f * fstop);
+        hs.desc.camera.focal_length = focal_distance;
+        hs.desc.camera.width = d.at("sensor_width").u32();
+        hs.desc.camera.height = d.at("sensor_height").u32();
+        hs.desc.camera._pad = 0;
+    }
+
+    // ---- instances (load.rs:195-237,287-292) ----
+    for (const auto &[name, inst] : root.at("instances").object()) {
+        AkrInstance d{};
+        const std::string &gname = inst.at("geometry").at("id").string();
+        auto git = geom_ids.find(gname);
+        if (git == geom_ids.end()) throw std::runtime_error("instance '" + name + "': unknown geometry '" + gname + "'");
+        d.geom_id = git->second;
+        load_transform(inst.at("transform"), false).store(d.transform);
+        const AkrHostScene::MeshStore &m = hs.mesh_store[d.geom_id];
+        uint32_t flags = 0;
+        if (m.has_normals) flags |= AKR_MESH_HAS_NORMALS;
+        if (m.has_uvs) flags |= AKR_MESH_HAS_UVS;
+        if (m.has_tangents) flags |= AKR_MESH_HAS_TANGENTS;
+        if (m.material_slots.size() > 1) flags |= AKR_MESH_HAS_MULTI_MATERIALS;
+        d.flags = flags;
+        std::vector<AkrShaderRef> mats;
+        for (const Value &mr : inst.at("materials").array()) {
+            auto mit = mat_refs.find(mr.at("id").string());
+            if (mit == mat_refs.end()) throw std::runtime_error("instance '" + name + "': unknown material");
+            mats.push_back(mit->second);
+        }
+        if (mats.empty()) throw std::runtime_error("instance '" + name + "' has no materials (mesh.rs:308)");
+        hs.instance_materials.push_back(std::move(mats));
+        hs.instances.push_back(d);
+        hs.instance_names.push_back(name);
+    }
+    hs.refresh_desc();
+}
+
+void parse_task(const akr::json::Value &root_in, AkrRenderTask *t) {
+    using akr::json::Value;
+    akr_host_default_task(t);
+    const Value *root = &root_in;
+    if (root->is_array()) {  // RenderTask::Multi: this entry point handles the first config
+        if (root->array().empty()) throw std::runtime_error("empty render task");
+        root = &root->array()[0];
+    }
+    const Value &method = root->at("method");
+    const std::string &type = method.at("type").string();
+    if (type != "pt") throw std::runtime_error("method '" + type + "' is outside the hot-path scope (only 'pt')");
+    auto opt_u32 = [&](const char *k, uint32_t &dst) { if (method.has(k)) dst = method.at(k).u32(); };
+    auto opt_bool = [&](const char *k, uint32_t &dst) { if (method.has(k)) dst = method.at(k).boolean() ? 1u : 0u; };
+    opt_u32("spp", t->pt.spp);
+    opt_u32("max_depth", t->pt.max_depth);
+    opt_u32("spp_per_pass", t->pt.spp_per_pass);
+    opt_u32("rr_depth", t->pt.rr_depth);
+    opt_bool("use_nee", t->pt.use_nee);
+    opt_bool("indirect_only", t->pt.indirect_only);
+    opt_bool("force_diffuse", t->pt.force_diffuse);
+    if (method.has("pixel_offset")) {
+        t->pt.pixel_offset[0] = method.at("pixel_offset").at(0).i32();
+        t->pt.pixel_offset[1] = method.at("pixel_offset").at(1).i32();
+    }
+    if (method.has("debug_depth") && !method.at("debug_depth").is_null()) t->pt.debug_depth = method.at("debug_depth").i32();
+    if (root->has("sampler")) {
+        const Value &s = root->at("sampler");
+        const std::string &st = s.at("type").string();
+        if (st == "pmj02bn") t->sampler.type = AKR_SAMPLER_PMJ02BN;
+        else if (st == "independent") t->sampler.type = AKR_SAMPLER_INDEPENDENT;
+        else throw std::runtime_error("unknown sampler '" + st + "'");
+        t->sampler.seed = s.at("seed").u64();
+    }
+    const Value &film = root->at("film");
+    if (film.has("out")) std::snprintf(t->out, sizeof(t->out), "%s", film.at("out").string().c_str());
+    if (film.has("filter")) {
+        const Value &f = film.at("filter");
+        const std::string &ft = f.at("type").string();
+        if (ft == "gaussian") t->filter.type = AKR_FILTER_GAUSSIAN;
+        else if (ft == "box") t->filter.type = AKR_FILTER_BOX;
+        else throw std::runtime_error("unknown filter '" + ft + "'");
+        t->filter.radius = f.at("radius").f32();
+    }
+    if (film.has("color")) {
+        const std::string &c = film.at("color").at("type").string();
+        if (c != "srgb") throw std::runtime_error("film color '" + c + "' is todo!() in the reference (film.rs:190,227)");
+    }
+}
+
+// ---- minimal OpenEXR writer: single-part scanline, NO_COMPRESSION, 3 x FLOAT channels ----------
+void put_u32(std::vector<uint8_t> &o, uint32_t v) {
+    for (int i = 0; i < 4; ++i) o.push_back(static_cast<uint8_t>((v >> (8 * i)) & 0xFF));
+}
+void put_u64(std::vector<uint8_t> &o, uint64_t v) {
+    for (int i = 0; i < 8; ++i) o.push_back(static_cast<uint8_t>((v >> (8 * i)) & 0xFF));
+}
+void put_str(std::vector<uint8_t> &o, const char *s) {
+    while (*s) o.push_back(static_cast<uint8_t>(*s++));
+    o.push_back(0);
+}
+void put_f32(std::vector<uint8_t> &o, float f) {
+    uint32_t v;
+    std::memcpy(&v, &f, 4);
+    put_u32(o, v);
+}
+void put_attr(std::vector<uint8_t> &o, const char *name, const char *type, const std::vector<uint8_t> &val) {
+    put_str(o, name);
+    put_str(o, type);
+    put_u32(o, static_cast<uint32_t>(val.size()));
+    o.insert(o.end(), val.begin(), val.end());
+}
+
+void write_exr(const std::string &path, const float *rgb, uint32_t w, uint32_t h) {
+    std::vector<uint8_t> o;
+    put_u32(o, 20000630u);  // magic
+    put_u32(o, 2u);         // version 2, scanline, single part
+    {
+        std::vector<uint8_t> ch;
+        for (const char *name : {"B", "G", "R"}) {  // channels sorted by name
+            put_str(ch, name);
+            put_u32(ch, 2u);  // FLOAT
+            ch.push_back(0);  // pLinear
+            ch.push_back(0);
+            ch.push_back(0);
+            ch.push_back(0);
+            put_u32(ch, 1u);
+            put_u32(ch, 1u);
+        }
+        ch.push_back(0);
+        put_attr(o, "channels", "chlist", ch);
+    }
+    {
+        std::vector<uint8_t> v{0};
+        put_attr(o, "compression", "compression", v);
+    }
+    {
+        std::vector<uint8_t> v;
+        put_u32(v, 0);
+        put_u32(v, 0);
+        put_u32(v, w - 1);
+        put_u32(v, h - 1);
+        put_attr(o, "dataWindow", "box2i", v);
+        put_attr(o, "displayWindow", "box2i", v);
+    }
+    {
+        std::vector<uint8_t> v{0};
+        put_attr(o, "lineOrder", "lineOrder", v);
+    }
+    {
+        std::vector<uint8_t> v;
+        put_f32(v, 1.0f);
+        put_attr(o, "pixelAspectRatio", "float", v);
+    }
+    {
+        std::vector<uint8_t> v;
+        put_f32(v, 0.0f);
+        put_f32(v, 0.0f);
+        put_attr(o, "screenWindowCenter", "v2f", v);
+    }
+    {
+        std::vector<uint8_t> v;
+        put_f32(v, 1.0f);
+        put_attr(o, "screenWindowWidth", "float", v);
+    }
+    o.push_back(0);  // end of header
+    const uint64_t line_bytes = static_cast<uint64_t>(w) * 4u * 3u;
+    const uint64_t table_pos = o.size();
+    const uint64_t data_pos = table_pos + 8ull * h;
+    for (uint32_t y = 0; y < h; ++y) put_u64(o, data_pos + y * (8ull + line_bytes));
+    for (uint32_t y = 0; y < h; ++y) {
+        put_u32(o, y);
+        put_u32(o, static_cast<uint32_t>(line_bytes));
+        for (int c : {2, 1, 0})  // B, G, R planes
+            for (uint32_t x = 0; x < w; ++x) put_f32(o, rgb[(static_cast<size_t>(y) * w + x) * 3 + c]);
+    }
+    std::ofstream f(path, std::ios::binary);
+    if (!f) throw std::runtime_error("cannot write '" + path + "'");
+    f.write(reinterpret_cast<const char *>(o.data()), static_cast<std::streamsize>(o.size()));
+}
+
+void write_pfm(const std::string &path, const float *rgb, uint32_t w, uint32_t h) {
+    std::ofstream f(path, std::ios::binary);
+    if (!f) throw std::runtime_error("cannot write '" + path + "'");
+    f << "PF\n" << w << " " << h << "\n-1.0\n";
+    for (uint32_t y = 0; y < h; ++y)  // PFM rows are bottom-to-top
+        f.write(reinterpret_cast<const char *>(rgb + static_cast<size_t>(h - 1 - y) * w * 3), static_cast<std::streamsize>(w) * 12);
+}
+
+}  // namespace
+
+extern "C" {
+
+int akr_host_load_scene(const char *scene_json_path, AkrHostScene **out_scene) {
+    if (!scene_json_path || !out_scene) return set_error(AKR_ERR_INVALID_ARGUMENT, "null argument");
+    *out_scene = nullptr;
+    try {
+        auto hs = std::make_unique<AkrHostScene>();
+        load_scene_impl(scene_json_path, *hs);
+        *out_scene = hs.release();
+        g_last_error.clear();
+        return AKR_OK;
+    } catch (const std::exception &e) {
+        return set_error(AKR_ERR_INVALID_ARGUMENT, std::string("akr_host_load_scene: ") + e.what());
+    }
+}
+
+void akr_host_free_scene(AkrHostScene *scene) { delete scene; }
+
+const AkrSceneDesc *akr_host_scene_desc(const AkrHostScene *scene) { return scene ? &scene->desc : nullptr; }
+
+int akr_host_scene_set_resolution(AkrHostScene *scene, uint32_t width, uint32_t height) {
+    if (!scene || width == 0 || height == 0) return set_error(AKR_ERR_INVALID_ARGUMENT, "bad resolution");
+    scene->desc.camera.width = width;
+    scene->desc.camera.height = height;
+    return AKR_OK;
+}
+
+void akr_host_default_task(AkrRenderTask *t) {
+    std::memset(t, 0, sizeof(*t));
+    t->pt.spp = 256;
+    t->pt.max_depth = 7;
+    t->pt.rr_depth = 5;
+    t->pt.spp_per_pass = 64;
+    t->pt.use_nee = 1;
+    t->pt.indirect_only = 0;
+    t->pt.force_diffuse = 0;
+    t->pt.pixel_offset[0] = t->pt.pixel_offset[1] = 0;
+    t->pt.debug_depth = -1;
+    t->sampler.type = AKR_SAMPLER_INDEPENDENT;  // SamplerConfig::default (sampler/mod.rs:291-295)
+    t->sampler.seed = 0;
+    t->filter.type = AKR_FILTER_GAUSSIAN;       // PixelFilter::default (film.rs:51-55)
+    t->filter.radius = 1.5f;
+    std::snprintf(t->out, sizeof(t->out), "out.exr");
+}
+
+int akr_host_parse_method_string(const char *method_json, AkrRenderTask *out_task) {
+    if (!method_json || !out_task) return set_error(AKR_ERR_INVALID_ARGUMENT, "null argument");
+    try {
+        parse_task(akr::json::parse(method_json), out_task);
+        g_last_error.clear();
+        return AKR_OK;
+    } catch (const std::exception &e) {
+        std::string msg = e.what();
+        int code = msg.find("outside the hot-path scope") != std::string::npos ? AKR_ERR_UNSUPPORTED : AKR_ERR_INVALID_ARGUMENT;
+        return set_error(code, std::string("akr_host_parse_method: ") + msg);
+    }
+}
+
+int akr_host_parse_method_file(const char *method_json_path, AkrRenderTask *out_task) {
+    if (!method_json_path || !out_task) return set_error(AKR_ERR_INVALID_ARGUMENT, "null argument");
+    try {
+        std::string text = read_file(method_json_path);
+        return akr_host_parse_method_string(text.c_str(), out_task);
+    } catch (const std::exception &e) {
+        return set_error(AKR_ERR_INVALID_ARGUMENT, std::string("akr_host_parse_method_file: ") + e.what());
+    }
+}
+
+int akr_host_write_image(const char *path, const float *rgb, uint32_t width, uint32_t height) {
+    if (!path || !rgb || width == 0 || height == 0) return set_error(AKR_ERR_INVALID_ARGUMENT, "null argument");
+    try {
+        std::string p = path;
+        if (p.size() >= 4 && p.substr(p.size() - 4) == ".exr") write_exr(p, rgb, width, height);
+        else if (p.size() >= 4 && p.substr(p.size() - 4) == ".pfm") write_pfm(p, rgb, width, height);
+        else return set_error(AKR_ERR_UNSUPPORTED, "only .exr and .pfm outputs are implemented");
+        return AKR_OK;
+    } catch (const std::exception &e) {
+        return set_error(AKR_ERR_INVALID_ARGUMENT, std::string("akr_host_write_image: ") + e.what());
+    }
+}
+
+const char *akr_host_last_error(void) { return g_last_error.c_str(); }
+
+}  // extern "C"
