@@ -1,0 +1,861 @@
+// akari_b200.cu — wavefront path-tracing kernels (sm_100a) and the C-ABI of include/akari_b200.h.
+//
+// Pipeline per wave of W paths (all state SoA in HBM, queues compacted with warp ballots):
+//
+//   k_raygen -> [ k_intersect -> k_shade -> k_shadow ] x (max_depth + 1) -> k_accumulate
+//
+// Every kernel is a persistent grid-stride kernel sized to the SM count; queue lengths live in
+// device memory, so a whole pass is enqueued without a single host round trip.  The scene's BVH and
+// triangles are staged into shared memory with one TMA bulk copy (cp.async.bulk + mbarrier) per CTA.
+// There is no tensor-core work on this path (no dense contraction exists in a path tracer) and no
+// CPU fallback: every entry point fails with AKR_ERR_CUDA when no device is usable.
+#include "../../include/akari_b200.h"
+#include "device/akr_path.cuh"
+#include "host/scene_build.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace akr;
+
+namespace {
+
+constexpr int kBlock = 256;
+constexpr uint32_t kMaxDepthSlots = 66;        // counters for depth 0 .. 64 (+1)
+constexpr uint32_t kSmemSceneBudget = 96 * 1024;  // bytes of BVH nodes + triangles staged per CTA
+
+// ------------------------------------------------------------------------------------------------
+// SoA queues
+// ------------------------------------------------------------------------------------------------
+struct PathQueue {  // 13 words per path
+    float *ox, *oy, *oz, *dx, *dy, *dz;
+    uint32_t *ex;
+    float *bx, *by, *bz;
+    float *prev_pdf;
+    uint32_t *path_id;
+};
+struct HitQueue {
+    uint32_t *gid;
+    float *u, *v;
+};
+struct ShadowQueue {  // 13 words per item
+    float *ox, *oy, *oz, *dx, *dy, *dz, *tmax;
+    uint32_t *ex0, *ex1;
+    float *cr, *cg, *cb;
+    uint32_t *path_id;
+};
+
+struct LaunchParams {
+    SceneView scene;
+    CornerAttribs corners;
+    SamplerTables tables;
+    RenderParams rp;
+    WaveInfo wave;
+    PathQueue q[2];
+    HitQueue hits;
+    ShadowQueue shadow;
+    AccView acc;
+    uint32_t *counters;       // [kMaxDepthSlots][2]: paths entering depth d, shadow items of depth d
+    float *film;
+    uint32_t n_film_pixels;
+    uint32_t scene_smem_nodes;  // nodes staged in shared memory
+    uint32_t scene_smem_tris;   // 1 when all triangles are staged too
+    uint32_t *dbg_first_hits;   // optional [n_film_pixels][2]
+};
+
+__device__ __forceinline__ PathState load_path(const PathQueue &q, uint32_t i) {
+    PathState p;
+    p.o = mk3(q.ox[i], q.oy[i], q.oz[i]);
+    p.d = mk3(q.dx[i], q.dy[i], q.dz[i]);
+    p.ex = q.ex[i];
+    p.beta = mk3(q.bx[i], q.by[i], q.bz[i]);
+    p.prev_bsdf_pdf = q.prev_pdf[i];
+    p.path_id = q.path_id[i];
+    return p;
+}
+__device__ __forceinline__ void store_path(const PathQueue &q, uint32_t i, const PathState &p) {
+    q.ox[i] = p.o.x; q.oy[i] = p.o.y; q.oz[i] = p.o.z;
+    q.dx[i] = p.d.x; q.dy[i] = p.d.y; q.dz[i] = p.d.z;
+    q.ex[i] = p.ex;
+    q.bx[i] = p.beta.x; q.by[i] = p.beta.y; q.bz[i] = p.beta.z;
+    q.prev_pdf[i] = p.prev_bsdf_pdf;
+    q.path_id[i] = p.path_id;
+}
+
+// ------------------------------------------------------------------------------------------------
+// TMA bulk copy of the traversal data into shared memory
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// Stages nodes[0 .. n_nodes) and (optionally) all triangles behind `smem`; returns the TraceData to use.
+__device__ __forceinline__ TraceData stage_scene(const LaunchParams &P, unsigned char *smem, uint64_t *bar) {
+    TraceData td;
+    const uint32_t node_bytes = P.scene_smem_nodes * (uint32_t)sizeof(BvhNode);
+    const uint32_t tri_bytes = P.scene_smem_tris ? P.scene.n_tris * (uint32_t)sizeof(TriGeom) : 0u;
+    BvhNode *s_nodes = reinterpret_cast<BvhNode *>(smem);
+    TriGeom *s_tris = reinterpret_cast<TriGeom *>(smem + node_bytes);
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && (node_bytes + tri_bytes) > 0) {
+        mbar_expect_tx(bar, node_bytes + tri_bytes);
+        if (node_bytes) tma_bulk_g2s(s_nodes, P.scene.nodes, node_bytes, bar);
+        if (tri_bytes) tma_bulk_g2s(s_tris, P.scene.tris, tri_bytes, bar);
+    }
+    if ((node_bytes + tri_bytes) > 0) mbar_wait(bar, 0);
+    td.fast_nodes = s_nodes;
+    td.n_fast_nodes = P.scene_smem_nodes;
+    td.nodes = P.scene.nodes;
+    td.tris = P.scene_smem_tris ? s_tris : P.scene.tris;
+    return td;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_raygen(const __grid_constant__ LaunchParams P) {
+    const uint32_t n = P.wave.n_pix * P.wave.n_spp;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        PathState ps = raygen_body(P.scene, P.tables, P.rp, P.wave, i);
+        store_path(P.q[0], i, ps);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) P.counters[0] = n;
+}
+
+__global__ void __launch_bounds__(kBlock) k_intersect(const __grid_constant__ LaunchParams P, uint32_t depth) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bar;
+    const uint32_t n = P.counters[depth * 2u];
+    if (blockIdx.x * blockDim.x >= n) return;  // whole CTA has no work: skip the staging too
+    TraceData td = stage_scene(P, smem, &bar);
+    const PathQueue &q = P.q[depth & 1u];
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        f3 o = mk3(q.ox[i], q.oy[i], q.oz[i]);
+        f3 d = mk3(q.dx[i], q.dy[i], q.dz[i]);
+        HitRec h = trace_ray<false>(P.scene, td, o, d, 0.0f, 1e20f, q.ex[i], 0xffffffffu);
+        P.hits.gid[i] = h.gid;
+        P.hits.u[i] = h.u;
+        P.hits.v[i] = h.v;
+    }
+}
+
+// warp-aggregated queue append: one atomic per warp, slots ordered by lane
+__device__ __forceinline__ uint32_t warp_append(uint32_t *counter, bool pred) {
+    const uint32_t mask = __ballot_sync(0xffffffffu, pred);
+    if (mask == 0u) return 0u;
+    const uint32_t lane = threadIdx.x & 31u;
+    const int leader = __ffs(mask) - 1;
+    uint32_t base = 0u;
+    if ((int)lane == leader) base = atomicAdd(counter, (uint32_t)__popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    return base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+}
+
+__global__ void __launch_bounds__(kBlock) k_shade(const __grid_constant__ LaunchParams P, uint32_t depth) {
+    const uint32_t n = P.counters[depth * 2u];
+    const PathQueue &qin = P.q[depth & 1u];
+    const PathQueue &qout = P.q[(depth + 1u) & 1u];
+    uint32_t *next_count = P.counters + (depth + 1u) * 2u;
+    uint32_t *shadow_count = P.counters + depth * 2u + 1u;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    // warp-uniform trip count so that every lane takes part in the ballots
+    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride) {
+        const uint32_t i = base + (threadIdx.x & 31u);
+        const bool active = i < n;
+        ShadeOut o;
+        o.has_shadow = false;
+        o.has_next = false;
+        if (active) {
+            PathState ps = load_path(qin, i);
+            HitRec h{P.hits.gid[i], P.hits.u[i], P.hits.v[i]};
+            o = shade_body(P.scene, P.corners, P.tables, P.rp, P.wave, depth, ps, h, P.acc);
+            if (depth == 0u && P.dbg_first_hits && ps.path_id < P.wave.n_pix && P.wave.s0 == 0u) {
+                uint32_t pix = P.wave.pix0 + ps.path_id;
+                P.dbg_first_hits[2u * pix + 0u] = h.gid == 0xffffffffu ? 0xffffffffu : P.scene.shade[h.gid].inst;
+                P.dbg_first_hits[2u * pix + 1u] = h.gid == 0xffffffffu ? 0xffffffffu : P.scene.shade[h.gid].prim;
+            }
+        }
+        const uint32_t ss = warp_append(shadow_count, o.has_shadow);
+        if (o.has_shadow) {
+            const ShadowQueue &s = P.shadow;
+            s.ox[ss] = o.shadow.o.x; s.oy[ss] = o.shadow.o.y; s.oz[ss] = o.shadow.o.z;
+            s.dx[ss] = o.shadow.d.x; s.dy[ss] = o.shadow.d.y; s.dz[ss] = o.shadow.d.z;
+            s.tmax[ss] = o.shadow.t_max;
+            s.ex0[ss] = o.shadow.ex0; s.ex1[ss] = o.shadow.ex1;
+            s.cr[ss] = o.shadow.contrib.x; s.cg[ss] = o.shadow.contrib.y; s.cb[ss] = o.shadow.contrib.z;
+            s.path_id[ss] = o.shadow.path_id;
+        }
+        const uint32_t ns = warp_append(next_count, o.has_next);
+        if (o.has_next) store_path(qout, ns, o.next);
+    }
+}
+
+__global__ void __launch_bounds__(kBlock) k_shadow(const __grid_constant__ LaunchParams P, uint32_t depth) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bar;
+    const uint32_t n = P.counters[depth * 2u + 1u];
+    if (blockIdx.x * blockDim.x >= n) return;
+    TraceData td = stage_scene(P, smem, &bar);
+    const ShadowQueue &s = P.shadow;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        ShadowItem it;
+        it.o = mk3(s.ox[i], s.oy[i], s.oz[i]);
+        it.d = mk3(s.dx[i], s.dy[i], s.dz[i]);
+        it.t_max = s.tmax[i];
+        it.ex0 = s.ex0[i];
+        it.ex1 = s.ex1[i];
+        it.contrib = mk3(s.cr[i], s.cg[i], s.cb[i]);
+        it.path_id = s.path_id[i];
+        HitRec h = trace_ray<true>(P.scene, td, it.o, it.d, 0.0f, it.t_max, it.ex0, it.ex1);
+        shadow_resolve(P.acc, it, h.gid != 0xffffffffu, depth + 1u);
+    }
+}
+
+__global__ void __launch_bounds__(kBlock) k_accumulate(const __grid_constant__ LaunchParams P) {
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < P.wave.n_pix; p += stride) accumulate_body(P.acc, P.wave, p, P.film, P.n_film_pixels);
+}
+
+// folds the per-depth counters of one wave into the 64-bit totals and clears them for the next wave
+__global__ void k_fold_counters(uint32_t *counters, unsigned long long *totals, uint32_t n_depth) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        unsigned long long seg = 0, sh = 0;
+        for (uint32_t d = 0; d < n_depth; ++d) {
+            seg += counters[d * 2u];
+            sh += counters[d * 2u + 1u];
+        }
+        totals[0] += seg;
+        totals[1] += sh;
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n_depth * 2u; i += blockDim.x) counters[i] = 0u;
+}
+
+// Film::copy_to_rgba_image(hdr = true) (film.rs:120-148), splat_scale = 1
+__global__ void k_resolve_film(const float *film, uint32_t n, float *out, int rgba) {
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float w = film[6u * n + i];
+        float d = (w == 0.0f) ? 1.0f : w;
+        float r = film[i * 3u + 0u] / d + film[3u * n + i * 3u + 0u] * 1.0f;
+        float g = film[i * 3u + 1u] / d + film[3u * n + i * 3u + 1u] * 1.0f;
+        float b = film[i * 3u + 2u] / d + film[3u * n + i * 3u + 2u] * 1.0f;
+        if (rgba) {
+            out[i * 4u + 0u] = r; out[i * 4u + 1u] = g; out[i * 4u + 2u] = b; out[i * 4u + 3u] = 1.0f;
+        } else {
+            out[i * 3u + 0u] = r; out[i * 3u + 1u] = g; out[i * 3u + 2u] = b;
+        }
+    }
+}
+
+__global__ void k_albedo_table(float *table, uint32_t n) {
+    uint32_t cell = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell < 4096u) table[cell] = albedo_table_cell(cell, n);
+}
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+struct DeviceBuffer {
+    void *ptr = nullptr;
+    size_t bytes = 0;
+};
+
+}  // namespace
+
+struct AkrContext {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    std::string error;
+
+    // sampler tables
+    DeviceBuffer pmj, bn, albedo;
+    bool albedo_ready = false;
+
+    // scene
+    DeviceBuffer nodes, tris, shade, instances, materials, lights, alias_j, alias_t, alias_pdf, corner_n, corner_t;
+    SceneView scene{};
+    CornerAttribs corners{};
+    bool scene_ready = false;
+    bool scene_needs_table = false;
+    uint32_t smem_nodes = 0, smem_tris = 0, smem_bytes = 0;
+
+    // render state
+    bool render_ready = false;
+    RenderParams rp{};
+    AkrPtConfig cfg{};
+    uint32_t tile_y0 = 0, tile_y1 = 0;
+    uint32_t n_pixels = 0;
+    uint32_t spp_done = 0;
+    DeviceBuffer film;
+
+    // wave buffers
+    uint32_t wave_capacity = 0;  // paths
+    DeviceBuffer wave_mem;
+    PathQueue q[2]{};
+    HitQueue hits{};
+    ShadowQueue shadow{};
+    AccView acc{};
+    DeviceBuffer counters, totals, dbg_hits;
+
+    AkrEngineOptions opts{0, 0, 0, 0};
+    AkrStats stats{};
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    std::vector<cudaEvent_t> stage_events;
+};
+
+namespace {
+
+int fail(AkrContext *ctx, int code, const std::string &msg) {
+    if (ctx) ctx->error = msg;
+    return code;
+}
+#define AKR_CUDA(ctx, call)                                                                                     \
+    do {                                                                                                        \
+        cudaError_t e__ = (call);                                                                               \
+        if (e__ != cudaSuccess) return fail((ctx), AKR_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
+    } while (0)
+
+int dev_alloc(AkrContext *ctx, DeviceBuffer &b, size_t bytes) {
+    if (b.ptr && b.bytes >= bytes) return AKR_OK;
+    if (b.ptr) {
+        cudaFree(b.ptr);
+        b.ptr = nullptr;
+        b.bytes = 0;
+    }
+    if (bytes == 0) return AKR_OK;
+    cudaError_t e = cudaMalloc(&b.ptr, bytes);
+    if (e != cudaSuccess) {
+        b.ptr = nullptr;
+        return fail(ctx, e == cudaErrorMemoryAllocation ? AKR_ERR_OUT_OF_MEMORY : AKR_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    }
+    b.bytes = bytes;
+    return AKR_OK;
+}
+void dev_free(DeviceBuffer &b) {
+    if (b.ptr) cudaFree(b.ptr);
+    b.ptr = nullptr;
+    b.bytes = 0;
+}
+template <class T> int upload_vec(AkrContext *ctx, DeviceBuffer &b, const std::vector<T> &v) {
+    size_t bytes = std::max<size_t>(v.size() * sizeof(T), 16);
+    int rc = dev_alloc(ctx, b, bytes);
+    if (rc != AKR_OK) return rc;
+    if (!v.empty()) AKR_CUDA(ctx, cudaMemcpyAsync(b.ptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    return AKR_OK;
+}
+
+int grid_for(const AkrContext *ctx, uint32_t n, int ctas_per_sm) {
+    uint32_t need = (n + kBlock - 1) / kBlock;
+    uint32_t cap = (uint32_t)(ctx->sm_count * ctas_per_sm);
+    return (int)std::max(1u, std::min(need, cap));
+}
+
+int ensure_wave_buffers(AkrContext *ctx, uint32_t capacity) {
+    if (ctx->wave_capacity >= capacity && ctx->wave_mem.ptr) return AKR_OK;
+    const size_t words_per_path = 13 * 2 + 3 + 13 + 6;  // two path queues, hits, shadow queue, accumulators
+    size_t cap = (size_t)capacity;
+    int rc = dev_alloc(ctx, ctx->wave_mem, cap * words_per_path * 4);
+    if (rc != AKR_OK) return rc;
+    uint32_t *base = static_cast<uint32_t *>(ctx->wave_mem.ptr);
+    size_t off = 0;
+    auto take_f = [&]() {
+        float *p = reinterpret_cast<float *>(base + off);
+        off += cap;
+        return p;
+    };
+    auto take_u = [&]() {
+        uint32_t *p = base + off;
+        off += cap;
+        return p;
+    };
+    for (int k = 0; k < 2; ++k) {
+        PathQueue &q = ctx->q[k];
+        q.ox = take_f(); q.oy = take_f(); q.oz = take_f();
+        q.dx = take_f(); q.dy = take_f(); q.dz = take_f();
+        q.ex = take_u();
+        q.bx = take_f(); q.by = take_f(); q.bz = take_f();
+        q.prev_pdf = take_f();
+        q.path_id = take_u();
+    }
+    ctx->hits.gid = take_u(); ctx->hits.u = take_f(); ctx->hits.v = take_f();
+    ShadowQueue &s = ctx->shadow;
+    s.ox = take_f(); s.oy = take_f(); s.oz = take_f();
+    s.dx = take_f(); s.dy = take_f(); s.dz = take_f();
+    s.tmax = take_f();
+    s.ex0 = take_u(); s.ex1 = take_u();
+    s.cr = take_f(); s.cg = take_f(); s.cb = take_f();
+    s.path_id = take_u();
+    AccView &a = ctx->acc;
+    a.lr = take_f(); a.lg = take_f(); a.lb = take_f();
+    a.br = take_f(); a.bg = take_f(); a.bb = take_f();
+    ctx->wave_capacity = capacity;
+    return AKR_OK;
+}
+
+int ensure_albedo_table(AkrContext *ctx) {
+    if (ctx->albedo_ready) return AKR_OK;
+    int rc = dev_alloc(ctx, ctx->albedo, 4096 * sizeof(float));
+    if (rc != AKR_OK) return rc;
+    k_albedo_table<<<16, 256, 0, ctx->stream>>>(static_cast<float *>(ctx->albedo.ptr), 64u);
+    AKR_CUDA(ctx, cudaGetLastError());
+    ctx->stats.kernel_launches += 1;
+    ctx->stats.launches_kernel[5] += 1;
+    ctx->albedo_ready = true;
+    return AKR_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int akr_b200_create(int device_ordinal, AkrContext **out_ctx) {
+    if (!out_ctx) return AKR_ERR_INVALID_ARGUMENT;
+    *out_ctx = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) return AKR_ERR_CUDA;  // no CPU fallback
+    if (device_ordinal < 0 || device_ordinal >= n) return AKR_ERR_INVALID_ARGUMENT;
+    if (cudaSetDevice(device_ordinal) != cudaSuccess) return AKR_ERR_CUDA;
+    AkrContext *ctx = new AkrContext();
+    ctx->device = device_ordinal;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device_ordinal) != cudaSuccess) {
+        delete ctx;
+        return AKR_ERR_CUDA;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cudaEventCreate(&ctx->ev_start) != cudaSuccess || cudaEventCreate(&ctx->ev_stop) != cudaSuccess) {
+        delete ctx;
+        return AKR_ERR_CUDA;
+    }
+    cudaFuncSetAttribute(k_intersect, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemSceneBudget);
+    cudaFuncSetAttribute(k_shadow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemSceneBudget);
+    if (dev_alloc(ctx, ctx->counters, kMaxDepthSlots * 2 * sizeof(uint32_t)) != AKR_OK || dev_alloc(ctx, ctx->totals, 2 * sizeof(unsigned long long)) != AKR_OK) {
+        delete ctx;
+        return AKR_ERR_CUDA;
+    }
+    cudaMemset(ctx->counters.ptr, 0, ctx->counters.bytes);
+    cudaMemset(ctx->totals.ptr, 0, ctx->totals.bytes);
+    *out_ctx = ctx;
+    return AKR_OK;
+}
+
+void akr_b200_destroy(AkrContext *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (DeviceBuffer *b : {&ctx->pmj, &ctx->bn, &ctx->albedo, &ctx->nodes, &ctx->tris, &ctx->shade, &ctx->instances, &ctx->materials, &ctx->lights,
+                            &ctx->alias_j, &ctx->alias_t, &ctx->alias_pdf, &ctx->corner_n, &ctx->corner_t, &ctx->film, &ctx->wave_mem, &ctx->counters,
+                            &ctx->totals, &ctx->dbg_hits})
+        dev_free(*b);
+    if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
+    if (ctx->ev_stop) cudaEventDestroy(ctx->ev_stop);
+    for (cudaEvent_t e : ctx->stage_events) cudaEventDestroy(e);
+    delete ctx;
+}
+
+const char *akr_b200_last_error(const AkrContext *ctx) { return ctx ? ctx->error.c_str() : "null context"; }
+
+int akr_b200_set_stream(AkrContext *ctx, void *stream) {
+    if (!ctx) return AKR_ERR_INVALID_ARGUMENT;
+    ctx->stream = static_cast<cudaStream_t>(stream);
+    return AKR_OK;
+}
+
+int akr_b200_upload_sampler_tables(AkrContext *ctx, const uint32_t *pmj02bn, const uint16_t *bluenoise) {
+    if (!ctx || !pmj02bn || !bluenoise) return fail(ctx, AKR_ERR_INVALID_ARGUMENT, "null argument");
+    AKR_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t pmj_bytes = (size_t)AKR_PMJ02BN_SETS * AKR_PMJ02BN_SAMPLES * 2 * sizeof(uint32_t);
+    const size_t bn_count = (size_t)AKR_BLUE_NOISE_TEXTURES * AKR_BLUE_NOISE_RESOLUTION * AKR_BLUE_NOISE_RESOLUTION;
+    int rc = dev_alloc(ctx, ctx->pmj, pmj_bytes);
+    if (rc != AKR_OK) return rc;
+    rc = dev_alloc(ctx, ctx->bn, bn_count * sizeof(uint16_t));
+    if (rc != AKR_OK) return rc;
+    std::vector<uint16_t> bnt(bn_count);
+    transpose_bluenoise(bluenoise, bnt.data());
+    AKR_CUDA(ctx, cudaMemcpyAsync(ctx->pmj.ptr, pmj02bn, pmj_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    AKR_CUDA(ctx, cudaMemcpyAsync(ctx->bn.ptr, bnt.data(), bn_count * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
+    AKR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // bnt is a local
+    return AKR_OK;
+}
+
+int akr_b200_upload_albedo_table(AkrContext *ctx, const float *table) {
+    if (!ctx || !table) return fail(ctx, AKR_ERR_INVALID_ARGUMENT, "null argument");
+    AKR_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = dev_alloc(ctx, ctx->albedo, 4096 * sizeof(float));
+    if (rc != AKR_OK) return rc;
+    AKR_CUDA(ctx, cudaMemcpyAsync(ctx->albedo.ptr, table, 4096 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    AKR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->albedo_ready = true;
+    ctx->scene.albedo_table = static_cast<const float *>(ctx->albedo.ptr);
+    return AKR_OK;
+}
+
+int akr_b200_upload_scene(AkrContext *ctx, const AkrSceneDesc *desc) {
+    if (!ctx || !desc) return fail(ctx, AKR_ERR_INVALID_ARGUMENT, "null argument");
+    AKR_CUDA(ctx, cudaSetDevice(ctx->device));
+    HostSceneBlob blob;
+    std::string err;
+    int rc = build_scene_blob(*desc, blob, err);
+    if (rc != AKR_OK) return fail(ctx, rc, "akr_b200_upload_scene: " + err);
+    ctx->scene_ready = false;
+    ctx->render_ready = false;
+    if ((rc = upload_vec(ctx, ctx->nodes, blob.nodes)) != AKR_OK) return rc;
+    if ((rc = upload_vec(ctx, ctx->tris, blob.tris)) != AKR_OK) return rc;
+    if ((rc = upload_vec(ctx, ctx->shade, blob.shade)) != AKR_OK) return rc;
+    if ((rc = upload_vec(ctx, ctx->instances, blob.instances)) != AKR_OK) return rc;
+    if ((rc = upload_vec(ctx, ctx->materials, blob.materials)) != AKR_OK) return rc;
+    if ((rc = upload_vec(ctx, ctx->lights, blob.lights)) != AKR_OK) return rc;
+    if ((rc = upload_vec(ctx, ctx->alias_j, blob.alias_j)) != AKR_OK) return rc;
+    if ((rc = upload_vec(ctx, ctx->alias_t, blob.alias_t)) != AKR_OK) return rc;
+    if ((rc = upload_vec(ctx, ctx->alias_pdf, blob.alias_pdf)) != AKR_OK) return rc;
+    if ((rc = upload_vec(ctx, ctx->corner_n, blob.corner_normals)) != AKR_OK) return rc;
+    if ((rc = upload_vec(ctx, ctx->corner_t, blob.corner_tangents)) != AKR_OK) return rc;
+    AKR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // blob is a local
+    SceneView &v = ctx->scene;
+    v.nodes = static_cast<const BvhNode *>(ctx->nodes.ptr);
+    v.tris = static_cast<const TriGeom *>(ctx->tris.ptr);
+    v.shade = static_cast<const TriShade *>(ctx->shade.ptr);
+    v.instances = static_cast<const InstanceRec *>(ctx->instances.ptr);
+    v.materials = static_cast<const Material *>(ctx->materials.ptr);
+    v.lights = static_cast<const LightRec *>(ctx->lights.ptr);
+    v.alias_j = static_cast<const uint32_t *>(ctx->alias_j.ptr);
+    v.alias_t = static_cast<const float *>(ctx->alias_t.ptr);
+    v.alias_pdf = static_cast<const float *>(ctx->alias_pdf.ptr);
+    v.n_nodes = (uint32_t)blob.nodes.size();
+    v.n_tris = (uint32_t)blob.tris.size();
+    v.n_instances = (uint32_t)blob.instances.size();
+    v.n_materials = (uint32_t)blob.materials.size();
+    v.n_lights = (uint32_t)blob.lights.size();
+    v.any_alpha = blob.any_alpha;
+    v.camera = blob.camera;
+    ctx->corners.normals = blob.corner_normals.empty() ? nullptr : static_cast<const float *>(ctx->corner_n.ptr);
+    ctx->corners.tangents = blob.corner_tangents.empty() ? nullptr : static_cast<const float *>(ctx->corner_t.ptr);
+    ctx->scene_needs_table = false;
+    for (const Material &m : blob.materials)
+        if (m.type == MAT_PRINCIPLED && (m.lobes & (LOBE_COAT | LOBE_SPECULAR))) ctx->scene_needs_table = true;
+    // shared-memory staging plan: top of the BVH first, then all triangles if they still fit
+    const uint32_t node_bytes = v.n_nodes * (uint32_t)sizeof(BvhNode);
+    const uint32_t tri_bytes = v.n_tris * (uint32_t)sizeof(TriGeom);
+    ctx->smem_nodes = std::min(v.n_nodes, kSmemSceneBudget / (uint32_t)sizeof(BvhNode));
+    uint32_t used = ctx->smem_nodes * (uint32_t)sizeof(BvhNode);
+    ctx->smem_tris = (ctx->smem_nodes == v.n_nodes && used + tri_bytes <= kSmemSceneBudget) ? 1u : 0u;
+    if (ctx->smem_tris) used += tri_bytes;
+    (void)node_bytes;
+    ctx->smem_bytes = used;
+    ctx->scene_ready = true;
+    return AKR_OK;
+}
+
+int akr_b200_set_engine_options(AkrContext *ctx, const AkrEngineOptions *opts) {
+    if (!ctx || !opts) return fail(ctx, AKR_ERR_INVALID_ARGUMENT, "null argument");
+    ctx->opts = *opts;
+    return AKR_OK;
+}
+
+int akr_b200_begin(AkrContext *ctx, const AkrPtConfig *cfg, const AkrSamplerConfig *sampler, const AkrFilterConfig *filter, const AkrTile *tile) {
+    if (!ctx || !cfg || !sampler || !filter) return fail(ctx, AKR_ERR_INVALID_ARGUMENT, "null argument");
+    if (!ctx->scene_ready) return fail(ctx, AKR_ERR_STATE, "akr_b200_begin: no scene uploaded");
+    if (!ctx->pmj.ptr || !ctx->bn.ptr) return fail(ctx, AKR_ERR_STATE, "akr_b200_begin: sampler tables not uploaded");
+    if (sampler->type != AKR_SAMPLER_PMJ02BN)
+        return fail(ctx, AKR_ERR_UNSUPPORTED, "only the pmj02bn sampler is implemented (independent seeds from rand::StdRng, sampler/mod.rs:148-160)");
+    if (cfg->spp == 0 || cfg->spp > AKR_PMJ02BN_SAMPLES) return fail(ctx, AKR_ERR_INVALID_ARGUMENT, "Pmj02BnSampler supports 1..65536 spp (sampler/mod.rs:374-380)");
+    if (cfg->max_depth + 2 > kMaxDepthSlots) return fail(ctx, AKR_ERR_UNSUPPORTED, "max_depth > 64");
+    if (filter->type != AKR_FILTER_BOX && filter->type != AKR_FILTER_GAUSSIAN) return fail(ctx, AKR_ERR_INVALID_ARGUMENT, "unknown filter");
+    AKR_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint32_t width = ctx->scene.camera.width, height = ctx->scene.camera.height;
+    uint32_t y0 = 0, y1 = height;
+    if (tile) {
+        y0 = tile->y0;
+        y1 = tile->y1;
+    }
+    if (y0 >= y1 || y1 > height) return fail(ctx, AKR_ERR_INVALID_ARGUMENT, "bad tile");
+    if (ctx->scene_needs_table) {
+        int rc = ensure_albedo_table(ctx);
+        if (rc != AKR_OK) return rc;
+    } else if (!ctx->albedo_ready) {
+        int rc = dev_alloc(ctx, ctx->albedo, 4096 * sizeof(float));  // never read, but keep the pointer valid
+        if (rc != AKR_OK) return rc;
+        AKR_CUDA(ctx, cudaMemsetAsync(ctx->albedo.ptr, 0, 4096 * sizeof(float), ctx->stream));
+    }
+    ctx->scene.albedo_table = static_cast<const float *>(ctx->albedo.ptr);
+    RenderParams &rp = ctx->rp;
+    std::memset(&rp, 0, sizeof(rp));
+    rp.spp_total = cfg->spp;
+    uint32_t w = cfg->spp - 1;  // sampler/mod.rs:381-386
+    w |= w >> 1; w |= w >> 2; w |= w >> 4; w |= w >> 8; w |= w >> 16;
+    rp.w_mask = w;
+    rp.seed = (uint32_t)sampler->seed;
+    rp.max_depth = cfg->max_depth;
+    rp.rr_depth = cfg->rr_depth;
+    rp.use_nee = cfg->use_nee ? 1u : 0u;
+    rp.indirect_only = cfg->indirect_only ? 1u : 0u;
+    rp.force_diffuse = cfg->force_diffuse ? 1u : 0u;
+    rp.pixel_offset_x = cfg->pixel_offset[0];
+    rp.pixel_offset_y = cfg->pixel_offset[1];
+    rp.debug_depth = cfg->debug_depth;
+    rp.filter_type = filter->type;
+    rp.filter_radius = filter->radius;
+    rp.width = width;
+    rp.height = height;
+    rp.y0 = y0;
+    ctx->cfg = *cfg;
+    ctx->tile_y0 = y0;
+    ctx->tile_y1 = y1;
+    ctx->n_pixels = width * (y1 - y0);
+    ctx->spp_done = 0;
+    int rc = dev_alloc(ctx, ctx->film, (size_t)ctx->n_pixels * 7 * sizeof(float));
+    if (rc != AKR_OK) return rc;
+    AKR_CUDA(ctx, cudaMemsetAsync(ctx->film.ptr, 0, (size_t)ctx->n_pixels * 7 * sizeof(float), ctx->stream));  // Film::clear (film.rs:230-233)
+    rc = dev_alloc(ctx, ctx->dbg_hits, (size_t)ctx->n_pixels * 2 * sizeof(uint32_t));
+    if (rc != AKR_OK) return rc;
+    AKR_CUDA(ctx, cudaMemsetAsync(ctx->dbg_hits.ptr, 0xff, (size_t)ctx->n_pixels * 2 * sizeof(uint32_t), ctx->stream));
+    AKR_CUDA(ctx, cudaMemsetAsync(ctx->counters.ptr, 0, ctx->counters.bytes, ctx->stream));
+    ctx->render_ready = true;
+    return AKR_OK;
+}
+
+int akr_b200_render_pass(AkrContext *ctx, uint32_t n_spp, int blocking) {
+    if (!ctx) return AKR_ERR_INVALID_ARGUMENT;
+    if (!ctx->render_ready) return fail(ctx, AKR_ERR_STATE, "akr_b200_render_pass: call akr_b200_begin first");
+    if (n_spp == 0) return AKR_OK;
+    if (ctx->spp_done + n_spp > ctx->cfg.spp) return fail(ctx, AKR_ERR_INVALID_ARGUMENT, "pass exceeds the configured spp (sampler/mod.rs:666-668)");
+    AKR_CUDA(ctx, cudaSetDevice(ctx->device));
+    // wave geometry: pixels x samples with pixels * samples <= capacity
+    uint32_t cap = ctx->opts.wave_size ? ctx->opts.wave_size : (1u << 20);
+    cap = std::max(cap, 1024u);
+    uint32_t spp_chunk = std::min(n_spp, std::max(1u, cap / 32u));
+    uint32_t pix_chunk = std::max(32u, (cap / spp_chunk) & ~31u);
+    pix_chunk = std::min(pix_chunk, ctx->n_pixels);
+    int rc = ensure_wave_buffers(ctx, pix_chunk * spp_chunk);
+    if (rc != AKR_OK) return rc;
+
+    LaunchParams P;
+    std::memset(&P, 0, sizeof(P));
+    P.scene = ctx->scene;
+    P.corners = ctx->corners;
+    P.tables = SamplerTables{static_cast<const uint32_t *>(ctx->pmj.ptr), static_cast<const uint16_t *>(ctx->bn.ptr)};
+    P.rp = ctx->rp;
+    P.q[0] = ctx->q[0];
+    P.q[1] = ctx->q[1];
+    P.hits = ctx->hits;
+    P.shadow = ctx->shadow;
+    P.acc = ctx->acc;
+    P.counters = static_cast<uint32_t *>(ctx->counters.ptr);
+    P.film = static_cast<float *>(ctx->film.ptr);
+    P.n_film_pixels = ctx->n_pixels;
+    P.scene_smem_nodes = ctx->smem_nodes;
+    P.scene_smem_tris = ctx->smem_tris;
+    P.dbg_first_hits = static_cast<uint32_t *>(ctx->dbg_hits.ptr);
+
+    const bool prof = ctx->opts.profile_stages != 0;
+    struct StageMark {
+        int stage;
+        size_t ev;
+    };
+    std::vector<StageMark> marks;
+    size_t ev_used = 0;
+    auto mark = [&](int stage) -> int {
+        if (!prof) return AKR_OK;
+        for (int k = 0; k < 2; ++k) {
+            if (ev_used >= ctx->stage_events.size()) {
+                cudaEvent_t e;
+                if (cudaEventCreate(&e) != cudaSuccess) return AKR_ERR_CUDA;
+                ctx->stage_events.push_back(e);
+            }
+            if (k == 0) marks.push_back({stage, ev_used});
+            ++ev_used;
+        }
+        return AKR_OK;
+    };
+    auto count_launch = [&](int stage) {
+        ctx->stats.kernel_launches += 1;
+        ctx->stats.launches_kernel[stage] += 1;
+    };
+#define AKR_LAUNCH(stage, kernel, grid, smem, ...)                                                            \
+    do {                                                                                                      \
+        if (prof) {                                                                                           \
+            if (mark(stage) != AKR_OK) return fail(ctx, AKR_ERR_CUDA, "cudaEventCreate failed");              \
+            cudaEventRecord(ctx->stage_events[marks.back().ev], ctx->stream);                                  \
+        }                                                                                                     \
+        kernel<<<(grid), kBlock, (smem), ctx->stream>>>(__VA_ARGS__);                                          \
+        if (prof) cudaEventRecord(ctx->stage_events[marks.back().ev + 1], ctx->stream);                        \
+        count_launch(stage);                                                                                  \
+    } while (0)
+
+    AKR_CUDA(ctx, cudaEventRecord(ctx->ev_start, ctx->stream));
+    const uint32_t s_begin = ctx->spp_done;
+    for (uint32_t pix0 = 0; pix0 < ctx->n_pixels; pix0 += pix_chunk) {
+        const uint32_t n_pix = std::min(pix_chunk, ctx->n_pixels - pix0);
+        for (uint32_t s0 = 0; s0 < n_spp; s0 += spp_chunk) {
+            const uint32_t k = std::min(spp_chunk, n_spp - s0);
+            P.wave = WaveInfo{pix0, n_pix, s_begin + s0, k};
+            const uint32_t n_paths = n_pix * k;
+            const int g_full = grid_for(ctx, n_paths, 8);
+            AKR_LAUNCH(0, k_raygen, g_full, 0, P);
+            for (uint32_t depth = 0; depth <= ctx->rp.max_depth; ++depth) {
+                AKR_LAUNCH(1, k_intersect, g_full, ctx->smem_bytes, P, depth);
+                AKR_LAUNCH(2, k_shade, g_full, 0, P, depth);
+                AKR_LAUNCH(3, k_shadow, g_full, ctx->smem_bytes, P, depth);
+            }
+            AKR_LAUNCH(4, k_accumulate, grid_for(ctx, n_pix, 8), 0, P);
+            k_fold_counters<<<1, 128, 0, ctx->stream>>>(P.counters, static_cast<unsigned long long *>(ctx->totals.ptr), ctx->rp.max_depth + 2u);
+            count_launch(5);
+            ctx->stats.samples += n_paths;
+        }
+    }
+#undef AKR_LAUNCH
+    AKR_CUDA(ctx, cudaEventRecord(ctx->ev_stop, ctx->stream));
+    AKR_CUDA(ctx, cudaGetLastError());
+    ctx->spp_done += n_spp;
+    if (blocking || prof) {
+        AKR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        float ms = 0.0f;
+        AKR_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev_start, ctx->ev_stop));
+        ctx->stats.gpu_ms += ms;
+        if (prof) {
+            for (const StageMark &m : marks) {
+                float t = 0.0f;
+                cudaEventElapsedTime(&t, ctx->stage_events[m.ev], ctx->stage_events[m.ev + 1]);
+                ctx->stats.gpu_ms_kernel[m.stage] += t;
+            }
+        }
+    }
+    return AKR_OK;
+}
+
+int akr_b200_render_pt(AkrContext *ctx, const AkrPtConfig *cfg, const AkrSamplerConfig *sampler, const AkrFilterConfig *filter, const AkrTile *tile) {
+    int rc = akr_b200_begin(ctx, cfg, sampler, filter, tile);
+    if (rc != AKR_OK) return rc;
+    // host pass loop of PathTracer::render (pt.rs:1126-1149)
+    uint32_t cnt = 0;
+    const uint32_t per_pass = std::max(1u, cfg->spp_per_pass);
+    while (cnt < cfg->spp) {
+        uint32_t cur = std::min(cfg->spp - cnt, per_pass);
+        rc = akr_b200_render_pass(ctx, cur, 0);
+        if (rc != AKR_OK) return rc;
+        cnt += cur;
+    }
+    return akr_b200_synchronize(ctx);
+}
+
+int akr_b200_synchronize(AkrContext *ctx) {
+    if (!ctx) return AKR_ERR_INVALID_ARGUMENT;
+    AKR_CUDA(ctx, cudaSetDevice(ctx->device));
+    AKR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return AKR_OK;
+}
+
+int akr_b200_download_film(AkrContext *ctx, float *out, size_t n_floats) {
+    if (!ctx || !out) return fail(ctx, AKR_ERR_INVALID_ARGUMENT, "null argument");
+    if (!ctx->render_ready) return fail(ctx, AKR_ERR_STATE, "no film");
+    if (n_floats != (size_t)ctx->n_pixels * 7) return fail(ctx, AKR_ERR_INVALID_ARGUMENT, "film size mismatch (expected 7 * width * rows floats)");
+    AKR_CUDA(ctx, cudaSetDevice(ctx->device));
+    AKR_CUDA(ctx, cudaMemcpyAsync(out, ctx->film.ptr, n_floats * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    AKR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return AKR_OK;
+}
+
+int akr_b200_resolve_film_device(AkrContext *ctx, void *out_device, size_t n_floats, int rgba) {
+    if (!ctx || !out_device) return fail(ctx, AKR_ERR_INVALID_ARGUMENT, "null argument");
+    if (!ctx->render_ready) return fail(ctx, AKR_ERR_STATE, "no film");
+    if (n_floats != (size_t)ctx->n_pixels * (rgba ? 4 : 3)) return fail(ctx, AKR_ERR_INVALID_ARGUMENT, "image size mismatch");
+    AKR_CUDA(ctx, cudaSetDevice(ctx->device));
+    k_resolve_film<<<grid_for(ctx, ctx->n_pixels, 8), kBlock, 0, ctx->stream>>>(static_cast<const float *>(ctx->film.ptr), ctx->n_pixels,
+                                                                                static_cast<float *>(out_device), rgba);
+    AKR_CUDA(ctx, cudaGetLastError());
+    ctx->stats.kernel_launches += 1;
+    ctx->stats.launches_kernel[5] += 1;
+    return AKR_OK;
+}
+
+int akr_b200_resolve_film(AkrContext *ctx, float *out_host, size_t n_floats, int rgba) {
+    if (!ctx || !out_host) return fail(ctx, AKR_ERR_INVALID_ARGUMENT, "null argument");
+    DeviceBuffer tmp;
+    int rc = dev_alloc(ctx, tmp, n_floats * sizeof(float));
+    if (rc != AKR_OK) return rc;
+    rc = akr_b200_resolve_film_device(ctx, tmp.ptr, n_floats, rgba);
+    if (rc == AKR_OK) {
+        cudaError_t e = cudaMemcpyAsync(out_host, tmp.ptr, n_floats * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = fail(ctx, AKR_ERR_CUDA, cudaGetErrorString(e));
+    }
+    dev_free(tmp);
+    return rc;
+}
+
+int akr_b200_get_stats(AkrContext *ctx, AkrStats *out) {
+    if (!ctx || !out) return fail(ctx, AKR_ERR_INVALID_ARGUMENT, "null argument");
+    AKR_CUDA(ctx, cudaSetDevice(ctx->device));
+    AKR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    unsigned long long t[2] = {0, 0};
+    AKR_CUDA(ctx, cudaMemcpy(t, ctx->totals.ptr, sizeof(t), cudaMemcpyDeviceToHost));
+    ctx->stats.segments = t[0];
+    ctx->stats.shadow_rays = t[1];
+    *out = ctx->stats;
+    return AKR_OK;
+}
+
+int akr_b200_reset_stats(AkrContext *ctx) {
+    if (!ctx) return AKR_ERR_INVALID_ARGUMENT;
+    AKR_CUDA(ctx, cudaSetDevice(ctx->device));
+    AKR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    AKR_CUDA(ctx, cudaMemset(ctx->totals.ptr, 0, ctx->totals.bytes));
+    std::memset(&ctx->stats, 0, sizeof(ctx->stats));
+    return AKR_OK;
+}
+
+int akr_b200_debug_first_hits(AkrContext *ctx, uint32_t *out_inst, uint32_t *out_prim, size_t n_pixels) {
+    if (!ctx || !out_inst || !out_prim) return fail(ctx, AKR_ERR_INVALID_ARGUMENT, "null argument");
+    if (!ctx->render_ready || n_pixels != ctx->n_pixels) return fail(ctx, AKR_ERR_STATE, "no render / size mismatch");
+    std::vector<uint32_t> tmp(n_pixels * 2);
+    AKR_CUDA(ctx, cudaSetDevice(ctx->device));
+    AKR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    AKR_CUDA(ctx, cudaMemcpy(tmp.data(), ctx->dbg_hits.ptr, tmp.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < n_pixels; ++i) {
+        out_inst[i] = tmp[2 * i];
+        out_prim[i] = tmp[2 * i + 1];
+    }
+    return AKR_OK;
+}
+
+}  // extern "C"

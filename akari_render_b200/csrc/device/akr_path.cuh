@@ -1,0 +1,401 @@
+// akr_path.cuh — per-path bodies of the wavefront stages (one call = one path of one stage).
+//
+// The radiance loop of the reference megakernel (crates/akari_integrator/src/pt.rs:329-900 with
+// shift_mapping = None; kernel body pt.rs:1075-1103) is cut at its two ray casts into stages:
+//
+//   raygen     sampler.start + camera.generate_ray                 pt.rs:1081-1098
+//   intersect  scene.intersect (closest hit)                       pt.rs:363-380
+//   shade      emitter MIS, depth cap, NEE sample + BSDF eval,     pt.rs:381-513 (minus the occlusion
+//              BSDF sample, beta update, Russian roulette, next ray           test), 775-865
+//   shadow     scene.occlude + add_radiance(direct)                pt.rs:504-513
+//   accumulate indirect clamp + film.add_sample                    pt.rs:871-876, 1100; film.rs:196-229
+//
+// All paths of one stage launch are at the same depth (no path regeneration inside a wave), so the
+// depth and the sampler dimension are launch constants, not per-path state.
+#pragma once
+#include "akr_trace.cuh"
+
+namespace akr {
+
+// ---- Pmj02BnSampler as a pure function of (pixel, sample index, dimension) -------------------------
+// sampler/mod.rs:551-623; state layout :513-520.  `dim` is passed explicitly.
+AKR_HD float bluenoise(const SamplerTables &tab, uint32_t tex, uint32_t px, uint32_t py) {
+    // reference texel: BLUE_NOISE_TEXTURES[tex % 48][px % 128][py % 128] (sampler/mod.rs:542-550);
+    // the table is transposed at upload so that consecutive px are consecutive in memory.
+    uint32_t t = tex % 48u;
+    uint16_t v = tab.bn[(t * 128u + (py & 127u)) * 128u + (px & 127u)];
+    return (float)v / 65535.0f;
+}
+AKR_HD float sampler_1d(const SamplerTables &tab, const RenderParams &rp, uint32_t px, uint32_t py, uint32_t sample_index, uint32_t dim) {
+    uint32_t hash = xxhash32_4(px, py, dim, rp.seed);
+    uint32_t index = permute_element(sample_index, rp.spp_total, rp.w_mask, hash);
+    float delta = bluenoise(tab, dim, px, py);
+    return fminf(((float)index + delta) / (float)rp.spp_total, AKR_ONE_MINUS_EPSILON);
+}
+AKR_HD f2 sampler_2d(const SamplerTables &tab, const RenderParams &rp, uint32_t px, uint32_t py, uint32_t sample_index, uint32_t dim) {
+    uint32_t index = sample_index;
+    uint32_t pmj_instance = dim / 2u;
+    if (pmj_instance >= 5u) {
+        uint32_t hash = xxhash32_4(px, py, dim, rp.seed);
+        index = permute_element(sample_index, rp.spp_total, rp.w_mask, hash);
+    }
+    uint32_t i = 65536u * (pmj_instance % 5u) + (index % 65536u);
+    float ux = (float)tab.pmj[i * 2u] * 0x1p-32f;
+    float uy = (float)tab.pmj[i * 2u + 1u] * 0x1p-32f;
+    ux = ux + bluenoise(tab, dim, px, py);
+    uy = uy + bluenoise(tab, dim + 1u, px, py);
+    ux = ux - floorf(ux);
+    uy = uy - floorf(uy);
+    return f2{fminf(ux, AKR_ONE_MINUS_EPSILON), fminf(uy, AKR_ONE_MINUS_EPSILON)};
+}
+// Dimension of the first draw of bounce `depth` (depth counted after the increment at pt.rs:469):
+// start() sets dim = 4, the filter takes 2, every earlier bounce took 3 + 3 and one more when it drew
+// the roulette sample (depth_j > rr_depth, pt.rs:843-846).
+AKR_HD uint32_t bounce_first_dim(uint32_t depth, uint32_t rr_depth) {
+    uint32_t prev = depth - 1u;
+    uint32_t rr = prev > rr_depth ? prev - rr_depth : 0u;
+    return 6u + 6u * prev + rr;
+}
+
+// ---- wave bookkeeping -------------------------------------------------------------------------------
+struct WaveInfo {
+    uint32_t pix0;      // first pixel (linear index inside the tile) of this wave
+    uint32_t n_pix;     // pixels in this wave
+    uint32_t s0;        // first sample index
+    uint32_t n_spp;     // samples per pixel in this wave; path_id = s_local * n_pix + p_local
+};
+struct PathCoord {
+    uint32_t px, py, sample_index, pixel_in_tile;
+};
+AKR_HD PathCoord path_coord(const RenderParams &rp, const WaveInfo &w, uint32_t path_id) {
+    uint32_t s_local = path_id / w.n_pix;
+    uint32_t p_local = path_id - s_local * w.n_pix;
+    uint32_t pix = w.pix0 + p_local;
+    uint32_t row = pix / rp.width;
+    return PathCoord{pix - row * rp.width, rp.y0 + row, w.s0 + s_local, pix};
+}
+
+struct PathState {  // what survives from one bounce to the next (13 words in the SoA queue)
+    f3 o, d;
+    uint32_t ex;        // global id of the triangle the ray leaves (exclude0)
+    f3 beta;
+    float prev_bsdf_pdf;
+    uint32_t path_id;
+};
+struct ShadowItem {    // 13 words
+    f3 o, d;
+    float t_max;
+    uint32_t ex0, ex1;
+    f3 contrib;         // beta * direct, added to L when unoccluded
+    uint32_t path_id;
+};
+struct AccView {       // per-path radiance accumulators, indexed by path_id (not compacted)
+    float *lr, *lg, *lb;     // radiance
+    float *br, *bg, *bb;     // base_replay_throughput
+};
+
+// ---- stage: raygen ------------------------------------------------------------------------------------
+AKR_HD f2 filter_sample(const RenderParams &rp, f2 u) {  // film.rs:32-49
+    if (rp.filter_type == 0u) return f2{(u.x - 0.5f) * rp.filter_radius, (u.y - 0.5f) * rp.filter_radius};
+    float width = rp.filter_radius;
+    float sigma = width / 3.0f;
+    float r = sqrtf(-2.0f * logf(u.x));
+    float theta = 2.0f * AKR_PI * u.y;
+    float s, c;
+#if defined(__CUDA_ARCH__)
+    sincosf(theta, &s, &c);
+#else
+    s = sinf(theta);
+    c = cosf(theta);
+#endif
+    return f2{clampf(r * c * sigma, -width, width), clampf(r * s * sigma, -width, width)};
+}
+AKR_HD PathState raygen_body(const SceneView &sc, const SamplerTables &tab, const RenderParams &rp, const WaveInfo &w, uint32_t path_id) {
+    PathCoord pc = path_coord(rp, w, path_id);
+    // shifted pixel (pt.rs:1084-1088); the sampler stays keyed by the unshifted pixel
+    int32_t sx = (int32_t)pc.px + rp.pixel_offset_x, sy = (int32_t)pc.py + rp.pixel_offset_y;
+    sx = sx < 0 ? 0 : (sx > (int32_t)rp.width - 1 ? (int32_t)rp.width - 1 : sx);
+    sy = sy < 0 ? 0 : (sy > (int32_t)rp.height - 1 ? (int32_t)rp.height - 1 : sy);
+    f2 u = sampler_2d(tab, rp, pc.px, pc.py, pc.sample_index, 4u);
+    f2 off = filter_sample(rp, u);
+    float fx = ((float)sx + 0.5f) + off.x, fy = ((float)sy + 0.5f) + off.y;
+    const CameraRec &cam = sc.camera;
+    // r2c.transform_point((fx, fy, 0)) with a scale+translate matrix, then normalize (camera/mod.rs:84-93)
+    f3 dc = normalize(mk3(cam.r2c_s[0] * fx + cam.r2c_t[0], cam.r2c_s[1] * fy + cam.r2c_t[1], cam.r2c_s[2] * 0.0f + cam.r2c_t[2]));
+    PathState ps;
+    if (cam.c2w_identity) {  // AffineTransform shortcuts (geometry.rs:228-247)
+        ps.o = splat3(0.0f);
+        ps.d = dc;
+    } else {
+        ps.o = mk3(cam.c2w[9], cam.c2w[10], cam.c2w[11]);
+        ps.d = mk3(cam.c2w[0] * dc.x + cam.c2w[3] * dc.y + cam.c2w[6] * dc.z, cam.c2w[1] * dc.x + cam.c2w[4] * dc.y + cam.c2w[7] * dc.z,
+                   cam.c2w[2] * dc.x + cam.c2w[5] * dc.y + cam.c2w[8] * dc.z);
+    }
+    ps.ex = 0xffffffffu;
+    ps.beta = splat3(1.0f);
+    ps.prev_bsdf_pdf = 0.0f;
+    ps.path_id = path_id;
+    return ps;
+}
+
+// ---- surface interaction (mesh.rs:487-654) from the per-triangle record --------------------------------
+struct Surface {
+    f3 p, ng;
+    Frame frame;
+    float area;
+};
+struct CornerAttribs {           // optional per-corner arrays indexed by gid * 3 + k
+    const float *normals;        // [n_tris * 3][3] or nullptr
+    const float *tangents;       // [n_tris * 3][3] or nullptr
+};
+AKR_HD Surface surface_from_hit(const SceneView &sc, const CornerAttribs &ca, uint32_t gid, float u, float v) {
+    const TriShade &ts = sc.shade[gid];
+    const InstanceRec &in = sc.instances[ts.inst];
+    float w0 = 1.0f - u - v;
+    f3 v0 = ld3(ts.v0), v1 = ld3(ts.v1), v2 = ld3(ts.v2);
+    f3 pl = w0 * v0 + u * v1 + v * v2;
+    f3 c0 = ld3(in.m), c1 = ld3(in.m + 3), c2 = ld3(in.m + 6);
+    Surface s;
+    s.p = (c0 * pl.x + c1 * pl.y + c2 * pl.z) + ld3(in.t);
+    s.ng = ld3(ts.ng);
+    s.area = ts.area;
+    if (!(ts.flags & (TRI_HAS_NORMALS | TRI_HAS_TANGENTS))) {
+        s.frame = Frame{s.ng, ld3(ts.ft), ld3(ts.fs)};
+        return s;
+    }
+    // per-hit frame: ns from interpolated corner normals (mesh.rs:594-602,620-621), tangent from the
+    // tangent buffer when present (mesh.rs:558-569) else the per-triangle dp/du stored in `ft`
+    f3 ns = s.ng;
+    f3 i0 = ld3(in.m_inv_t), i1 = ld3(in.m_inv_t + 3), i2 = ld3(in.m_inv_t + 6);
+    if (ts.flags & TRI_HAS_NORMALS) {
+        const float *n = ca.normals + (size_t)gid * 9u;
+        f3 nl = w0 * ld3(n) + u * ld3(n + 3) + v * ld3(n + 6);
+        ns = normalize(i0 * nl.x + i1 * nl.y + i2 * nl.z);
+    }
+    f3 tt = ld3(ts.ft);
+    if (ts.flags & TRI_HAS_TANGENTS) {
+        const float *t = ca.tangents + (size_t)gid * 9u;
+        f3 t0 = ld3(t), t1 = ld3(t + 3), t2 = ld3(t + 6);
+        bool fin = is_finite(t0.x) && is_finite(t0.y) && is_finite(t0.z) && is_finite(t1.x) && is_finite(t1.y) && is_finite(t1.z) &&
+                   is_finite(t2.x) && is_finite(t2.y) && is_finite(t2.z);
+        if (fin) {
+            f3 tl = normalize(w0 * t0 + u * t1 + v * t2);
+            tt = c0 * tl.x + c1 * tl.y + c2 * tl.z;
+        } else {
+            tt = ld3(ts.fs);  // fallback dp/du tangent is kept in `fs` for tangent-buffer meshes
+        }
+    }
+    s.frame = (tt.x != 0.0f || tt.y != 0.0f || tt.z != 0.0f) ? frame_from_n_t(ns, tt) : frame_from_n(ns);
+    return s;
+}
+
+AKR_HD float mis_weight(float a, float b) { return a / (a + b); }  // pt.rs:962-973, power 1
+
+// ---- stage: shade ----------------------------------------------------------------------------------------
+struct ShadeOut {
+    bool has_shadow, has_next;
+    ShadowItem shadow;
+    PathState next;
+};
+
+AKR_HD void acc_add(const AccView &acc, uint32_t id, f3 c) {
+    acc.lr[id] += c.x;
+    acc.lg[id] += c.y;
+    acc.lb[id] += c.z;
+}
+
+// `depth` = path depth when the ray was cast (0 for camera rays).
+AKR_HD ShadeOut shade_body(const SceneView &sc, const CornerAttribs &ca, const SamplerTables &tab, const RenderParams &rp, const WaveInfo &wave,
+                           uint32_t depth, const PathState &ps, HitRec hit, const AccView &acc) {
+    ShadeOut out;
+    out.has_shadow = false;
+    out.has_next = false;
+    const uint32_t id = ps.path_id;
+    const bool dbg_on = rp.debug_depth < 0;
+    if (hit.gid == 0xffffffffu) {
+        // miss: hit_envmap = (0, 0) (pt.rs:226-228): add_radiance(0) and stop
+        if (depth == 0u) {
+            acc.lr[id] = 0.0f; acc.lg[id] = 0.0f; acc.lb[id] = 0.0f;
+            acc.br[id] = 0.0f; acc.bg[id] = 0.0f; acc.bb[id] = 0.0f;
+        } else if (dbg_on || depth == (uint32_t)rp.debug_depth) {
+            f3 c = ps.beta * (splat3(0.0f) * 0.0f);  // NaN/inf throughput poisons the sample, as in the reference
+            if (c.x != 0.0f || c.y != 0.0f || c.z != 0.0f) acc_add(acc, id, c);
+        }
+        return out;
+    }
+    const TriShade &ts = sc.shade[hit.gid];
+    const Material &mat = sc.materials[ts.mat];
+    Surface si = surface_from_hit(sc, ca, hit.gid, hit.u, hit.v);
+    f3 wo = -ps.d;
+    // handle_surface_light (pt.rs:230-258)
+    {
+        f3 direct = splat3(0.0f);
+        float w = 0.0f;
+        if ((ts.flags & TRI_IS_LIGHT) && (!rp.indirect_only || depth > 1u)) {
+            f3 emission = ld3(mat.emission);  // AreaLight::le (light/area.rs:36-49)
+            direct = dot(si.ng, ps.d) < 0.0f ? emission : splat3(0.0f);
+            if (depth == 0u || !rp.use_nee) {
+                w = 1.0f;
+            } else {
+                // LightAggregate::pdf_direct (light/mod.rs:134-147), AreaLight::pdf_direct (light/area.rs:109-130)
+                const InstanceRec &in = sc.instances[ts.inst];
+                float light_choice_pdf = sc.alias_pdf[in.light_id];
+                f3 wi = si.p - ps.o;
+                float dist2 = length_squared(wi);
+                wi = wi / sqrtf(dist2);
+                float pdf = ts.prim_pdf / si.area * dist2 / fmaxf(fabsf(dot(si.ng, wi)), 1e-6f);
+                w = mis_weight(ps.prev_bsdf_pdf, light_choice_pdf * pdf);
+            }
+        }
+        f3 c = ps.beta * (direct * w);
+        if (depth == 0u) {
+            // radiance starts at 0; base_replay_throughput = radiance (pt.rs:415-417)
+            f3 l = (dbg_on || rp.debug_depth == 0) ? splat3(0.0f) + c : splat3(0.0f);
+            acc.lr[id] = l.x; acc.lg[id] = l.y; acc.lb[id] = l.z;
+            acc.br[id] = l.x; acc.bg[id] = l.y; acc.bb[id] = l.z;
+        } else if (dbg_on || depth == (uint32_t)rp.debug_depth) {
+            if (c.x != 0.0f || c.y != 0.0f || c.z != 0.0f) acc_add(acc, id, c);
+        }
+    }
+    if (depth >= rp.max_depth) return out;  // pt.rs:466-468
+    const uint32_t d1 = depth + 1u;         // pt.rs:469
+    PathCoord pc = path_coord(rp, wave, id);
+    const uint32_t dim0 = bounce_first_dim(d1, rp.rr_depth);
+    // u_direct = next_3d, u_bsdf = next_3d — both are always drawn (pt.rs:471-481)
+    float ul0 = sampler_1d(tab, rp, pc.px, pc.py, pc.sample_index, dim0);
+    f2 ul12 = sampler_2d(tab, rp, pc.px, pc.py, pc.sample_index, dim0 + 1u);
+    float ub0 = sampler_1d(tab, rp, pc.px, pc.py, pc.sample_index, dim0 + 3u);
+    f2 ub12 = sampler_2d(tab, rp, pc.px, pc.py, pc.sample_index, dim0 + 4u);
+
+    // sample_light (pt.rs:170-209) -> LightAggregate::sample_direct -> AreaLight::sample_direct (light/area.rs:51-107)
+    bool dl_valid = false;
+    f3 dl_li = splat3(0.0f), dl_wi = splat3(0.0f);
+    float dl_pdf = 0.0f;
+    if (rp.use_nee && (!rp.indirect_only || d1 > 1u) && sc.n_lights > 0u) {
+        AliasSample ls = alias_sample_and_remap(sc.alias_j, sc.alias_t, sc.alias_pdf, sc.n_lights, ul0);
+        const LightRec &light = sc.lights[ls.idx];
+        AliasSample prs = alias_sample_and_remap(sc.alias_j + light.alias_offset, sc.alias_t + light.alias_offset,
+                                                 sc.alias_pdf + light.alias_offset, light.n_prims, ls.u);
+        f2 bary = uniform_sample_triangle(ul12);
+        uint32_t lgid = light.tri_offset + prs.idx;
+        Surface lsi = surface_from_hit(sc, ca, lgid, bary.x, bary.y);
+        f3 wi = lsi.p - si.p;
+        if (length_squared(wi) != 0.0f) {
+            float dist2 = length_squared(wi);
+            wi = wi / sqrtf(dist2);
+            f3 emission = ld3(sc.materials[sc.shade[lgid].mat].emission);
+            f3 li = dot(wi, lsi.ng) < 0.0f ? emission : splat3(0.0f);
+            float cos_theta_i = fabsf(dot(lsi.ng, wi));
+            float pdf = prs.pdf / lsi.area * dist2 / cos_theta_i;
+            if (is_finite(pdf)) {  // LightSample.valid (light/area.rs:104)
+                f3 ro = offset_ray_origin(si.p, face_forward(si.ng, wi));
+                float dist = sqrtf(dist2);
+                dl_valid = true;
+                dl_li = li;
+                dl_wi = wi;
+                dl_pdf = pdf * ls.pdf;  // light/mod.rs:130
+                out.shadow.o = ro;
+                out.shadow.d = wi;
+                out.shadow.t_max = dist * (1.0f - 1e-3f);
+                out.shadow.ex0 = hit.gid;  // pt.rs:189-190
+                out.shadow.ex1 = lgid;     // light/area.rs:95
+                out.shadow.path_id = id;
+            }
+        }
+    }
+
+    // sample_surface_and_shade_direct (pt.rs:297-323)
+    Material fd;
+    const Material *m = &mat;
+    if (rp.force_diffuse) {  // pt.rs:268-279
+        fd = mat;
+        fd.type = MAT_LAMBERT;
+        fd.wrap_inner = 0u;
+        fd.diffuse[0] = fd.diffuse[1] = fd.diffuse[2] = 1.0f * AKR_FRAC_1_PI * 0.8f;
+        m = &fd;
+    }
+    ClosureFrames cf = make_closure_frames(*m, si.frame, si.ng);
+    f3 direct = splat3(0.0f);
+    if (dl_valid) {
+        BsdfEval e = closure_eval(*m, sc.albedo_table, cf, wo, dl_wi);
+        float w = mis_weight(dl_pdf, e.pdf);
+        direct = dl_li * e.f * w / dl_pdf;
+    }
+    // SurfaceClosure::sample (mod.rs:795-815)
+    BsdfDir sd = closure_sample_wi(*m, sc.albedo_table, cf, wo, ub0, ub12);
+    f3 bs_wi = splat3(0.0f), bs_color = splat3(0.0f);
+    float bs_pdf = 0.0f;
+    bool bs_valid = false;
+    if (sd.valid) {
+        BsdfEval e = closure_eval(*m, sc.albedo_table, cf, wo, sd.wi);
+        bs_wi = sd.wi;
+        bs_color = e.f;
+        bs_pdf = e.pdf;
+        bs_valid = e.pdf > 0.0f;
+    }
+    if (dl_valid) {  // the occlusion test and add_radiance(direct) happen in the shadow stage (pt.rs:504-513)
+        out.has_shadow = true;
+        bool add = dbg_on || d1 == (uint32_t)rp.debug_depth;
+        out.shadow.contrib = add ? ps.beta * direct : splat3(0.0f);
+    }
+    f3 beta = ps.beta * (bs_color / bs_pdf);  // mul_beta(f / pdf) (pt.rs:783)
+    if (bs_pdf <= 0.0f || !bs_valid || reduce_min(bs_color) < 0.0f) return out;  // pt.rs:832-842
+    if (d1 > rp.rr_depth) {  // pt.rs:211-218,843-850
+        float cont_prob = clampf(reduce_max(beta), 0.0f, 1.0f) * 0.95f;
+        float ur = sampler_1d(tab, rp, pc.px, pc.py, pc.sample_index, dim0 + 6u);
+        if (ur >= cont_prob) return out;
+        beta = beta * (splat3(1.0f) / cont_prob);
+    }
+    out.has_next = true;
+    out.next.o = offset_ray_origin(si.p, face_forward(si.ng, bs_wi));  // pt.rs:856
+    out.next.d = bs_wi;
+    out.next.ex = hit.gid;
+    out.next.beta = beta;
+    out.next.prev_bsdf_pdf = bs_pdf;
+    out.next.path_id = id;
+    return out;
+}
+
+// ---- stage: shadow (pt.rs:504-513) ----------------------------------------------------------------------------
+// `depth1` = depth after the increment of the bounce that produced the item.
+AKR_HD void shadow_resolve(const AccView &acc, const ShadowItem &it, bool occluded, uint32_t depth1) {
+    uint32_t id = it.path_id;
+    if (!occluded) {
+        f3 c = it.contrib;
+        if (c.x != 0.0f || c.y != 0.0f || c.z != 0.0f) acc_add(acc, id, c);
+    }
+    if (depth1 == 1u) {  // base_replay_throughput = radiance (pt.rs:510-512)
+        acc.br[id] = acc.lr[id];
+        acc.bg[id] = acc.lg[id];
+        acc.bb[id] = acc.lb[id];
+    }
+}
+
+// ---- stage: accumulate (pt.rs:871-876 + film.rs:196-229) -------------------------------------------------------
+// One call per pixel of the wave; samples are added in sample-index order like the reference's
+// per-thread loop (pt.rs:1080-1101).  film = | rgb 3N | splat 3N | weight N | (film.rs:66-76).
+AKR_HD void accumulate_body(const AccView &acc, const WaveInfo &w, uint32_t p_local, float *film, uint32_t n_film_pixels) {
+    uint32_t i = w.pix0 + p_local;
+    float r = film[i * 3u + 0u], g = film[i * 3u + 1u], b = film[i * 3u + 2u];
+    float wt = film[6u * n_film_pixels + i];
+    for (uint32_t s = 0; s < w.n_spp; ++s) {
+        uint32_t id = s * w.n_pix + p_local;
+        f3 L = mk3(acc.lr[id], acc.lg[id], acc.lb[id]);
+        f3 B = mk3(acc.br[id], acc.bg[id], acc.bb[id]);
+        f3 ind = L - B;  // clamp_indirect = 1000, Color::clamp -> [0, max] (pt.rs:130,871-876; color.rs:352-361)
+        ind = mk3(clampf(ind.x, 0.0f, 1000.0f), clampf(ind.y, 0.0f, 1000.0f), clampf(ind.z, 0.0f, 1000.0f));
+        L = B + ind;
+        if (has_nan(L)) L = splat3(0.0f);  // remove_nan (color.rs:343-351)
+        L = L * 1.0f;                       // * ray weight
+        r += L.x;
+        g += L.y;
+        b += L.z;
+        wt += 1.0f;
+    }
+    film[i * 3u + 0u] = r;
+    film[i * 3u + 1u] = g;
+    film[i * 3u + 2u] = b;
+    film[6u * n_film_pixels + i] = wt;
+}
+
+}  // namespace akr

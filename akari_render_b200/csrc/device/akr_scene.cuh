@@ -1,0 +1,123 @@
+// akr_scene.cuh — flat, pointer-based scene layout consumed by the kernels ("scene blob" in HBM).
+//
+// Replaces what the reference keeps in luisa buffers / bindless heap / rtx::Accel:
+//   MeshAggregate + MeshHeader + MeshInstance   crates/akari_render/src/mesh.rs:189-348
+//   LightAggregate + AliasTable                  light/mod.rs:87-92, util/distribution.rs:12-33
+//   PerspectiveCameraData                        camera/mod.rs:108-153
+//   Svm shader data                              svm/mod.rs:240-255  (constant-folded into Material[])
+// Everything is read-only during rendering and small enough on `cbox` (a few KB) to be staged in
+// shared memory by a TMA bulk copy at kernel start; larger scenes keep the top of the BVH in shared
+// memory and the rest in L2.
+#pragma once
+#include "akr_bsdf.cuh"
+
+namespace akr {
+
+// BVH2 node holding both children's boxes (one 64-byte fetch decides both children).
+struct alignas(16) BvhNode {
+    float lo0[3], hi0[3];
+    float lo1[3], hi1[3];
+    int32_t c0, c1;  // >= 0: inner node index; < 0: leaf, ~c = (first_tri << 3) | count
+    uint32_t _pad[2];
+};
+static_assert(sizeof(BvhNode) == 64, "BvhNode must be 64 bytes");
+
+// World-space triangle for traversal, stored in BVH leaf order.  48 bytes.
+struct alignas(16) TriGeom {
+    float v0[3];
+    uint32_t gid;  // global triangle id = instance.tri_offset + prim (instances in id order)
+    float e1[3];
+    uint32_t _p0;
+    float e2[3];
+    uint32_t _p1;
+};
+static_assert(sizeof(TriGeom) == 48, "TriGeom must be 48 bytes");
+
+enum TriFlags : uint32_t {
+    TRI_IS_LIGHT = 1u << 0,     // instance.light.valid()
+    TRI_HAS_NORMALS = 1u << 1,  // per-corner normals: ns interpolated per hit
+    TRI_HAS_TANGENTS = 1u << 2,
+    TRI_HAS_UVS = 1u << 3,
+    TRI_ALPHA = 1u << 4,        // material alpha < 1: stochastic alpha test applies
+};
+
+// Shading record per global triangle id: the bary-independent part of
+// MeshAggregate::surface_interaction (mesh.rs:487-654), precomputed at upload with the same f32
+// operations.  For flat triangles (no per-corner normals) the whole frame is constant.  96 bytes.
+struct alignas(16) TriShade {
+    float v0[3], v1[3], v2[3];  // local-space vertices (p = M * interp + t is evaluated per hit)
+    float ng[3];                // world geometric normal  normalize((M^T)^-1 ng_local)
+    float ft[3], fs[3];         // frame.t, frame.s for flat triangles (frame.n = ng)
+    float area;                 // world prim_area
+    float prim_pdf;             // area_sampler.pdf(prim) when the instance is a light
+    uint32_t inst;
+    uint32_t mat;               // index into Material[]
+    uint32_t flags;             // TriFlags
+    uint32_t prim;
+};
+static_assert(sizeof(TriShade) == 96, "TriShade must be 96 bytes");
+
+struct alignas(16) InstanceRec {
+    float m[9];        // upper 3x3, column-major
+    float t[3];        // translation
+    float m_inv_t[9];  // (M^T)^-1, column-major
+    float det;         // MeshInstance.transform_det (mesh.rs:311-312)
+    uint32_t light_id; // 0xffffffff = not a light
+    uint32_t tri_offset;
+    uint32_t n_tris;
+    uint32_t geom_id;
+    uint32_t flags;
+    uint32_t _pad[5];
+};
+static_assert(sizeof(InstanceRec) == 128, "InstanceRec must be 128 bytes");
+
+struct LightRec {  // AreaLight (light/area.rs:12-16) + its per-instance alias table
+    uint32_t inst;
+    uint32_t tri_offset;    // gid of prim 0
+    uint32_t alias_offset;  // into alias_j / alias_t / alias_pdf
+    uint32_t n_prims;
+};
+
+struct CameraRec {
+    float c2w[12];   // columns 0..2 (xyz) then translation
+    uint32_t c2w_identity;  // AffineTransform.close_to_identity (geometry.rs:212-218)
+    float r2c_s[3], r2c_t[3];  // raster->camera is scale+translate (camera/mod.rs:129-145)
+    uint32_t width, height;
+};
+
+struct SceneView {
+    const BvhNode *nodes;
+    const TriGeom *tris;
+    const TriShade *shade;
+    const InstanceRec *instances;
+    const Material *materials;
+    const LightRec *lights;
+    const uint32_t *alias_j;   // light distribution first (n_lights entries), then per-light tables
+    const float *alias_t;
+    const float *alias_pdf;
+    const float *albedo_table; // 16^3
+    uint32_t n_nodes, n_tris, n_instances, n_materials, n_lights;
+    uint32_t any_alpha;        // some material has alpha < 1
+    CameraRec camera;
+};
+
+struct SamplerTables {
+    const uint32_t *pmj;   // [5][65536][2]
+    const uint16_t *bn;    // [48][128][128], transposed at upload to [t][py % 128][px % 128]
+};
+
+struct RenderParams {  // pt::Config + sampler + filter, resolved for one pass
+    uint32_t spp_total;      // Pmj02BnState.spp
+    uint32_t w_mask;         // Pmj02BnState.w
+    uint32_t seed;
+    uint32_t max_depth, rr_depth;
+    uint32_t use_nee, indirect_only, force_diffuse;
+    int32_t pixel_offset_x, pixel_offset_y;
+    int32_t debug_depth;     // < 0: none
+    uint32_t filter_type;
+    float filter_radius;
+    uint32_t width, height;  // full sensor
+    uint32_t y0;             // first row of this context's tile
+};
+
+}  // namespace akr

@@ -1,0 +1,133 @@
+// akr_trace.cuh — BVH2 traversal + ray/triangle intersection.
+//
+// Replaces the third-party layer the reference calls through luisa `rtx::Accel`
+// (crates/akari_render/src/scene.rs:88-110 `_trace_closest_rq`, :155-185 `occlude`; OptiX on
+// `-d cuda`, Embree on `-d cpu`).  Semantics reproduced here:
+//   * candidates equal to ray.exclude0 / exclude1 are skipped (scene.rs:99-101,167-170);
+//   * stochastic alpha test on candidates of materials with alpha < 1 (scene.rs:49-86);
+//   * closest hit = minimum t in (t_min, t_max); exact ties resolve to the lower global triangle id
+//     so the result does not depend on traversal order (and equals a brute-force scan in id order).
+#pragma once
+#include "akr_scene.cuh"
+
+namespace akr {
+
+struct HitRec {
+    uint32_t gid;  // 0xffffffff = miss
+    float u, v;
+};
+
+// Moeller-Trumbore on a precomputed (v0, e1, e2) triangle; bary (u, v) weights v1, v2.
+AKR_HD bool tri_test(const TriGeom &tr, f3 o, f3 d, float t_min, float t_max, float &t_out, float &u_out, float &v_out) {
+    f3 e1 = mk3(tr.e1[0], tr.e1[1], tr.e1[2]);
+    f3 e2 = mk3(tr.e2[0], tr.e2[1], tr.e2[2]);
+    f3 pvec = cross(d, e2);
+    float det = dot(e1, pvec);
+    if (det == 0.0f) return false;
+    float inv_det = 1.0f / det;
+    f3 tvec = o - mk3(tr.v0[0], tr.v0[1], tr.v0[2]);
+    float u = dot(tvec, pvec) * inv_det;
+    if (!(u >= 0.0f && u <= 1.0f)) return false;
+    f3 qvec = cross(tvec, e1);
+    float v = dot(d, qvec) * inv_det;
+    if (!(v >= 0.0f && u + v <= 1.0f)) return false;
+    float t = dot(e2, qvec) * inv_det;
+    if (!(t > t_min && t < t_max)) return false;
+    t_out = t;
+    u_out = u;
+    v_out = v;
+    return true;
+}
+
+// Conservative slab test (boxes are padded at build time); NaNs from 0 * inf drop out of fminf/fmaxf.
+AKR_HD bool box_test(const float *lo, const float *hi, f3 o, f3 inv_d, float t_min, float t_max, float &t_near) {
+    float tx0 = (lo[0] - o.x) * inv_d.x, tx1 = (hi[0] - o.x) * inv_d.x;
+    float ty0 = (lo[1] - o.y) * inv_d.y, ty1 = (hi[1] - o.y) * inv_d.y;
+    float tz0 = (lo[2] - o.z) * inv_d.z, tz1 = (hi[2] - o.z) * inv_d.z;
+    float tn = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), t_min));
+    float tf = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fminf(fmaxf(tz0, tz1), t_max));
+    t_near = tn;
+    return tn <= tf;
+}
+
+// scene.rs:49-86 for constant-alpha materials: pass if alpha >= 1 or alpha > hash / 2^32
+AKR_HD bool alpha_test(const SceneView &sc, uint32_t gid, float u, float v) {
+    const TriShade &ts = sc.shade[gid];
+    if (!(ts.flags & TRI_ALPHA)) return true;
+    float alpha = sc.materials[ts.mat].alpha;
+    uint32_t h = xxhash32_4(ts.inst, ts.prim, f2u(u), f2u(v));
+    float hf = (float)h * (float)(1.0 / 4294967295.0);
+    return (alpha >= 1.0f) || (alpha > hf);
+}
+
+#define AKR_BVH_STACK 48
+
+// ANY_HIT = false: closest hit (Scene::intersect).  ANY_HIT = true: first accepted hit (Scene::occlude).
+// Where traversal data lives.  On the device the first `n_fast_nodes` nodes (breadth-first order = the
+// top of the tree) and, when they fit, all triangles are staged in shared memory by a TMA bulk copy;
+// the rest is read from global memory (L2-resident).  The host simulation passes n_fast_nodes = 0.
+struct TraceData {
+    const BvhNode *fast_nodes;  // shared memory copy of nodes[0 .. n_fast_nodes)
+    const BvhNode *nodes;       // global
+    const TriGeom *tris;        // shared or global
+    uint32_t n_fast_nodes;
+};
+
+template <bool ANY_HIT>
+AKR_HD HitRec trace_ray(const SceneView &sc, const TraceData &td, f3 o, f3 d, float t_min, float t_max, uint32_t ex0, uint32_t ex1) {
+    const TriGeom *tris = td.tris;
+    HitRec best{0xffffffffu, 0.0f, 0.0f};
+    float best_t = t_max;
+    f3 inv_d = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    int32_t stack[AKR_BVH_STACK];
+    int sp = 0;
+    int32_t node = 0;
+    while (true) {
+        if (node >= 0) {
+            const BvhNode n = ((uint32_t)node < td.n_fast_nodes) ? td.fast_nodes[node] : td.nodes[node];
+            float tn0, tn1;
+            // `<=` culling keeps boxes that may hold an equal-t triangle with a lower id
+            bool h0 = box_test(n.lo0, n.hi0, o, inv_d, t_min, best_t, tn0);
+            bool h1 = box_test(n.lo1, n.hi1, o, inv_d, t_min, best_t, tn1);
+            if (h0 && h1) {
+                int32_t near = n.c0, far = n.c1;
+                if (tn1 < tn0) {
+                    near = n.c1;
+                    far = n.c0;
+                }
+                if (sp < AKR_BVH_STACK) stack[sp++] = far;
+                node = near;
+                continue;
+            }
+            if (h0) {
+                node = n.c0;
+                continue;
+            }
+            if (h1) {
+                node = n.c1;
+                continue;
+            }
+        } else {
+            uint32_t leaf = (uint32_t)(~node);
+            uint32_t first = leaf >> 3, count = leaf & 7u;
+            for (uint32_t k = 0; k < count; ++k) {
+                const TriGeom &tr = tris[first + k];
+                uint32_t gid = tr.gid;
+                if (gid == ex0 || gid == ex1) continue;
+                float t, u, v;
+                if (!tri_test(tr, o, d, t_min, t_max, t, u, v)) continue;
+                bool closer = (t < best_t) || (t == best_t && gid < best.gid);
+                if (!closer) continue;
+                if (sc.any_alpha && !alpha_test(sc, gid, u, v)) continue;
+                best = HitRec{gid, u, v};
+                best_t = t;
+                if (ANY_HIT) return best;
+            }
+        }
+        if (sp == 0) break;
+        node = stack[--sp];
+    }
+    return best;
+}
+
+}  // namespace akr

@@ -1,0 +1,842 @@
+// scene_build.cpp — see scene_build.h.  Compiled with -ffp-contract=off: every f32 operation here is
+// one IEEE operation, in the order the cited reference code performs it.
+#include "scene_build.h"
+#include "../device/akr_trace.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <deque>
+#include <limits>
+#include <map>
+
+namespace akr {
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// SVM constant folding (svm/eval.rs:97-269 for the constant node set)
+// ---------------------------------------------------------------------------------------------
+struct Val {
+    enum K { None, F, F3, F4, ColorAlpha, Closure } k = None;
+    float f = 0.0f;
+    float v[4] = {0, 0, 0, 0};
+};
+
+float as_float(const Val &v) { return v.k == Val::F ? v.f : v.v[0]; }  // eval_float_auto_convert (eval.rs:327-343)
+void as_float3(const Val &v, float out[3]) {                             // eval_float3_auto_convert (eval.rs:311-326)
+    if (v.k == Val::F3 || v.k == Val::F4) {
+        out[0] = v.v[0];
+        out[1] = v.v[1];
+        out[2] = v.v[2];
+    } else {
+        out[0] = v.f;
+        out[1] = 0.0f;
+        out[2] = 0.0f;
+    }
+}
+
+// Gulbrandsen parametrisation (svm/surface/mod.rs:1040-1052), per channel
+void artistic_to_conductor(float c, float g, float &n, float &k) {
+    float r = std::fmin(std::fmax(c, 0.0f), 0.99f);
+    float r_sqrt = std::sqrt(r);
+    float n_min = (1.0f - r) / (1.0f + r);
+    float n_max = (1.0f + r_sqrt) / (1.0f - r_sqrt);
+    n = g * (n_min - n_max) + n_max;  // n_max.lerp(n_min, g)
+    float k2 = ((n + 1.0f) * (n + 1.0f) * r - (n - 1.0f) * (n - 1.0f)) / (1.0f - r);
+    k2 = std::fmax(k2, 0.0f);
+    k = std::sqrt(k2);
+}
+float ior_from_f0(float f0) {  // mod.rs:1090-1094
+    float s = std::sqrt(std::fmin(std::fmax(f0, 0.0f), 0.99f));
+    return (1.0f + s) / (1.0f - s);
+}
+float f0_from_ior(float ior) {  // mod.rs:1095-1098
+    float f = (ior - 1.0f) / (ior + 1.0f);
+    return f * f;
+}
+
+int fold_material(const AkrSceneDesc &d, AkrShaderRef ref, Material &m, std::string &err) {
+    if (ref.shader_kind >= d.n_shader_kinds) {
+        err = "shader_kind out of range";
+        return AKR_ERR_INVALID_ARGUMENT;
+    }
+    const AkrShaderKind &kind = d.shader_kinds[ref.shader_kind];
+    if (kind.n_nodes == 0 || kind.n_nodes > 256) {
+        err = "shader kind has an unsupported node count";
+        return AKR_ERR_UNSUPPORTED;
+    }
+    std::vector<Val> vals(kind.n_nodes);
+    auto rd = [&](uint32_t off, float &dst) -> bool {
+        size_t o = static_cast<size_t>(ref.data_offset) + off;
+        if (o + 4 > d.shader_data_size) return false;
+        std::memcpy(&dst, d.shader_data + o, 4);
+        return true;
+    };
+    std::memset(&m, 0, sizeof(m));
+    m.alpha = 1.0f;
+    m.type = MAT_EMISSION;
+    bool have_closure = false;
+    for (uint32_t i = 0; i < kind.n_nodes; ++i) {
+        const AkrSvmNode &n = kind.nodes[i];
+        for (uint32_t k = 0; k < n.n_args; ++k) {
+            bool is_ref = !(n.op == AKR_SVM_FLOAT || n.op == AKR_SVM_FLOAT3 || (n.op == AKR_SVM_RGB_TEX && k == 1));
+            if (is_ref && n.a[k] >= i) {
+                err = "SVM node refers to a later node";
+                return AKR_ERR_INVALID_ARGUMENT;
+            }
+        }
+        Val &r = vals[i];
+        switch (n.op) {
+        case AKR_SVM_FLOAT:
+            r.k = Val::F;
+            if (!rd(n.a[0], r.f)) {
+                err = "constant offset out of range";
+                return AKR_ERR_INVALID_ARGUMENT;
+            }
+            break;
+        case AKR_SVM_FLOAT3:
+            r.k = Val::F3;
+            if (!rd(n.a[0], r.v[0]) || !rd(n.a[0] + 4, r.v[1]) || !rd(n.a[0] + 8, r.v[2])) {
+                err = "constant offset out of range";
+                return AKR_ERR_INVALID_ARGUMENT;
+            }
+            break;
+        case AKR_SVM_RGB_TEX:  // eval.rs:127-136; sRGB -> sRGB working space is the identity (texture/mod.rs:9-31)
+            if (n.a[1] != 1u) {
+                err = "rgb node in a non-sRGB colour space is not supported";
+                return AKR_ERR_UNSUPPORTED;
+            }
+            r.k = Val::F4;
+            r.v[0] = vals[n.a[0]].v[0];
+            r.v[1] = vals[n.a[0]].v[1];
+            r.v[2] = vals[n.a[0]].v[2];
+            r.v[3] = 1.0f;
+            break;
+        case AKR_SVM_SPECTRAL_UPLIFT:  // eval.rs:160-180 (RGB pass-through)
+            r.k = Val::ColorAlpha;
+            std::memcpy(r.v, vals[n.a[0]].v, sizeof(r.v));
+            break;
+        case AKR_SVM_DIFFUSE_BSDF: {  // diffuse.rs:82-104
+            const Val &c = vals[n.a[0]];
+            r.k = Val::Closure;
+            m.type = MAT_LAMBERT;
+            m.wrap_inner = 0;
+            for (int c3 = 0; c3 < 3; ++c3) {
+                m.color[c3] = c.v[c3];
+                m.diffuse[c3] = c.v[c3] * AKR_FRAC_1_PI;
+            }
+            m.alpha = c.v[3];
+            have_closure = true;
+            break;
+        }
+        case AKR_SVM_EMISSION: {  // svm/mod.rs:124-133
+            const Val &c = vals[n.a[0]];
+            float s = vals[n.a[1]].f;
+            r.k = Val::Closure;
+            m.type = MAT_EMISSION;
+            for (int c3 = 0; c3 < 3; ++c3) m.emission[c3] = c.v[c3] * s;
+            have_closure = true;
+            break;
+        }
+        case AKR_SVM_GLASS_BSDF: {  // glass.rs:13-45
+            r.k = Val::Closure;
+            m.type = MAT_GLASS;
+            for (int c3 = 0; c3 < 3; ++c3) {
+                m.color[c3] = vals[n.a[0]].v[c3];
+                m.trans_color[c3] = vals[n.a[1]].v[c3];
+            }
+            m.roughness_raw = vals[n.a[2]].f;
+            m.roughness = m.roughness_raw;
+            m.eta = vals[n.a[3]].f;
+            have_closure = true;
+            break;
+        }
+        case AKR_SVM_PRINCIPLED_BSDF: {  // principled.rs:23-49
+            if (n.n_args != 25) {
+                err = "principled node needs 25 inputs";
+                return AKR_ERR_INVALID_ARGUMENT;
+            }
+            r.k = Val::Closure;
+            auto col = [&](uint32_t k, float out[3]) {
+                const Val &c = vals[n.a[k]];
+                out[0] = c.v[0];
+                out[1] = c.v[1];
+                out[2] = c.v[2];
+            };
+            auto flt = [&](uint32_t k) { return as_float(vals[n.a[k]]); };
+            col(AKR_P_BASE_COLOR, m.color);
+            m.alpha = vals[n.a[AKR_P_BASE_COLOR]].v[3];
+            float em[3];
+            col(AKR_P_EMISSION_COLOR, em);
+            float es = flt(AKR_P_EMISSION_STRENGTH);
+            for (int c3 = 0; c3 < 3; ++c3) {
+                m.emission[c3] = em[c3] * es;
+                m.diffuse[c3] = m.color[c3] * AKR_FRAC_1_PI;
+                m.trans_color[c3] = std::sqrt(m.color[c3]);
+            }
+            m.metallic = flt(AKR_P_METALLIC);
+            m.roughness = flt(AKR_P_ROUGHNESS);
+            m.roughness_raw = vals[n.a[AKR_P_ROUGHNESS]].f;
+            m.eta = flt(AKR_P_IOR);
+            m.transmission = flt(AKR_P_TRANSMISSION_WEIGHT);
+            float level = flt(AKR_P_SPECULAR_IOR_LEVEL);
+            col(AKR_P_SPECULAR_TINT, m.spec_tint);
+            // specular layer (principled.rs:55-61)
+            float eta_s = m.eta;
+            float f0 = f0_from_ior(eta_s);
+            if (level != 0.5f) {
+                f0 *= 2.0f * level;
+                eta_s = ior_from_f0(f0);
+            }
+            m.f0 = f0;
+            m.eta_s = eta_s;
+            m.coat_weight = flt(AKR_P_COAT_WEIGHT);
+            m.coat_roughness = flt(AKR_P_COAT_ROUGHNESS);
+            m.coat_ior = flt(AKR_P_COAT_IOR);
+            float tint[3];
+            col(AKR_P_COAT_TINT, tint);
+            for (int c3 = 0; c3 < 3; ++c3) m.coat_scale[c3] = m.coat_weight * (tint[c3] - 1.0f) + 1.0f;  // white.lerp(tint, w)
+            for (int c3 = 0; c3 < 3; ++c3) artistic_to_conductor(m.color[c3], m.spec_tint[c3], m.metal_n[c3], m.metal_k[c3]);
+            float nrm[3];
+            as_float3(vals[n.a[AKR_P_NORMAL]], nrm);
+            m.normal[0] = -nrm[0];
+            m.normal[1] = -nrm[1];
+            m.normal[2] = nrm[2];
+            m.has_normal = (m.normal[0] != 0.0f || m.normal[1] != 0.0f || m.normal[2] != 0.0f) ? 1u : 0u;
+            m.wrap_inner = 1;
+            const float EPS = 1e-4f;  // BsdfMixture::EPS
+            uint32_t lobes = 0;
+            bool spec_zero = (m.f0 == 0.0f) || (m.spec_tint[0] == 0.0f && m.spec_tint[1] == 0.0f && m.spec_tint[2] == 0.0f);
+            if (m.coat_weight != 0.0f) lobes |= LOBE_COAT;
+            if (!spec_zero) lobes |= LOBE_SPECULAR;
+            if (m.metallic < 1.0f - EPS) lobes |= LOBE_BASE;
+            if (m.metallic > EPS) lobes |= LOBE_METAL;
+            if ((lobes & LOBE_BASE) && m.transmission < 1.0f - EPS) lobes |= LOBE_DIFFUSE;
+            if ((lobes & LOBE_BASE) && m.transmission > EPS) lobes |= LOBE_TRANSMISSION;
+            m.lobes = lobes;
+            // exact reductions (see akr_bsdf.cuh header): only when the mix fractions are exactly 0 / 1
+            if (!(lobes & LOBE_COAT) && m.metallic == 0.0f && !(lobes & LOBE_SPECULAR) && m.transmission == 0.0f) m.type = MAT_LAMBERT;
+            else if (!(lobes & LOBE_COAT) && m.metallic == 1.0f) m.type = MAT_CONDUCTOR;
+            else m.type = MAT_PRINCIPLED;
+            have_closure = true;
+            break;
+        }
+        case AKR_SVM_MATERIAL_OUTPUT:
+            r.k = Val::Closure;
+            break;
+        default:
+            err = "SVM op " + std::to_string(n.op) + " is outside the implemented hot-path scope";
+            return AKR_ERR_UNSUPPORTED;
+        }
+    }
+    if (!have_closure) {
+        err = "shader has no surface closure";
+        return AKR_ERR_INVALID_ARGUMENT;
+    }
+    return AKR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// small linear algebra with explicit operation order (mirrors the device helpers)
+// ---------------------------------------------------------------------------------------------
+struct H3 {
+    float x, y, z;
+};
+H3 operator+(H3 a, H3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+H3 operator-(H3 a, H3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+H3 operator*(H3 a, float s) { return {a.x * s, a.y * s, a.z * s}; }
+H3 operator/(H3 a, float s) { return {a.x / s, a.y / s, a.z / s}; }
+float hdot(H3 a, H3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+H3 hcross(H3 a, H3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+float hlen(H3 a) { return std::sqrt(hdot(a, a)); }
+H3 hnorm(H3 a) { return a * (1.0f / std::sqrt(hdot(a, a))); }
+struct HM3 {
+    H3 c0, c1, c2;
+};
+H3 hmul(const HM3 &m, H3 v) { return m.c0 * v.x + m.c1 * v.y + m.c2 * v.z; }
+HM3 htranspose(const HM3 &m) { return {{m.c0.x, m.c1.x, m.c2.x}, {m.c0.y, m.c1.y, m.c2.y}, {m.c0.z, m.c1.z, m.c2.z}}; }
+HM3 hinverse(const HM3 &m) {  // adjugate / determinant
+    H3 a = m.c0, b = m.c1, c = m.c2;
+    H3 r0 = hcross(b, c), r1 = hcross(c, a), r2 = hcross(a, b);
+    float inv_det = 1.0f / hdot(r2, c);
+    return {H3{r0.x, r1.x, r2.x} * inv_det, H3{r0.y, r1.y, r2.y} * inv_det, H3{r0.z, r1.z, r2.z} * inv_det};
+}
+float mat4_det(const float *m) {  // glam Mat4::determinant, scalar form (mesh.rs:311-312)
+    float m00 = m[0], m01 = m[1], m02 = m[2], m03 = m[3];
+    float m10 = m[4], m11 = m[5], m12 = m[6], m13 = m[7];
+    float m20 = m[8], m21 = m[9], m22 = m[10], m23 = m[11];
+    float m30 = m[12], m31 = m[13], m32 = m[14], m33 = m[15];
+    float a2323 = m22 * m33 - m23 * m32;
+    float a1323 = m21 * m33 - m23 * m31;
+    float a1223 = m21 * m32 - m22 * m31;
+    float a0323 = m20 * m33 - m23 * m30;
+    float a0223 = m20 * m32 - m22 * m30;
+    float a0123 = m20 * m31 - m21 * m30;
+    return m00 * (m11 * a2323 - m12 * a1323 + m13 * a1223) - m01 * (m10 * a2323 - m12 * a0323 + m13 * a0223) +
+           m02 * (m10 * a1323 - m11 * a0323 + m13 * a0123) - m03 * (m10 * a1223 - m11 * a0223 + m12 * a0123);
+}
+void st3(float *dst, H3 v) {
+    dst[0] = v.x;
+    dst[1] = v.y;
+    dst[2] = v.z;
+}
+
+// Vose alias table exactly as util/distribution.rs:34-78
+void build_alias(const std::vector<float> &weights, std::vector<uint32_t> &j, std::vector<float> &t, std::vector<float> &pdf) {
+    size_t n = weights.size();
+    float sum = 0.0f;
+    for (float x : weights) sum += x;
+    std::vector<float> prob(n);
+    for (size_t i = 0; i < n; ++i) prob[i] = weights[i] / sum * static_cast<float>(n);
+    std::deque<size_t> small, large;
+    for (size_t i = 0; i < n; ++i) (prob[i] >= 1.0f ? large : small).push_back(i);
+    j.assign(n, 0);
+    t.assign(n, 0.0f);
+    while (!small.empty() && !large.empty()) {
+        size_t l = small.front();
+        small.pop_front();
+        size_t g = large.front();
+        large.pop_front();
+        t[l] = prob[l];
+        j[l] = static_cast<uint32_t>(g);
+        prob[g] = (prob[g] + prob[l]) - 1.0f;
+        (prob[g] < 1.0f ? small : large).push_back(g);
+    }
+    while (!large.empty()) {
+        size_t g = large.front();
+        large.pop_front();
+        t[g] = 1.0f;
+        j[g] = static_cast<uint32_t>(g);
+    }
+    while (!small.empty()) {
+        size_t l = small.front();
+        small.pop_front();
+        t[l] = 1.0f;
+        j[l] = static_cast<uint32_t>(l);
+    }
+    pdf.resize(n);
+    for (size_t i = 0; i < n; ++i) pdf[i] = weights[i] / sum;
+}
+
+// ---------------------------------------------------------------------------------------------
+// BVH: binned SAH, leaves of <= 4 triangles, flattened breadth-first into BvhNode[]
+// ---------------------------------------------------------------------------------------------
+struct Box {
+    float lo[3], hi[3];
+    void reset() {
+        for (int a = 0; a < 3; ++a) {
+            lo[a] = std::numeric_limits<float>::infinity();
+            hi[a] = -std::numeric_limits<float>::infinity();
+        }
+    }
+    void grow(const float *p) {
+        for (int a = 0; a < 3; ++a) {
+            lo[a] = std::min(lo[a], p[a]);
+            hi[a] = std::max(hi[a], p[a]);
+        }
+    }
+    void grow(const Box &b) {
+        for (int a = 0; a < 3; ++a) {
+            lo[a] = std::min(lo[a], b.lo[a]);
+            hi[a] = std::max(hi[a], b.hi[a]);
+        }
+    }
+    float half_area() const {
+        float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+        if (dx < 0 || dy < 0 || dz < 0) return 0.0f;
+        return dx * dy + dy * dz + dz * dx;
+    }
+};
+struct BuildTri {
+    Box box;
+    float centroid[3];
+    uint32_t index;  // into the world-triangle list (gid)
+};
+struct BuildNode {
+    Box box;
+    int32_t left = -1, right = -1;  // children (build-node indices) or leaf range
+    uint32_t first = 0, count = 0;
+};
+
+constexpr uint32_t kLeafMax = 4;
+constexpr int kBins = 16;
+
+int32_t build_recursive(std::vector<BuildNode> &nodes, std::vector<BuildTri> &tris, uint32_t first, uint32_t count, uint32_t depth,
+                        uint32_t &max_depth) {
+    BuildNode node;
+    node.box.reset();
+    Box cbox;
+    cbox.reset();
+    for (uint32_t i = first; i < first + count; ++i) {
+        node.box.grow(tris[i].box);
+        cbox.grow(tris[i].centroid);
+    }
+    max_depth = std::max(max_depth, depth);
+    int32_t self = static_cast<int32_t>(nodes.size());
+    nodes.push_back(node);
+    if (count <= kLeafMax) {
+        nodes[self].first = first;
+        nodes[self].count = count;
+        return self;
+    }
+    // pick the best binned SAH split over the three axes
+    float best_cost = std::numeric_limits<float>::infinity();
+    int best_axis = -1, best_bin = -1;
+    for (int axis = 0; axis < 3; ++axis) {
+        float lo = cbox.lo[axis], hi = cbox.hi[axis];
+        if (!(hi > lo)) continue;
+        Box bin_box[kBins];
+        uint32_t bin_cnt[kBins] = {0};
+        for (auto &b : bin_box) b.reset();
+        float scale = static_cast<float>(kBins) / (hi - lo);
+        for (uint32_t i = first; i < first + count; ++i) {
+            int b = std::min(kBins - 1, std::max(0, static_cast<int>((tris[i].centroid[axis] - lo) * scale)));
+            bin_box[b].grow(tris[i].box);
+            bin_cnt[b]++;
+        }
+        float right_area[kBins];
+        uint32_t right_cnt[kBins];
+        Box acc;
+        acc.reset();
+        uint32_t cnt = 0;
+        for (int b = kBins - 1; b > 0; --b) {
+            acc.grow(bin_box[b]);
+            cnt += bin_cnt[b];
+            right_area[b] = acc.half_area();
+            right_cnt[b] = cnt;
+        }
+        acc.reset();
+        cnt = 0;
+        for (int b = 0; b < kBins - 1; ++b) {
+            acc.grow(bin_box[b]);
+            cnt += bin_cnt[b];
+            if (cnt == 0 || right_cnt[b + 1] == 0) continue;
+            float cost = acc.half_area() * static_cast<float>(cnt) + right_area[b + 1] * static_cast<float>(right_cnt[b + 1]);
+            if (cost < best_cost) {
+                best_cost = cost;
+                best_axis = axis;
+                best_bin = b;
+            }
+        }
+    }
+    uint32_t mid;
+    if (best_axis < 0) {
+        mid = first + count / 2;  // all centroids coincide: split by index
+    } else {
+        float lo = cbox.lo[best_axis], hi = cbox.hi[best_axis];
+        float scale = static_cast<float>(kBins) / (hi - lo);
+        auto it = std::stable_partition(tris.begin() + first, tris.begin() + first + count, [&](const BuildTri &t) {
+            int b = std::min(kBins - 1, std::max(0, static_cast<int>((t.centroid[best_axis] - lo) * scale)));
+            return b <= best_bin;
+        });
+        mid = static_cast<uint32_t>(it - tris.begin());
+        if (mid == first || mid == first + count) mid = first + count / 2;
+    }
+    int32_t l = build_recursive(nodes, tris, first, mid - first, depth + 1, max_depth);
+    int32_t r = build_recursive(nodes, tris, mid, first + count - mid, depth + 1, max_depth);
+    nodes[self].left = l;
+    nodes[self].right = r;
+    return self;
+}
+
+}  // namespace
+
+void transpose_bluenoise(const uint16_t *src, uint16_t *dst) {
+    for (uint32_t t = 0; t < 48; ++t)
+        for (uint32_t x = 0; x < 128; ++x)
+            for (uint32_t y = 0; y < 128; ++y) dst[(t * 128u + y) * 128u + x] = src[(t * 128u + x) * 128u + y];
+}
+
+int build_scene_blob(const AkrSceneDesc &d, HostSceneBlob &out, std::string &err) {
+    if (d.abi_version != AKR_B200_ABI_VERSION) {
+        err = "AkrSceneDesc.abi_version mismatch";
+        return AKR_ERR_INVALID_ARGUMENT;
+    }
+    if (d.n_instances == 0 || d.n_meshes == 0 || !d.meshes || !d.instances || !d.shader_kinds || !d.shader_data) {
+        err = "empty scene";
+        return AKR_ERR_INVALID_ARGUMENT;
+    }
+    out = HostSceneBlob{};
+    // ---- materials: one record per distinct ShaderRef ----
+    std::map<std::pair<uint32_t, uint32_t>, uint32_t> mat_index;
+    auto material_of = [&](AkrShaderRef ref, uint32_t &idx) -> int {
+        auto key = std::make_pair(ref.shader_kind, ref.data_offset);
+        auto it = mat_index.find(key);
+        if (it != mat_index.end()) {
+            idx = it->second;
+            return AKR_OK;
+        }
+        Material m;
+        int rc = fold_material(d, ref, m, err);
+        if (rc != AKR_OK) return rc;
+        idx = static_cast<uint32_t>(out.materials.size());
+        out.materials.push_back(m);
+        mat_index[key] = idx;
+        return AKR_OK;
+    };
+
+    // ---- instances + per-triangle records ----
+    bool any_normals = false, any_tangents = false;
+    uint32_t total_tris = 0;
+    for (uint32_t i = 0; i < d.n_instances; ++i) {
+        if (d.instances[i].geom_id >= d.n_meshes) {
+            err = "instance geom_id out of range";
+            return AKR_ERR_INVALID_ARGUMENT;
+        }
+        const AkrMesh &g = d.meshes[d.instances[i].geom_id];
+        total_tris += g.n_triangles;
+        any_normals |= g.normals != nullptr;
+        any_tangents |= g.tangents != nullptr;
+    }
+    if (total_tris == 0 || total_tris >= (1u << 28)) {
+        err = "triangle count out of range";
+        return AKR_ERR_INVALID_ARGUMENT;
+    }
+    out.shade.resize(total_tris);
+    if (any_normals) out.corner_normals.assign(static_cast<size_t>(total_tris) * 9, 0.0f);
+    if (any_tangents) out.corner_tangents.assign(static_cast<size_t>(total_tris) * 9, 0.0f);
+    std::vector<float> world(static_cast<size_t>(total_tris) * 9);  // v0,v1,v2 world per gid
+    out.instances.resize(d.n_instances);
+    uint32_t tri_offset = 0;
+    for (uint32_t i = 0; i < d.n_instances; ++i) {
+        const AkrInstance &in = d.instances[i];
+        const AkrMesh &g = d.meshes[in.geom_id];
+        if (in.n_materials == 0 || !in.materials) {
+            err = "instance without materials (mesh.rs:308)";
+            return AKR_ERR_INVALID_ARGUMENT;
+        }
+        InstanceRec &ir = out.instances[i];
+        std::memset(&ir, 0, sizeof(ir));
+        const float *mm = in.transform;
+        HM3 m{{mm[0], mm[1], mm[2]}, {mm[4], mm[5], mm[6]}, {mm[8], mm[9], mm[10]}};
+        H3 tr{mm[12], mm[13], mm[14]};
+        HM3 m_inv_t = hinverse(htranspose(m));
+        st3(ir.m, m.c0);
+        st3(ir.m + 3, m.c1);
+        st3(ir.m + 6, m.c2);
+        st3(ir.t, tr);
+        st3(ir.m_inv_t, m_inv_t.c0);
+        st3(ir.m_inv_t + 3, m_inv_t.c1);
+        st3(ir.m_inv_t + 6, m_inv_t.c2);
+        ir.det = mat4_det(mm);
+        ir.light_id = 0xffffffffu;
+        ir.tri_offset = tri_offset;
+        ir.n_tris = g.n_triangles;
+        ir.geom_id = in.geom_id;
+        ir.flags = in.flags;
+        std::vector<uint32_t> mats(in.n_materials);
+        for (uint32_t k = 0; k < in.n_materials; ++k) {
+            int rc = material_of(in.materials[k], mats[k]);
+            if (rc != AKR_OK) return rc;
+        }
+        const bool multi = (in.flags & AKR_MESH_HAS_MULTI_MATERIALS) != 0;
+        for (uint32_t p = 0; p < g.n_triangles; ++p) {
+            uint32_t gid = tri_offset + p;
+            TriShade &ts = out.shade[gid];
+            std::memset(&ts, 0, sizeof(ts));
+            const uint32_t *idx = g.indices + 3 * p;
+            for (int k = 0; k < 3; ++k)
+                if (idx[k] >= g.n_vertices) {
+                    err = "vertex index out of range";
+                    return AKR_ERR_INVALID_ARGUMENT;
+                }
+            auto vert = [&](uint32_t k) { return H3{g.vertices[3 * k], g.vertices[3 * k + 1], g.vertices[3 * k + 2]}; };
+            H3 v0 = vert(idx[0]), v1 = vert(idx[1]), v2 = vert(idx[2]);
+            st3(ts.v0, v0);
+            st3(ts.v1, v1);
+            st3(ts.v2, v2);
+            // mesh.rs:526-533
+            H3 ngu = hcross(v1 - v0, v2 - v0);
+            float len = hlen(ngu);
+            float area_local = len * 0.5f;
+            H3 ng_local = ngu / len;
+            // uv (mesh.rs:534-546)
+            float uv0[2], uv1[2], uv2[2];
+            if (g.uvs) {
+                const float *u = g.uvs + static_cast<size_t>(p) * 6;
+                uv0[0] = u[0]; uv0[1] = u[1]; uv1[0] = u[2]; uv1[1] = u[3]; uv2[0] = u[4]; uv2[1] = u[5];
+            } else {
+                uv0[0] = 0.0f; uv0[1] = 0.0f; uv1[0] = 1.0f; uv1[1] = 0.0f; uv2[0] = 1.0f; uv2[1] = 0.1f;
+            }
+            // dp/du fallback tangent (mesh.rs:571-590)
+            H3 tt_local{0, 0, 0};
+            {
+                float duv02[2] = {uv0[0] - uv2[0], uv0[1] - uv2[1]};
+                float duv12[2] = {uv1[0] - uv2[0], uv1[1] - uv2[1]};
+                H3 dp02 = v0 - v2, dp12 = v1 - v2;
+                float determinant = difference_of_products(duv02[0], duv12[1], duv02[1], duv12[0]);
+                bool degenerate_uv = std::fabs(determinant) < 1e-8f;
+                H3 t{0, 0, 0};
+                if (!degenerate_uv) {
+                    float inv_det = 1.0f / determinant;
+                    t.x = difference_of_products(duv12[1], dp02.x, duv02[1], dp12.x) * inv_det;
+                    t.y = difference_of_products(duv12[1], dp02.y, duv02[1], dp12.y) * inv_det;
+                    t.z = difference_of_products(duv12[1], dp02.z, duv02[1], dp12.z) * inv_det;
+                }
+                if (degenerate_uv || hdot(t, t) == 0.0f) {
+                    Frame f = frame_from_n(mk3(ng_local.x, ng_local.y, ng_local.z));
+                    t = H3{f.t.x, f.t.y, f.t.z};
+                }
+                tt_local = t;
+            }
+            // world transform (mesh.rs:608-628)
+            H3 tt = hmul(m, tt_local);
+            H3 c = hmul(m, ng_local);
+            H3 ng = hnorm(hmul(m_inv_t, ng_local));
+            float area = (area_local == 0.0f || ir.det == 0.0f) ? 0.0f : std::fabs(area_local * ir.det / hdot(ng, c));
+            st3(ts.ng, ng);
+            ts.area = area;
+            ts.inst = i;
+            ts.prim = p;
+            uint32_t slot = 0;
+            if (multi) {
+                if (p >= g.n_material_slots || g.material_slots[p] >= in.n_materials) {
+                    err = "material slot out of range";
+                    return AKR_ERR_INVALID_ARGUMENT;
+                }
+                slot = g.material_slots[p];
+            }
+            ts.mat = mats[slot];
+            uint32_t flags = 0;
+            if (g.normals) flags |= TRI_HAS_NORMALS;
+            if (g.tangents) flags |= TRI_HAS_TANGENTS;
+            if (g.uvs) flags |= TRI_HAS_UVS;
+            if (!(out.materials[ts.mat].alpha >= 1.0f)) {
+                flags |= TRI_ALPHA;
+                out.any_alpha = 1;
+            }
+            ts.flags = flags;
+            if (!g.normals && !g.tangents) {
+                // flat triangle: ns = ng and the frame is constant (mesh.rs:629-633)
+                Frame f = (tt.x != 0.0f || tt.y != 0.0f || tt.z != 0.0f) ? frame_from_n_t(mk3(ng.x, ng.y, ng.z), mk3(tt.x, tt.y, tt.z))
+                                                                           : frame_from_n(mk3(ng.x, ng.y, ng.z));
+                st3(ts.ft, H3{f.t.x, f.t.y, f.t.z});
+                st3(ts.fs, H3{f.s.x, f.s.y, f.s.z});
+            } else {
+                st3(ts.ft, tt);  // world dp/du tangent
+                st3(ts.fs, tt);  // fallback when the tangent buffer holds non-finite values
+            }
+            if (g.normals) std::memcpy(out.corner_normals.data() + static_cast<size_t>(gid) * 9, g.normals + static_cast<size_t>(p) * 9, 36);
+            if (g.tangents) std::memcpy(out.corner_tangents.data() + static_cast<size_t>(gid) * 9, g.tangents + static_cast<size_t>(p) * 9, 36);
+            // world-space vertices for traversal
+            H3 w0 = hmul(m, v0) + tr, w1 = hmul(m, v1) + tr, w2 = hmul(m, v2) + tr;
+            st3(world.data() + static_cast<size_t>(gid) * 9, w0);
+            st3(world.data() + static_cast<size_t>(gid) * 9 + 3, w1);
+            st3(world.data() + static_cast<size_t>(gid) * 9 + 6, w2);
+        }
+        tri_offset += g.n_triangles;
+    }
+
+    // ---- mesh lights (load.rs:312-415).  All supported emission closures are constant, so the 16 samples
+    // of the estimation kernel (load.rs:319-341) contribute the same value; the f32 accumulation is literal.
+    std::vector<float> light_weights;
+    out.alias_j.clear();
+    std::vector<std::vector<uint32_t>> per_light_j;
+    std::vector<std::vector<float>> per_light_t, per_light_pdf;
+    for (uint32_t i = 0; i < d.n_instances; ++i) {
+        InstanceRec &ir = out.instances[i];
+        std::vector<float> powers(ir.n_tris);
+        for (uint32_t p = 0; p < ir.n_tris; ++p) {
+            const TriShade &ts = out.shade[ir.tri_offset + p];
+            const Material &mat = out.materials[ts.mat];
+            float e = std::fmax(mat.emission[0], std::fmax(mat.emission[1], mat.emission[2]));
+            float acc = 0.0f;
+            for (int s = 0; s < 16; ++s) acc += e * ts.area;
+            powers[p] = acc / 16.0f;
+        }
+        float total = 0.0f;
+        for (float x : powers) total += x;
+        if (total > 1e-4f) {
+            ir.light_id = static_cast<uint32_t>(out.lights.size());
+            LightRec lr{i, ir.tri_offset, 0, ir.n_tris};
+            out.lights.push_back(lr);
+            light_weights.push_back(total);
+            out.light_powers.push_back(total);
+            std::vector<uint32_t> j;
+            std::vector<float> t, pdf;
+            build_alias(powers, j, t, pdf);
+            for (uint32_t p = 0; p < ir.n_tris; ++p) {
+                out.shade[ir.tri_offset + p].prim_pdf = pdf[p];
+                out.shade[ir.tri_offset + p].flags |= TRI_IS_LIGHT;
+            }
+            per_light_j.push_back(j);
+            per_light_t.push_back(t);
+            per_light_pdf.push_back(pdf);
+        }
+    }
+    if (!light_weights.empty()) {
+        build_alias(light_weights, out.alias_j, out.alias_t, out.alias_pdf);
+        for (size_t l = 0; l < out.lights.size(); ++l) {
+            out.lights[l].alias_offset = static_cast<uint32_t>(out.alias_j.size());
+            out.alias_j.insert(out.alias_j.end(), per_light_j[l].begin(), per_light_j[l].end());
+            out.alias_t.insert(out.alias_t.end(), per_light_t[l].begin(), per_light_t[l].end());
+            out.alias_pdf.insert(out.alias_pdf.end(), per_light_pdf[l].begin(), per_light_pdf[l].end());
+        }
+    } else {
+        out.alias_j.push_back(0);
+        out.alias_t.push_back(1.0f);
+        out.alias_pdf.push_back(0.0f);
+    }
+
+    // ---- BVH over world-space triangles ----
+    std::vector<BuildTri> btris(total_tris);
+    Box scene_box;
+    scene_box.reset();
+    for (uint32_t gid = 0; gid < total_tris; ++gid) {
+        BuildTri &bt = btris[gid];
+        bt.box.reset();
+        const float *w = world.data() + static_cast<size_t>(gid) * 9;
+        bt.box.grow(w);
+        bt.box.grow(w + 3);
+        bt.box.grow(w + 6);
+        for (int a = 0; a < 3; ++a) bt.centroid[a] = 0.5f * (bt.box.lo[a] + bt.box.hi[a]);
+        bt.index = gid;
+        scene_box.grow(bt.box);
+    }
+    std::vector<BuildNode> bnodes;
+    bnodes.reserve(static_cast<size_t>(total_tris) * 2);
+    uint32_t max_depth = 0;
+    build_recursive(bnodes, btris, 0, total_tris, 0, max_depth);
+    out.bvh_depth = max_depth;
+    if (max_depth + 2 >= AKR_BVH_STACK) {
+        err = "BVH too deep for the traversal stack";
+        return AKR_ERR_UNSUPPORTED;
+    }
+    // conservative padding so that rounding in the slab test can never reject a box whose triangle the
+    // (independent) triangle test accepts
+    float diag = 0.0f;
+    for (int a = 0; a < 3; ++a) diag = std::max(diag, scene_box.hi[a] - scene_box.lo[a]);
+    const float pad_abs = 1e-5f * diag;
+    auto padded = [&](const Box &b, float *lo, float *hi) {
+        for (int a = 0; a < 3; ++a) {
+            float mag = std::max(std::fabs(b.lo[a]), std::fabs(b.hi[a]));
+            float pad = pad_abs + mag * 4e-7f;
+            lo[a] = b.lo[a] - pad;
+            hi[a] = b.hi[a] + pad;
+        }
+    };
+    // triangles in leaf order
+    out.tris.resize(total_tris);
+    for (uint32_t k = 0; k < total_tris; ++k) {
+        uint32_t gid = btris[k].index;
+        const float *w = world.data() + static_cast<size_t>(gid) * 9;
+        TriGeom &tg = out.tris[k];
+        std::memset(&tg, 0, sizeof(tg));
+        H3 w0{w[0], w[1], w[2]}, w1{w[3], w[4], w[5]}, w2{w[6], w[7], w[8]};
+        st3(tg.v0, w0);
+        st3(tg.e1, w1 - w0);
+        st3(tg.e2, w2 - w0);
+        tg.gid = gid;
+    }
+    // flatten: breadth-first over inner nodes; a leaf root becomes an inner node with an empty second child
+    auto leaf_code = [&](const BuildNode &n) { return ~static_cast<int32_t>((n.first << 3) | n.count); };
+    std::vector<int32_t> inner_of(bnodes.size(), -1);
+    std::vector<int32_t> order;
+    if (bnodes[0].left < 0) {
+        BvhNode root;
+        std::memset(&root, 0, sizeof(root));
+        padded(bnodes[0].box, root.lo0, root.hi0);
+        for (int a = 0; a < 3; ++a) {
+            root.lo1[a] = std::numeric_limits<float>::infinity();
+            root.hi1[a] = -std::numeric_limits<float>::infinity();
+        }
+        root.c0 = leaf_code(bnodes[0]);
+        root.c1 = ~0;  // empty leaf
+        out.nodes.push_back(root);
+    } else {
+        order.push_back(0);
+        inner_of[0] = 0;
+        for (size_t h = 0; h < order.size(); ++h) {
+            const BuildNode &n = bnodes[order[h]];
+            for (int32_t ch : {n.left, n.right})
+                if (bnodes[ch].left >= 0) {
+                    inner_of[ch] = static_cast<int32_t>(order.size());
+                    order.push_back(ch);
+                }
+        }
+        out.nodes.resize(order.size());
+        for (size_t h = 0; h < order.size(); ++h) {
+            const BuildNode &n = bnodes[order[h]];
+            BvhNode &o = out.nodes[h];
+            std::memset(&o, 0, sizeof(o));
+            const BuildNode &l = bnodes[n.left], &r = bnodes[n.right];
+            padded(l.box, o.lo0, o.hi0);
+            padded(r.box, o.lo1, o.hi1);
+            o.c0 = l.left >= 0 ? inner_of[n.left] : leaf_code(l);
+            o.c1 = r.left >= 0 ? inner_of[n.right] : leaf_code(r);
+        }
+    }
+
+    // ---- camera (camera/mod.rs:119-153; load.rs:172-194) ----
+    {
+        const AkrPerspectiveCamera &cam = d.camera;
+        if (cam.width == 0 || cam.height == 0) {
+            err = "camera resolution is zero";
+            return AKR_ERR_INVALID_ARGUMENT;
+        }
+        CameraRec &c = out.camera;
+        std::memset(&c, 0, sizeof(c));
+        const float *m = cam.c2w;
+        for (int col = 0; col < 3; ++col)
+            for (int r = 0; r < 3; ++r) c.c2w[col * 3 + r] = m[col * 4 + r];
+        c.c2w[9] = m[12];
+        c.c2w[10] = m[13];
+        c.c2w[11] = m[14];
+        bool ident = true;  // Mat4::abs_diff_eq(IDENTITY, 1e-4)
+        for (int col = 0; col < 4; ++col)
+            for (int r = 0; r < 4; ++r) {
+                float idv = col == r ? 1.0f : 0.0f;
+                if (!(std::fabs(m[col * 4 + r] - idv) <= 1e-4f)) ident = false;
+            }
+        c.c2w_identity = ident ? 1u : 0u;
+        float fx = static_cast<float>(cam.width), fy = static_cast<float>(cam.height);
+        float sx = 1.0f / fx, sy = 1.0f / fy, sz = 1.0f, tx = 0.0f, ty = 0.0f, tz = 0.0f;
+        auto scale = [&](float a, float b, float cc) {
+            sx = a * sx; sy = b * sy; sz = cc * sz;
+            tx = a * tx; ty = b * ty; tz = cc * tz;
+        };
+        auto translate = [&](float a, float b, float cc) { tx = tx + a; ty = ty + b; tz = tz + cc; };
+        scale(2.0f, 2.0f, 1.0f);
+        translate(-1.0f, -1.0f, 0.0f);
+        scale(1.0f, -1.0f, 1.0f);
+        float s = std::tan(cam.fov / 2.0f);
+        if (cam.width > cam.height) scale(s, s * fy / fx, 1.0f);
+        else scale(s * fx / fy, s, 1.0f);
+        translate(0.0f, 0.0f, -1.0f);
+        c.r2c_s[0] = sx; c.r2c_s[1] = sy; c.r2c_s[2] = sz;
+        c.r2c_t[0] = tx; c.r2c_t[1] = ty; c.r2c_t[2] = tz;
+        c.width = cam.width;
+        c.height = cam.height;
+    }
+    return AKR_OK;
+}
+
+SceneView host_scene_view(const HostSceneBlob &b, const float *albedo_table) {
+    SceneView v;
+    std::memset(&v, 0, sizeof(v));
+    v.nodes = b.nodes.data();
+    v.tris = b.tris.data();
+    v.shade = b.shade.data();
+    v.instances = b.instances.data();
+    v.materials = b.materials.data();
+    v.lights = b.lights.data();
+    v.alias_j = b.alias_j.data();
+    v.alias_t = b.alias_t.data();
+    v.alias_pdf = b.alias_pdf.data();
+    v.albedo_table = albedo_table;
+    v.n_nodes = static_cast<uint32_t>(b.nodes.size());
+    v.n_tris = static_cast<uint32_t>(b.tris.size());
+    v.n_instances = static_cast<uint32_t>(b.instances.size());
+    v.n_materials = static_cast<uint32_t>(b.materials.size());
+    v.n_lights = static_cast<uint32_t>(b.lights.size());
+    v.any_alpha = b.any_alpha;
+    v.camera = b.camera;
+    return v;
+}
+
+void make_albedo_table(float *table, uint32_t n) {
+    for (uint32_t cell = 0; cell < 4096; ++cell) table[cell] = albedo_table_cell(cell, n);
+}
+
+}  // namespace akr

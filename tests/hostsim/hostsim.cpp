@@ -1,0 +1,130 @@
+// hostsim.cpp — TEST-ONLY host-side simulation of the wavefront kernels.
+//
+// Runs the exact per-path stage bodies of akari_render_b200/csrc/device/*.cuh (the code the CUDA
+// kernels execute per thread) in plain loops on the CPU, with the same queue/compaction semantics,
+// so kernel logic can be debugged and compared with the oracle in a container without a GPU.
+// It is NOT part of the product: libakari_b200.so contains no CPU execution path, and nothing in
+// akari_render_b200/ links or loads this file.
+#include "../../akari_render_b200/csrc/device/akr_path.cuh"
+#include "../../akari_render_b200/csrc/host/scene_build.h"
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace akr;
+
+extern "C" {
+
+static thread_local std::string g_err;
+const char *hostsim_last_error(void) { return g_err.c_str(); }
+
+struct HostsimStats {
+    uint64_t samples, segments, shadow_rays;
+    uint32_t n_nodes, n_tris, n_materials, n_lights, bvh_depth;
+    uint32_t material_types[8];
+};
+
+int hostsim_render(const AkrSceneDesc *desc, const AkrPtConfig *cfg, const AkrSamplerConfig *scfg, const AkrFilterConfig *filter,
+                   const uint32_t *pmj, const uint16_t *bn, const float *albedo_table, uint32_t y0, uint32_t y1, uint32_t spp_begin,
+                   uint32_t spp_end, uint32_t wave_pixels, float *film_7n, uint32_t *first_hits, HostsimStats *stats) {
+    HostSceneBlob blob;
+    std::string err;
+    int rc = build_scene_blob(*desc, blob, err);
+    if (rc != AKR_OK) {
+        g_err = err;
+        return rc;
+    }
+    if (scfg->type != AKR_SAMPLER_PMJ02BN) {
+        g_err = "pmj02bn only";
+        return AKR_ERR_UNSUPPORTED;
+    }
+    std::vector<uint16_t> bnt(48u * 128u * 128u);
+    transpose_bluenoise(bn, bnt.data());
+    SceneView sc = host_scene_view(blob, albedo_table);
+    CornerAttribs ca{blob.corner_normals.empty() ? nullptr : blob.corner_normals.data(),
+                     blob.corner_tangents.empty() ? nullptr : blob.corner_tangents.data()};
+    SamplerTables tab{pmj, bnt.data()};
+    TraceData td{nullptr, sc.nodes, sc.tris, 0u};
+    RenderParams rp;
+    std::memset(&rp, 0, sizeof(rp));
+    rp.spp_total = cfg->spp;
+    uint32_t w = cfg->spp - 1;
+    w |= w >> 1; w |= w >> 2; w |= w >> 4; w |= w >> 8; w |= w >> 16;
+    rp.w_mask = w;
+    rp.seed = (uint32_t)scfg->seed;
+    rp.max_depth = cfg->max_depth;
+    rp.rr_depth = cfg->rr_depth;
+    rp.use_nee = cfg->use_nee;
+    rp.indirect_only = cfg->indirect_only;
+    rp.force_diffuse = cfg->force_diffuse;
+    rp.pixel_offset_x = cfg->pixel_offset[0];
+    rp.pixel_offset_y = cfg->pixel_offset[1];
+    rp.debug_depth = cfg->debug_depth;
+    rp.filter_type = filter->type;
+    rp.filter_radius = filter->radius;
+    rp.width = desc->camera.width;
+    rp.height = desc->camera.height;
+    rp.y0 = y0;
+    const uint32_t rows = y1 - y0;
+    const uint32_t n_pixels = rp.width * rows;
+    const uint32_t k = spp_end - spp_begin;
+    if (wave_pixels == 0) wave_pixels = n_pixels;
+    uint64_t segments = 0, shadows = 0;
+    for (uint32_t pix0 = 0; pix0 < n_pixels; pix0 += wave_pixels) {
+        WaveInfo wave{pix0, std::min(wave_pixels, n_pixels - pix0), spp_begin, k};
+        const uint32_t n_paths = wave.n_pix * wave.n_spp;
+        std::vector<float> acc(6u * (size_t)n_paths, 0.0f);
+        AccView av{acc.data(), acc.data() + n_paths, acc.data() + 2u * n_paths, acc.data() + 3u * n_paths, acc.data() + 4u * n_paths,
+                   acc.data() + 5u * n_paths};
+        std::vector<PathState> cur(n_paths), next;
+        for (uint32_t i = 0; i < n_paths; ++i) cur[i] = raygen_body(sc, tab, rp, wave, i);
+        for (uint32_t depth = 0; depth <= rp.max_depth && !cur.empty(); ++depth) {
+            std::vector<HitRec> hits(cur.size());
+            for (size_t i = 0; i < cur.size(); ++i)
+                hits[i] = trace_ray<false>(sc, td, cur[i].o, cur[i].d, 0.0f, 1e20f, cur[i].ex, 0xffffffffu);
+            segments += cur.size();
+            if (depth == 0 && first_hits && spp_begin == wave.s0)
+                for (size_t i = 0; i < cur.size(); ++i) {
+                    uint32_t id = cur[i].path_id;
+                    if (id >= wave.n_pix) continue;  // sample s0 only
+                    uint32_t pix = wave.pix0 + id;
+                    uint32_t gid = hits[i].gid;
+                    first_hits[2 * pix + 0] = gid == 0xffffffffu ? 0xffffffffu : sc.shade[gid].inst;
+                    first_hits[2 * pix + 1] = gid == 0xffffffffu ? 0xffffffffu : sc.shade[gid].prim;
+                }
+            next.clear();
+            std::vector<ShadowItem> shq;
+            for (size_t i = 0; i < cur.size(); ++i) {
+                ShadeOut o = shade_body(sc, ca, tab, rp, wave, depth, cur[i], hits[i], av);
+                if (o.has_shadow) shq.push_back(o.shadow);
+                if (o.has_next) next.push_back(o.next);
+            }
+            shadows += shq.size();
+            for (const ShadowItem &it : shq) {
+                HitRec h = trace_ray<true>(sc, td, it.o, it.d, 0.0f, it.t_max, it.ex0, it.ex1);
+                shadow_resolve(av, it, h.gid != 0xffffffffu, depth + 1u);
+            }
+            cur.swap(next);
+        }
+        for (uint32_t p = 0; p < wave.n_pix; ++p) accumulate_body(av, wave, p, film_7n, n_pixels);
+    }
+    if (stats) {
+        std::memset(stats, 0, sizeof(*stats));
+        stats->samples = (uint64_t)n_pixels * k;
+        stats->segments = segments;
+        stats->shadow_rays = shadows;
+        stats->n_nodes = (uint32_t)blob.nodes.size();
+        stats->n_tris = (uint32_t)blob.tris.size();
+        stats->n_materials = (uint32_t)blob.materials.size();
+        stats->n_lights = (uint32_t)blob.lights.size();
+        stats->bvh_depth = blob.bvh_depth;
+        for (const Material &m : blob.materials) stats->material_types[m.type & 7u]++;
+    }
+    return AKR_OK;
+}
+
+void hostsim_make_albedo_table(float *table, uint32_t n) { make_albedo_table(table, n); }
+
+}  // extern "C"
