@@ -127,7 +127,7 @@ class AkrEngineOptions(C.Structure):
         ("wave_size", C.c_uint32),
         ("sort_by_material", C.c_uint32),
         ("profile_stages", C.c_uint32),
-        ("_pad", C.c_uint32),
+        ("trace_mode", C.c_uint32),
     ]
 
 

@@ -26,28 +26,33 @@ using namespace akr;
 namespace {
 
 constexpr int kBlock = 256;
-constexpr uint32_t kMaxDepthSlots = 66;        // counters for depth 0 .. 64 (+1)
-constexpr uint32_t kSmemSceneBudget = 96 * 1024;  // bytes of BVH nodes + triangles staged per CTA
+constexpr int kWarpsPerBlock = kBlock / 32;
+constexpr uint32_t kMaxDepthSlots = 66;           // counters for depth 0 .. 64 (+1)
+constexpr uint32_t kCtrStride = 8;                // words per depth: [0] paths in, [1] shadow rays out, [2 + c] hits of class c
+constexpr uint32_t kSmemSceneBudget = 48 * 1024;  // bytes of BVH nodes + triangles staged per CTA
+constexpr uint32_t kSmemMax = 200 * 1024;         // opt-in ceiling for the trace kernels (staging + stacks)
+constexpr uint32_t kFlatMaxTris = 64;             // scenes this small are traced as one flat triangle list
 
 // ------------------------------------------------------------------------------------------------
-// SoA queues
+// wave state in HBM: structure-of-arrays of 16-byte records (one LDG.128 / STG.128 per record, fully
+// coalesced across a warp)
 // ------------------------------------------------------------------------------------------------
-struct PathQueue {  // 13 words per path
-    float *ox, *oy, *oz, *dx, *dy, *dz;
-    uint32_t *ex;
-    float *bx, *by, *bz;
-    float *prev_pdf;
-    uint32_t *path_id;
+struct PathQueue {   // 48 B per path
+    f4 *a;           // origin.xyz, dir.x
+    f4 *b;           // dir.y, dir.z, exclude gid (bits), prev_bsdf_pdf
+    f4 *c;           // beta.rgb, path_id (bits)
 };
-struct HitQueue {
-    uint32_t *gid;
-    float *u, *v;
+struct HitQueue {    // 16 B per traced path, same slot as the path
+    f4 *h;           // gid (bits), u, v, -
 };
-struct ShadowQueue {  // 13 words per item
-    float *ox, *oy, *oz, *dx, *dy, *dz, *tmax;
-    uint32_t *ex0, *ex1;
-    float *cr, *cg, *cb;
-    uint32_t *path_id;
+struct ShadowQueue { // 52 B per shadow ray
+    f4 *a;           // origin.xyz, t_max
+    f4 *b;           // dir.xyz, exclude0 (bits)
+    f4 *c;           // contribution.rgb, path_id (bits)
+    uint32_t *ex1;
+};
+struct ClassQueues { // per shade class: slots (into the path queue) of the hits of that class
+    uint32_t *idx[CLS_COUNT];
 };
 
 struct LaunchParams {
@@ -59,32 +64,32 @@ struct LaunchParams {
     PathQueue q[2];
     HitQueue hits;
     ShadowQueue shadow;
+    ClassQueues cls;
     AccView acc;
-    uint32_t *counters;       // [kMaxDepthSlots][2]: paths entering depth d, shadow items of depth d
+    uint32_t *counters;       // [kMaxDepthSlots][kCtrStride]
     float *film;
     uint32_t n_film_pixels;
     uint32_t scene_smem_nodes;  // nodes staged in shared memory
     uint32_t scene_smem_tris;   // 1 when all triangles are staged too
+    uint32_t stack_depth;       // traversal stack entries per thread (shared memory)
     uint32_t *dbg_first_hits;   // optional [n_film_pixels][2]
 };
 
 __device__ __forceinline__ PathState load_path(const PathQueue &q, uint32_t i) {
+    const f4 a = ld4(q.a + i), b = ld4(q.b + i), c = ld4(q.c + i);
     PathState p;
-    p.o = mk3(q.ox[i], q.oy[i], q.oz[i]);
-    p.d = mk3(q.dx[i], q.dy[i], q.dz[i]);
-    p.ex = q.ex[i];
-    p.beta = mk3(q.bx[i], q.by[i], q.bz[i]);
-    p.prev_bsdf_pdf = q.prev_pdf[i];
-    p.path_id = q.path_id[i];
+    p.o = mk3(a.x, a.y, a.z);
+    p.d = mk3(a.w, b.x, b.y);
+    p.ex = f2u(b.z);
+    p.prev_bsdf_pdf = b.w;
+    p.beta = mk3(c.x, c.y, c.z);
+    p.path_id = f2u(c.w);
     return p;
 }
 __device__ __forceinline__ void store_path(const PathQueue &q, uint32_t i, const PathState &p) {
-    q.ox[i] = p.o.x; q.oy[i] = p.o.y; q.oz[i] = p.o.z;
-    q.dx[i] = p.d.x; q.dy[i] = p.d.y; q.dz[i] = p.d.z;
-    q.ex[i] = p.ex;
-    q.bx[i] = p.beta.x; q.by[i] = p.beta.y; q.bz[i] = p.beta.z;
-    q.prev_pdf[i] = p.prev_bsdf_pdf;
-    q.path_id[i] = p.path_id;
+    st4(q.a + i, f4{p.o.x, p.o.y, p.o.z, p.d.x});
+    st4(q.b + i, f4{p.d.y, p.d.z, u2f(p.ex), p.prev_bsdf_pdf});
+    st4(q.c + i, f4{p.beta.x, p.beta.y, p.beta.z, u2f(p.path_id)});
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -117,9 +122,15 @@ __device__ __forceinline__ void tma_bulk_g2s(void *smem_dst, const void *gsrc, u
                  : "memory");
 }
 
-// Stages nodes[0 .. n_nodes) and (optionally) all triangles behind `smem`; returns the TraceData to use.
-__device__ __forceinline__ TraceData stage_scene(const LaunchParams &P, unsigned char *smem, uint64_t *bar) {
-    TraceData td;
+// Shared-memory plan of the trace kernel: [ nodes | triangles | per-thread traversal stacks ].
+struct TraceSmem {
+    const BvhNode *nodes;   // shared copy of nodes[0 .. n_fast_nodes)
+    const TriGeom *tris;    // shared copy of all triangles, or the global array
+    int32_t *stack;         // this thread's stack: entry k lives at stack[k * kBlock]
+};
+
+// Stages nodes[0 .. n_nodes) and (optionally) all triangles behind `smem` with one TMA bulk copy each.
+__device__ __forceinline__ TraceSmem stage_scene(const LaunchParams &P, unsigned char *smem, uint64_t *bar) {
     const uint32_t node_bytes = P.scene_smem_nodes * (uint32_t)sizeof(BvhNode);
     const uint32_t tri_bytes = P.scene_smem_tris ? P.scene.n_tris * (uint32_t)sizeof(TriGeom) : 0u;
     BvhNode *s_nodes = reinterpret_cast<BvhNode *>(smem);
@@ -135,41 +146,87 @@ __device__ __forceinline__ TraceData stage_scene(const LaunchParams &P, unsigned
         if (tri_bytes) tma_bulk_g2s(s_tris, P.scene.tris, tri_bytes, bar);
     }
     if ((node_bytes + tri_bytes) > 0) mbar_wait(bar, 0);
-    td.fast_nodes = s_nodes;
-    td.n_fast_nodes = P.scene_smem_nodes;
-    td.nodes = P.scene.nodes;
-    td.tris = P.scene_smem_tris ? s_tris : P.scene.tris;
-    return td;
+    TraceSmem t;
+    t.nodes = s_nodes;
+    t.tris = P.scene_smem_tris ? s_tris : P.scene.tris;
+    t.stack = reinterpret_cast<int32_t *>(smem + node_bytes + tri_bytes) + threadIdx.x;
+    return t;
 }
 
 // ------------------------------------------------------------------------------------------------
-// kernels
+// device traversal (same candidate set and tie rule as akr_trace.cuh::trace_ray, so the closest hit is
+// identical for any visiting order; the host simulation keeps using trace_ray)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock) k_raygen(const __grid_constant__ LaunchParams P) {
-    const uint32_t n = P.wave.n_pix * P.wave.n_spp;
-    const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        PathState ps = raygen_body(P.scene, P.tables, P.rp, P.wave, i);
-        store_path(P.q[0], i, ps);
+struct DevHit {
+    uint32_t gid, cls;
+    float u, v;
+};
+
+__device__ __forceinline__ void leaf_test(const SceneView &sc, const TriGeom &tr, f3 o, f3 d, float t_min, float t_max, uint32_t ex0, uint32_t ex1,
+                                          DevHit &best, float &best_t) {
+    const uint32_t gid = tr.gid;
+    if (gid == ex0 || gid == ex1) return;
+    float t, u, v;
+    if (!tri_test(tr, o, d, t_min, t_max, t, u, v)) return;
+    const bool closer = (t < best_t) || (t == best_t && gid < best.gid);
+    if (!closer) return;
+    if (sc.any_alpha && !alpha_test(sc, gid, u, v)) return;
+    best = DevHit{gid, tr.cls, u, v};
+    best_t = t;
+}
+
+enum TraceMode : int { TRACE_BVH = 0, TRACE_FLAT = 1 };
+
+// TRACE_FLAT: every lane tests every triangle in list order (shared-memory broadcast reads, no divergence,
+// no stack) — the cheapest schedule when the whole scene is a few dozen triangles.
+// TRACE_BVH : while-while traversal; lanes first descend to their next leaf together, then test leaves.
+template <bool ANY_HIT, int MODE>
+__device__ __forceinline__ DevHit trace_dev(const LaunchParams &P, const TraceSmem &ts, f3 o, f3 d, float t_min, float t_max, uint32_t ex0, uint32_t ex1) {
+    const SceneView &sc = P.scene;
+    DevHit best{0xffffffffu, 0u, 0.0f, 0.0f};
+    float best_t = t_max;
+    if (MODE == TRACE_FLAT) {
+        const uint32_t n = sc.n_tris;
+        for (uint32_t k = 0; k < n; ++k) {
+            leaf_test(sc, ts.tris[k], o, d, t_min, t_max, ex0, ex1, best, best_t);
+            if (ANY_HIT && best.gid != 0xffffffffu) break;
+        }
+        return best;
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) P.counters[0] = n;
-}
-
-__global__ void __launch_bounds__(kBlock) k_intersect(const __grid_constant__ LaunchParams P, uint32_t depth) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ uint64_t bar;
-    const uint32_t n = P.counters[depth * 2u];
-    if (blockIdx.x * blockDim.x >= n) return;  // whole CTA has no work: skip the staging too
-    TraceData td = stage_scene(P, smem, &bar);
-    const PathQueue &q = P.q[depth & 1u];
-    const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        f3 o = mk3(q.ox[i], q.oy[i], q.oz[i]);
-        f3 d = mk3(q.dx[i], q.dy[i], q.dz[i]);
-        HitRec h = trace_ray<false>(P.scene, td, o, d, 0.0f, 1e20f, q.ex[i], 0xffffffffu);
-        P.hits.gid[i] = h.gid;
-        P.hits.u[i] = h.u;
-        P.hits.v[i] = h.v;
+    const f3 inv_d = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    const uint32_t n_fast = P.scene_smem_nodes;
+    int32_t *stack = ts.stack;
+    int sp = 0;
+    int32_t node = 0;  // the root is always an inner node
+    while (true) {
+        while (node >= 0) {
+            const BvhNode &n = ((uint32_t)node < n_fast) ? ts.nodes[node] : sc.nodes[node];
+            float tn0, tn1;
+            const bool h0 = box_test(n.lo0, n.hi0, o, inv_d, t_min, best_t, tn0);
+            const bool h1 = box_test(n.lo1, n.hi1, o, inv_d, t_min, best_t, tn1);
+            const int32_t c0 = n.c0, c1 = n.c1;
+            if (h0 && h1) {
+                const bool swap = tn1 < tn0;
+                stack[sp * kBlock] = swap ? c0 : c1;
+                ++sp;
+                node = swap ? c1 : c0;
+            } else if (h0) {
+                node = c0;
+            } else if (h1) {
+                node = c1;
+            } else {
+                if (sp == 0) return best;
+                --sp;
+                node = stack[sp * kBlock];
+            }
+        }
+        const uint32_t leaf = (uint32_t)(~node);
+        const uint32_t first = leaf >> 3, count = leaf & 7u;
+        for (uint32_t k = 0; k < count; ++k) leaf_test(sc, ts.tris[first + k], o, d, t_min, t_max, ex0, ex1, best, best_t);
+        if (ANY_HIT && best.gid != 0xffffffffu) return best;
+        if (sp == 0) return best;
+        --sp;
+        node = stack[sp * kBlock];
     }
 }
 
@@ -185,64 +242,119 @@ __device__ __forceinline__ uint32_t warp_append(uint32_t *counter, bool pred) {
     return base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
 }
 
-__global__ void __launch_bounds__(kBlock) k_shade(const __grid_constant__ LaunchParams P, uint32_t depth) {
-    const uint32_t n = P.counters[depth * 2u];
+// ------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_raygen(const __grid_constant__ LaunchParams P) {
+    const uint32_t n = P.wave.n_pix * P.wave.n_spp;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        PathState ps = raygen_body(P.scene, P.tables, P.rp, P.wave, i);
+        store_path(P.q[0], i, ps);
+        st4(P.acc.l + i, f4{0.0f, 0.0f, 0.0f, 0.0f});
+        st4(P.acc.b + i, f4{0.0f, 0.0f, 0.0f, 0.0f});
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) P.counters[0] = n;
+}
+
+// One launch per depth traces BOTH ray kinds: the closest-hit rays of the paths entering `depth` and the
+// shadow rays the previous depth's shade stage produced.  Work is handed out in warp-sized tasks
+// (closest-hit tasks first, the shorter any-hit tasks fill the tail), so a warp is never mixed.
+template <int MODE> __global__ void __launch_bounds__(kBlock) k_trace(const __grid_constant__ LaunchParams P, uint32_t depth) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bar;
+    const uint32_t n_cl = P.counters[depth * kCtrStride];
+    const uint32_t n_sh = depth > 0u ? P.counters[(depth - 1u) * kCtrStride + 1u] : 0u;
+    const uint32_t t_cl = (n_cl + 31u) >> 5, t_sh = (n_sh + 31u) >> 5;
+    const uint32_t n_tasks = t_cl + t_sh;
+    if (blockIdx.x * kWarpsPerBlock >= n_tasks) return;  // whole CTA has no work: skip the staging too
+    const TraceSmem ts = stage_scene(P, smem, &bar);
+    const PathQueue &q = P.q[depth & 1u];
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t *ctr = P.counters + depth * kCtrStride;
+    const bool miss_work = depth != 0u && (P.rp.debug_depth < 0 || depth == (uint32_t)P.rp.debug_depth);
+    for (uint32_t task = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); task < n_tasks; task += gridDim.x * kWarpsPerBlock) {
+        if (task < t_cl) {
+            const uint32_t i = task * 32u + lane;
+            const bool active = i < n_cl;
+            DevHit h{0xffffffffu, 0u, 0.0f, 0.0f};
+            if (active) {
+                const f4 a = ld4(q.a + i), b = ld4(q.b + i);
+                h = trace_dev<false, MODE>(P, ts, mk3(a.x, a.y, a.z), mk3(a.w, b.x, b.y), 0.0f, 1e20f, f2u(b.z), 0xffffffffu);
+                st4(P.hits.h + i, f4{u2f(h.gid), h.u, h.v, 0.0f});
+            }
+            const bool hit = active && h.gid != 0xffffffffu;
+            const uint32_t cls = P.rp.force_diffuse ? (uint32_t)CLS_LAMBERT : h.cls;
+#pragma unroll
+            for (uint32_t c = 0; c < (uint32_t)CLS_COUNT; ++c) {
+                const bool mine = hit && cls == c;
+                const uint32_t slot = warp_append(ctr + 2u + c, mine);
+                if (mine) P.cls.idx[c][slot] = i;
+            }
+            if (active && !hit && miss_work) {
+                const f4 c = ld4(q.c + i);
+                miss_body(P.rp, depth, mk3(c.x, c.y, c.z), f2u(c.w), P.acc);
+            }
+        } else {
+            const uint32_t i = (task - t_cl) * 32u + lane;
+            if (i < n_sh) {
+                const f4 a = ld4(P.shadow.a + i), b = ld4(P.shadow.b + i);
+                const DevHit h = trace_dev<true, MODE>(P, ts, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), 0.0f, a.w, f2u(b.w), P.shadow.ex1[i]);
+                const f4 c = ld4(P.shadow.c + i);
+                ShadowItem it;
+                it.contrib = mk3(c.x, c.y, c.z);
+                it.path_id = f2u(c.w);
+                shadow_resolve(P.acc, it, h.gid != 0xffffffffu, depth);  // produced at depth - 1: depth1 = depth
+            }
+        }
+    }
+}
+
+template <int CLS> struct ShadeLaunch {
+    static constexpr int kMinBlocks = (CLS == CLS_LAMBERT || CLS == CLS_CONDUCTOR) ? 2 : 1;
+};
+
+// One shade kernel per material class; `CLS_ANY` (unsorted: every hit in slot order) exists for A/B runs.
+template <int CLS> __global__ void __launch_bounds__(kBlock, ShadeLaunch<CLS>::kMinBlocks) k_shade(const __grid_constant__ LaunchParams P, uint32_t depth) {
+    uint32_t *ctr = P.counters + depth * kCtrStride;
+    const uint32_t n = CLS == CLS_ANY ? ctr[0] : ctr[2u + (CLS == CLS_ANY ? 0 : CLS)];
+    const uint32_t *slots = CLS == CLS_ANY ? nullptr : P.cls.idx[CLS == CLS_ANY ? 0 : CLS];
     const PathQueue &qin = P.q[depth & 1u];
     const PathQueue &qout = P.q[(depth + 1u) & 1u];
-    uint32_t *next_count = P.counters + (depth + 1u) * 2u;
-    uint32_t *shadow_count = P.counters + depth * 2u + 1u;
+    uint32_t *next_count = ctr + kCtrStride;
+    uint32_t *shadow_count = ctr + 1u;
     const uint32_t stride = gridDim.x * blockDim.x;
     // warp-uniform trip count so that every lane takes part in the ballots
     for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride) {
-        const uint32_t i = base + (threadIdx.x & 31u);
-        const bool active = i < n;
+        const uint32_t k = base + (threadIdx.x & 31u);
+        bool active = k < n;
         ShadeOut o;
         o.has_shadow = false;
         o.has_next = false;
         if (active) {
-            PathState ps = load_path(qin, i);
-            HitRec h{P.hits.gid[i], P.hits.u[i], P.hits.v[i]};
-            o = shade_body(P.scene, P.corners, P.tables, P.rp, P.wave, depth, ps, h, P.acc);
-            if (depth == 0u && P.dbg_first_hits && ps.path_id < P.wave.n_pix && P.wave.s0 == 0u) {
-                uint32_t pix = P.wave.pix0 + ps.path_id;
-                P.dbg_first_hits[2u * pix + 0u] = h.gid == 0xffffffffu ? 0xffffffffu : P.scene.shade[h.gid].inst;
-                P.dbg_first_hits[2u * pix + 1u] = h.gid == 0xffffffffu ? 0xffffffffu : P.scene.shade[h.gid].prim;
+            const uint32_t i = CLS == CLS_ANY ? k : slots[k];
+            const f4 hr = ld4(P.hits.h + i);
+            HitRec h{f2u(hr.x), hr.y, hr.z};
+            if (CLS != CLS_ANY || h.gid != 0xffffffffu) {
+                PathState ps = load_path(qin, i);
+                o = shade_body<CLS>(P.scene, P.corners, P.tables, P.rp, P.wave, depth, ps, h, P.acc);
+                if (depth == 0u && P.dbg_first_hits && ps.path_id < P.wave.n_pix && P.wave.s0 == 0u) {
+                    uint32_t pix = P.wave.pix0 + ps.path_id;
+                    P.dbg_first_hits[2u * pix + 0u] = P.scene.shade[h.gid].inst;
+                    P.dbg_first_hits[2u * pix + 1u] = P.scene.shade[h.gid].prim;
+                }
             }
         }
         const uint32_t ss = warp_append(shadow_count, o.has_shadow);
         if (o.has_shadow) {
             const ShadowQueue &s = P.shadow;
-            s.ox[ss] = o.shadow.o.x; s.oy[ss] = o.shadow.o.y; s.oz[ss] = o.shadow.o.z;
-            s.dx[ss] = o.shadow.d.x; s.dy[ss] = o.shadow.d.y; s.dz[ss] = o.shadow.d.z;
-            s.tmax[ss] = o.shadow.t_max;
-            s.ex0[ss] = o.shadow.ex0; s.ex1[ss] = o.shadow.ex1;
-            s.cr[ss] = o.shadow.contrib.x; s.cg[ss] = o.shadow.contrib.y; s.cb[ss] = o.shadow.contrib.z;
-            s.path_id[ss] = o.shadow.path_id;
+            st4(s.a + ss, f4{o.shadow.o.x, o.shadow.o.y, o.shadow.o.z, o.shadow.t_max});
+            st4(s.b + ss, f4{o.shadow.d.x, o.shadow.d.y, o.shadow.d.z, u2f(o.shadow.ex0)});
+            st4(s.c + ss, f4{o.shadow.contrib.x, o.shadow.contrib.y, o.shadow.contrib.z, u2f(o.shadow.path_id)});
+            s.ex1[ss] = o.shadow.ex1;
         }
         const uint32_t ns = warp_append(next_count, o.has_next);
         if (o.has_next) store_path(qout, ns, o.next);
-    }
-}
-
-__global__ void __launch_bounds__(kBlock) k_shadow(const __grid_constant__ LaunchParams P, uint32_t depth) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ uint64_t bar;
-    const uint32_t n = P.counters[depth * 2u + 1u];
-    if (blockIdx.x * blockDim.x >= n) return;
-    TraceData td = stage_scene(P, smem, &bar);
-    const ShadowQueue &s = P.shadow;
-    const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        ShadowItem it;
-        it.o = mk3(s.ox[i], s.oy[i], s.oz[i]);
-        it.d = mk3(s.dx[i], s.dy[i], s.dz[i]);
-        it.t_max = s.tmax[i];
-        it.ex0 = s.ex0[i];
-        it.ex1 = s.ex1[i];
-        it.contrib = mk3(s.cr[i], s.cg[i], s.cb[i]);
-        it.path_id = s.path_id[i];
-        HitRec h = trace_ray<true>(P.scene, td, it.o, it.d, 0.0f, it.t_max, it.ex0, it.ex1);
-        shadow_resolve(P.acc, it, h.gid != 0xffffffffu, depth + 1u);
     }
 }
 
@@ -256,14 +368,14 @@ __global__ void k_fold_counters(uint32_t *counters, unsigned long long *totals, 
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         unsigned long long seg = 0, sh = 0;
         for (uint32_t d = 0; d < n_depth; ++d) {
-            seg += counters[d * 2u];
-            sh += counters[d * 2u + 1u];
+            seg += counters[d * kCtrStride];
+            sh += counters[d * kCtrStride + 1u];
         }
         totals[0] += seg;
         totals[1] += sh;
     }
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < n_depth * 2u; i += blockDim.x) counters[i] = 0u;
+    for (uint32_t i = threadIdx.x; i < n_depth * kCtrStride; i += blockDim.x) counters[i] = 0u;
 }
 
 // Film::copy_to_rgba_image(hdr = true) (film.rs:120-148), splat_scale = 1
@@ -314,7 +426,10 @@ struct AkrContext {
     CornerAttribs corners{};
     bool scene_ready = false;
     bool scene_needs_table = false;
-    uint32_t smem_nodes = 0, smem_tris = 0, smem_bytes = 0;
+    uint32_t smem_nodes = 0, smem_tris = 0, smem_bytes = 0;  // smem_bytes = nodes + triangles (stacks come on top)
+    uint32_t bvh_depth = 0;
+    uint32_t class_mask = 0;   // shade classes present in the scene
+    int occ_trace[2] = {1, 1}, occ_shade[4] = {1, 1, 1, 1};  // resident CTAs per SM, per kernel variant
 
     // render state
     bool render_ready = false;
@@ -331,6 +446,7 @@ struct AkrContext {
     PathQueue q[2]{};
     HitQueue hits{};
     ShadowQueue shadow{};
+    ClassQueues cls{};
     AccView acc{};
     DeviceBuffer counters, totals, dbg_hits;
 
@@ -389,42 +505,33 @@ int grid_for(const AkrContext *ctx, uint32_t n, int ctas_per_sm) {
 
 int ensure_wave_buffers(AkrContext *ctx, uint32_t capacity) {
     if (ctx->wave_capacity >= capacity && ctx->wave_mem.ptr) return AKR_OK;
-    const size_t words_per_path = 13 * 2 + 3 + 13 + 6;  // two path queues, hits, shadow queue, accumulators
-    size_t cap = (size_t)capacity;
-    int rc = dev_alloc(ctx, ctx->wave_mem, cap * words_per_path * 4);
+    // 16-byte records per path: two path queues (3 + 3), hits (1), shadow queue (3), accumulators (2);
+    // 4-byte words per path: shadow exclude1 (1), class slot lists (CLS_COUNT)
+    const size_t cap = ((size_t)capacity + 31u) & ~(size_t)31u;
+    const size_t n_vec = 3 + 3 + 1 + 3 + 2, n_word = 1 + (size_t)CLS_COUNT;
+    int rc = dev_alloc(ctx, ctx->wave_mem, cap * (n_vec * 16 + n_word * 4));
     if (rc != AKR_OK) return rc;
-    uint32_t *base = static_cast<uint32_t *>(ctx->wave_mem.ptr);
-    size_t off = 0;
-    auto take_f = [&]() {
-        float *p = reinterpret_cast<float *>(base + off);
-        off += cap;
-        return p;
-    };
-    auto take_u = [&]() {
-        uint32_t *p = base + off;
-        off += cap;
+    f4 *vbase = static_cast<f4 *>(ctx->wave_mem.ptr);
+    size_t voff = 0;
+    auto take_v = [&]() {
+        f4 *p = vbase + voff;
+        voff += cap;
         return p;
     };
     for (int k = 0; k < 2; ++k) {
-        PathQueue &q = ctx->q[k];
-        q.ox = take_f(); q.oy = take_f(); q.oz = take_f();
-        q.dx = take_f(); q.dy = take_f(); q.dz = take_f();
-        q.ex = take_u();
-        q.bx = take_f(); q.by = take_f(); q.bz = take_f();
-        q.prev_pdf = take_f();
-        q.path_id = take_u();
+        ctx->q[k].a = take_v();
+        ctx->q[k].b = take_v();
+        ctx->q[k].c = take_v();
     }
-    ctx->hits.gid = take_u(); ctx->hits.u = take_f(); ctx->hits.v = take_f();
-    ShadowQueue &s = ctx->shadow;
-    s.ox = take_f(); s.oy = take_f(); s.oz = take_f();
-    s.dx = take_f(); s.dy = take_f(); s.dz = take_f();
-    s.tmax = take_f();
-    s.ex0 = take_u(); s.ex1 = take_u();
-    s.cr = take_f(); s.cg = take_f(); s.cb = take_f();
-    s.path_id = take_u();
-    AccView &a = ctx->acc;
-    a.lr = take_f(); a.lg = take_f(); a.lb = take_f();
-    a.br = take_f(); a.bg = take_f(); a.bb = take_f();
+    ctx->hits.h = take_v();
+    ctx->shadow.a = take_v();
+    ctx->shadow.b = take_v();
+    ctx->shadow.c = take_v();
+    ctx->acc.l = take_v();
+    ctx->acc.b = take_v();
+    uint32_t *wbase = reinterpret_cast<uint32_t *>(vbase + voff);
+    ctx->shadow.ex1 = wbase;
+    for (uint32_t c = 0; c < (uint32_t)CLS_COUNT; ++c) ctx->cls.idx[c] = wbase + cap * (1 + c);
     ctx->wave_capacity = capacity;
     return AKR_OK;
 }
@@ -467,9 +574,9 @@ int akr_b200_create(int device_ordinal, AkrContext **out_ctx) {
         delete ctx;
         return AKR_ERR_CUDA;
     }
-    cudaFuncSetAttribute(k_intersect, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemSceneBudget);
-    cudaFuncSetAttribute(k_shadow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemSceneBudget);
-    if (dev_alloc(ctx, ctx->counters, kMaxDepthSlots * 2 * sizeof(uint32_t)) != AKR_OK || dev_alloc(ctx, ctx->totals, 2 * sizeof(unsigned long long)) != AKR_OK) {
+    cudaFuncSetAttribute(k_trace<TRACE_BVH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
+    cudaFuncSetAttribute(k_trace<TRACE_FLAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
+    if (dev_alloc(ctx, ctx->counters, kMaxDepthSlots * kCtrStride * sizeof(uint32_t)) != AKR_OK || dev_alloc(ctx, ctx->totals, 2 * sizeof(unsigned long long)) != AKR_OK) {
         delete ctx;
         return AKR_ERR_CUDA;
     }
@@ -574,14 +681,28 @@ int akr_b200_upload_scene(AkrContext *ctx, const AkrSceneDesc *desc) {
     for (const Material &m : blob.materials)
         if (m.type == MAT_PRINCIPLED && (m.lobes & (LOBE_COAT | LOBE_SPECULAR))) ctx->scene_needs_table = true;
     // shared-memory staging plan: top of the BVH first, then all triangles if they still fit
-    const uint32_t node_bytes = v.n_nodes * (uint32_t)sizeof(BvhNode);
     const uint32_t tri_bytes = v.n_tris * (uint32_t)sizeof(TriGeom);
     ctx->smem_nodes = std::min(v.n_nodes, kSmemSceneBudget / (uint32_t)sizeof(BvhNode));
     uint32_t used = ctx->smem_nodes * (uint32_t)sizeof(BvhNode);
     ctx->smem_tris = (ctx->smem_nodes == v.n_nodes && used + tri_bytes <= kSmemSceneBudget) ? 1u : 0u;
     if (ctx->smem_tris) used += tri_bytes;
-    (void)node_bytes;
     ctx->smem_bytes = used;
+    ctx->bvh_depth = blob.bvh_depth;
+    ctx->class_mask = 0;
+    for (const Material &m : blob.materials) ctx->class_mask |= 1u << shade_class_of(m.type);
+    // resident CTAs per SM of every kernel variant with this scene's shared-memory footprint
+    {
+        const size_t smem_bvh = used + (size_t)(blob.bvh_depth + 2u) * kBlock * sizeof(int32_t);
+        const size_t smem_flat = used;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_trace[TRACE_BVH], k_trace<TRACE_BVH>, kBlock, smem_bvh);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_trace[TRACE_FLAT], k_trace<TRACE_FLAT>, kBlock, smem_flat);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_shade[0], k_shade<CLS_LAMBERT>, kBlock, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_shade[1], k_shade<CLS_CONDUCTOR>, kBlock, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_shade[2], k_shade<CLS_GENERAL>, kBlock, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_shade[3], k_shade<CLS_ANY>, kBlock, 0);
+        for (int &o : ctx->occ_trace) o = std::max(o, 1);
+        for (int &o : ctx->occ_shade) o = std::max(o, 1);
+    }
     ctx->scene_ready = true;
     return AKR_OK;
 }
@@ -638,6 +759,7 @@ int akr_b200_begin(AkrContext *ctx, const AkrPtConfig *cfg, const AkrSamplerConf
     rp.width = width;
     rp.height = height;
     rp.y0 = y0;
+    finish_render_params(rp);
     ctx->cfg = *cfg;
     ctx->tile_y0 = y0;
     ctx->tile_y1 = y1;
@@ -661,7 +783,7 @@ int akr_b200_render_pass(AkrContext *ctx, uint32_t n_spp, int blocking) {
     if (ctx->spp_done + n_spp > ctx->cfg.spp) return fail(ctx, AKR_ERR_INVALID_ARGUMENT, "pass exceeds the configured spp (sampler/mod.rs:666-668)");
     AKR_CUDA(ctx, cudaSetDevice(ctx->device));
     // wave geometry: pixels x samples with pixels * samples <= capacity
-    uint32_t cap = ctx->opts.wave_size ? ctx->opts.wave_size : (1u << 20);
+    uint32_t cap = ctx->opts.wave_size ? ctx->opts.wave_size : (1u << 22);
     cap = std::max(cap, 1024u);
     uint32_t spp_chunk = std::min(n_spp, std::max(1u, cap / 32u));
     uint32_t pix_chunk = std::max(32u, (cap / spp_chunk) & ~31u);
@@ -679,13 +801,24 @@ int akr_b200_render_pass(AkrContext *ctx, uint32_t n_spp, int blocking) {
     P.q[1] = ctx->q[1];
     P.hits = ctx->hits;
     P.shadow = ctx->shadow;
+    P.cls = ctx->cls;
     P.acc = ctx->acc;
     P.counters = static_cast<uint32_t *>(ctx->counters.ptr);
     P.film = static_cast<float *>(ctx->film.ptr);
     P.n_film_pixels = ctx->n_pixels;
     P.scene_smem_nodes = ctx->smem_nodes;
     P.scene_smem_tris = ctx->smem_tris;
+    P.stack_depth = ctx->bvh_depth + 2u;
     P.dbg_first_hits = static_cast<uint32_t *>(ctx->dbg_hits.ptr);
+
+    // trace schedule: flat list for tiny scenes that fit in shared memory, BVH otherwise (opts.trace_mode overrides)
+    int trace_mode = (ctx->scene.n_tris <= kFlatMaxTris && ctx->smem_tris) ? TRACE_FLAT : TRACE_BVH;
+    if (ctx->opts.trace_mode == 1u) trace_mode = TRACE_BVH;
+    if (ctx->opts.trace_mode == 2u && ctx->smem_tris) trace_mode = TRACE_FLAT;
+    const size_t trace_smem = ctx->smem_bytes + (trace_mode == TRACE_BVH ? (size_t)P.stack_depth * kBlock * sizeof(int32_t) : 0);
+    if (trace_smem > kSmemMax) return fail(ctx, AKR_ERR_UNSUPPORTED, "BVH too deep for the shared-memory traversal stack");
+    const bool binned = ctx->opts.sort_by_material != 2u;
+    const uint32_t class_mask = ctx->rp.force_diffuse ? (1u << CLS_LAMBERT) : ctx->class_mask;
 
     const bool prof = ctx->opts.profile_stages != 0;
     struct StageMark {
@@ -728,14 +861,20 @@ int akr_b200_render_pass(AkrContext *ctx, uint32_t n_spp, int blocking) {
         const uint32_t n_pix = std::min(pix_chunk, ctx->n_pixels - pix0);
         for (uint32_t s0 = 0; s0 < n_spp; s0 += spp_chunk) {
             const uint32_t k = std::min(spp_chunk, n_spp - s0);
-            P.wave = WaveInfo{pix0, n_pix, s_begin + s0, k};
+            P.wave = make_wave(pix0, n_pix, s_begin + s0, k);
             const uint32_t n_paths = n_pix * k;
-            const int g_full = grid_for(ctx, n_paths, 8);
-            AKR_LAUNCH(0, k_raygen, g_full, 0, P);
+            AKR_LAUNCH(0, k_raygen, grid_for(ctx, n_paths, 8), 0, P);
+            const int g_trace = grid_for(ctx, n_paths, ctx->occ_trace[trace_mode]);
             for (uint32_t depth = 0; depth <= ctx->rp.max_depth; ++depth) {
-                AKR_LAUNCH(1, k_intersect, g_full, ctx->smem_bytes, P, depth);
-                AKR_LAUNCH(2, k_shade, g_full, 0, P, depth);
-                AKR_LAUNCH(3, k_shadow, g_full, ctx->smem_bytes, P, depth);
+                if (trace_mode == TRACE_FLAT) AKR_LAUNCH(1, k_trace<TRACE_FLAT>, g_trace, trace_smem, P, depth);
+                else AKR_LAUNCH(1, k_trace<TRACE_BVH>, g_trace, trace_smem, P, depth);
+                if (!binned) {
+                    AKR_LAUNCH(6, k_shade<CLS_ANY>, grid_for(ctx, n_paths, ctx->occ_shade[3]), 0, P, depth);
+                    continue;
+                }
+                if (class_mask & (1u << CLS_LAMBERT)) AKR_LAUNCH(2, k_shade<CLS_LAMBERT>, grid_for(ctx, n_paths, ctx->occ_shade[0]), 0, P, depth);
+                if (class_mask & (1u << CLS_CONDUCTOR)) AKR_LAUNCH(3, k_shade<CLS_CONDUCTOR>, grid_for(ctx, n_paths, ctx->occ_shade[1]), 0, P, depth);
+                if (class_mask & (1u << CLS_GENERAL)) AKR_LAUNCH(6, k_shade<CLS_GENERAL>, grid_for(ctx, n_paths, ctx->occ_shade[2]), 0, P, depth);
             }
             AKR_LAUNCH(4, k_accumulate, grid_for(ctx, n_pix, 8), 0, P);
             k_fold_counters<<<1, 128, 0, ctx->stream>>>(P.counters, static_cast<unsigned long long *>(ctx->totals.ptr), ctx->rp.max_depth + 2u);

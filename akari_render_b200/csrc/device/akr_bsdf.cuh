@@ -56,6 +56,14 @@ struct Material {  // 56 words
     uint32_t _pad;
 };
 
+// Shade classes: the trace stage bins every hit by the class of its material and one shade kernel is
+// compiled per class, so a warp never interleaves Lambert, conductor and full-tree code (the
+// "material-key sort" of the wavefront design).  CLS_ANY compiles the generic switch (host simulation).
+enum ShadeClass : uint32_t { CLS_LAMBERT = 0, CLS_CONDUCTOR = 1, CLS_GENERAL = 2, CLS_COUNT = 3, CLS_ANY = 7 };
+AKR_HD uint32_t shade_class_of(uint32_t material_type) {
+    return material_type == MAT_LAMBERT ? (uint32_t)CLS_LAMBERT : (material_type == MAT_CONDUCTOR ? (uint32_t)CLS_CONDUCTOR : (uint32_t)CLS_GENERAL);
+}
+
 struct BsdfEval {
     f3 f;
     float pdf;
@@ -393,7 +401,9 @@ AKR_HD float albedo_table_cell(uint32_t cell, uint32_t n) {
 }
 
 // ---- material dispatch in the material-local frame -----------------------------------------------
-AKR_HD BsdfEval material_eval(const Material &m, const float *table, f3 wo, f3 wi) {
+template <int CLS> AKR_HD BsdfEval material_eval(const Material &m, const float *table, f3 wo, f3 wi) {
+    if (CLS == CLS_LAMBERT) return diffuse_eval(ld3(m.diffuse), wo, wi);
+    if (CLS == CLS_CONDUCTOR) return mf_reflection_eval<1>(splat3(1.0f), 0.0f, m.metal_n, m.metal_k, tr_from_roughness(m.roughness), wo, wi);
     switch (m.type) {
     case MAT_LAMBERT: return diffuse_eval(ld3(m.diffuse), wo, wi);
     case MAT_CONDUCTOR: return mf_reflection_eval<1>(splat3(1.0f), 0.0f, m.metal_n, m.metal_k, tr_from_roughness(m.roughness), wo, wi);
@@ -402,7 +412,9 @@ AKR_HD BsdfEval material_eval(const Material &m, const float *table, f3 wo, f3 w
     default: return zero_eval();
     }
 }
-AKR_HD BsdfDir material_sample(const Material &m, const float *table, f3 wo, float u_select, f2 u) {
+template <int CLS> AKR_HD BsdfDir material_sample(const Material &m, const float *table, f3 wo, float u_select, f2 u) {
+    if (CLS == CLS_LAMBERT) return diffuse_sample(wo, u);
+    if (CLS == CLS_CONDUCTOR) return mf_reflection_sample(tr_from_roughness(m.roughness), wo, u);
     switch (m.type) {
     case MAT_LAMBERT: return diffuse_sample(wo, u);
     case MAT_CONDUCTOR: return mf_reflection_sample(tr_from_roughness(m.roughness), wo, u);
@@ -437,7 +449,7 @@ AKR_HD ClosureFrames make_closure_frames(const Material &m, const Frame &frame, 
     return c;
 }
 // SurfaceClosure::evaluate_impl applied twice (mod.rs:729-748)
-AKR_HD BsdfEval closure_eval(const Material &m, const float *table, const ClosureFrames &c, f3 wo, f3 wi) {
+template <int CLS> AKR_HD BsdfEval closure_eval(const Material &m, const float *table, const ClosureFrames &c, f3 wo, f3 wi) {
     if (!check_wo_wi_valid(c.outer.n, c.ng, wo, wi)) return zero_eval();
     f3 wo_l = to_local(c.outer, wo), wi_l = to_local(c.outer, wi);
     if (c.has_inner) {
@@ -445,20 +457,20 @@ AKR_HD BsdfEval closure_eval(const Material &m, const float *table, const Closur
         wo_l = to_local(c.inner, wo_l);
         wi_l = to_local(c.inner, wi_l);
     }
-    return material_eval(m, table, wo_l, wi_l);
+    return material_eval<CLS>(m, table, wo_l, wi_l);
 }
 // SurfaceClosure::sample_wi_impl applied twice (mod.rs:750-764)
-AKR_HD BsdfDir closure_sample_wi(const Material &m, const float *table, const ClosureFrames &c, f3 wo, float u_select, f2 u) {
+template <int CLS> AKR_HD BsdfDir closure_sample_wi(const Material &m, const float *table, const ClosureFrames &c, f3 wo, float u_select, f2 u) {
     f3 wo_l = to_local(c.outer, wo);
     BsdfDir s;
     if (c.has_inner) {
         f3 wo_ll = to_local(c.inner, wo_l);
-        s = material_sample(m, table, wo_ll, u_select, u);
+        s = material_sample<CLS>(m, table, wo_ll, u_select, u);
         f3 wi_l = to_world(c.inner, s.wi);
         s.valid = s.valid && check_wo_wi_valid(c.inner.n, c.ng_local, wo_l, wi_l);
         s.wi = wi_l;
     } else {
-        s = material_sample(m, table, wo_l, u_select, u);
+        s = material_sample<CLS>(m, table, wo_l, u_select, u);
     }
     f3 wi = to_world(c.outer, s.wi);
     bool valid = s.valid && check_wo_wi_valid(c.outer.n, c.ng, wo, wi);

@@ -148,6 +148,40 @@ AKR_HD float offset_axis(float p, float n) {
 }
 AKR_HD f3 offset_ray_origin(f3 p, f3 n) { return mk3(offset_axis(p.x, n.x), offset_axis(p.y, n.y), offset_axis(p.z, n.z)); }
 
+// ---- exact unsigned division by a launch-constant divisor -----------------------------------------
+// q = floor(n / d) without the ~20-instruction hardware-less divide: one mul.hi estimate that is either
+// exact or one too small (m = floor(2^(32+s) / d) clamped to 32 bits, s = floor(log2 d)), then one fix-up.
+struct FastDiv {
+    uint32_t d, m, s;
+};
+inline FastDiv make_fastdiv(uint32_t d) {
+    FastDiv f;
+    f.d = d ? d : 1u;
+    uint32_t s = 0;
+    while ((2u << s) <= f.d && s < 31u) ++s;
+    f.s = s;
+    unsigned long long m = ((1ull << (32u + s)) / f.d);
+    f.m = m > 0xffffffffull ? 0xffffffffu : (uint32_t)m;
+    return f;
+}
+AKR_HD uint32_t mulhi_u32(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((unsigned long long)a * (unsigned long long)b) >> 32);
+#endif
+}
+AKR_HD uint32_t fastdiv(uint32_t n, const FastDiv &f, uint32_t &rem) {
+    uint32_t q = mulhi_u32(n, f.m) >> f.s;
+    uint32_t r = n - q * f.d;
+    if (r >= f.d) {
+        q += 1u;
+        r -= f.d;
+    }
+    rem = r;
+    return q;
+}
+
 // ---- integer hashes (util/hash.rs:44-59, sampler/mod.rs:473-505) ----------------------------------
 AKR_HD uint32_t rotl17(uint32_t h) { return (h << 17) | (h >> 15); }
 AKR_HD uint32_t xxhash32_4(uint32_t px, uint32_t py, uint32_t pz, uint32_t pw) {
@@ -183,7 +217,8 @@ AKR_HD uint32_t permute_element(uint32_t i, uint32_t l, uint32_t w, uint32_t p) 
         i &= w;
         i ^= i >> 5;
     } while (i >= l);
-    return (i + p) % l;
+    // l == w + 1 (power-of-two sample counts): x % l == x & w
+    return (l == w + 1u) ? ((i + p) & w) : ((i + p) % l);
 }
 
 // ---- sampling.rs -------------------------------------------------------------------------------

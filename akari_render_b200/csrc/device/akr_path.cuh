@@ -30,7 +30,10 @@ AKR_HD float sampler_1d(const SamplerTables &tab, const RenderParams &rp, uint32
     uint32_t hash = xxhash32_4(px, py, dim, rp.seed);
     uint32_t index = permute_element(sample_index, rp.spp_total, rp.w_mask, hash);
     float delta = bluenoise(tab, dim, px, py);
-    return fminf(((float)index + delta) / (float)rp.spp_total, AKR_ONE_MINUS_EPSILON);
+    float x = (float)index + delta;
+    // division by a power of two is exact, so the reciprocal multiply returns the same bits
+    float q = rp.spp_pow2 ? x * rp.inv_spp : x / (float)rp.spp_total;
+    return fminf(q, AKR_ONE_MINUS_EPSILON);
 }
 AKR_HD f2 sampler_2d(const SamplerTables &tab, const RenderParams &rp, uint32_t px, uint32_t py, uint32_t sample_index, uint32_t dim) {
     uint32_t index = sample_index;
@@ -63,16 +66,26 @@ struct WaveInfo {
     uint32_t n_pix;     // pixels in this wave
     uint32_t s0;        // first sample index
     uint32_t n_spp;     // samples per pixel in this wave; path_id = s_local * n_pix + p_local
+    FastDiv n_pix_div;  // path_id -> (s_local, p_local)
 };
+inline WaveInfo make_wave(uint32_t pix0, uint32_t n_pix, uint32_t s0, uint32_t n_spp) {
+    WaveInfo w;
+    w.pix0 = pix0;
+    w.n_pix = n_pix;
+    w.s0 = s0;
+    w.n_spp = n_spp;
+    w.n_pix_div = make_fastdiv(n_pix);
+    return w;
+}
 struct PathCoord {
     uint32_t px, py, sample_index, pixel_in_tile;
 };
 AKR_HD PathCoord path_coord(const RenderParams &rp, const WaveInfo &w, uint32_t path_id) {
-    uint32_t s_local = path_id / w.n_pix;
-    uint32_t p_local = path_id - s_local * w.n_pix;
+    uint32_t p_local, col;
+    uint32_t s_local = fastdiv(path_id, w.n_pix_div, p_local);
     uint32_t pix = w.pix0 + p_local;
-    uint32_t row = pix / rp.width;
-    return PathCoord{pix - row * rp.width, rp.y0 + row, w.s0 + s_local, pix};
+    uint32_t row = fastdiv(pix, rp.width_div, col);
+    return PathCoord{col, rp.y0 + row, w.s0 + s_local, pix};
 }
 
 struct PathState {  // what survives from one bounce to the next (13 words in the SoA queue)
@@ -89,10 +102,28 @@ struct ShadowItem {    // 13 words
     f3 contrib;         // beta * direct, added to L when unoccluded
     uint32_t path_id;
 };
-struct AccView {       // per-path radiance accumulators, indexed by path_id (not compacted)
-    float *lr, *lg, *lb;     // radiance
-    float *br, *bg, *bb;     // base_replay_throughput
+struct f4 {             // 16-byte record: one vector load/store per access
+    float x, y, z, w;
 };
+struct AccView {       // per-path radiance accumulators, indexed by path_id (not compacted); zeroed by raygen
+    f4 *l;             // radiance (xyz)
+    f4 *b;             // base_replay_throughput (xyz)
+};
+AKR_HD f4 ld4(const f4 *p) {
+#if defined(__CUDA_ARCH__)
+    float4 v = *reinterpret_cast<const float4 *>(p);
+    return f4{v.x, v.y, v.z, v.w};
+#else
+    return *p;
+#endif
+}
+AKR_HD void st4(f4 *p, f4 v) {
+#if defined(__CUDA_ARCH__)
+    *reinterpret_cast<float4 *>(p) = make_float4(v.x, v.y, v.z, v.w);
+#else
+    *p = v;
+#endif
+}
 
 // ---- stage: raygen ------------------------------------------------------------------------------------
 AKR_HD f2 filter_sample(const RenderParams &rp, f2 u) {  // film.rs:32-49
@@ -199,12 +230,24 @@ struct ShadeOut {
 };
 
 AKR_HD void acc_add(const AccView &acc, uint32_t id, f3 c) {
-    acc.lr[id] += c.x;
-    acc.lg[id] += c.y;
-    acc.lb[id] += c.z;
+    f4 l = ld4(acc.l + id);
+    st4(acc.l + id, f4{l.x + c.x, l.y + c.y, l.z + c.z, 0.0f});
 }
 
-// `depth` = path depth when the ray was cast (0 for camera rays).
+// ---- a ray that left the scene: hit_envmap = (0, 0) (pt.rs:226-228,381-396) -----------------------------
+// add_radiance(beta * 0): a NaN/inf throughput poisons the sample exactly as in the reference; a finite
+// one adds nothing.  Depth-0 misses need no work at all (raygen zeroed the accumulators).
+AKR_HD void miss_body(const RenderParams &rp, uint32_t depth, f3 beta, uint32_t id, const AccView &acc) {
+    const bool dbg_on = rp.debug_depth < 0;
+    if (depth != 0u && (dbg_on || depth == (uint32_t)rp.debug_depth)) {
+        f3 c = beta * (splat3(0.0f) * 0.0f);
+        if (c.x != 0.0f || c.y != 0.0f || c.z != 0.0f) acc_add(acc, id, c);
+    }
+}
+
+// `depth` = path depth when the ray was cast (0 for camera rays).  `hit` is a real hit (misses end in
+// miss_body).  CLS is the shade class of the hit material (CLS_ANY: decide per call).
+template <int CLS>
 AKR_HD ShadeOut shade_body(const SceneView &sc, const CornerAttribs &ca, const SamplerTables &tab, const RenderParams &rp, const WaveInfo &wave,
                            uint32_t depth, const PathState &ps, HitRec hit, const AccView &acc) {
     ShadeOut out;
@@ -212,17 +255,6 @@ AKR_HD ShadeOut shade_body(const SceneView &sc, const CornerAttribs &ca, const S
     out.has_next = false;
     const uint32_t id = ps.path_id;
     const bool dbg_on = rp.debug_depth < 0;
-    if (hit.gid == 0xffffffffu) {
-        // miss: hit_envmap = (0, 0) (pt.rs:226-228): add_radiance(0) and stop
-        if (depth == 0u) {
-            acc.lr[id] = 0.0f; acc.lg[id] = 0.0f; acc.lb[id] = 0.0f;
-            acc.br[id] = 0.0f; acc.bg[id] = 0.0f; acc.bb[id] = 0.0f;
-        } else if (dbg_on || depth == (uint32_t)rp.debug_depth) {
-            f3 c = ps.beta * (splat3(0.0f) * 0.0f);  // NaN/inf throughput poisons the sample, as in the reference
-            if (c.x != 0.0f || c.y != 0.0f || c.z != 0.0f) acc_add(acc, id, c);
-        }
-        return out;
-    }
     const TriShade &ts = sc.shade[hit.gid];
     const Material &mat = sc.materials[ts.mat];
     Surface si = surface_from_hit(sc, ca, hit.gid, hit.u, hit.v);
@@ -251,8 +283,8 @@ AKR_HD ShadeOut shade_body(const SceneView &sc, const CornerAttribs &ca, const S
         if (depth == 0u) {
             // radiance starts at 0; base_replay_throughput = radiance (pt.rs:415-417)
             f3 l = (dbg_on || rp.debug_depth == 0) ? splat3(0.0f) + c : splat3(0.0f);
-            acc.lr[id] = l.x; acc.lg[id] = l.y; acc.lb[id] = l.z;
-            acc.br[id] = l.x; acc.bg[id] = l.y; acc.bb[id] = l.z;
+            st4(acc.l + id, f4{l.x, l.y, l.z, 0.0f});
+            st4(acc.b + id, f4{l.x, l.y, l.z, 0.0f});
         } else if (dbg_on || depth == (uint32_t)rp.debug_depth) {
             if (c.x != 0.0f || c.y != 0.0f || c.z != 0.0f) acc_add(acc, id, c);
         }
@@ -317,17 +349,17 @@ AKR_HD ShadeOut shade_body(const SceneView &sc, const CornerAttribs &ca, const S
     ClosureFrames cf = make_closure_frames(*m, si.frame, si.ng);
     f3 direct = splat3(0.0f);
     if (dl_valid) {
-        BsdfEval e = closure_eval(*m, sc.albedo_table, cf, wo, dl_wi);
+        BsdfEval e = closure_eval<CLS>(*m, sc.albedo_table, cf, wo, dl_wi);
         float w = mis_weight(dl_pdf, e.pdf);
         direct = dl_li * e.f * w / dl_pdf;
     }
     // SurfaceClosure::sample (mod.rs:795-815)
-    BsdfDir sd = closure_sample_wi(*m, sc.albedo_table, cf, wo, ub0, ub12);
+    BsdfDir sd = closure_sample_wi<CLS>(*m, sc.albedo_table, cf, wo, ub0, ub12);
     f3 bs_wi = splat3(0.0f), bs_color = splat3(0.0f);
     float bs_pdf = 0.0f;
     bool bs_valid = false;
     if (sd.valid) {
-        BsdfEval e = closure_eval(*m, sc.albedo_table, cf, wo, sd.wi);
+        BsdfEval e = closure_eval<CLS>(*m, sc.albedo_table, cf, wo, sd.wi);
         bs_wi = sd.wi;
         bs_color = e.f;
         bs_pdf = e.pdf;
@@ -364,11 +396,7 @@ AKR_HD void shadow_resolve(const AccView &acc, const ShadowItem &it, bool occlud
         f3 c = it.contrib;
         if (c.x != 0.0f || c.y != 0.0f || c.z != 0.0f) acc_add(acc, id, c);
     }
-    if (depth1 == 1u) {  // base_replay_throughput = radiance (pt.rs:510-512)
-        acc.br[id] = acc.lr[id];
-        acc.bg[id] = acc.lg[id];
-        acc.bb[id] = acc.lb[id];
-    }
+    if (depth1 == 1u) st4(acc.b + id, ld4(acc.l + id));  // base_replay_throughput = radiance (pt.rs:510-512)
 }
 
 // ---- stage: accumulate (pt.rs:871-876 + film.rs:196-229) -------------------------------------------------------
@@ -380,8 +408,9 @@ AKR_HD void accumulate_body(const AccView &acc, const WaveInfo &w, uint32_t p_lo
     float wt = film[6u * n_film_pixels + i];
     for (uint32_t s = 0; s < w.n_spp; ++s) {
         uint32_t id = s * w.n_pix + p_local;
-        f3 L = mk3(acc.lr[id], acc.lg[id], acc.lb[id]);
-        f3 B = mk3(acc.br[id], acc.bg[id], acc.bb[id]);
+        f4 l4 = ld4(acc.l + id), b4 = ld4(acc.b + id);
+        f3 L = mk3(l4.x, l4.y, l4.z);
+        f3 B = mk3(b4.x, b4.y, b4.z);
         f3 ind = L - B;  // clamp_indirect = 1000, Color::clamp -> [0, max] (pt.rs:130,871-876; color.rs:352-361)
         ind = mk3(clampf(ind.x, 0.0f, 1000.0f), clampf(ind.y, 0.0f, 1000.0f), clampf(ind.z, 0.0f, 1000.0f));
         L = B + ind;

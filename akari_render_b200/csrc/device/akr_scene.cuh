@@ -27,7 +27,7 @@ struct alignas(16) TriGeom {
     float v0[3];
     uint32_t gid;  // global triangle id = instance.tri_offset + prim (instances in id order)
     float e1[3];
-    uint32_t _p0;
+    uint32_t cls;  // ShadeClass of the triangle's material: the trace stage bins hits by it
     float e2[3];
     uint32_t _p1;
 };
@@ -118,6 +118,15 @@ struct RenderParams {  // pt::Config + sampler + filter, resolved for one pass
     float filter_radius;
     uint32_t width, height;  // full sensor
     uint32_t y0;             // first row of this context's tile
+    // derived (finish_render_params)
+    FastDiv width_div;       // pixel -> (row, column)
+    uint32_t spp_pow2;       // spp_total is a power of two: x / spp == x * inv_spp exactly
+    float inv_spp;
 };
+inline void finish_render_params(RenderParams &rp) {
+    rp.width_div = make_fastdiv(rp.width);
+    rp.spp_pow2 = (rp.spp_total & (rp.spp_total - 1u)) == 0u ? 1u : 0u;
+    rp.inv_spp = 1.0f / (float)rp.spp_total;
+}
 
 }  // namespace akr

@@ -728,6 +728,7 @@ int build_scene_blob(const AkrSceneDesc &d, HostSceneBlob &out, std::string &err
         st3(tg.e1, w1 - w0);
         st3(tg.e2, w2 - w0);
         tg.gid = gid;
+        tg.cls = shade_class_of(out.materials[out.shade[gid].mat].type);
     }
     // flatten: breadth-first over inner nodes; a leaf root becomes an inner node with an empty second child
     auto leaf_code = [&](const BuildNode &n) { return ~static_cast<int32_t>((n.first << 3) | n.count); };

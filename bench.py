@@ -26,7 +26,9 @@ sys.path.insert(0, ROOT)
 WIDTH, HEIGHT, SPP = 1280, 720, 1024
 # packed record sizes -> algorithmic bytes
 B_SAMPLE, B_SEG, B_SHADOW = 168, 300, 152
-B_SHADE_PER_SEG = 228  # shade stage share of B_SEG (R HIT + wo + PATH, W PATH + RAY + key/idx)
+# split of those per-unit figures over the two stages of one bounce (DESIGN.md "algorithmic bytes"):
+B_TRACE_PER_SEG, B_SHADE_PER_SEG = 72, 228   # trace: R RAY + W HIT + idx; shade: R HIT + wo + PATH, W PATH + RAY + key/idx
+B_TRACE_PER_SHADOW, B_SHADE_PER_SHADOW = 88, 64  # trace: R RAY+NEE+idx (64) + RMW L (24); shade: W RAY+NEE+idx (64)
 
 
 def sample_clocks(stop, out):
@@ -98,7 +100,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--spp", type=int, default=SPP, help="override for quick experiments (the reported config is 1024)")
-    ap.add_argument("--wave", type=int, default=0)
+    ap.add_argument("--wave", type=int, default=0, help="paths per wave (0 = engine default)")
+    ap.add_argument("--trace-mode", type=int, default=0, help="0 auto, 1 BVH, 2 flat list")
+    ap.add_argument("--sort", type=int, default=0, help="0/1 per-class shade kernels, 2 one generic shade kernel")
     ap.add_argument("--profile-stages", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     args = ap.parse_args()
@@ -130,7 +134,8 @@ def main():
     my_rows = tile[1] - tile[0]
     stream = torch.cuda.current_stream().cuda_stream
     pt = akr.PathTracer(local_rank, stream=stream)
-    pt.set_engine_options(wave_size=args.wave, profile_stages=1 if args.profile_stages else 0)
+    eng = dict(wave_size=args.wave, sort_by_material=args.sort, trace_mode=args.trace_mode)
+    pt.set_engine_options(profile_stages=1 if args.profile_stages else 0, **eng)
     pt.upload_scene(scene)
     max_rows = max(rows[r + 1] - rows[r] for r in range(world))
     img_local = torch.zeros((max_rows, WIDTH, 3), device="cuda", dtype=torch.float32)
@@ -208,26 +213,32 @@ def main():
     d2h = film_host.nbytes
 
     # ---- roofline of the dominant kernel, measured live with per-stage CUDA events ----
-    pt.set_engine_options(wave_size=args.wave, profile_stages=1)
+    pt.set_engine_options(profile_stages=1, **eng)
     pt.reset_stats()
     pt.begin(task, tile)
     prof_spp = min(spp, task.pt.spp_per_pass)
     pt.render_pass(prof_spp, blocking=True)
     ps = pt.stats()
-    pt.set_engine_options(wave_size=args.wave, profile_stages=0)
-    names = ["raygen", "intersect", "shade", "shadow", "accumulate", "misc"]
-    stage_ms = {names[i]: ps.gpu_ms_kernel[i] for i in range(6)}
-    stage_launches = {names[i]: int(ps.launches_kernel[i]) for i in range(6)}
-    dom = max(("intersect", "shade", "shadow"), key=lambda k: stage_ms[k])
-    per_seg = {"intersect": 72, "shade": B_SHADE_PER_SEG, "shadow": B_SHADOW}[dom]
-    units = ps.shadow_rays if dom == "shadow" else ps.segments
+    pt.set_engine_options(profile_stages=0, **eng)
+    names = ["raygen", "trace", "shade_lambert", "shade_conductor", "accumulate", "misc", "shade_general"]
+    stage_ms = {names[i]: ps.gpu_ms_kernel[i] for i in range(7)}
+    stage_launches = {names[i]: int(ps.launches_kernel[i]) for i in range(7)}
+    shade_ms = stage_ms["shade_lambert"] + stage_ms["shade_conductor"] + stage_ms["shade_general"]
+    shade_n = stage_launches["shade_lambert"] + stage_launches["shade_conductor"] + stage_launches["shade_general"]
+    # algorithmic bytes of the profiled pass, per stage (every launch of the stage together)
+    trace_bytes = ps.segments * B_TRACE_PER_SEG + ps.shadow_rays * B_TRACE_PER_SHADOW
+    shade_bytes = ps.segments * B_SHADE_PER_SEG + ps.shadow_rays * B_SHADE_PER_SHADOW
+    if shade_ms >= stage_ms["trace"]:
+        dom, dom_ms, dom_bytes, dom_n = "k_shade<class>", shade_ms, shade_bytes, shade_n
+    else:
+        dom, dom_ms, dom_bytes, dom_n = "k_trace", stage_ms["trace"], trace_bytes, stage_launches["trace"]
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    achieved = (units * per_seg / 1e9) / (stage_ms[dom] * 1e-3) if stage_ms[dom] > 0 else 0.0
+    achieved = (dom_bytes / 1e9) / (dom_ms * 1e-3) if dom_ms > 0 else 0.0
     n_seg = st.segments / max(1, st.samples)
     s_ratio = st.shadow_rays / max(1, st.segments)
     bytes_per_sample = B_SAMPLE + n_seg * (B_SEG + B_SHADOW * s_ratio)
@@ -256,12 +267,13 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"cbox 1280x720 @ {spp}spp, pmj02bn seed 0, gaussian r=1.5, max_depth 12, rr_depth 5, 64 spp/pass",
                        "parallelism": f"image rows x{world}", "l2": "working set (wave state) > L2; no inter-step reuse (film cleared each step)",
-                       "wave_paths": args.wave or (1 << 20)},
+                       "wave_paths": args.wave or (1 << 22), "trace_mode": args.trace_mode, "sort": args.sort},
             "clocks": summarize_clocks(clocks),
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(st.kernel_launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                         "kernel": "k_" + dom, "peak_source": "measured" if peaks else "fallback",
+                         "kernel": dom, "kernel_launches": dom_n, "kernel_ms": dom_ms, "kernel_algorithmic_bytes": dom_bytes,
+                         "peak_source": "measured" if peaks else "fallback",
                          "pipeline_algorithmic_gbs": pipeline_gbs, "pipeline_frac": pipeline_gbs / peak,
                          "n_seg": n_seg, "shadow_per_seg": s_ratio, "bytes_per_sample": bytes_per_sample,
                          "stage_ms": stage_ms, "stage_launches": stage_launches, "profiled_spp": prof_spp},

@@ -184,7 +184,9 @@ typedef struct AkrStats {
     uint64_t shadow_rays;           /* any-hit rays traced                                      */
     uint64_t kernel_launches;       /* CUDA kernels launched by render calls since reset        */
     double gpu_ms;                  /* CUDA-event time of render calls since reset              */
-    double gpu_ms_kernel[8];        /* per stage: 0 raygen 1 intersect 2 shade 3 shadow 4 accumulate 5 misc */
+    double gpu_ms_kernel[8];        /* per stage (profile_stages): 0 raygen, 1 trace (closest-hit + shadow rays),
+                                     * 2 shade/Lambert, 3 shade/conductor, 4 accumulate, 5 misc,
+                                     * 6 shade/general (or the unsorted shade kernel)                */
     uint64_t launches_kernel[8];
 } AkrStats;
 
@@ -246,9 +248,11 @@ int akr_b200_reset_stats(AkrContext *ctx);
 /* Tunables of the wavefront engine (not part of the reference surface). */
 typedef struct AkrEngineOptions {
     uint32_t wave_size;             /* paths in flight per wave; 0 = default                    */
-    uint32_t sort_by_material;      /* 0 = off, 1 = on, 2 = auto                                */
+    uint32_t sort_by_material;      /* 0 = default (hits binned per shade class, one shade kernel
+                                     * per class), 1 = same, 2 = off (one generic shade kernel)  */
     uint32_t profile_stages;        /* record per-stage CUDA-event times (adds syncs)           */
-    uint32_t _pad;
+    uint32_t trace_mode;            /* 0 = auto, 1 = BVH traversal, 2 = flat triangle list (only
+                                     * honoured when every triangle fits in shared memory)       */
 } AkrEngineOptions;
 int akr_b200_set_engine_options(AkrContext *ctx, const AkrEngineOptions *opts);
 

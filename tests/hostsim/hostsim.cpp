@@ -67,17 +67,17 @@ int hostsim_render(const AkrSceneDesc *desc, const AkrPtConfig *cfg, const AkrSa
     rp.width = desc->camera.width;
     rp.height = desc->camera.height;
     rp.y0 = y0;
+    finish_render_params(rp);
     const uint32_t rows = y1 - y0;
     const uint32_t n_pixels = rp.width * rows;
     const uint32_t k = spp_end - spp_begin;
     if (wave_pixels == 0) wave_pixels = n_pixels;
     uint64_t segments = 0, shadows = 0;
     for (uint32_t pix0 = 0; pix0 < n_pixels; pix0 += wave_pixels) {
-        WaveInfo wave{pix0, std::min(wave_pixels, n_pixels - pix0), spp_begin, k};
+        WaveInfo wave = make_wave(pix0, std::min(wave_pixels, n_pixels - pix0), spp_begin, k);
         const uint32_t n_paths = wave.n_pix * wave.n_spp;
-        std::vector<float> acc(6u * (size_t)n_paths, 0.0f);
-        AccView av{acc.data(), acc.data() + n_paths, acc.data() + 2u * n_paths, acc.data() + 3u * n_paths, acc.data() + 4u * n_paths,
-                   acc.data() + 5u * n_paths};
+        std::vector<f4> acc(2u * (size_t)n_paths, f4{0.0f, 0.0f, 0.0f, 0.0f});  // raygen zeroes the accumulators
+        AccView av{acc.data(), acc.data() + n_paths};
         std::vector<PathState> cur(n_paths), next;
         for (uint32_t i = 0; i < n_paths; ++i) cur[i] = raygen_body(sc, tab, rp, wave, i);
         for (uint32_t depth = 0; depth <= rp.max_depth && !cur.empty(); ++depth) {
@@ -97,7 +97,15 @@ int hostsim_render(const AkrSceneDesc *desc, const AkrPtConfig *cfg, const AkrSa
             next.clear();
             std::vector<ShadowItem> shq;
             for (size_t i = 0; i < cur.size(); ++i) {
-                ShadeOut o = shade_body(sc, ca, tab, rp, wave, depth, cur[i], hits[i], av);
+                if (hits[i].gid == 0xffffffffu) {  // the trace stage ends missed paths itself
+                    miss_body(rp, depth, cur[i].beta, cur[i].path_id, av);
+                    continue;
+                }
+                // bin by shade class like the trace kernel does; each class runs its own specialisation
+                uint32_t cls = rp.force_diffuse ? (uint32_t)CLS_LAMBERT : shade_class_of(sc.materials[sc.shade[hits[i].gid].mat].type);
+                ShadeOut o = cls == CLS_LAMBERT     ? shade_body<CLS_LAMBERT>(sc, ca, tab, rp, wave, depth, cur[i], hits[i], av)
+                             : cls == CLS_CONDUCTOR ? shade_body<CLS_CONDUCTOR>(sc, ca, tab, rp, wave, depth, cur[i], hits[i], av)
+                                                    : shade_body<CLS_GENERAL>(sc, ca, tab, rp, wave, depth, cur[i], hits[i], av);
                 if (o.has_shadow) shq.push_back(o.shadow);
                 if (o.has_next) next.push_back(o.next);
             }
