@@ -31,7 +31,7 @@ constexpr uint32_t kMaxDepthSlots = 66;           // counters for depth 0 .. 64 
 constexpr uint32_t kCtrStride = 8;                // words per depth: [0] paths in, [1] shadow rays out, [2 + c] hits of class c
 constexpr uint32_t kSmemSceneBudget = 48 * 1024;  // bytes of BVH nodes + triangles staged per CTA
 constexpr uint32_t kSmemMax = 200 * 1024;         // opt-in ceiling for the trace kernels (staging + stacks)
-constexpr uint32_t kFlatMaxTris = 64;             // scenes this small are traced as one flat triangle list
+constexpr uint32_t kFlatMaxPrims = 64;            // scenes this small are traced as one flat primitive list
 
 // ------------------------------------------------------------------------------------------------
 // wave state in HBM: structure-of-arrays of 16-byte records (one LDG.128 / STG.128 per record, fully
@@ -70,7 +70,7 @@ struct LaunchParams {
     float *film;
     uint32_t n_film_pixels;
     uint32_t scene_smem_nodes;  // nodes staged in shared memory
-    uint32_t scene_smem_tris;   // 1 when all triangles are staged too
+    uint32_t scene_smem_prims;  // 1 when all primitives are staged too
     uint32_t stack_depth;       // traversal stack entries per thread (shared memory)
     uint32_t *dbg_first_hits;   // optional [n_film_pixels][2]
 };
@@ -122,19 +122,19 @@ __device__ __forceinline__ void tma_bulk_g2s(void *smem_dst, const void *gsrc, u
                  : "memory");
 }
 
-// Shared-memory plan of the trace kernel: [ nodes | triangles | per-thread traversal stacks ].
+// Shared-memory plan of the trace kernel: [ nodes | primitives | per-thread traversal stacks ].
 struct TraceSmem {
     const BvhNode *nodes;   // shared copy of nodes[0 .. n_fast_nodes)
-    const TriGeom *tris;    // shared copy of all triangles, or the global array
+    const PrimRec *prims;   // shared copy of all primitives, or the global array
     int32_t *stack;         // this thread's stack: entry k lives at stack[k * kBlock]
 };
 
-// Stages nodes[0 .. n_nodes) and (optionally) all triangles behind `smem` with one TMA bulk copy each.
+// Stages nodes[0 .. n_nodes) and (optionally) all primitives behind `smem` with one TMA bulk copy each.
 __device__ __forceinline__ TraceSmem stage_scene(const LaunchParams &P, unsigned char *smem, uint64_t *bar) {
     const uint32_t node_bytes = P.scene_smem_nodes * (uint32_t)sizeof(BvhNode);
-    const uint32_t tri_bytes = P.scene_smem_tris ? P.scene.n_tris * (uint32_t)sizeof(TriGeom) : 0u;
+    const uint32_t tri_bytes = P.scene_smem_prims ? P.scene.n_prims * (uint32_t)sizeof(PrimRec) : 0u;
     BvhNode *s_nodes = reinterpret_cast<BvhNode *>(smem);
-    TriGeom *s_tris = reinterpret_cast<TriGeom *>(smem + node_bytes);
+    PrimRec *s_tris = reinterpret_cast<PrimRec *>(smem + node_bytes);
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -143,91 +143,86 @@ __device__ __forceinline__ TraceSmem stage_scene(const LaunchParams &P, unsigned
     if (threadIdx.x == 0 && (node_bytes + tri_bytes) > 0) {
         mbar_expect_tx(bar, node_bytes + tri_bytes);
         if (node_bytes) tma_bulk_g2s(s_nodes, P.scene.nodes, node_bytes, bar);
-        if (tri_bytes) tma_bulk_g2s(s_tris, P.scene.tris, tri_bytes, bar);
+        if (tri_bytes) tma_bulk_g2s(s_tris, P.scene.prims, tri_bytes, bar);
     }
     if ((node_bytes + tri_bytes) > 0) mbar_wait(bar, 0);
     TraceSmem t;
     t.nodes = s_nodes;
-    t.tris = P.scene_smem_tris ? s_tris : P.scene.tris;
+    t.prims = P.scene_smem_prims ? s_tris : P.scene.prims;
     t.stack = reinterpret_cast<int32_t *>(smem + node_bytes + tri_bytes) + threadIdx.x;
     return t;
 }
 
 // ------------------------------------------------------------------------------------------------
-// device traversal (same candidate set and tie rule as akr_trace.cuh::trace_ray, so the closest hit is
-// identical for any visiting order; the host simulation keeps using trace_ray)
+// device traversal over primitives (akr_trace.cuh::prim_test): one plane + two-coordinate test decides a
+// triangle or both halves of a parallelogram.  The host simulation keeps the Moeller-Trumbore
+// trace_ray on the same BVH; the two agree up to rounding at primitive edges.
 // ------------------------------------------------------------------------------------------------
 struct DevHit {
     uint32_t gid, cls;
     float u, v;
 };
 
-__device__ __forceinline__ void leaf_test(const SceneView &sc, const TriGeom &tr, f3 o, f3 d, float t_min, float t_max, uint32_t ex0, uint32_t ex1,
-                                          DevHit &best, float &best_t) {
-    const uint32_t gid = tr.gid;
-    if (gid == ex0 || gid == ex1) return;
-    float t, u, v;
-    if (!tri_test(tr, o, d, t_min, t_max, t, u, v)) return;
-    const bool closer = (t < best_t) || (t == best_t && gid < best.gid);
-    if (!closer) return;
-    if (sc.any_alpha && !alpha_test(sc, gid, u, v)) return;
-    best = DevHit{gid, tr.cls, u, v};
-    best_t = t;
-}
-
 enum TraceMode : int { TRACE_BVH = 0, TRACE_FLAT = 1 };
 
-// TRACE_FLAT: every lane tests every triangle in list order (shared-memory broadcast reads, no divergence,
-// no stack) — the cheapest schedule when the whole scene is a few dozen triangles.
+// TRACE_FLAT: every lane tests every primitive in list order (shared-memory broadcast reads, no divergence,
+// no stack) — the cheapest schedule when the whole scene is a few dozen primitives.
 // TRACE_BVH : while-while traversal; lanes first descend to their next leaf together, then test leaves.
 template <bool ANY_HIT, int MODE>
 __device__ __forceinline__ DevHit trace_dev(const LaunchParams &P, const TraceSmem &ts, f3 o, f3 d, float t_min, float t_max, uint32_t ex0, uint32_t ex1) {
     const SceneView &sc = P.scene;
-    DevHit best{0xffffffffu, 0u, 0.0f, 0.0f};
-    float best_t = t_max;
+    PrimHit best{t_max, 0.0f, 0.0f, 0xffffffffu};
     if (MODE == TRACE_FLAT) {
-        const uint32_t n = sc.n_tris;
+        const uint32_t n = sc.n_prims;
         for (uint32_t k = 0; k < n; ++k) {
-            leaf_test(sc, ts.tris[k], o, d, t_min, t_max, ex0, ex1, best, best_t);
-            if (ANY_HIT && best.gid != 0xffffffffu) break;
+            prim_test(sc, ts.prims[k], k, o, d, t_min, ex0, ex1, best);
+            if (ANY_HIT && best.k != 0xffffffffu) break;
         }
-        return best;
-    }
-    const f3 inv_d = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-    const uint32_t n_fast = P.scene_smem_nodes;
-    int32_t *stack = ts.stack;
-    int sp = 0;
-    int32_t node = 0;  // the root is always an inner node
-    while (true) {
-        while (node >= 0) {
-            const BvhNode &n = ((uint32_t)node < n_fast) ? ts.nodes[node] : sc.nodes[node];
-            float tn0, tn1;
-            const bool h0 = box_test(n.lo0, n.hi0, o, inv_d, t_min, best_t, tn0);
-            const bool h1 = box_test(n.lo1, n.hi1, o, inv_d, t_min, best_t, tn1);
-            const int32_t c0 = n.c0, c1 = n.c1;
-            if (h0 && h1) {
-                const bool swap = tn1 < tn0;
-                stack[sp * kBlock] = swap ? c0 : c1;
-                ++sp;
-                node = swap ? c1 : c0;
-            } else if (h0) {
-                node = c0;
-            } else if (h1) {
-                node = c1;
-            } else {
-                if (sp == 0) return best;
-                --sp;
-                node = stack[sp * kBlock];
+    } else {
+        const f3 inv_d = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+        const uint32_t n_fast = P.scene_smem_nodes;
+        int32_t *stack = ts.stack;
+        int sp = 0;
+        int32_t node = 0;  // the root is always an inner node
+        while (true) {
+            bool done = false;
+            while (node >= 0) {
+                const BvhNode &n = ((uint32_t)node < n_fast) ? ts.nodes[node] : sc.nodes[node];
+                float tn0, tn1;
+                const bool h0 = box_test(n.lo0, n.hi0, o, inv_d, t_min, best.t, tn0);
+                const bool h1 = box_test(n.lo1, n.hi1, o, inv_d, t_min, best.t, tn1);
+                const int32_t c0 = n.c0, c1 = n.c1;
+                if (h0 && h1) {
+                    const bool swap = tn1 < tn0;
+                    stack[sp * kBlock] = swap ? c0 : c1;
+                    ++sp;
+                    node = swap ? c1 : c0;
+                } else if (h0) {
+                    node = c0;
+                } else if (h1) {
+                    node = c1;
+                } else {
+                    if (sp == 0) {
+                        done = true;
+                        break;
+                    }
+                    --sp;
+                    node = stack[sp * kBlock];
+                }
             }
+            if (done) break;
+            const uint32_t leaf = (uint32_t)(~node);
+            const uint32_t first = leaf >> 3, count = leaf & 7u;
+            for (uint32_t k = 0; k < count; ++k) prim_test(sc, ts.prims[first + k], first + k, o, d, t_min, ex0, ex1, best);
+            if (ANY_HIT && best.k != 0xffffffffu) break;
+            if (sp == 0) break;
+            --sp;
+            node = stack[sp * kBlock];
         }
-        const uint32_t leaf = (uint32_t)(~node);
-        const uint32_t first = leaf >> 3, count = leaf & 7u;
-        for (uint32_t k = 0; k < count; ++k) leaf_test(sc, ts.tris[first + k], o, d, t_min, t_max, ex0, ex1, best, best_t);
-        if (ANY_HIT && best.gid != 0xffffffffu) return best;
-        if (sp == 0) return best;
-        --sp;
-        node = stack[sp * kBlock];
     }
+    if (best.k == 0xffffffffu) return DevHit{0xffffffffu, 0u, 0.0f, 0.0f};
+    const PrimDecoded dec = prim_decode(ts.prims[best.k], best.s, best.q);
+    return DevHit{dec.gid, dec.cls, dec.u, dec.v};
 }
 
 // warp-aggregated queue append: one atomic per warp, slots ordered by lane
@@ -421,12 +416,12 @@ struct AkrContext {
     bool albedo_ready = false;
 
     // scene
-    DeviceBuffer nodes, tris, shade, instances, materials, lights, alias_j, alias_t, alias_pdf, corner_n, corner_t;
+    DeviceBuffer nodes, prims, shade, instances, materials, lights, alias_j, alias_t, alias_pdf, corner_n, corner_t;
     SceneView scene{};
     CornerAttribs corners{};
     bool scene_ready = false;
     bool scene_needs_table = false;
-    uint32_t smem_nodes = 0, smem_tris = 0, smem_bytes = 0;  // smem_bytes = nodes + triangles (stacks come on top)
+    uint32_t smem_nodes = 0, smem_prims = 0, smem_bytes = 0;  // smem_bytes = nodes + primitives (stacks come on top)
     uint32_t bvh_depth = 0;
     uint32_t class_mask = 0;   // shade classes present in the scene
     int occ_trace[2] = {1, 1}, occ_shade[4] = {1, 1, 1, 1};  // resident CTAs per SM, per kernel variant
@@ -590,7 +585,7 @@ void akr_b200_destroy(AkrContext *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    for (DeviceBuffer *b : {&ctx->pmj, &ctx->bn, &ctx->albedo, &ctx->nodes, &ctx->tris, &ctx->shade, &ctx->instances, &ctx->materials, &ctx->lights,
+    for (DeviceBuffer *b : {&ctx->pmj, &ctx->bn, &ctx->albedo, &ctx->nodes, &ctx->prims, &ctx->shade, &ctx->instances, &ctx->materials, &ctx->lights,
                             &ctx->alias_j, &ctx->alias_t, &ctx->alias_pdf, &ctx->corner_n, &ctx->corner_t, &ctx->film, &ctx->wave_mem, &ctx->counters,
                             &ctx->totals, &ctx->dbg_hits})
         dev_free(*b);
@@ -647,7 +642,7 @@ int akr_b200_upload_scene(AkrContext *ctx, const AkrSceneDesc *desc) {
     ctx->scene_ready = false;
     ctx->render_ready = false;
     if ((rc = upload_vec(ctx, ctx->nodes, blob.nodes)) != AKR_OK) return rc;
-    if ((rc = upload_vec(ctx, ctx->tris, blob.tris)) != AKR_OK) return rc;
+    if ((rc = upload_vec(ctx, ctx->prims, blob.prims)) != AKR_OK) return rc;
     if ((rc = upload_vec(ctx, ctx->shade, blob.shade)) != AKR_OK) return rc;
     if ((rc = upload_vec(ctx, ctx->instances, blob.instances)) != AKR_OK) return rc;
     if ((rc = upload_vec(ctx, ctx->materials, blob.materials)) != AKR_OK) return rc;
@@ -660,7 +655,8 @@ int akr_b200_upload_scene(AkrContext *ctx, const AkrSceneDesc *desc) {
     AKR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // blob is a local
     SceneView &v = ctx->scene;
     v.nodes = static_cast<const BvhNode *>(ctx->nodes.ptr);
-    v.tris = static_cast<const TriGeom *>(ctx->tris.ptr);
+    v.prims = static_cast<const PrimRec *>(ctx->prims.ptr);
+    v.tris = nullptr;  // the Moeller-Trumbore triangle list is host-simulation data; the kernels intersect primitives
     v.shade = static_cast<const TriShade *>(ctx->shade.ptr);
     v.instances = static_cast<const InstanceRec *>(ctx->instances.ptr);
     v.materials = static_cast<const Material *>(ctx->materials.ptr);
@@ -669,7 +665,8 @@ int akr_b200_upload_scene(AkrContext *ctx, const AkrSceneDesc *desc) {
     v.alias_t = static_cast<const float *>(ctx->alias_t.ptr);
     v.alias_pdf = static_cast<const float *>(ctx->alias_pdf.ptr);
     v.n_nodes = (uint32_t)blob.nodes.size();
-    v.n_tris = (uint32_t)blob.tris.size();
+    v.n_prims = (uint32_t)blob.prims.size();
+    v.n_tris = (uint32_t)blob.shade.size();
     v.n_instances = (uint32_t)blob.instances.size();
     v.n_materials = (uint32_t)blob.materials.size();
     v.n_lights = (uint32_t)blob.lights.size();
@@ -680,12 +677,12 @@ int akr_b200_upload_scene(AkrContext *ctx, const AkrSceneDesc *desc) {
     ctx->scene_needs_table = false;
     for (const Material &m : blob.materials)
         if (m.type == MAT_PRINCIPLED && (m.lobes & (LOBE_COAT | LOBE_SPECULAR))) ctx->scene_needs_table = true;
-    // shared-memory staging plan: top of the BVH first, then all triangles if they still fit
-    const uint32_t tri_bytes = v.n_tris * (uint32_t)sizeof(TriGeom);
+    // shared-memory staging plan: top of the BVH first, then all primitives if they still fit
+    const uint32_t tri_bytes = v.n_prims * (uint32_t)sizeof(PrimRec);
     ctx->smem_nodes = std::min(v.n_nodes, kSmemSceneBudget / (uint32_t)sizeof(BvhNode));
     uint32_t used = ctx->smem_nodes * (uint32_t)sizeof(BvhNode);
-    ctx->smem_tris = (ctx->smem_nodes == v.n_nodes && used + tri_bytes <= kSmemSceneBudget) ? 1u : 0u;
-    if (ctx->smem_tris) used += tri_bytes;
+    ctx->smem_prims = (ctx->smem_nodes == v.n_nodes && used + tri_bytes <= kSmemSceneBudget) ? 1u : 0u;
+    if (ctx->smem_prims) used += tri_bytes;
     ctx->smem_bytes = used;
     ctx->bvh_depth = blob.bvh_depth;
     ctx->class_mask = 0;
@@ -807,14 +804,14 @@ int akr_b200_render_pass(AkrContext *ctx, uint32_t n_spp, int blocking) {
     P.film = static_cast<float *>(ctx->film.ptr);
     P.n_film_pixels = ctx->n_pixels;
     P.scene_smem_nodes = ctx->smem_nodes;
-    P.scene_smem_tris = ctx->smem_tris;
+    P.scene_smem_prims = ctx->smem_prims;
     P.stack_depth = ctx->bvh_depth + 2u;
     P.dbg_first_hits = static_cast<uint32_t *>(ctx->dbg_hits.ptr);
 
     // trace schedule: flat list for tiny scenes that fit in shared memory, BVH otherwise (opts.trace_mode overrides)
-    int trace_mode = (ctx->scene.n_tris <= kFlatMaxTris && ctx->smem_tris) ? TRACE_FLAT : TRACE_BVH;
+    int trace_mode = (ctx->scene.n_prims <= kFlatMaxPrims && ctx->smem_prims) ? TRACE_FLAT : TRACE_BVH;
     if (ctx->opts.trace_mode == 1u) trace_mode = TRACE_BVH;
-    if (ctx->opts.trace_mode == 2u && ctx->smem_tris) trace_mode = TRACE_FLAT;
+    if (ctx->opts.trace_mode == 2u && ctx->smem_prims) trace_mode = TRACE_FLAT;
     const size_t trace_smem = ctx->smem_bytes + (trace_mode == TRACE_BVH ? (size_t)P.stack_depth * kBlock * sizeof(int32_t) : 0);
     if (trace_smem > kSmemMax) return fail(ctx, AKR_ERR_UNSUPPORTED, "BVH too deep for the shared-memory traversal stack");
     const bool binned = ctx->opts.sort_by_material != 2u;

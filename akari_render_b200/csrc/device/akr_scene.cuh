@@ -22,7 +22,7 @@ struct alignas(16) BvhNode {
 };
 static_assert(sizeof(BvhNode) == 64, "BvhNode must be 64 bytes");
 
-// World-space triangle for traversal, stored in BVH leaf order.  48 bytes.
+// World-space triangle for the Moeller-Trumbore traversal, stored in primitive order (2 per PrimRec).  48 bytes.
 struct alignas(16) TriGeom {
     float v0[3];
     uint32_t gid;  // global triangle id = instance.tri_offset + prim (instances in id order)
@@ -32,6 +32,25 @@ struct alignas(16) TriGeom {
     uint32_t _p1;
 };
 static_assert(sizeof(TriGeom) == 48, "TriGeom must be 48 bytes");
+
+// Traversal primitive of the CUDA kernels: one triangle, or two triangles that share an edge and form a
+// parallelogram (both halves of a quad are decided by ONE plane + two-coordinate test).  The record
+// holds the plane and the two rows of the world -> (s, q) affine map (Baldwin & Weber's precomputed
+// transformation): for a hit point P,  s = r0 . P + r0.w,  q = r1 . P + r1.w.
+//   single   : (s, q) are the barycentrics (u, v) of the triangle; inside  <=>  s, q >= 0, s + q <= 1
+//   pair     : P = p0 + s a + q b over the parallelogram (p0, p1 = p0 + a, p2 = p0 + a + b, p3 = p0 + b);
+//              inside <=> 0 <= s, q <= 1;  s >= q is triangle A = (p0, p1, p2), else B = (p0, p2, p3);
+//              weights A: (1 - s, s - q, q), B: (1 - q, s, q - s) for (p0, p1|p2, p2|p3); `meta` says which
+//              weight is the triangle's own u (of v1) and v (of v2).
+struct alignas(16) PrimRec {
+    float n[4];
+    float r0[4];
+    float r1[4];
+    uint32_t gid_a, gid_b;  // gid_b == 0xffffffff: single triangle
+    uint32_t meta;          // bits 0-1 iu_a, 2-3 iv_a, 4-5 iu_b, 6-7 iv_b, 8-9 cls_a, 10-11 cls_b
+    uint32_t _pad;
+};
+static_assert(sizeof(PrimRec) == 64, "PrimRec must be 64 bytes");
 
 enum TriFlags : uint32_t {
     TRI_IS_LIGHT = 1u << 0,     // instance.light.valid()
@@ -86,8 +105,9 @@ struct CameraRec {
 };
 
 struct SceneView {
-    const BvhNode *nodes;
-    const TriGeom *tris;
+    const BvhNode *nodes;      // leaves address primitives: ~c = (first_prim << 3) | count
+    const PrimRec *prims;      // BVH leaf order (CUDA kernels)
+    const TriGeom *tris;       // two slots per primitive, gid 0xffffffff = empty (Moeller-Trumbore path of the host simulation)
     const TriShade *shade;
     const InstanceRec *instances;
     const Material *materials;
@@ -96,7 +116,7 @@ struct SceneView {
     const float *alias_t;
     const float *alias_pdf;
     const float *albedo_table; // 16^3
-    uint32_t n_nodes, n_tris, n_instances, n_materials, n_lights;
+    uint32_t n_nodes, n_prims, n_tris, n_instances, n_materials, n_lights;
     uint32_t any_alpha;        // some material has alpha < 1
     CameraRec camera;
 };

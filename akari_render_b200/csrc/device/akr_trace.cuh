@@ -109,11 +109,11 @@ AKR_HD HitRec trace_ray(const SceneView &sc, const TraceData &td, f3 o, f3 d, fl
             }
         } else {
             uint32_t leaf = (uint32_t)(~node);
-            uint32_t first = leaf >> 3, count = leaf & 7u;
+            uint32_t first = (leaf >> 3) * 2u, count = (leaf & 7u) * 2u;  // primitives -> triangle slots
             for (uint32_t k = 0; k < count; ++k) {
                 const TriGeom &tr = tris[first + k];
                 uint32_t gid = tr.gid;
-                if (gid == ex0 || gid == ex1) continue;
+                if (gid == 0xffffffffu || gid == ex0 || gid == ex1) continue;
                 float t, u, v;
                 if (!tri_test(tr, o, d, t_min, t_max, t, u, v)) continue;
                 bool closer = (t < best_t) || (t == best_t && gid < best.gid);
@@ -128,6 +128,114 @@ AKR_HD HitRec trace_ray(const SceneView &sc, const TraceData &td, f3 o, f3 d, fl
         node = stack[--sp];
     }
     return best;
+}
+
+// ---- primitive (triangle / parallelogram pair) intersector used by the CUDA kernels -----------------
+struct PrimHit {
+    float t, s, q;
+    uint32_t k;  // primitive index, 0xffffffff = none
+};
+struct PrimDecoded {
+    uint32_t gid, cls;
+    float u, v;
+};
+AKR_HD float fast_div(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fdividef(a, b);
+#else
+    return a / b;
+#endif
+}
+// which triangle of the primitive a point (s, q) belongs to, and that triangle's own barycentrics
+AKR_HD PrimDecoded prim_decode(const PrimRec &p, float s, float q) {
+    PrimDecoded r;
+    if (p.gid_b == 0xffffffffu) {
+        r.gid = p.gid_a;
+        r.cls = (p.meta >> 8) & 3u;
+        r.u = s;
+        r.v = q;
+        return r;
+    }
+    const bool half = s < q;
+    const float w0 = half ? 1.0f - q : 1.0f - s;
+    const float w1 = half ? s : s - q;
+    const float w2 = half ? q - s : q;
+    const uint32_t m = half ? (p.meta >> 4) : p.meta;
+    const uint32_t iu = m & 3u, iv = (m >> 2) & 3u;
+    r.gid = half ? p.gid_b : p.gid_a;
+    r.cls = (half ? (p.meta >> 10) : (p.meta >> 8)) & 3u;
+    r.u = iu == 0u ? w0 : (iu == 1u ? w1 : w2);
+    r.v = iv == 0u ? w0 : (iv == 1u ? w1 : w2);
+    return r;
+}
+// One candidate: updates `best` when primitive k is hit at t in (t_min, best.t) by a triangle that is not excluded.
+AKR_HD void prim_test(const SceneView &sc, const PrimRec &p, uint32_t k, f3 o, f3 d, float t_min, uint32_t ex0, uint32_t ex1, PrimHit &best) {
+    const float dz = p.n[0] * d.x + p.n[1] * d.y + p.n[2] * d.z;
+    const float oz = p.n[0] * o.x + p.n[1] * o.y + p.n[2] * o.z + p.n[3];
+    const float t = fast_div(-oz, dz);
+    if (!(t > t_min && t < best.t)) return;  // also rejects NaN (parallel ray, degenerate primitive)
+    const f3 hp = mk3(o.x + t * d.x, o.y + t * d.y, o.z + t * d.z);
+    const float s = p.r0[0] * hp.x + p.r0[1] * hp.y + p.r0[2] * hp.z + p.r0[3];
+    const float q = p.r1[0] * hp.x + p.r1[1] * hp.y + p.r1[2] * hp.z + p.r1[3];
+    const bool pair = p.gid_b != 0xffffffffu;
+    const bool inside = s >= 0.0f && q >= 0.0f && (pair ? (s <= 1.0f && q <= 1.0f) : (s + q <= 1.0f));
+    if (!inside) return;
+    const uint32_t gid = (pair && s < q) ? p.gid_b : p.gid_a;
+    if (gid == ex0 || gid == ex1) return;
+    if (sc.any_alpha) {
+        PrimDecoded dec = prim_decode(p, s, q);
+        if (!alpha_test(sc, dec.gid, dec.u, dec.v)) return;
+    }
+    best = PrimHit{t, s, q, k};
+}
+
+// Reference (host / CLS-agnostic) traversal over primitives: same BVH, same candidate order as trace_ray.
+template <bool ANY_HIT>
+AKR_HD HitRec trace_ray_prims(const SceneView &sc, f3 o, f3 d, float t_min, float t_max, uint32_t ex0, uint32_t ex1) {
+    PrimHit best{t_max, 0.0f, 0.0f, 0xffffffffu};
+    f3 inv_d = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    int32_t stack[AKR_BVH_STACK];
+    int sp = 0;
+    int32_t node = 0;
+    while (true) {
+        if (node >= 0) {
+            const BvhNode n = sc.nodes[node];
+            float tn0, tn1;
+            bool h0 = box_test(n.lo0, n.hi0, o, inv_d, t_min, best.t, tn0);
+            bool h1 = box_test(n.lo1, n.hi1, o, inv_d, t_min, best.t, tn1);
+            if (h0 && h1) {
+                int32_t near = n.c0, far = n.c1;
+                if (tn1 < tn0) {
+                    near = n.c1;
+                    far = n.c0;
+                }
+                if (sp < AKR_BVH_STACK) stack[sp++] = far;
+                node = near;
+                continue;
+            }
+            if (h0) {
+                node = n.c0;
+                continue;
+            }
+            if (h1) {
+                node = n.c1;
+                continue;
+            }
+        } else {
+            uint32_t leaf = (uint32_t)(~node);
+            uint32_t first = leaf >> 3, count = leaf & 7u;
+            for (uint32_t k = 0; k < count; ++k) {
+                prim_test(sc, sc.prims[first + k], first + k, o, d, t_min, ex0, ex1, best);
+                if (ANY_HIT && best.k != 0xffffffffu) break;
+            }
+            if (ANY_HIT && best.k != 0xffffffffu) break;
+        }
+        if (sp == 0) break;
+        node = stack[--sp];
+    }
+    if (best.k == 0xffffffffu) return HitRec{0xffffffffu, 0.0f, 0.0f};
+    PrimDecoded dec = prim_decode(sc.prims[best.k], best.s, best.q);
+    return HitRec{dec.gid, dec.u, dec.v};
 }
 
 }  // namespace akr

@@ -679,32 +679,130 @@ int build_scene_blob(const AkrSceneDesc &d, HostSceneBlob &out, std::string &err
         out.alias_pdf.push_back(0.0f);
     }
 
-    // ---- BVH over world-space triangles ----
-    std::vector<BuildTri> btris(total_tris);
+    // ---- traversal primitives: pair triangles that form a parallelogram, then a BVH over the primitives ----
+    struct HostPrim {
+        uint32_t gid_a, gid_b;  // gid_b = 0xffffffff: single
+        double p0[3], a[3], b[3];
+        uint32_t iu_a, iv_a, iu_b, iv_b;
+    };
+    std::vector<HostPrim> hprims;
+    hprims.reserve(total_tris);
+    {
+        auto vtx = [&](uint32_t gid, int k) { return world.data() + static_cast<size_t>(gid) * 9 + 3 * k; };
+        auto same = [&](const float *x, const float *y) { return std::memcmp(x, y, 12) == 0; };
+        std::vector<uint8_t> used(total_tris, 0);
+        // candidates share an edge; only triangles of the same instance are tried, in a small gid window
+        // (mesh exporters emit the two halves of a quad next to each other)
+        const uint32_t kWindow = 8;
+        for (uint32_t ii = 0; ii < d.n_instances; ++ii) {
+            const InstanceRec &ir = out.instances[ii];
+            for (uint32_t i = ir.tri_offset; i < ir.tri_offset + ir.n_tris; ++i) {
+                if (used[i]) continue;
+                used[i] = 1;
+                HostPrim hp;
+                hp.gid_a = i;
+                hp.gid_b = 0xffffffffu;
+                hp.iu_a = hp.iv_a = hp.iu_b = hp.iv_b = 0;
+                for (int c = 0; c < 3; ++c) {
+                    hp.p0[c] = vtx(i, 0)[c];
+                    hp.a[c] = static_cast<double>(vtx(i, 1)[c]) - vtx(i, 0)[c];
+                    hp.b[c] = static_cast<double>(vtx(i, 2)[c]) - vtx(i, 0)[c];
+                }
+                bool paired = false;
+                for (uint32_t j = i + 1; j < std::min(i + 1 + kWindow, ir.tri_offset + ir.n_tris) && !paired; ++j) {
+                    if (used[j]) continue;
+                    // shared edge (xa, xb) = two vertices of i equal to two vertices of j
+                    for (int e = 0; e < 3 && !paired; ++e) {
+                        const int ia = e, ib = (e + 1) % 3, ic = (e + 2) % 3;
+                        int ja = -1, jb = -1;
+                        for (int k = 0; k < 3; ++k) {
+                            if (same(vtx(j, k), vtx(i, ia))) ja = k;
+                            if (same(vtx(j, k), vtx(i, ib))) jb = k;
+                        }
+                        if (ja < 0 || jb < 0 || ja == jb) continue;
+                        const int jd = 3 - ja - jb;
+                        const float *xa = vtx(i, ia), *xb = vtx(i, ib), *xc = vtx(i, ic), *yd = vtx(j, jd);
+                        // parallelogram <=> the diagonals bisect each other: xc + yd == xa + xb
+                        double scale = 0.0, dev = 0.0;
+                        for (int c = 0; c < 3; ++c) {
+                            double av = static_cast<double>(xc[c]) - xa[c], bv = static_cast<double>(yd[c]) - xa[c];
+                            scale = std::max(scale, std::max(std::fabs(av), std::fabs(bv)));
+                            dev = std::max(dev, std::fabs((static_cast<double>(xc[c]) + yd[c]) - (static_cast<double>(xa[c]) + xb[c])));
+                        }
+                        if (!(dev <= 1e-6 * scale)) continue;
+                        // p0 = xa, p1 = xc (triangle A = i), p2 = xb, p3 = yd (triangle B = j)
+                        double cr[3], av[3], bv[3];
+                        for (int c = 0; c < 3; ++c) {
+                            av[c] = static_cast<double>(xc[c]) - xa[c];
+                            bv[c] = static_cast<double>(yd[c]) - xa[c];
+                        }
+                        cr[0] = av[1] * bv[2] - av[2] * bv[1];
+                        cr[1] = av[2] * bv[0] - av[0] * bv[2];
+                        cr[2] = av[0] * bv[1] - av[1] * bv[0];
+                        if (!(cr[0] * cr[0] + cr[1] * cr[1] + cr[2] * cr[2] > 0.0)) continue;
+                        for (int c = 0; c < 3; ++c) {
+                            hp.p0[c] = xa[c];
+                            hp.a[c] = av[c];
+                            hp.b[c] = bv[c];
+                        }
+                        hp.gid_b = j;
+                        // local corner index (0 = p0, 1 = p1|p2, 2 = p2|p3) of each triangle's v1 and v2
+                        auto local_a = [&](int k) { return k == ia ? 0u : (k == ic ? 1u : 2u); };  // A = (p0 = xa, p1 = xc, p2 = xb)
+                        auto local_b = [&](int k) { return k == ja ? 0u : (k == jb ? 1u : 2u); };  // B = (p0 = xa, p2 = xb, p3 = yd)
+                        hp.iu_a = local_a(1);
+                        hp.iv_a = local_a(2);
+                        hp.iu_b = local_b(1);
+                        hp.iv_b = local_b(2);
+                        used[j] = 1;
+                        paired = true;
+                    }
+                }
+                hprims.push_back(hp);
+            }
+        }
+    }
+    const uint32_t n_prims = static_cast<uint32_t>(hprims.size());
+    auto prim_corners = [&](const HostPrim &hp, float (*c)[3]) -> int {  // world corners for the bounds
+        for (int k = 0; k < 3; ++k) {
+            c[0][k] = static_cast<float>(hp.p0[k]);
+            c[1][k] = static_cast<float>(hp.p0[k] + hp.a[k]);
+            c[2][k] = static_cast<float>(hp.p0[k] + hp.b[k]);
+            c[3][k] = static_cast<float>(hp.p0[k] + hp.a[k] + hp.b[k]);
+        }
+        return hp.gid_b == 0xffffffffu ? 3 : 4;
+    };
+    std::vector<BuildTri> btris(n_prims);
     Box scene_box;
     scene_box.reset();
-    for (uint32_t gid = 0; gid < total_tris; ++gid) {
-        BuildTri &bt = btris[gid];
+    for (uint32_t k = 0; k < n_prims; ++k) {
+        BuildTri &bt = btris[k];
         bt.box.reset();
-        const float *w = world.data() + static_cast<size_t>(gid) * 9;
-        bt.box.grow(w);
-        bt.box.grow(w + 3);
-        bt.box.grow(w + 6);
+        // bounds from the triangles' own vertices (exact), plus the derived fourth corner of a pair
+        for (uint32_t gid : {hprims[k].gid_a, hprims[k].gid_b}) {
+            if (gid == 0xffffffffu) continue;
+            const float *w = world.data() + static_cast<size_t>(gid) * 9;
+            bt.box.grow(w);
+            bt.box.grow(w + 3);
+            bt.box.grow(w + 6);
+        }
+        float c4[4][3];
+        int nc = prim_corners(hprims[k], c4);
+        for (int c = 0; c < nc; ++c) bt.box.grow(c4[c]);
         for (int a = 0; a < 3; ++a) bt.centroid[a] = 0.5f * (bt.box.lo[a] + bt.box.hi[a]);
-        bt.index = gid;
+        bt.index = k;
         scene_box.grow(bt.box);
     }
     std::vector<BuildNode> bnodes;
-    bnodes.reserve(static_cast<size_t>(total_tris) * 2);
+    bnodes.reserve(static_cast<size_t>(n_prims) * 2);
     uint32_t max_depth = 0;
-    build_recursive(bnodes, btris, 0, total_tris, 0, max_depth);
+    build_recursive(bnodes, btris, 0, n_prims, 0, max_depth);
     out.bvh_depth = max_depth;
     if (max_depth + 2 >= AKR_BVH_STACK) {
         err = "BVH too deep for the traversal stack";
         return AKR_ERR_UNSUPPORTED;
     }
-    // conservative padding so that rounding in the slab test can never reject a box whose triangle the
-    // (independent) triangle test accepts
+    // conservative padding so that rounding in the slab test can never reject a box whose primitive the
+    // (independent) primitive test accepts
     float diag = 0.0f;
     for (int a = 0; a < 3; ++a) diag = std::max(diag, scene_box.hi[a] - scene_box.lo[a]);
     const float pad_abs = 1e-5f * diag;
@@ -716,19 +814,59 @@ int build_scene_blob(const AkrSceneDesc &d, HostSceneBlob &out, std::string &err
             hi[a] = b.hi[a] + pad;
         }
     };
-    // triangles in leaf order
-    out.tris.resize(total_tris);
-    for (uint32_t k = 0; k < total_tris; ++k) {
-        uint32_t gid = btris[k].index;
-        const float *w = world.data() + static_cast<size_t>(gid) * 9;
-        TriGeom &tg = out.tris[k];
+    // primitives in leaf order; two Moeller-Trumbore triangle slots per primitive for the host simulation
+    out.prims.resize(n_prims);
+    out.tris.resize(static_cast<size_t>(n_prims) * 2);
+    auto fill_tri = [&](TriGeom &tg, uint32_t gid) {
         std::memset(&tg, 0, sizeof(tg));
+        tg.gid = gid;
+        if (gid == 0xffffffffu) return;
+        const float *w = world.data() + static_cast<size_t>(gid) * 9;
         H3 w0{w[0], w[1], w[2]}, w1{w[3], w[4], w[5]}, w2{w[6], w[7], w[8]};
         st3(tg.v0, w0);
         st3(tg.e1, w1 - w0);
         st3(tg.e2, w2 - w0);
-        tg.gid = gid;
         tg.cls = shade_class_of(out.materials[out.shade[gid].mat].type);
+    };
+    for (uint32_t k = 0; k < n_prims; ++k) {
+        const HostPrim &hp = hprims[btris[k].index];
+        fill_tri(out.tris[2 * k], hp.gid_a);
+        fill_tri(out.tris[2 * k + 1], hp.gid_b);
+        PrimRec &pr = out.prims[k];
+        std::memset(&pr, 0, sizeof(pr));
+        pr.gid_a = hp.gid_a;
+        pr.gid_b = hp.gid_b;
+        // rows of the world -> (s, q) map, in double, rounded once:
+        //   n = a x b;  s = (P - p0) . (b x n) / (a . (b x n));  q = (P - p0) . (n x a) / (b . (n x a))
+        const double *A = hp.a, *B = hp.b, *P0 = hp.p0;
+        double n[3] = {A[1] * B[2] - A[2] * B[1], A[2] * B[0] - A[0] * B[2], A[0] * B[1] - A[1] * B[0]};
+        double bxn[3] = {B[1] * n[2] - B[2] * n[1], B[2] * n[0] - B[0] * n[2], B[0] * n[1] - B[1] * n[0]};
+        double nxa[3] = {n[1] * A[2] - n[2] * A[1], n[2] * A[0] - n[0] * A[2], n[0] * A[1] - n[1] * A[0]};
+        double ds = A[0] * bxn[0] + A[1] * bxn[1] + A[2] * bxn[2];
+        double dq = B[0] * nxa[0] + B[1] * nxa[1] + B[2] * nxa[2];
+        double nl = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+        if (!(nl > 0.0) || ds == 0.0 || dq == 0.0) {  // degenerate: can never be hit (NaN plane)
+            for (int c = 0; c < 4; ++c) pr.n[c] = pr.r0[c] = pr.r1[c] = std::numeric_limits<float>::quiet_NaN();
+        } else {
+            double r0w = 0.0, r1w = 0.0, nw = 0.0;
+            for (int c = 0; c < 3; ++c) {
+                pr.n[c] = static_cast<float>(n[c] / nl);
+                pr.r0[c] = static_cast<float>(bxn[c] / ds);
+                pr.r1[c] = static_cast<float>(nxa[c] / dq);
+            }
+            // the offsets are computed against the ROUNDED rows so that p0 maps to (0, 0) as exactly as possible
+            for (int c = 0; c < 3; ++c) {
+                nw -= static_cast<double>(pr.n[c]) * P0[c];
+                r0w -= static_cast<double>(pr.r0[c]) * P0[c];
+                r1w -= static_cast<double>(pr.r1[c]) * P0[c];
+            }
+            pr.n[3] = static_cast<float>(nw);
+            pr.r0[3] = static_cast<float>(r0w);
+            pr.r1[3] = static_cast<float>(r1w);
+        }
+        uint32_t cls_a = shade_class_of(out.materials[out.shade[hp.gid_a].mat].type);
+        uint32_t cls_b = hp.gid_b == 0xffffffffu ? 0u : shade_class_of(out.materials[out.shade[hp.gid_b].mat].type);
+        pr.meta = hp.iu_a | (hp.iv_a << 2) | (hp.iu_b << 4) | (hp.iv_b << 6) | (cls_a << 8) | (cls_b << 10);
     }
     // flatten: breadth-first over inner nodes; a leaf root becomes an inner node with an empty second child
     auto leaf_code = [&](const BuildNode &n) { return ~static_cast<int32_t>((n.first << 3) | n.count); };
@@ -817,6 +955,7 @@ SceneView host_scene_view(const HostSceneBlob &b, const float *albedo_table) {
     SceneView v;
     std::memset(&v, 0, sizeof(v));
     v.nodes = b.nodes.data();
+    v.prims = b.prims.data();
     v.tris = b.tris.data();
     v.shade = b.shade.data();
     v.instances = b.instances.data();
@@ -827,7 +966,8 @@ SceneView host_scene_view(const HostSceneBlob &b, const float *albedo_table) {
     v.alias_pdf = b.alias_pdf.data();
     v.albedo_table = albedo_table;
     v.n_nodes = static_cast<uint32_t>(b.nodes.size());
-    v.n_tris = static_cast<uint32_t>(b.tris.size());
+    v.n_prims = static_cast<uint32_t>(b.prims.size());
+    v.n_tris = static_cast<uint32_t>(b.shade.size());
     v.n_instances = static_cast<uint32_t>(b.instances.size());
     v.n_materials = static_cast<uint32_t>(b.materials.size());
     v.n_lights = static_cast<uint32_t>(b.lights.size());

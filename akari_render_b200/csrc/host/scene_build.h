@@ -17,7 +17,8 @@ namespace akr {
 
 struct HostSceneBlob {
     std::vector<BvhNode> nodes;
-    std::vector<TriGeom> tris;        // BVH leaf order
+    std::vector<PrimRec> prims;       // BVH leaf order (what the CUDA kernels intersect)
+    std::vector<TriGeom> tris;        // two per primitive, same order (host simulation's Moeller-Trumbore path)
     std::vector<TriShade> shade;      // by global triangle id
     std::vector<InstanceRec> instances;
     std::vector<Material> materials;

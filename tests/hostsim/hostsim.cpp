@@ -24,7 +24,13 @@ struct HostsimStats {
     uint64_t samples, segments, shadow_rays;
     uint32_t n_nodes, n_tris, n_materials, n_lights, bvh_depth;
     uint32_t material_types[8];
+    uint32_t n_prims, n_pairs;
 };
+
+// 0: Moeller-Trumbore triangles (bit-exact twin of the oracle); 1: the CUDA kernels' primitive intersector
+static thread_local int g_use_prims = 0;
+void hostsim_set_intersector(int use_prims) { g_use_prims = use_prims; }
+
 
 int hostsim_render(const AkrSceneDesc *desc, const AkrPtConfig *cfg, const AkrSamplerConfig *scfg, const AkrFilterConfig *filter,
                    const uint32_t *pmj, const uint16_t *bn, const float *albedo_table, uint32_t y0, uint32_t y1, uint32_t spp_begin,
@@ -83,7 +89,8 @@ int hostsim_render(const AkrSceneDesc *desc, const AkrPtConfig *cfg, const AkrSa
         for (uint32_t depth = 0; depth <= rp.max_depth && !cur.empty(); ++depth) {
             std::vector<HitRec> hits(cur.size());
             for (size_t i = 0; i < cur.size(); ++i)
-                hits[i] = trace_ray<false>(sc, td, cur[i].o, cur[i].d, 0.0f, 1e20f, cur[i].ex, 0xffffffffu);
+                hits[i] = g_use_prims ? trace_ray_prims<false>(sc, cur[i].o, cur[i].d, 0.0f, 1e20f, cur[i].ex, 0xffffffffu)
+                                      : trace_ray<false>(sc, td, cur[i].o, cur[i].d, 0.0f, 1e20f, cur[i].ex, 0xffffffffu);
             segments += cur.size();
             if (depth == 0 && first_hits && spp_begin == wave.s0)
                 for (size_t i = 0; i < cur.size(); ++i) {
@@ -111,7 +118,8 @@ int hostsim_render(const AkrSceneDesc *desc, const AkrPtConfig *cfg, const AkrSa
             }
             shadows += shq.size();
             for (const ShadowItem &it : shq) {
-                HitRec h = trace_ray<true>(sc, td, it.o, it.d, 0.0f, it.t_max, it.ex0, it.ex1);
+                HitRec h = g_use_prims ? trace_ray_prims<true>(sc, it.o, it.d, 0.0f, it.t_max, it.ex0, it.ex1)
+                                       : trace_ray<true>(sc, td, it.o, it.d, 0.0f, it.t_max, it.ex0, it.ex1);
                 shadow_resolve(av, it, h.gid != 0xffffffffu, depth + 1u);
             }
             cur.swap(next);
@@ -124,7 +132,9 @@ int hostsim_render(const AkrSceneDesc *desc, const AkrPtConfig *cfg, const AkrSa
         stats->segments = segments;
         stats->shadow_rays = shadows;
         stats->n_nodes = (uint32_t)blob.nodes.size();
-        stats->n_tris = (uint32_t)blob.tris.size();
+        stats->n_tris = (uint32_t)blob.shade.size();
+        stats->n_prims = (uint32_t)blob.prims.size();
+        for (const PrimRec &pr : blob.prims) stats->n_pairs += pr.gid_b != 0xffffffffu ? 1u : 0u;
         stats->n_materials = (uint32_t)blob.materials.size();
         stats->n_lights = (uint32_t)blob.lights.size();
         stats->bvh_depth = blob.bvh_depth;

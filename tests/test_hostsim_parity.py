@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 class HostsimStats(C.Structure):
     _fields_ = [("samples", C.c_uint64), ("segments", C.c_uint64), ("shadow_rays", C.c_uint64), ("n_nodes", C.c_uint32),
                 ("n_tris", C.c_uint32), ("n_materials", C.c_uint32), ("n_lights", C.c_uint32), ("bvh_depth", C.c_uint32),
-                ("material_types", C.c_uint32 * 8)]
+                ("material_types", C.c_uint32 * 8), ("n_prims", C.c_uint32), ("n_pairs", C.c_uint32)]
 
 
 @pytest.fixture(scope="module")
@@ -137,3 +137,57 @@ def test_albedo_table_generators_agree(hostsim, oracle):
     oracle.lib().akr_oracle_make_albedo_table(C.c_void_p(o.ctypes.data), 16)
     assert np.array_equal(t, o)
     assert (t >= 0).all() and (t <= 1.0 + 1e-3).all()
+
+
+def _gate(film, ofilm, fh, ofh, n, oracle):
+    """The GPU parity gate (tests/test_gpu_parity.py) applied to a host simulation run."""
+    from conftest import image_rel_l2, rel_l2_per_pixel
+    a = oracle.resolve(film, n).reshape(-1, 3)
+    b = oracle.resolve(ofilm, n).reshape(-1, 3)
+    same = (fh[:, 0] == ofh[:, 0]) & (fh[:, 1] == ofh[:, 1])
+    rel = rel_l2_per_pixel(a, b)
+    return same.mean(), float((rel > 1e-3).mean()), image_rel_l2(a, b)
+
+
+def test_primitive_intersector_vs_oracle(hostsim, oracle, tables, cbox, cbox_task):
+    """The CUDA kernels intersect primitives (a triangle, or two triangles forming a parallelogram, decided by one
+    plane + two-coordinate test) instead of Moeller-Trumbore triangles.  Same BVH, same shading code: the image must
+    stay inside the stated GPU tolerance and the pairing must find every parallelogram of the Cornell box."""
+    w = h = 96
+    scene, task = cbox(w, h), cbox_task(16)
+    pmj, bn = tables
+    table = oracle.albedo_table()
+    ofilm, ost, ofh = oracle.render(scene.desc, w, h, task.pt, task.sampler, task.filter, pmj, bn, want_first_hits=True)
+    hostsim.hostsim_set_intersector(1)
+    try:
+        film, fh, st = run_hostsim(hostsim, scene, task, tables, table, w, h)
+    finally:
+        hostsim.hostsim_set_intersector(0)
+    # 14 of the 18 quads are exact parallelograms; floor, back wall, left wall and the short box top are trapezoids
+    assert (st.n_tris, st.n_prims, st.n_pairs) == (36, 22, 14)
+    same, frac_bad, img = _gate(film, ofilm, fh, ofh, w * h, oracle)
+    print(f"first hits identical {same:.5%}; pixels over 1e-3: {frac_bad:.5%}; image rel-L2 {img:.3e}")
+    assert same >= 0.9999
+    assert frac_bad <= 1e-3
+    assert img <= 1e-3
+    assert abs(int(st.segments) - int(ost.segments)) <= 1e-4 * ost.segments
+    assert abs(int(st.shadow_rays) - int(ost.shadow_rays)) <= 1e-4 * ost.shadow_rays
+
+
+@pytest.mark.parametrize("variant", ["principled_mix", "nodes"])
+def test_primitive_intersector_variants(hostsim, oracle, tables, akr, cbox_task, tmp_path, variant):
+    w = h = 48
+    path = sv.write_variant(tmp_path, variant, getattr(sv, "variant_" + variant))
+    scene = akr.load_scene(path).set_resolution(w, h)
+    task = cbox_task(16)
+    pmj, bn = tables
+    table = oracle.albedo_table()
+    ofilm, ost, ofh = oracle.render(scene.desc, w, h, task.pt, task.sampler, task.filter, pmj, bn, want_first_hits=True)
+    hostsim.hostsim_set_intersector(1)
+    try:
+        film, fh, st = run_hostsim(hostsim, scene, task, tables, table, w, h)
+    finally:
+        hostsim.hostsim_set_intersector(0)
+    same, frac_bad, img = _gate(film, ofilm, fh, ofh, w * h, oracle)
+    print(f"{variant}: first hits identical {same:.5%}; pixels over 1e-3: {frac_bad:.5%}; image rel-L2 {img:.3e}")
+    assert same >= 0.999 and frac_bad <= 5e-3 and img <= 5e-3
