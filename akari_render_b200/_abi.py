@@ -141,7 +141,8 @@ class AkrRenderTask(C.Structure):
 
 
 HOST_LIB = os.path.join(HERE, "libakari_b200_host.so")
-CUDA_LIB = os.path.join(HERE, "libakari_b200.so")
+# AKR_B200_CUDA_LIB points at an alternative build of the same library (kernel-tuning experiments only)
+CUDA_LIB = os.environ.get("AKR_B200_CUDA_LIB") or os.path.join(HERE, "libakari_b200.so")
 
 # every symbol the two headers declare (tests check the built libraries export exactly these)
 HOST_SYMBOLS = [

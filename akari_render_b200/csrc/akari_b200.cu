@@ -28,7 +28,12 @@ namespace {
 constexpr int kBlock = 256;
 constexpr int kWarpsPerBlock = kBlock / 32;
 constexpr uint32_t kMaxDepthSlots = 66;           // counters for depth 0 .. 64 (+1)
-constexpr uint32_t kCtrStride = 8;                // words per depth: [0] paths in, [1] shadow rays out, [2 + c] hits of class c
+// Queue counters, one 32-byte block per depth d:
+//   [0] paths entering depth d (raygen for d = 0, else the survivors of shade(d - 1))
+//   [1] shadow rays produced by shade(d - 1), traced together with [0] by trace(d)
+//   [2 + c] hits of shade class c found by trace(d)
+// [0]/[1] and [2]/[3] are 8-byte aligned pairs, so one 64-bit atomic reserves slots in two queues at once.
+constexpr uint32_t kCtrStride = 8;
 constexpr uint32_t kSmemSceneBudget = 48 * 1024;  // bytes of BVH nodes + triangles staged per CTA
 constexpr uint32_t kSmemMax = 200 * 1024;         // opt-in ceiling for the trace kernels (staging + stacks)
 constexpr uint32_t kFlatMaxPrims = 64;            // scenes this small are traced as one flat primitive list
@@ -39,8 +44,8 @@ constexpr uint32_t kFlatMaxPrims = 64;            // scenes this small are trace
 // ------------------------------------------------------------------------------------------------
 struct PathQueue {   // 48 B per path
     f4 *a;           // origin.xyz, dir.x
-    f4 *b;           // dir.y, dir.z, exclude gid (bits), prev_bsdf_pdf
-    f4 *c;           // beta.rgb, path_id (bits)
+    f4 *b;           // dir.y, dir.z, exclude gid (bits), path_id (bits)   -- a + b is all the trace stage reads
+    f4 *c;           // beta.rgb, prev_bsdf_pdf
 };
 struct HitQueue {    // 16 B per traced path, same slot as the path
     f4 *h;           // gid (bits), u, v, -
@@ -51,8 +56,8 @@ struct ShadowQueue { // 52 B per shadow ray
     f4 *c;           // contribution.rgb, path_id (bits)
     uint32_t *ex1;
 };
-struct ClassQueues { // per shade class: slots (into the path queue) of the hits of that class
-    uint32_t *idx[CLS_COUNT];
+struct ClassQueues { // per shade class: (slot in the path queue, path_id) of the hits of that class
+    uint2 *idx[CLS_COUNT];
 };
 
 struct LaunchParams {
@@ -81,15 +86,15 @@ __device__ __forceinline__ PathState load_path(const PathQueue &q, uint32_t i) {
     p.o = mk3(a.x, a.y, a.z);
     p.d = mk3(a.w, b.x, b.y);
     p.ex = f2u(b.z);
-    p.prev_bsdf_pdf = b.w;
+    p.path_id = f2u(b.w);
     p.beta = mk3(c.x, c.y, c.z);
-    p.path_id = f2u(c.w);
+    p.prev_bsdf_pdf = c.w;
     return p;
 }
 __device__ __forceinline__ void store_path(const PathQueue &q, uint32_t i, const PathState &p) {
     st4(q.a + i, f4{p.o.x, p.o.y, p.o.z, p.d.x});
-    st4(q.b + i, f4{p.d.y, p.d.z, u2f(p.ex), p.prev_bsdf_pdf});
-    st4(q.c + i, f4{p.beta.x, p.beta.y, p.beta.z, u2f(p.path_id)});
+    st4(q.b + i, f4{p.d.y, p.d.z, u2f(p.ex), u2f(p.path_id)});
+    st4(q.c + i, f4{p.beta.x, p.beta.y, p.beta.z, p.prev_bsdf_pdf});
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -225,6 +230,21 @@ __device__ __forceinline__ DevHit trace_dev(const LaunchParams &P, const TraceSm
     return DevHit{dec.gid, dec.cls, dec.u, dec.v};
 }
 
+// Warp-aggregated append to TWO queues whose counters are an aligned 32-bit pair: one 64-bit atomic per
+// warp reserves both ranges (half the traffic to the hot L2 lines of per-queue atomics).
+__device__ __forceinline__ void warp_append2(uint32_t *counter_pair, bool pred0, bool pred1, uint32_t &slot0, uint32_t &slot1) {
+    const uint32_t m0 = __ballot_sync(0xffffffffu, pred0), m1 = __ballot_sync(0xffffffffu, pred1);
+    slot0 = slot1 = 0u;
+    if ((m0 | m1) == 0u) return;
+    const uint32_t lane = threadIdx.x & 31u;
+    unsigned long long base = 0ull;
+    if (lane == 0u)
+        base = atomicAdd(reinterpret_cast<unsigned long long *>(counter_pair), (unsigned long long)__popc(m0) | ((unsigned long long)__popc(m1) << 32));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    const uint32_t below = (1u << lane) - 1u;
+    slot0 = (uint32_t)base + (uint32_t)__popc(m0 & below);
+    slot1 = (uint32_t)(base >> 32) + (uint32_t)__popc(m1 & below);
+}
 // warp-aggregated queue append: one atomic per warp, slots ordered by lane
 __device__ __forceinline__ uint32_t warp_append(uint32_t *counter, bool pred) {
     const uint32_t mask = __ballot_sync(0xffffffffu, pred);
@@ -259,7 +279,7 @@ template <int MODE> __global__ void __launch_bounds__(kBlock) k_trace(const __gr
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bar;
     const uint32_t n_cl = P.counters[depth * kCtrStride];
-    const uint32_t n_sh = depth > 0u ? P.counters[(depth - 1u) * kCtrStride + 1u] : 0u;
+    const uint32_t n_sh = P.counters[depth * kCtrStride + 1u];
     const uint32_t t_cl = (n_cl + 31u) >> 5, t_sh = (n_sh + 31u) >> 5;
     const uint32_t n_tasks = t_cl + t_sh;
     if (blockIdx.x * kWarpsPerBlock >= n_tasks) return;  // whole CTA has no work: skip the staging too
@@ -273,22 +293,22 @@ template <int MODE> __global__ void __launch_bounds__(kBlock) k_trace(const __gr
             const uint32_t i = task * 32u + lane;
             const bool active = i < n_cl;
             DevHit h{0xffffffffu, 0u, 0.0f, 0.0f};
+            uint32_t path_id = 0u;
             if (active) {
                 const f4 a = ld4(q.a + i), b = ld4(q.b + i);
+                path_id = f2u(b.w);
                 h = trace_dev<false, MODE>(P, ts, mk3(a.x, a.y, a.z), mk3(a.w, b.x, b.y), 0.0f, 1e20f, f2u(b.z), 0xffffffffu);
                 st4(P.hits.h + i, f4{u2f(h.gid), h.u, h.v, 0.0f});
             }
             const bool hit = active && h.gid != 0xffffffffu;
             const uint32_t cls = P.rp.force_diffuse ? (uint32_t)CLS_LAMBERT : h.cls;
-#pragma unroll
-            for (uint32_t c = 0; c < (uint32_t)CLS_COUNT; ++c) {
-                const bool mine = hit && cls == c;
-                const uint32_t slot = warp_append(ctr + 2u + c, mine);
-                if (mine) P.cls.idx[c][slot] = i;
-            }
+            uint32_t s0, s1;
+            warp_append2(ctr + 2u, hit && cls == CLS_LAMBERT, hit && cls == CLS_CONDUCTOR, s0, s1);
+            const uint32_t s2 = warp_append(ctr + 4u, hit && cls == CLS_GENERAL);
+            if (hit) P.cls.idx[cls][cls == CLS_LAMBERT ? s0 : (cls == CLS_CONDUCTOR ? s1 : s2)] = make_uint2(i, path_id);
             if (active && !hit && miss_work) {
                 const f4 c = ld4(q.c + i);
-                miss_body(P.rp, depth, mk3(c.x, c.y, c.z), f2u(c.w), P.acc);
+                miss_body(P.rp, depth, mk3(c.x, c.y, c.z), path_id, P.acc);
             }
         } else {
             const uint32_t i = (task - t_cl) * 32u + lane;
@@ -305,33 +325,45 @@ template <int MODE> __global__ void __launch_bounds__(kBlock) k_trace(const __gr
     }
 }
 
+// resident CTAs per SM the shade kernels are compiled for (register budget = 65536 / (256 * n)); tuned on B200
+#ifndef AKR_SHADE_MINB_LAMBERT
+#define AKR_SHADE_MINB_LAMBERT 4
+#endif
+#ifndef AKR_SHADE_MINB_CONDUCTOR
+#define AKR_SHADE_MINB_CONDUCTOR 3
+#endif
 template <int CLS> struct ShadeLaunch {
-    static constexpr int kMinBlocks = (CLS == CLS_LAMBERT || CLS == CLS_CONDUCTOR) ? 2 : 1;
+    static constexpr int kMinBlocks = CLS == CLS_LAMBERT ? AKR_SHADE_MINB_LAMBERT : (CLS == CLS_CONDUCTOR ? AKR_SHADE_MINB_CONDUCTOR : 1);
 };
 
 // One shade kernel per material class; `CLS_ANY` (unsorted: every hit in slot order) exists for A/B runs.
 template <int CLS> __global__ void __launch_bounds__(kBlock, ShadeLaunch<CLS>::kMinBlocks) k_shade(const __grid_constant__ LaunchParams P, uint32_t depth) {
     uint32_t *ctr = P.counters + depth * kCtrStride;
     const uint32_t n = CLS == CLS_ANY ? ctr[0] : ctr[2u + (CLS == CLS_ANY ? 0 : CLS)];
-    const uint32_t *slots = CLS == CLS_ANY ? nullptr : P.cls.idx[CLS == CLS_ANY ? 0 : CLS];
+    const uint2 *slots = CLS == CLS_ANY ? nullptr : P.cls.idx[CLS == CLS_ANY ? 0 : CLS];
     const PathQueue &qin = P.q[depth & 1u];
     const PathQueue &qout = P.q[(depth + 1u) & 1u];
-    uint32_t *next_count = ctr + kCtrStride;
-    uint32_t *shadow_count = ctr + 1u;
+    uint32_t *out_pair = ctr + kCtrStride;  // [0] next-depth paths, [1] shadow rays: reserved together
     const uint32_t stride = gridDim.x * blockDim.x;
-    // warp-uniform trip count so that every lane takes part in the ballots
-    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride) {
-        const uint32_t k = base + (threadIdx.x & 31u);
-        bool active = k < n;
+    // warp-uniform trip count so that every lane takes part in the ballots; the (slot, path_id) entry of the
+    // next trip is fetched one trip ahead so that its latency is off the dependent chain
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    uint2 ent = make_uint2(k, 0u);
+    if (CLS != CLS_ANY && k < n) ent = slots[k];
+    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride, k += stride) {
+        const bool active = k < n;
+        const uint2 cur = ent;
+        if (CLS != CLS_ANY && k + stride < n) ent = slots[k + stride];
         ShadeOut o;
         o.has_shadow = false;
         o.has_next = false;
         if (active) {
-            const uint32_t i = CLS == CLS_ANY ? k : slots[k];
+            const uint32_t i = CLS == CLS_ANY ? k : cur.x;
             const f4 hr = ld4(P.hits.h + i);
             HitRec h{f2u(hr.x), hr.y, hr.z};
             if (CLS != CLS_ANY || h.gid != 0xffffffffu) {
                 PathState ps = load_path(qin, i);
+                if (CLS != CLS_ANY) ps.path_id = cur.y;  // same value, but already in a register: the sampler loads do not wait for the record
                 o = shade_body<CLS>(P.scene, P.corners, P.tables, P.rp, P.wave, depth, ps, h, P.acc);
                 if (depth == 0u && P.dbg_first_hits && ps.path_id < P.wave.n_pix && P.wave.s0 == 0u) {
                     uint32_t pix = P.wave.pix0 + ps.path_id;
@@ -340,7 +372,8 @@ template <int CLS> __global__ void __launch_bounds__(kBlock, ShadeLaunch<CLS>::k
                 }
             }
         }
-        const uint32_t ss = warp_append(shadow_count, o.has_shadow);
+        uint32_t ns, ss;
+        warp_append2(out_pair, o.has_next, o.has_shadow, ns, ss);
         if (o.has_shadow) {
             const ShadowQueue &s = P.shadow;
             st4(s.a + ss, f4{o.shadow.o.x, o.shadow.o.y, o.shadow.o.z, o.shadow.t_max});
@@ -348,7 +381,6 @@ template <int CLS> __global__ void __launch_bounds__(kBlock, ShadeLaunch<CLS>::k
             st4(s.c + ss, f4{o.shadow.contrib.x, o.shadow.contrib.y, o.shadow.contrib.z, u2f(o.shadow.path_id)});
             s.ex1[ss] = o.shadow.ex1;
         }
-        const uint32_t ns = warp_append(next_count, o.has_next);
         if (o.has_next) store_path(qout, ns, o.next);
     }
 }
@@ -501,9 +533,9 @@ int grid_for(const AkrContext *ctx, uint32_t n, int ctas_per_sm) {
 int ensure_wave_buffers(AkrContext *ctx, uint32_t capacity) {
     if (ctx->wave_capacity >= capacity && ctx->wave_mem.ptr) return AKR_OK;
     // 16-byte records per path: two path queues (3 + 3), hits (1), shadow queue (3), accumulators (2);
-    // 4-byte words per path: shadow exclude1 (1), class slot lists (CLS_COUNT)
+    // 4-byte words per path: shadow exclude1 (1), class (slot, path_id) lists (2 * CLS_COUNT)
     const size_t cap = ((size_t)capacity + 31u) & ~(size_t)31u;
-    const size_t n_vec = 3 + 3 + 1 + 3 + 2, n_word = 1 + (size_t)CLS_COUNT;
+    const size_t n_vec = 3 + 3 + 1 + 3 + 2, n_word = 1 + 2 * (size_t)CLS_COUNT;
     int rc = dev_alloc(ctx, ctx->wave_mem, cap * (n_vec * 16 + n_word * 4));
     if (rc != AKR_OK) return rc;
     f4 *vbase = static_cast<f4 *>(ctx->wave_mem.ptr);
@@ -525,8 +557,8 @@ int ensure_wave_buffers(AkrContext *ctx, uint32_t capacity) {
     ctx->acc.l = take_v();
     ctx->acc.b = take_v();
     uint32_t *wbase = reinterpret_cast<uint32_t *>(vbase + voff);
-    ctx->shadow.ex1 = wbase;
-    for (uint32_t c = 0; c < (uint32_t)CLS_COUNT; ++c) ctx->cls.idx[c] = wbase + cap * (1 + c);
+    for (uint32_t c = 0; c < (uint32_t)CLS_COUNT; ++c) ctx->cls.idx[c] = reinterpret_cast<uint2 *>(wbase + cap * 2 * c);
+    ctx->shadow.ex1 = wbase + cap * 2 * (size_t)CLS_COUNT;
     ctx->wave_capacity = capacity;
     return AKR_OK;
 }
