@@ -128,11 +128,62 @@ __device__ __forceinline__ void tma_bulk_g2s(void *smem_dst, const void *gsrc, u
 }
 
 // Shared-memory plan of the trace kernel: [ nodes | primitives | per-thread traversal stacks ].
+// Addresses are kept as 32-bit shared-space addresses and dereferenced with explicit ld.shared / st.shared:
+// through a generic pointer the compiler emits generic LD/ST, which are slower than LDS/STS.
 struct TraceSmem {
-    const BvhNode *nodes;   // shared copy of nodes[0 .. n_fast_nodes)
-    const PrimRec *prims;   // shared copy of all primitives, or the global array
-    int32_t *stack;         // this thread's stack: entry k lives at stack[k * kBlock]
+    uint32_t nodes;         // shared copy of nodes[0 .. n_fast_nodes)
+    uint32_t prims;         // shared copy of all primitives (when staged)
+    uint32_t stack;         // this thread's stack: entry k lives at stack + k * kBlock * 4
 };
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ int32_t lds32(uint32_t addr) {
+    int32_t v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts32(uint32_t addr, int32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+template <bool SHARED> __device__ __forceinline__ void load64(uint32_t saddr, const void *gptr, float4 &a, float4 &b, float4 &c, float4 &d) {
+    if (SHARED) {
+        a = lds128(saddr);
+        b = lds128(saddr + 16u);
+        c = lds128(saddr + 32u);
+        d = lds128(saddr + 48u);
+    } else {
+        const float4 *g = static_cast<const float4 *>(gptr);
+        a = __ldg(g);
+        b = __ldg(g + 1);
+        c = __ldg(g + 2);
+        d = __ldg(g + 3);
+    }
+}
+template <bool SHARED> __device__ __forceinline__ PrimRec load_prim(uint32_t s_prims, const PrimRec *g_prims, uint32_t k) {
+    float4 a, b, c, d;
+    load64<SHARED>(s_prims + k * (uint32_t)sizeof(PrimRec), g_prims + k, a, b, c, d);
+    PrimRec p;
+    p.n[0] = a.x; p.n[1] = a.y; p.n[2] = a.z; p.n[3] = a.w;
+    p.r0[0] = b.x; p.r0[1] = b.y; p.r0[2] = b.z; p.r0[3] = b.w;
+    p.r1[0] = c.x; p.r1[1] = c.y; p.r1[2] = c.z; p.r1[3] = c.w;
+    p.gid_a = __float_as_uint(d.x);
+    p.gid_b = __float_as_uint(d.y);
+    p.meta = __float_as_uint(d.z);
+    p._pad = 0u;
+    return p;
+}
+template <bool SHARED> __device__ __forceinline__ BvhNode load_node(uint32_t s_nodes, const BvhNode *g_nodes, uint32_t k) {
+    float4 a, b, c, d;
+    load64<SHARED>(s_nodes + k * (uint32_t)sizeof(BvhNode), g_nodes + k, a, b, c, d);
+    BvhNode n;
+    n.lo0[0] = a.x; n.lo0[1] = a.y; n.lo0[2] = a.z; n.hi0[0] = a.w;
+    n.hi0[1] = b.x; n.hi0[2] = b.y; n.lo1[0] = b.z; n.lo1[1] = b.w;
+    n.lo1[2] = c.x; n.hi1[0] = c.y; n.hi1[1] = c.z; n.hi1[2] = c.w;
+    n.c0 = (int32_t)__float_as_uint(d.x);
+    n.c1 = (int32_t)__float_as_uint(d.y);
+    return n;
+}
 
 // Stages nodes[0 .. n_nodes) and (optionally) all primitives behind `smem` with one TMA bulk copy each.
 __device__ __forceinline__ TraceSmem stage_scene(const LaunchParams &P, unsigned char *smem, uint64_t *bar) {
@@ -152,9 +203,9 @@ __device__ __forceinline__ TraceSmem stage_scene(const LaunchParams &P, unsigned
     }
     if ((node_bytes + tri_bytes) > 0) mbar_wait(bar, 0);
     TraceSmem t;
-    t.nodes = s_nodes;
-    t.prims = P.scene_smem_prims ? s_tris : P.scene.prims;
-    t.stack = reinterpret_cast<int32_t *>(smem + node_bytes + tri_bytes) + threadIdx.x;
+    t.nodes = smem_u32(s_nodes);
+    t.prims = smem_u32(s_tris);
+    t.stack = smem_u32(smem + node_bytes + tri_bytes) + threadIdx.x * 4u;
     return t;
 }
 
@@ -168,65 +219,75 @@ struct DevHit {
     float u, v;
 };
 
-enum TraceMode : int { TRACE_BVH = 0, TRACE_FLAT = 1 };
+// TRACE_BVH: top of the BVH in shared memory, the rest of the nodes and the primitives in global memory (L1/L2);
+// TRACE_FLAT / TRACE_BVH_SMEM: the whole scene is staged in shared memory.
+enum TraceMode : int { TRACE_BVH = 0, TRACE_FLAT = 1, TRACE_BVH_SMEM = 2 };
 
 // TRACE_FLAT: every lane tests every primitive in list order (shared-memory broadcast reads, no divergence,
 // no stack) — the cheapest schedule when the whole scene is a few dozen primitives.
 // TRACE_BVH : while-while traversal; lanes first descend to their next leaf together, then test leaves.
-template <bool ANY_HIT, int MODE>
-__device__ __forceinline__ DevHit trace_dev(const LaunchParams &P, const TraceSmem &ts, f3 o, f3 d, float t_min, float t_max, uint32_t ex0, uint32_t ex1) {
+// Every lane of the warp calls this together (`active` = the lane carries a ray); any-hit rays leave the
+// primitive loop only when the whole warp is done, which is the only exit that saves issue slots.
+template <bool ANY_HIT, int MODE, bool ALPHA>
+__device__ __forceinline__ DevHit trace_dev(const LaunchParams &P, const TraceSmem &ts, bool active, f3 o, f3 d, float t_min, float t_max, uint32_t ex0,
+                                            uint32_t ex1) {
     const SceneView &sc = P.scene;
-    PrimHit best{t_max, 0.0f, 0.0f, 0xffffffffu};
+    PrimHit best{active ? t_max : 0.0f, 0.0f, 0.0f, 0xffffffffu};  // an idle lane accepts nothing (t < 0 is never true for t > t_min = 0)
+    constexpr bool PRIMS_SHARED = MODE != TRACE_BVH;
     if (MODE == TRACE_FLAT) {
         const uint32_t n = sc.n_prims;
+#pragma unroll 2
         for (uint32_t k = 0; k < n; ++k) {
-            prim_test(sc, ts.prims[k], k, o, d, t_min, ex0, ex1, best);
-            if (ANY_HIT && best.k != 0xffffffffu) break;
+            prim_test<ALPHA>(sc, load_prim<true>(ts.prims, nullptr, k), k, o, d, t_min, ex0, ex1, best);
+            if (ANY_HIT && (k & 3u) == 3u && __all_sync(0xffffffffu, !active || best.k != 0xffffffffu)) break;
         }
-    } else {
+    } else if (active) {
         const f3 inv_d = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
         const uint32_t n_fast = P.scene_smem_nodes;
-        int32_t *stack = ts.stack;
-        int sp = 0;
+        constexpr uint32_t kStackStride = kBlock * 4u;
+        uint32_t sp = ts.stack;
         int32_t node = 0;  // the root is always an inner node
         while (true) {
             bool done = false;
             while (node >= 0) {
-                const BvhNode &n = ((uint32_t)node < n_fast) ? ts.nodes[node] : sc.nodes[node];
+                BvhNode n;
+                if (MODE == TRACE_BVH_SMEM || (uint32_t)node < n_fast) n = load_node<true>(ts.nodes, nullptr, (uint32_t)node);
+                else n = load_node<false>(0u, sc.nodes, (uint32_t)node);
                 float tn0, tn1;
                 const bool h0 = box_test(n.lo0, n.hi0, o, inv_d, t_min, best.t, tn0);
                 const bool h1 = box_test(n.lo1, n.hi1, o, inv_d, t_min, best.t, tn1);
                 const int32_t c0 = n.c0, c1 = n.c1;
                 if (h0 && h1) {
                     const bool swap = tn1 < tn0;
-                    stack[sp * kBlock] = swap ? c0 : c1;
-                    ++sp;
+                    sts32(sp, swap ? c0 : c1);
+                    sp += kStackStride;
                     node = swap ? c1 : c0;
                 } else if (h0) {
                     node = c0;
                 } else if (h1) {
                     node = c1;
                 } else {
-                    if (sp == 0) {
+                    if (sp == ts.stack) {
                         done = true;
                         break;
                     }
-                    --sp;
-                    node = stack[sp * kBlock];
+                    sp -= kStackStride;
+                    node = lds32(sp);
                 }
             }
             if (done) break;
             const uint32_t leaf = (uint32_t)(~node);
             const uint32_t first = leaf >> 3, count = leaf & 7u;
-            for (uint32_t k = 0; k < count; ++k) prim_test(sc, ts.prims[first + k], first + k, o, d, t_min, ex0, ex1, best);
+            for (uint32_t k = 0; k < count; ++k)
+                prim_test<ALPHA>(sc, load_prim<PRIMS_SHARED>(ts.prims, sc.prims, first + k), first + k, o, d, t_min, ex0, ex1, best);
             if (ANY_HIT && best.k != 0xffffffffu) break;
-            if (sp == 0) break;
-            --sp;
-            node = stack[sp * kBlock];
+            if (sp == ts.stack) break;
+            sp -= kStackStride;
+            node = lds32(sp);
         }
     }
     if (best.k == 0xffffffffu) return DevHit{0xffffffffu, 0u, 0.0f, 0.0f};
-    const PrimDecoded dec = prim_decode(ts.prims[best.k], best.s, best.q);
+    const PrimDecoded dec = prim_decode(load_prim<PRIMS_SHARED>(ts.prims, sc.prims, best.k), best.s, best.q);
     return DevHit{dec.gid, dec.cls, dec.u, dec.v};
 }
 
@@ -275,7 +336,7 @@ __global__ void __launch_bounds__(kBlock) k_raygen(const __grid_constant__ Launc
 // One launch per depth traces BOTH ray kinds: the closest-hit rays of the paths entering `depth` and the
 // shadow rays the previous depth's shade stage produced.  Work is handed out in warp-sized tasks
 // (closest-hit tasks first, the shorter any-hit tasks fill the tail), so a warp is never mixed.
-template <int MODE> __global__ void __launch_bounds__(kBlock) k_trace(const __grid_constant__ LaunchParams P, uint32_t depth) {
+template <int MODE, bool ALPHA> __global__ void __launch_bounds__(kBlock) k_trace(const __grid_constant__ LaunchParams P, uint32_t depth) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bar;
     const uint32_t n_cl = P.counters[depth * kCtrStride];
@@ -292,14 +353,14 @@ template <int MODE> __global__ void __launch_bounds__(kBlock) k_trace(const __gr
         if (task < t_cl) {
             const uint32_t i = task * 32u + lane;
             const bool active = i < n_cl;
-            DevHit h{0xffffffffu, 0u, 0.0f, 0.0f};
-            uint32_t path_id = 0u;
+            f4 a{0.0f, 0.0f, 0.0f, 1.0f}, b{0.0f, 0.0f, 0.0f, 0.0f};
             if (active) {
-                const f4 a = ld4(q.a + i), b = ld4(q.b + i);
-                path_id = f2u(b.w);
-                h = trace_dev<false, MODE>(P, ts, mk3(a.x, a.y, a.z), mk3(a.w, b.x, b.y), 0.0f, 1e20f, f2u(b.z), 0xffffffffu);
-                st4(P.hits.h + i, f4{u2f(h.gid), h.u, h.v, 0.0f});
+                a = ld4(q.a + i);
+                b = ld4(q.b + i);
             }
+            const uint32_t path_id = f2u(b.w);
+            const DevHit h = trace_dev<false, MODE, ALPHA>(P, ts, active, mk3(a.x, a.y, a.z), mk3(a.w, b.x, b.y), 0.0f, 1e20f, f2u(b.z), 0xffffffffu);
+            if (active) st4(P.hits.h + i, f4{u2f(h.gid), h.u, h.v, 0.0f});
             const bool hit = active && h.gid != 0xffffffffu;
             const uint32_t cls = P.rp.force_diffuse ? (uint32_t)CLS_LAMBERT : h.cls;
             uint32_t s0, s1;
@@ -312,9 +373,16 @@ template <int MODE> __global__ void __launch_bounds__(kBlock) k_trace(const __gr
             }
         } else {
             const uint32_t i = (task - t_cl) * 32u + lane;
-            if (i < n_sh) {
-                const f4 a = ld4(P.shadow.a + i), b = ld4(P.shadow.b + i);
-                const DevHit h = trace_dev<true, MODE>(P, ts, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), 0.0f, a.w, f2u(b.w), P.shadow.ex1[i]);
+            const bool active = i < n_sh;
+            f4 a{0.0f, 0.0f, 0.0f, 0.0f}, b{1.0f, 0.0f, 0.0f, 0.0f};
+            uint32_t ex1 = 0xffffffffu;
+            if (active) {
+                a = ld4(P.shadow.a + i);
+                b = ld4(P.shadow.b + i);
+                ex1 = P.shadow.ex1[i];
+            }
+            const DevHit h = trace_dev<true, MODE, ALPHA>(P, ts, active, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), 0.0f, a.w, f2u(b.w), ex1);
+            if (active) {
                 const f4 c = ld4(P.shadow.c + i);
                 ShadowItem it;
                 it.contrib = mk3(c.x, c.y, c.z);
@@ -456,7 +524,7 @@ struct AkrContext {
     uint32_t smem_nodes = 0, smem_prims = 0, smem_bytes = 0;  // smem_bytes = nodes + primitives (stacks come on top)
     uint32_t bvh_depth = 0;
     uint32_t class_mask = 0;   // shade classes present in the scene
-    int occ_trace[2] = {1, 1}, occ_shade[4] = {1, 1, 1, 1};  // resident CTAs per SM, per kernel variant
+    int occ_trace[3] = {1, 1, 1}, occ_shade[4] = {1, 1, 1, 1};  // resident CTAs per SM, per kernel variant
 
     // render state
     bool render_ready = false;
@@ -601,8 +669,12 @@ int akr_b200_create(int device_ordinal, AkrContext **out_ctx) {
         delete ctx;
         return AKR_ERR_CUDA;
     }
-    cudaFuncSetAttribute(k_trace<TRACE_BVH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
-    cudaFuncSetAttribute(k_trace<TRACE_FLAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
+    cudaFuncSetAttribute(k_trace<TRACE_BVH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
+    cudaFuncSetAttribute(k_trace<TRACE_FLAT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
+    cudaFuncSetAttribute(k_trace<TRACE_BVH_SMEM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
+    cudaFuncSetAttribute(k_trace<TRACE_BVH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
+    cudaFuncSetAttribute(k_trace<TRACE_FLAT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
+    cudaFuncSetAttribute(k_trace<TRACE_BVH_SMEM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
     if (dev_alloc(ctx, ctx->counters, kMaxDepthSlots * kCtrStride * sizeof(uint32_t)) != AKR_OK || dev_alloc(ctx, ctx->totals, 2 * sizeof(unsigned long long)) != AKR_OK) {
         delete ctx;
         return AKR_ERR_CUDA;
@@ -723,8 +795,15 @@ int akr_b200_upload_scene(AkrContext *ctx, const AkrSceneDesc *desc) {
     {
         const size_t smem_bvh = used + (size_t)(blob.bvh_depth + 2u) * kBlock * sizeof(int32_t);
         const size_t smem_flat = used;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_trace[TRACE_BVH], k_trace<TRACE_BVH>, kBlock, smem_bvh);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_trace[TRACE_FLAT], k_trace<TRACE_FLAT>, kBlock, smem_flat);
+        if (blob.any_alpha) {
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_trace[TRACE_BVH], k_trace<TRACE_BVH, true>, kBlock, smem_bvh);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_trace[TRACE_FLAT], k_trace<TRACE_FLAT, true>, kBlock, smem_flat);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_trace[TRACE_BVH_SMEM], k_trace<TRACE_BVH_SMEM, true>, kBlock, smem_bvh);
+        } else {
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_trace[TRACE_BVH], k_trace<TRACE_BVH, false>, kBlock, smem_bvh);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_trace[TRACE_FLAT], k_trace<TRACE_FLAT, false>, kBlock, smem_flat);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_trace[TRACE_BVH_SMEM], k_trace<TRACE_BVH_SMEM, false>, kBlock, smem_bvh);
+        }
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_shade[0], k_shade<CLS_LAMBERT>, kBlock, 0);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_shade[1], k_shade<CLS_CONDUCTOR>, kBlock, 0);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_shade[2], k_shade<CLS_GENERAL>, kBlock, 0);
@@ -841,12 +920,14 @@ int akr_b200_render_pass(AkrContext *ctx, uint32_t n_spp, int blocking) {
     P.dbg_first_hits = static_cast<uint32_t *>(ctx->dbg_hits.ptr);
 
     // trace schedule: flat list for tiny scenes that fit in shared memory, BVH otherwise (opts.trace_mode overrides)
-    int trace_mode = (ctx->scene.n_prims <= kFlatMaxPrims && ctx->smem_prims) ? TRACE_FLAT : TRACE_BVH;
-    if (ctx->opts.trace_mode == 1u) trace_mode = TRACE_BVH;
+    const int bvh_mode = ctx->smem_prims ? TRACE_BVH_SMEM : TRACE_BVH;
+    int trace_mode = (ctx->scene.n_prims <= kFlatMaxPrims && ctx->smem_prims) ? TRACE_FLAT : bvh_mode;
+    if (ctx->opts.trace_mode == 1u) trace_mode = bvh_mode;
     if (ctx->opts.trace_mode == 2u && ctx->smem_prims) trace_mode = TRACE_FLAT;
-    const size_t trace_smem = ctx->smem_bytes + (trace_mode == TRACE_BVH ? (size_t)P.stack_depth * kBlock * sizeof(int32_t) : 0);
+    const size_t trace_smem = ctx->smem_bytes + (trace_mode != TRACE_FLAT ? (size_t)P.stack_depth * kBlock * sizeof(int32_t) : 0);
     if (trace_smem > kSmemMax) return fail(ctx, AKR_ERR_UNSUPPORTED, "BVH too deep for the shared-memory traversal stack");
     const bool binned = ctx->opts.sort_by_material != 2u;
+    const bool alpha = ctx->scene.any_alpha != 0u;
     const uint32_t class_mask = ctx->rp.force_diffuse ? (1u << CLS_LAMBERT) : ctx->class_mask;
 
     const bool prof = ctx->opts.profile_stages != 0;
@@ -895,8 +976,16 @@ int akr_b200_render_pass(AkrContext *ctx, uint32_t n_spp, int blocking) {
             AKR_LAUNCH(0, k_raygen, grid_for(ctx, n_paths, 8), 0, P);
             const int g_trace = grid_for(ctx, n_paths, ctx->occ_trace[trace_mode]);
             for (uint32_t depth = 0; depth <= ctx->rp.max_depth; ++depth) {
-                if (trace_mode == TRACE_FLAT) AKR_LAUNCH(1, k_trace<TRACE_FLAT>, g_trace, trace_smem, P, depth);
-                else AKR_LAUNCH(1, k_trace<TRACE_BVH>, g_trace, trace_smem, P, depth);
+                if (trace_mode == TRACE_FLAT) {
+                    if (alpha) AKR_LAUNCH(1, (k_trace<TRACE_FLAT, true>), g_trace, trace_smem, P, depth);
+                    else AKR_LAUNCH(1, (k_trace<TRACE_FLAT, false>), g_trace, trace_smem, P, depth);
+                } else if (trace_mode == TRACE_BVH_SMEM) {
+                    if (alpha) AKR_LAUNCH(1, (k_trace<TRACE_BVH_SMEM, true>), g_trace, trace_smem, P, depth);
+                    else AKR_LAUNCH(1, (k_trace<TRACE_BVH_SMEM, false>), g_trace, trace_smem, P, depth);
+                } else {
+                    if (alpha) AKR_LAUNCH(1, (k_trace<TRACE_BVH, true>), g_trace, trace_smem, P, depth);
+                    else AKR_LAUNCH(1, (k_trace<TRACE_BVH, false>), g_trace, trace_smem, P, depth);
+                }
                 if (!binned) {
                     AKR_LAUNCH(6, k_shade<CLS_ANY>, grid_for(ctx, n_paths, ctx->occ_shade[3]), 0, P, depth);
                     continue;

@@ -139,11 +139,13 @@ struct PrimDecoded {
     uint32_t gid, cls;
     float u, v;
 };
-AKR_HD float fast_div(float a, float b) {
+AKR_HD float fast_rcp(float x) {
 #if defined(__CUDA_ARCH__)
-    return __fdividef(a, b);
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));  // one MUFU; 1 ulp, 0 -> inf
+    return r;
 #else
-    return a / b;
+    return 1.0f / x;
 #endif
 }
 // which triangle of the primitive a point (s, q) belongs to, and that triangle's own barycentrics
@@ -168,25 +170,31 @@ AKR_HD PrimDecoded prim_decode(const PrimRec &p, float s, float q) {
     r.v = iv == 0u ? w0 : (iv == 1u ? w1 : w2);
     return r;
 }
-// One candidate: updates `best` when primitive k is hit at t in (t_min, best.t) by a triangle that is not excluded.
+// One candidate: updates `best` when primitive k is hit at t in (t_min, best.t) by a triangle that is not
+// excluded.  Branch-free on purpose: every lane of a warp runs the same ~30 instructions per candidate and
+// commits with one predicate (a NaN from a parallel ray or a degenerate primitive fails every comparison).
+template <bool ALPHA>
 AKR_HD void prim_test(const SceneView &sc, const PrimRec &p, uint32_t k, f3 o, f3 d, float t_min, uint32_t ex0, uint32_t ex1, PrimHit &best) {
     const float dz = p.n[0] * d.x + p.n[1] * d.y + p.n[2] * d.z;
     const float oz = p.n[0] * o.x + p.n[1] * o.y + p.n[2] * o.z + p.n[3];
-    const float t = fast_div(-oz, dz);
-    if (!(t > t_min && t < best.t)) return;  // also rejects NaN (parallel ray, degenerate primitive)
+    const float t = -oz * fast_rcp(dz);
     const f3 hp = mk3(o.x + t * d.x, o.y + t * d.y, o.z + t * d.z);
     const float s = p.r0[0] * hp.x + p.r0[1] * hp.y + p.r0[2] * hp.z + p.r0[3];
     const float q = p.r1[0] * hp.x + p.r1[1] * hp.y + p.r1[2] * hp.z + p.r1[3];
     const bool pair = p.gid_b != 0xffffffffu;
-    const bool inside = s >= 0.0f && q >= 0.0f && (pair ? (s <= 1.0f && q <= 1.0f) : (s + q <= 1.0f));
-    if (!inside) return;
-    const uint32_t gid = (pair && s < q) ? p.gid_b : p.gid_a;
-    if (gid == ex0 || gid == ex1) return;
-    if (sc.any_alpha) {
-        PrimDecoded dec = prim_decode(p, s, q);
-        if (!alpha_test(sc, dec.gid, dec.u, dec.v)) return;
+    const float m = pair ? fmaxf(s, q) : s + q;  // pair: both <= 1; single: s + q <= 1
+    const uint32_t gid = (pair & (s < q)) ? p.gid_b : p.gid_a;
+    bool ok = (t > t_min) & (t < best.t) & (fminf(s, q) >= 0.0f) & (m <= 1.0f) & (gid != ex0) & (gid != ex1);
+    if (ALPHA) {
+        if (ok) {
+            PrimDecoded dec = prim_decode(p, s, q);
+            ok = alpha_test(sc, dec.gid, dec.u, dec.v);
+        }
     }
-    best = PrimHit{t, s, q, k};
+    best.t = ok ? t : best.t;
+    best.s = ok ? s : best.s;
+    best.q = ok ? q : best.q;
+    best.k = ok ? k : best.k;
 }
 
 // Reference (host / CLS-agnostic) traversal over primitives: same BVH, same candidate order as trace_ray.
@@ -225,7 +233,8 @@ AKR_HD HitRec trace_ray_prims(const SceneView &sc, f3 o, f3 d, float t_min, floa
             uint32_t leaf = (uint32_t)(~node);
             uint32_t first = leaf >> 3, count = leaf & 7u;
             for (uint32_t k = 0; k < count; ++k) {
-                prim_test(sc, sc.prims[first + k], first + k, o, d, t_min, ex0, ex1, best);
+                if (sc.any_alpha) prim_test<true>(sc, sc.prims[first + k], first + k, o, d, t_min, ex0, ex1, best);
+                else prim_test<false>(sc, sc.prims[first + k], first + k, o, d, t_min, ex0, ex1, best);
                 if (ANY_HIT && best.k != 0xffffffffu) break;
             }
             if (ANY_HIT && best.k != 0xffffffffu) break;

@@ -58,11 +58,22 @@ def summarize_clocks(samples):
     return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons}
 
 
+def workload_config(spp, world, wave, trace_mode, sort):
+    return {"workload": f"cbox 1280x720 @ {spp}spp, pmj02bn seed 0, gaussian r=1.5, max_depth 12, rr_depth 5, 64 spp/pass",
+            "parallelism": f"image rows x{world}", "l2": "working set (wave state) > L2; no inter-step reuse (film cleared each step)",
+            "wave_paths": wave or (1 << 22), "trace_mode": trace_mode, "sort": sort}
+
+
+REF_SPP_PER_STEP = 4
+
+
 def run_reference(args, rank, world):
-    """CPU arm: the oracle (restatement of the reference's CPU path) with every host thread, bounded sample."""
+    """Reference arm.  The reference itself cannot be built here (Rust + un-vendored luisa_compute), so
+    this times the CPU oracle — the restatement of its `-d cpu` path — with every host thread, on a bounded sample of
+    the same workload: each step renders REF_SPP_PER_STEP of the 1024 samples per pixel of the full 1280x720 frame
+    (cost is linear in spp, pt.rs:1126-1149).  Rank 0 only; other ranks exit without work."""
     if rank != 0:
         return
-    import numpy as np
     import akari_render_b200 as akr
     from oracle import binding as oracle
     scene = akr.load_scene(os.path.join(ROOT, "scenes", "cbox", "scene.json")).set_resolution(WIDTH, HEIGHT)
@@ -70,24 +81,24 @@ def run_reference(args, rank, world):
     task.pt.spp = SPP
     pmj, bn = akr.sampler_tables()
     cores = os.cpu_count() or 1
-    # one step = 1 spp of the full 1280x720 frame with the 1024-spp sampler configuration (cost is linear in spp)
     vals = []
     for it in range(args.warmup + args.steps):
-        t0 = time.perf_counter()
-        _, st, _ = oracle.render(scene.desc, WIDTH, HEIGHT, task.pt, task.sampler, task.filter, pmj, bn, spp_begin=it, spp_end=it + 1, threads=cores)
-        dt = time.perf_counter() - t0
+        s0 = (it * REF_SPP_PER_STEP) % SPP
+        _, st, _ = oracle.render(scene.desc, WIDTH, HEIGHT, task.pt, task.sampler, task.filter, pmj, bn, spp_begin=s0, spp_end=s0 + REF_SPP_PER_STEP,
+                                 threads=cores)
         if it >= args.warmup:
-            vals.append((st.samples, dt))
+            vals.append((st.samples, st.seconds))  # the oracle's render-loop time == the window the reference times (pt.rs:1126-1157)
     samples = sum(v[0] for v in vals)
     secs = sum(v[1] for v in vals)
     value = samples / secs
     line = {
         "impl": "reference", "metric": "path samples/sec on cbox 1280x720", "value": value, "unit": "samples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(1, args.steps), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "cbox 1280x720 @ 1024spp pmj02bn seed 0, max_depth 12, rr_depth 5 (1 spp of it per step, linear in spp)"},
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(SPP, args.gpus, args.wave, args.trace_mode, args.sort),
         "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} x 1 spp of the 1280x720 frame = {samples} samples"},
+                         "sample": f"{args.steps} steps x {REF_SPP_PER_STEP} of the 1024 spp of the full 1280x720 frame = {samples} samples, "
+                                   f"{secs:.1f} s; CPU oracle (restatement of the reference's -d cpu path), all {cores} host threads"},
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -100,7 +111,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--spp", type=int, default=SPP, help="override for quick experiments (the reported config is 1024)")
-    ap.add_argument("--wave", type=int, default=0, help="paths per wave (0 = engine default)")
+    ap.add_argument("--wave", type=int, default=1 << 26, help="paths in flight per wave (0 = engine default of 4 Mi)")
     ap.add_argument("--trace-mode", type=int, default=0, help="0 auto, 1 BVH, 2 flat list")
     ap.add_argument("--sort", type=int, default=0, help="0/1 per-class shade kernels, 2 one generic shade kernel")
     ap.add_argument("--profile-stages", action="store_true")
@@ -129,15 +140,15 @@ def main():
     # image-plane shard: contiguous row bands; per-GPU work shrinks with N => strong scaling of one frame.
     # Weak scaling as the contract defines it (fixed per-GPU work) = every rank renders the full 1280x720 band count / world? No:
     # the BASELINE metric is quoted on the fixed 1280x720 frame, so the frame is split and `scaling` is "strong".
-    rows = [(HEIGHT * r) // world for r in range(world + 1)]
-    tile = (rows[rank], rows[rank + 1])
+    from akari_render_b200.sharding import gather_bands, max_band_rows, row_bands
+    tile = row_bands(HEIGHT, world)[rank]
     my_rows = tile[1] - tile[0]
     stream = torch.cuda.current_stream().cuda_stream
     pt = akr.PathTracer(local_rank, stream=stream)
     eng = dict(wave_size=args.wave, sort_by_material=args.sort, trace_mode=args.trace_mode)
     pt.set_engine_options(profile_stages=1 if args.profile_stages else 0, **eng)
     pt.upload_scene(scene)
-    max_rows = max(rows[r + 1] - rows[r] for r in range(world))
+    max_rows = max_band_rows(HEIGHT, world)
     img_local = torch.zeros((max_rows, WIDTH, 3), device="cuda", dtype=torch.float32)
     gathered = torch.zeros((world, max_rows, WIDTH, 3), device="cuda", dtype=torch.float32) if world > 1 else None
     host_img = torch.zeros((HEIGHT, WIDTH, 3), dtype=torch.float32).pin_memory()
@@ -152,7 +163,7 @@ def main():
             done += cur
         pt.resolve_into_device(img_local.data_ptr(), my_rows * WIDTH * 3)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, img_local)
+            gather_bands(img_local, HEIGHT, WIDTH, rank, world, dist, out=gathered)  # the one collective: NCCL all_gather of the HDR bands
 
     def barrier():
         torch.cuda.synchronize()
@@ -245,29 +256,26 @@ def main():
     pipeline_gbs = value / world * bytes_per_sample / 1e9
 
     # ---- CPU baseline on rank 0, N = 1 only, bounded sample ----
+    # Timed window = the oracle's own render loop (AkrOracleStats.seconds), the window the reference times itself
+    # (Instant around each dispatch, pt.rs:1126-1157): scene preparation and the Python binding are excluded.
     cpu = None
     if rank == 0 and world == 1:
         from oracle import binding as oracle
         cores = os.cpu_count() or 1
-        probe_rows = 16
-        t0 = time.perf_counter()
-        _, ost, _ = oracle.render(scene.desc, WIDTH, HEIGHT, task.pt, task.sampler, task.filter, pmj, bn, y0=0, y1=probe_rows, spp_begin=0, spp_end=1, threads=cores)
-        rate = ost.samples / (time.perf_counter() - t0)
-        rows_n = int(min(HEIGHT, max(probe_rows, rate * args.cpu_seconds / WIDTH)))
-        t0 = time.perf_counter()
-        _, ost, _ = oracle.render(scene.desc, WIDTH, HEIGHT, task.pt, task.sampler, task.filter, pmj, bn, y0=0, y1=rows_n, spp_begin=0, spp_end=1, threads=cores)
-        dt = time.perf_counter() - t0
-        cpu = {"value": ost.samples / dt, "unit": "samples/s", "cores": cores, "kind": "port",
-               "sample": f"rows 0..{rows_n} of the 1280x720 frame, 1 of 1024 spp ({ost.samples} samples, {dt:.1f} s)"}
+        _, ost, _ = oracle.render(scene.desc, WIDTH, HEIGHT, task.pt, task.sampler, task.filter, pmj, bn, spp_begin=0, spp_end=1, threads=cores)
+        rate = ost.samples / max(ost.seconds, 1e-6)
+        n_spp = int(min(64, max(1, rate * args.cpu_seconds / (WIDTH * HEIGHT))))
+        _, ost, _ = oracle.render(scene.desc, WIDTH, HEIGHT, task.pt, task.sampler, task.filter, pmj, bn, spp_begin=1, spp_end=1 + n_spp, threads=cores)
+        cpu = {"value": ost.samples / ost.seconds, "unit": "samples/s", "cores": cores, "kind": "port",
+               "sample": f"{n_spp} of the 1024 spp of the full 1280x720 frame ({ost.samples} samples, {ost.seconds:.1f} s), CPU oracle on all "
+                         f"{cores} host threads"}
 
     if rank == 0:
         line = {
             "metric": "path samples/sec on cbox 1280x720", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"cbox 1280x720 @ {spp}spp, pmj02bn seed 0, gaussian r=1.5, max_depth 12, rr_depth 5, 64 spp/pass",
-                       "parallelism": f"image rows x{world}", "l2": "working set (wave state) > L2; no inter-step reuse (film cleared each step)",
-                       "wave_paths": args.wave or (1 << 22), "trace_mode": args.trace_mode, "sort": args.sort},
+            "config": workload_config(spp, world, args.wave, args.trace_mode, args.sort),
             "clocks": summarize_clocks(clocks),
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(st.kernel_launches),

@@ -89,34 +89,51 @@ def summarize_rep(path, out):
 
 
 def summarize_list(path, out):
-    rows = []
+    """Launch list (gpu__time_duration.sum, optionally dram__bytes_read.sum / dram__bytes_write.sum per launch)."""
+    import json
     with open(path) as f:
         txt = [l for l in f if l.startswith('"')]
     rd = csv.reader(txt)
     hdr = next(rd)
     ix = {h: i for i, h in enumerate(hdr)}
-    agg = defaultdict(lambda: [0, 0.0, 0.0])
-    total = 0.0
-    n = 0
+    scale_t = {"ns": 1e-3, "nsecond": 1e-3, "us": 1.0, "usecond": 1.0, "ms": 1e3, "msecond": 1e3, "s": 1e6, "second": 1e6}
+    scale_b = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    per_launch = {}
+    order = []
     for r in rd:
-        if r[ix["Metric Name"]] != "gpu__time_duration.sum":
-            continue
-        t = float(r[ix["Metric Value"]].replace(",", ""))
-        unit = r[ix["Metric Unit"]]
-        t_us = t / 1e3 if unit in ("ns", "nsecond") else (t if unit in ("us", "usecond") else t * 1e3)
-        name = r[ix["Kernel Name"]].split("(")[0].replace("<unnamed>::", "")
-        a = agg[name]
-        a[0] += 1
-        a[1] += t_us
-        a[2] = max(a[2], t_us)
-        total += t_us
-        n += 1
-    lines = [f"# launch list from {path.split('/')[-1]}: {n} launches, {total / 1e3:.3f} ms of kernel time "
-             f"(ncu --metrics gpu__time_duration.sum --clock-control none; serialised, cold-cache)", "",
-             f"{'kernel':<34}{'launches':>9}{'total ms':>12}{'mean us':>11}{'max us':>11}{'share':>8}"]
-    for name, a in sorted(agg.items(), key=lambda x: -x[1][1]):
-        lines.append(f"{name:<34}{a[0]:>9}{a[1] / 1e3:>12.3f}{a[1] / a[0]:>11.1f}{a[2]:>11.1f}{100 * a[1] / total:>7.1f}%")
+        lid = r[ix["ID"]]
+        name = r[ix["Kernel Name"]].split("(")[0].replace("<unnamed>::", "").replace("void ", "")
+        if lid not in per_launch:
+            per_launch[lid] = {"name": name, "us": 0.0, "rd": 0.0, "wr": 0.0}
+            order.append(lid)
+        v = float(r[ix["Metric Value"]].replace(",", ""))
+        m, u = r[ix["Metric Name"]], r[ix["Metric Unit"]]
+        if m == "gpu__time_duration.sum":
+            per_launch[lid]["us"] = v * scale_t.get(u, 1.0)
+        elif m == "dram__bytes_read.sum":
+            per_launch[lid]["rd"] = v * scale_b.get(u, 1.0)
+        elif m == "dram__bytes_write.sum":
+            per_launch[lid]["wr"] = v * scale_b.get(u, 1.0)
+    agg = defaultdict(lambda: {"launches": 0, "us": 0.0, "max_us": 0.0, "dram_read": 0.0, "dram_write": 0.0})
+    total = 0.0
+    for lid in order:
+        L = per_launch[lid]
+        a = agg[L["name"]]
+        a["launches"] += 1
+        a["us"] += L["us"]
+        a["max_us"] = max(a["max_us"], L["us"])
+        a["dram_read"] += L["rd"]
+        a["dram_write"] += L["wr"]
+        total += L["us"]
+    lines = [f"# launch list from {path.split('/')[-1]}: {len(order)} launches, {total / 1e3:.3f} ms of kernel time "
+             f"(ncu --clock-control none; launches are serialised and cold-cache, so only the SHARES are comparable with bench.py)", "",
+             f"{'kernel':<34}{'launches':>9}{'total ms':>12}{'mean us':>11}{'max us':>11}{'share':>8}{'DRAM rd MB':>13}{'DRAM wr MB':>13}{'DRAM B/launch':>15}"]
+    for name, a in sorted(agg.items(), key=lambda x: -x[1]["us"]):
+        lines.append(f"{name:<34}{a['launches']:>9}{a['us'] / 1e3:>12.3f}{a['us'] / a['launches']:>11.1f}{a['max_us']:>11.1f}"
+                     f"{100 * a['us'] / total:>7.1f}%{a['dram_read'] / 1e6:>13.1f}{a['dram_write'] / 1e6:>13.1f}"
+                     f"{(a['dram_read'] + a['dram_write']) / a['launches']:>15.0f}")
     open(out, "w").write("\n".join(lines) + "\n")
+    json.dump({k: v for k, v in agg.items()}, open(out.rsplit(".", 1)[0] + ".json", "w"), indent=1)
 
 
 if __name__ == "__main__":
