@@ -36,7 +36,6 @@ constexpr uint32_t kMaxDepthSlots = 66;           // counters for depth 0 .. 64 
 constexpr uint32_t kCtrStride = 8;
 constexpr uint32_t kSmemSceneBudget = 48 * 1024;  // bytes of BVH nodes + triangles staged per CTA
 constexpr uint32_t kSmemMax = 200 * 1024;         // opt-in ceiling for the trace kernels (staging + stacks)
-constexpr uint32_t kFlatMaxPrims = 64;            // scenes this small are traced as one flat primitive list
 
 // ------------------------------------------------------------------------------------------------
 // wave state in HBM: structure-of-arrays of 16-byte records (one LDG.128 / STG.128 per record, fully
@@ -77,6 +76,7 @@ struct LaunchParams {
     uint32_t scene_smem_nodes;  // nodes staged in shared memory
     uint32_t scene_smem_prims;  // 1 when all primitives are staged too
     uint32_t stack_depth;       // traversal stack entries per thread (shared memory)
+    uint32_t stage_flat;        // stage the pairs-first flat list instead of the BVH-ordered primitives
     uint32_t *dbg_first_hits;   // optional [n_film_pixels][2]
 };
 
@@ -199,7 +199,7 @@ __device__ __forceinline__ TraceSmem stage_scene(const LaunchParams &P, unsigned
     if (threadIdx.x == 0 && (node_bytes + tri_bytes) > 0) {
         mbar_expect_tx(bar, node_bytes + tri_bytes);
         if (node_bytes) tma_bulk_g2s(s_nodes, P.scene.nodes, node_bytes, bar);
-        if (tri_bytes) tma_bulk_g2s(s_tris, P.scene.prims, tri_bytes, bar);
+        if (tri_bytes) tma_bulk_g2s(s_tris, P.stage_flat ? P.scene.flat_prims : P.scene.prims, tri_bytes, bar);
     }
     if ((node_bytes + tri_bytes) > 0) mbar_wait(bar, 0);
     TraceSmem t;
@@ -235,11 +235,23 @@ __device__ __forceinline__ DevHit trace_dev(const LaunchParams &P, const TraceSm
     PrimHit best{active ? t_max : 0.0f, 0.0f, 0.0f, 0xffffffffu};  // an idle lane accepts nothing (t < 0 is never true for t > t_min = 0)
     constexpr bool PRIMS_SHARED = MODE != TRACE_BVH;
     if (MODE == TRACE_FLAT) {
-        const uint32_t n = sc.n_prims;
+        // the staged list is sorted pairs first, so neither loop decides the primitive kind per candidate
+        const uint32_t n = sc.n_prims, n_pairs = sc.n_flat_pairs;
+        bool all_done = false;
 #pragma unroll 2
-        for (uint32_t k = 0; k < n; ++k) {
-            prim_test<ALPHA>(sc, load_prim<true>(ts.prims, nullptr, k), k, o, d, t_min, ex0, ex1, best);
-            if (ANY_HIT && (k & 3u) == 3u && __all_sync(0xffffffffu, !active || best.k != 0xffffffffu)) break;
+        for (uint32_t k = 0; k < n_pairs; ++k) {
+            prim_test<ALPHA, 1>(sc, load_prim<true>(ts.prims, nullptr, k), k, o, d, t_min, ex0, ex1, best);
+            if (ANY_HIT && (k & 7u) == 7u && __all_sync(0xffffffffu, !active || best.k != 0xffffffffu)) {
+                all_done = true;
+                break;
+            }
+        }
+        if (!all_done) {
+#pragma unroll 2
+            for (uint32_t k = n_pairs; k < n; ++k) {
+                prim_test<ALPHA, 2>(sc, load_prim<true>(ts.prims, nullptr, k), k, o, d, t_min, ex0, ex1, best);
+                if (ANY_HIT && (k & 7u) == 7u && __all_sync(0xffffffffu, !active || best.k != 0xffffffffu)) break;
+            }
         }
     } else if (active) {
         const f3 inv_d = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
@@ -400,12 +412,16 @@ template <int MODE, bool ALPHA> __global__ void __launch_bounds__(kBlock) k_trac
 #ifndef AKR_SHADE_MINB_CONDUCTOR
 #define AKR_SHADE_MINB_CONDUCTOR 3
 #endif
+#ifndef AKR_SHADE_BLOCK
+#define AKR_SHADE_BLOCK 256
+#endif
+constexpr int kShadeBlock = AKR_SHADE_BLOCK;
 template <int CLS> struct ShadeLaunch {
     static constexpr int kMinBlocks = CLS == CLS_LAMBERT ? AKR_SHADE_MINB_LAMBERT : (CLS == CLS_CONDUCTOR ? AKR_SHADE_MINB_CONDUCTOR : 1);
 };
 
 // One shade kernel per material class; `CLS_ANY` (unsorted: every hit in slot order) exists for A/B runs.
-template <int CLS> __global__ void __launch_bounds__(kBlock, ShadeLaunch<CLS>::kMinBlocks) k_shade(const __grid_constant__ LaunchParams P, uint32_t depth) {
+template <int CLS> __global__ void __launch_bounds__(kShadeBlock, ShadeLaunch<CLS>::kMinBlocks) k_shade(const __grid_constant__ LaunchParams P, uint32_t depth) {
     uint32_t *ctr = P.counters + depth * kCtrStride;
     const uint32_t n = CLS == CLS_ANY ? ctr[0] : ctr[2u + (CLS == CLS_ANY ? 0 : CLS)];
     const uint2 *slots = CLS == CLS_ANY ? nullptr : P.cls.idx[CLS == CLS_ANY ? 0 : CLS];
@@ -516,7 +532,7 @@ struct AkrContext {
     bool albedo_ready = false;
 
     // scene
-    DeviceBuffer nodes, prims, shade, instances, materials, lights, alias_j, alias_t, alias_pdf, corner_n, corner_t;
+    DeviceBuffer nodes, prims, flat_prims, shade, instances, materials, lights, alias_j, alias_t, alias_pdf, corner_n, corner_t;
     SceneView scene{};
     CornerAttribs corners{};
     bool scene_ready = false;
@@ -689,7 +705,7 @@ void akr_b200_destroy(AkrContext *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    for (DeviceBuffer *b : {&ctx->pmj, &ctx->bn, &ctx->albedo, &ctx->nodes, &ctx->prims, &ctx->shade, &ctx->instances, &ctx->materials, &ctx->lights,
+    for (DeviceBuffer *b : {&ctx->pmj, &ctx->bn, &ctx->albedo, &ctx->nodes, &ctx->prims, &ctx->flat_prims, &ctx->shade, &ctx->instances, &ctx->materials, &ctx->lights,
                             &ctx->alias_j, &ctx->alias_t, &ctx->alias_pdf, &ctx->corner_n, &ctx->corner_t, &ctx->film, &ctx->wave_mem, &ctx->counters,
                             &ctx->totals, &ctx->dbg_hits})
         dev_free(*b);
@@ -747,6 +763,7 @@ int akr_b200_upload_scene(AkrContext *ctx, const AkrSceneDesc *desc) {
     ctx->render_ready = false;
     if ((rc = upload_vec(ctx, ctx->nodes, blob.nodes)) != AKR_OK) return rc;
     if ((rc = upload_vec(ctx, ctx->prims, blob.prims)) != AKR_OK) return rc;
+    if ((rc = upload_vec(ctx, ctx->flat_prims, blob.flat_prims)) != AKR_OK) return rc;
     if ((rc = upload_vec(ctx, ctx->shade, blob.shade)) != AKR_OK) return rc;
     if ((rc = upload_vec(ctx, ctx->instances, blob.instances)) != AKR_OK) return rc;
     if ((rc = upload_vec(ctx, ctx->materials, blob.materials)) != AKR_OK) return rc;
@@ -760,6 +777,8 @@ int akr_b200_upload_scene(AkrContext *ctx, const AkrSceneDesc *desc) {
     SceneView &v = ctx->scene;
     v.nodes = static_cast<const BvhNode *>(ctx->nodes.ptr);
     v.prims = static_cast<const PrimRec *>(ctx->prims.ptr);
+    v.flat_prims = blob.flat_prims.empty() ? nullptr : static_cast<const PrimRec *>(ctx->flat_prims.ptr);
+    v.n_flat_pairs = blob.n_flat_pairs;
     v.tris = nullptr;  // the Moeller-Trumbore triangle list is host-simulation data; the kernels intersect primitives
     v.shade = static_cast<const TriShade *>(ctx->shade.ptr);
     v.instances = static_cast<const InstanceRec *>(ctx->instances.ptr);
@@ -804,10 +823,10 @@ int akr_b200_upload_scene(AkrContext *ctx, const AkrSceneDesc *desc) {
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_trace[TRACE_FLAT], k_trace<TRACE_FLAT, false>, kBlock, smem_flat);
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_trace[TRACE_BVH_SMEM], k_trace<TRACE_BVH_SMEM, false>, kBlock, smem_bvh);
         }
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_shade[0], k_shade<CLS_LAMBERT>, kBlock, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_shade[1], k_shade<CLS_CONDUCTOR>, kBlock, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_shade[2], k_shade<CLS_GENERAL>, kBlock, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_shade[3], k_shade<CLS_ANY>, kBlock, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_shade[0], k_shade<CLS_LAMBERT>, kShadeBlock, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_shade[1], k_shade<CLS_CONDUCTOR>, kShadeBlock, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_shade[2], k_shade<CLS_GENERAL>, kShadeBlock, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_shade[3], k_shade<CLS_ANY>, kShadeBlock, 0);
         for (int &o : ctx->occ_trace) o = std::max(o, 1);
         for (int &o : ctx->occ_shade) o = std::max(o, 1);
     }
@@ -921,9 +940,11 @@ int akr_b200_render_pass(AkrContext *ctx, uint32_t n_spp, int blocking) {
 
     // trace schedule: flat list for tiny scenes that fit in shared memory, BVH otherwise (opts.trace_mode overrides)
     const int bvh_mode = ctx->smem_prims ? TRACE_BVH_SMEM : TRACE_BVH;
-    int trace_mode = (ctx->scene.n_prims <= kFlatMaxPrims && ctx->smem_prims) ? TRACE_FLAT : bvh_mode;
+    const bool flat_ok = ctx->scene.flat_prims != nullptr && ctx->smem_prims;
+    int trace_mode = flat_ok ? TRACE_FLAT : bvh_mode;
     if (ctx->opts.trace_mode == 1u) trace_mode = bvh_mode;
-    if (ctx->opts.trace_mode == 2u && ctx->smem_prims) trace_mode = TRACE_FLAT;
+    if (ctx->opts.trace_mode == 2u && flat_ok) trace_mode = TRACE_FLAT;
+    P.stage_flat = trace_mode == TRACE_FLAT ? 1u : 0u;
     const size_t trace_smem = ctx->smem_bytes + (trace_mode != TRACE_FLAT ? (size_t)P.stack_depth * kBlock * sizeof(int32_t) : 0);
     if (trace_smem > kSmemMax) return fail(ctx, AKR_ERR_UNSUPPORTED, "BVH too deep for the shared-memory traversal stack");
     const bool binned = ctx->opts.sort_by_material != 2u;
@@ -954,13 +975,14 @@ int akr_b200_render_pass(AkrContext *ctx, uint32_t n_spp, int blocking) {
         ctx->stats.kernel_launches += 1;
         ctx->stats.launches_kernel[stage] += 1;
     };
-#define AKR_LAUNCH(stage, kernel, grid, smem, ...)                                                            \
+#define AKR_LAUNCH(stage, kernel, grid, smem, ...) AKR_LAUNCH_B(stage, kernel, grid, kBlock, smem, __VA_ARGS__)
+#define AKR_LAUNCH_B(stage, kernel, grid, block, smem, ...)                                                   \
     do {                                                                                                      \
         if (prof) {                                                                                           \
             if (mark(stage) != AKR_OK) return fail(ctx, AKR_ERR_CUDA, "cudaEventCreate failed");              \
             cudaEventRecord(ctx->stage_events[marks.back().ev], ctx->stream);                                  \
         }                                                                                                     \
-        kernel<<<(grid), kBlock, (smem), ctx->stream>>>(__VA_ARGS__);                                          \
+        kernel<<<(grid), (block), (smem), ctx->stream>>>(__VA_ARGS__);                                         \
         if (prof) cudaEventRecord(ctx->stage_events[marks.back().ev + 1], ctx->stream);                        \
         count_launch(stage);                                                                                  \
     } while (0)
@@ -975,6 +997,10 @@ int akr_b200_render_pass(AkrContext *ctx, uint32_t n_spp, int blocking) {
             const uint32_t n_paths = n_pix * k;
             AKR_LAUNCH(0, k_raygen, grid_for(ctx, n_paths, 8), 0, P);
             const int g_trace = grid_for(ctx, n_paths, ctx->occ_trace[trace_mode]);
+            auto shade_grid = [&](int variant) {
+                uint32_t need = (n_paths + kShadeBlock - 1) / kShadeBlock, capn = (uint32_t)(ctx->sm_count * ctx->occ_shade[variant]);
+                return (int)std::max(1u, std::min(need, capn));
+            };
             for (uint32_t depth = 0; depth <= ctx->rp.max_depth; ++depth) {
                 if (trace_mode == TRACE_FLAT) {
                     if (alpha) AKR_LAUNCH(1, (k_trace<TRACE_FLAT, true>), g_trace, trace_smem, P, depth);
@@ -987,12 +1013,12 @@ int akr_b200_render_pass(AkrContext *ctx, uint32_t n_spp, int blocking) {
                     else AKR_LAUNCH(1, (k_trace<TRACE_BVH, false>), g_trace, trace_smem, P, depth);
                 }
                 if (!binned) {
-                    AKR_LAUNCH(6, k_shade<CLS_ANY>, grid_for(ctx, n_paths, ctx->occ_shade[3]), 0, P, depth);
+                    AKR_LAUNCH_B(6, k_shade<CLS_ANY>, shade_grid(3), kShadeBlock, 0, P, depth);
                     continue;
                 }
-                if (class_mask & (1u << CLS_LAMBERT)) AKR_LAUNCH(2, k_shade<CLS_LAMBERT>, grid_for(ctx, n_paths, ctx->occ_shade[0]), 0, P, depth);
-                if (class_mask & (1u << CLS_CONDUCTOR)) AKR_LAUNCH(3, k_shade<CLS_CONDUCTOR>, grid_for(ctx, n_paths, ctx->occ_shade[1]), 0, P, depth);
-                if (class_mask & (1u << CLS_GENERAL)) AKR_LAUNCH(6, k_shade<CLS_GENERAL>, grid_for(ctx, n_paths, ctx->occ_shade[2]), 0, P, depth);
+                if (class_mask & (1u << CLS_LAMBERT)) AKR_LAUNCH_B(2, k_shade<CLS_LAMBERT>, shade_grid(0), kShadeBlock, 0, P, depth);
+                if (class_mask & (1u << CLS_CONDUCTOR)) AKR_LAUNCH_B(3, k_shade<CLS_CONDUCTOR>, shade_grid(1), kShadeBlock, 0, P, depth);
+                if (class_mask & (1u << CLS_GENERAL)) AKR_LAUNCH_B(6, k_shade<CLS_GENERAL>, shade_grid(2), kShadeBlock, 0, P, depth);
             }
             AKR_LAUNCH(4, k_accumulate, grid_for(ctx, n_pix, 8), 0, P);
             k_fold_counters<<<1, 128, 0, ctx->stream>>>(P.counters, static_cast<unsigned long long *>(ctx->totals.ptr), ctx->rp.max_depth + 2u);
@@ -1001,6 +1027,7 @@ int akr_b200_render_pass(AkrContext *ctx, uint32_t n_spp, int blocking) {
         }
     }
 #undef AKR_LAUNCH
+#undef AKR_LAUNCH_B
     AKR_CUDA(ctx, cudaEventRecord(ctx->ev_stop, ctx->stream));
     AKR_CUDA(ctx, cudaGetLastError());
     ctx->spp_done += n_spp;

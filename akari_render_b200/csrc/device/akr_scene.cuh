@@ -107,6 +107,8 @@ struct CameraRec {
 struct SceneView {
     const BvhNode *nodes;      // leaves address primitives: ~c = (first_prim << 3) | count
     const PrimRec *prims;      // BVH leaf order (CUDA kernels)
+    const PrimRec *flat_prims; // small scenes only: the same primitives sorted pairs first (flat trace mode), else nullptr
+    uint32_t n_flat_pairs;
     const TriGeom *tris;       // two slots per primitive, gid 0xffffffff = empty (Moeller-Trumbore path of the host simulation)
     const TriShade *shade;
     const InstanceRec *instances;

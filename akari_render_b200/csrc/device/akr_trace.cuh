@@ -173,7 +173,8 @@ AKR_HD PrimDecoded prim_decode(const PrimRec &p, float s, float q) {
 // One candidate: updates `best` when primitive k is hit at t in (t_min, best.t) by a triangle that is not
 // excluded.  Branch-free on purpose: every lane of a warp runs the same ~30 instructions per candidate and
 // commits with one predicate (a NaN from a parallel ray or a degenerate primitive fails every comparison).
-template <bool ALPHA>
+// KIND: 0 = decide per primitive, 1 = known pair, 2 = known single (the flat list is sorted pairs first).
+template <bool ALPHA, int KIND = 0>
 AKR_HD void prim_test(const SceneView &sc, const PrimRec &p, uint32_t k, f3 o, f3 d, float t_min, uint32_t ex0, uint32_t ex1, PrimHit &best) {
     const float dz = p.n[0] * d.x + p.n[1] * d.y + p.n[2] * d.z;
     const float oz = p.n[0] * o.x + p.n[1] * o.y + p.n[2] * o.z + p.n[3];
@@ -181,7 +182,7 @@ AKR_HD void prim_test(const SceneView &sc, const PrimRec &p, uint32_t k, f3 o, f
     const f3 hp = mk3(o.x + t * d.x, o.y + t * d.y, o.z + t * d.z);
     const float s = p.r0[0] * hp.x + p.r0[1] * hp.y + p.r0[2] * hp.z + p.r0[3];
     const float q = p.r1[0] * hp.x + p.r1[1] * hp.y + p.r1[2] * hp.z + p.r1[3];
-    const bool pair = p.gid_b != 0xffffffffu;
+    const bool pair = KIND == 1 ? true : (KIND == 2 ? false : p.gid_b != 0xffffffffu);
     const float m = pair ? fmaxf(s, q) : s + q;  // pair: both <= 1; single: s + q <= 1
     const uint32_t gid = (pair & (s < q)) ? p.gid_b : p.gid_a;
     bool ok = (t > t_min) & (t < best.t) & (fminf(s, q) >= 0.0f) & (m <= 1.0f) & (gid != ex0) & (gid != ex1);

@@ -868,6 +868,13 @@ int build_scene_blob(const AkrSceneDesc &d, HostSceneBlob &out, std::string &err
         uint32_t cls_b = hp.gid_b == 0xffffffffu ? 0u : shade_class_of(out.materials[out.shade[hp.gid_b].mat].type);
         pr.meta = hp.iu_a | (hp.iv_a << 2) | (hp.iu_b << 4) | (hp.iv_b << 6) | (cls_a << 8) | (cls_b << 10);
     }
+    if (n_prims <= kFlatMaxPrims) {
+        for (const PrimRec &pr : out.prims)
+            if (pr.gid_b != 0xffffffffu) out.flat_prims.push_back(pr);
+        out.n_flat_pairs = static_cast<uint32_t>(out.flat_prims.size());
+        for (const PrimRec &pr : out.prims)
+            if (pr.gid_b == 0xffffffffu) out.flat_prims.push_back(pr);
+    }
     // flatten: breadth-first over inner nodes; a leaf root becomes an inner node with an empty second child
     auto leaf_code = [&](const BuildNode &n) { return ~static_cast<int32_t>((n.first << 3) | n.count); };
     std::vector<int32_t> inner_of(bnodes.size(), -1);
@@ -956,6 +963,8 @@ SceneView host_scene_view(const HostSceneBlob &b, const float *albedo_table) {
     std::memset(&v, 0, sizeof(v));
     v.nodes = b.nodes.data();
     v.prims = b.prims.data();
+    v.flat_prims = b.flat_prims.empty() ? nullptr : b.flat_prims.data();
+    v.n_flat_pairs = b.n_flat_pairs;
     v.tris = b.tris.data();
     v.shade = b.shade.data();
     v.instances = b.instances.data();

@@ -15,9 +15,13 @@
 
 namespace akr {
 
+constexpr uint32_t kFlatMaxPrims = 64;  // scenes this small are traced as one flat primitive list
+
 struct HostSceneBlob {
     std::vector<BvhNode> nodes;
     std::vector<PrimRec> prims;       // BVH leaf order (what the CUDA kernels intersect)
+    std::vector<PrimRec> flat_prims;  // scenes of <= kFlatMaxPrims primitives: the same records, pairs first (flat trace mode)
+    uint32_t n_flat_pairs = 0;
     std::vector<TriGeom> tris;        // two per primitive, same order (host simulation's Moeller-Trumbore path)
     std::vector<TriShade> shade;      // by global triangle id
     std::vector<InstanceRec> instances;

@@ -141,8 +141,8 @@ def test_bvh_and_flat_trace_modes_agree(akr, cbox, cbox_task):
 
 def test_full_size_frame_properties(akr, cbox, cbox_task):
     """BASELINE config size (1280x720): size-independent properties instead of an oracle run — film weights equal
-    spp everywhere, everything finite, a second render is bit-identical, and a 4x4-block downsample stays close to
-    the same camera rendered at 320x180 (same scene, independent sample sets)."""
+    spp everywhere, everything finite, a second render is bit-identical, and the frame's mean radiance agrees with
+    the same camera rendered at 320x180 @ 256 spp (independent sample sets)."""
     w, h = 1280, 720
     scene, task = cbox(w, h), cbox_task(16)
     film, st = _gpu_film(akr, scene, task)
@@ -152,9 +152,11 @@ def test_full_size_frame_properties(akr, cbox, cbox_task):
     assert np.isfinite(film.data).all() and (film.data[:3 * n] >= 0).all()
     again, _ = _gpu_film(akr, scene, task)
     assert np.array_equal(again.data, film.data)
-    big = film.to_rgb().reshape(h // 4, 4, w // 4, 4, 3).mean(axis=(1, 3))
-    small_scene = cbox(w // 4, h // 4)
-    small, _ = _gpu_film(akr, small_scene, cbox_task(256))
-    rel = np.linalg.norm(big - small.to_rgb()) / np.linalg.norm(small.to_rgb())
-    print(f"1280x720 block means vs 320x180 @256spp: rel-L2 {rel:.3e}")
-    assert rel < 0.08
+    # mean radiance per channel against an independent estimate (other resolution => other pixels, other
+    # blue-noise offsets): 14.7 M vs 14.7 M samples, Monte-Carlo error of the means ~1e-3
+    small, _ = _gpu_film(akr, cbox(w // 4, h // 4), cbox_task(256))
+    m_big = film.to_rgb().reshape(-1, 3).mean(axis=0)
+    m_small = small.to_rgb().reshape(-1, 3).mean(axis=0)
+    rel = np.abs(m_big - m_small) / m_small
+    print(f"mean radiance 1280x720@16 {m_big} vs 320x180@256 {m_small}: rel {rel}")
+    assert (rel < 0.02).all()
