@@ -173,6 +173,21 @@ template <bool SHARED> __device__ __forceinline__ PrimRec load_prim(uint32_t s_p
     p._pad = 0u;
     return p;
 }
+// primitive h (0 / 1) of a staged PrimBlock2, back in PrimRec form
+__device__ __forceinline__ PrimRec load_block_prim(uint32_t block_addr, uint32_t h) {
+    PrimRec p;
+    const uint32_t a = block_addr + h * 4u;
+    for (int c = 0; c < 4; ++c) {
+        p.n[c] = __int_as_float(lds32(a + c * 8u));
+        p.r0[c] = __int_as_float(lds32(a + 32u + c * 8u));
+        p.r1[c] = __int_as_float(lds32(a + 64u + c * 8u));
+    }
+    p.gid_a = (uint32_t)lds32(block_addr + 96u + h * 8u);
+    p.gid_b = (uint32_t)lds32(block_addr + 100u + h * 8u);
+    p.meta = (uint32_t)lds32(block_addr + 112u + h * 4u);
+    p._pad = 0u;
+    return p;
+}
 template <bool SHARED> __device__ __forceinline__ BvhNode load_node(uint32_t s_nodes, const BvhNode *g_nodes, uint32_t k) {
     float4 a, b, c, d;
     load64<SHARED>(s_nodes + k * (uint32_t)sizeof(BvhNode), g_nodes + k, a, b, c, d);
@@ -188,7 +203,8 @@ template <bool SHARED> __device__ __forceinline__ BvhNode load_node(uint32_t s_n
 // Stages nodes[0 .. n_nodes) and (optionally) all primitives behind `smem` with one TMA bulk copy each.
 __device__ __forceinline__ TraceSmem stage_scene(const LaunchParams &P, unsigned char *smem, uint64_t *bar) {
     const uint32_t node_bytes = P.scene_smem_nodes * (uint32_t)sizeof(BvhNode);
-    const uint32_t tri_bytes = P.scene_smem_prims ? P.scene.n_prims * (uint32_t)sizeof(PrimRec) : 0u;
+    const uint32_t tri_bytes = P.stage_flat ? (P.scene.n_pair_blocks + P.scene.n_single_blocks) * (uint32_t)sizeof(PrimBlock2)
+                                            : (P.scene_smem_prims ? P.scene.n_prims * (uint32_t)sizeof(PrimRec) : 0u);
     BvhNode *s_nodes = reinterpret_cast<BvhNode *>(smem);
     PrimRec *s_tris = reinterpret_cast<PrimRec *>(smem + node_bytes);
     if (threadIdx.x == 0) {
@@ -199,7 +215,7 @@ __device__ __forceinline__ TraceSmem stage_scene(const LaunchParams &P, unsigned
     if (threadIdx.x == 0 && (node_bytes + tri_bytes) > 0) {
         mbar_expect_tx(bar, node_bytes + tri_bytes);
         if (node_bytes) tma_bulk_g2s(s_nodes, P.scene.nodes, node_bytes, bar);
-        if (tri_bytes) tma_bulk_g2s(s_tris, P.stage_flat ? P.scene.flat_prims : P.scene.prims, tri_bytes, bar);
+        if (tri_bytes) tma_bulk_g2s(s_tris, P.stage_flat ? (const void *)P.scene.flat_blocks : (const void *)P.scene.prims, tri_bytes, bar);
     }
     if ((node_bytes + tri_bytes) > 0) mbar_wait(bar, 0);
     TraceSmem t;
@@ -226,6 +242,144 @@ enum TraceMode : int { TRACE_BVH = 0, TRACE_FLAT = 1, TRACE_BVH_SMEM = 2 };
 // TRACE_FLAT: every lane tests every primitive in list order (shared-memory broadcast reads, no divergence,
 // no stack) — the cheapest schedule when the whole scene is a few dozen primitives.
 // TRACE_BVH : while-while traversal; lanes first descend to their next leaf together, then test leaves.
+// ---- flat mode with packed FP32 (FFMA2) ----------------------------------------------------------------
+// Blackwell issues fma.rn.f32x2: one instruction = two FP32 FMAs per lane.  The staged PrimBlock2 layout puts
+// the same coefficient of two primitives side by side, so the 16 FMAs of a primitive test advance TWO
+// primitives per instruction (the FMA pipe was the limiter of the scalar loop).  Only (t, k) of the best
+// candidate are kept; (s, q) are recomputed once after the loop with the same operation order.
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk2(float lo, float hi) {
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(u64 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+    u64 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
+    u64 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ u64 add2(u64 a, u64 b) {
+    u64 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ void lds2x64(uint32_t addr, u64 &a, u64 &b) {
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr));
+}
+__device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float rcp_neg(float x) {  // 1 / (-x): the negation folds into the MUFU operand modifier
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-x));
+    return r;
+}
+
+// one PrimBlock2 (two primitives of the same kind) against one ray
+template <bool PAIR, bool ALPHA>
+__device__ __forceinline__ void flat2_block(const SceneView &sc, uint32_t addr, uint32_t b, f3 o, f3 d, float t_min, uint32_t ex0, uint32_t ex1, float &best_t,
+                                            uint32_t &best_k) {
+    const u64 ox2 = pk2(o.x, o.x), oy2 = pk2(o.y, o.y), oz2 = pk2(o.z, o.z);  // ptxas turns these into the scalar-broadcast operand form
+    const u64 dx2 = pk2(d.x, d.x), dy2 = pk2(d.y, d.y), dz2 = pk2(d.z, d.z);
+    u64 n0, n1, n2, nw, r00, r01, r02, r0w, r10, r11, r12, r1w;
+    lds2x64(addr, n0, n1);
+    lds2x64(addr + 16u, n2, nw);
+    lds2x64(addr + 32u, r00, r01);
+    lds2x64(addr + 48u, r02, r0w);
+    lds2x64(addr + 64u, r10, r11);
+    lds2x64(addr + 80u, r12, r1w);
+    const uint4 g = lds_u4(addr + 96u);
+    const u64 den = fma2(n2, dz2, fma2(n1, dy2, mul2(n0, dx2)));
+    const u64 num = fma2(n2, oz2, fma2(n1, oy2, fma2(n0, ox2, nw)));
+    float den0, den1;
+    upk2(den, den0, den1);
+    const u64 t2 = mul2(num, pk2(rcp_neg(den0), rcp_neg(den1)));  // t = -(n.o + nw) / (n.d)
+    const u64 hx = fma2(t2, dx2, ox2), hy = fma2(t2, dy2, oy2), hz = fma2(t2, dz2, oz2);
+    const u64 s2 = fma2(r00, hx, fma2(r01, hy, fma2(r02, hz, r0w)));
+    const u64 q2 = fma2(r10, hx, fma2(r11, hy, fma2(r12, hz, r1w)));
+    float t0, t1, s0, s1, q0, q1;
+    upk2(t2, t0, t1);
+    upk2(s2, s0, s1);
+    upk2(q2, q0, q1);
+    bool in0, in1;
+    uint32_t gid0, gid1;
+    if (PAIR) {  // akr_trace.cuh: prim_inside(pair = true)
+        const u64 mhalf2 = pk2(-0.5f, -0.5f);
+        float a0, a1, c0, c1;
+        upk2(add2(s2, mhalf2), a0, a1);
+        upk2(add2(q2, mhalf2), c0, c1);
+        in0 = (fabsf(a0) <= 0.5f) & (fabsf(c0) <= 0.5f);
+        in1 = (fabsf(a1) <= 0.5f) & (fabsf(c1) <= 0.5f);
+        gid0 = s0 < q0 ? g.y : g.x;
+        gid1 = s1 < q1 ? g.w : g.z;
+    } else {
+        float m0, m1;
+        upk2(add2(s2, q2), m0, m1);
+        in0 = (s0 >= 0.0f) & (q0 >= 0.0f) & (m0 <= 1.0f);
+        in1 = (s1 >= 0.0f) & (q1 >= 0.0f) & (m1 <= 1.0f);
+        gid0 = g.x;
+        gid1 = g.z;
+    }
+    bool ok0 = in0 & (t0 > t_min) & (t0 < best_t) & (gid0 != ex0) & (gid0 != ex1);
+    if (ALPHA) {
+        if (ok0) {
+            PrimDecoded dec = prim_decode(load_block_prim(addr, 0u), s0, q0);
+            ok0 = alpha_test(sc, dec.gid, dec.u, dec.v);
+        }
+    }
+    best_t = ok0 ? t0 : best_t;
+    best_k = ok0 ? 2u * b : best_k;
+    bool ok1 = in1 & (t1 > t_min) & (t1 < best_t) & (gid1 != ex0) & (gid1 != ex1);
+    if (ALPHA) {
+        if (ok1) {
+            PrimDecoded dec = prim_decode(load_block_prim(addr, 1u), s1, q1);
+            ok1 = alpha_test(sc, dec.gid, dec.u, dec.v);
+        }
+    }
+    best_t = ok1 ? t1 : best_t;
+    best_k = ok1 ? 2u * b + 1u : best_k;
+}
+
+template <bool ANY_HIT, bool ALPHA>
+__device__ __forceinline__ DevHit trace_flat2(const LaunchParams &P, const TraceSmem &ts, bool active, f3 o, f3 d, float t_min, float t_max, uint32_t ex0,
+                                              uint32_t ex1) {
+    const SceneView &sc = P.scene;
+    float best_t = active ? t_max : 0.0f;  // an idle lane accepts nothing
+    uint32_t best_k = 0xffffffffu;
+    const uint32_t n_pair_blocks = sc.n_pair_blocks, n_blocks = n_pair_blocks + sc.n_single_blocks;
+    bool all_done = false;
+#pragma unroll 1
+    for (uint32_t b = 0; b < n_pair_blocks; ++b) {
+        flat2_block<true, ALPHA>(sc, ts.prims + b * (uint32_t)sizeof(PrimBlock2), b, o, d, t_min, ex0, ex1, best_t, best_k);
+        if (ANY_HIT && (b & 3u) == 3u && __all_sync(0xffffffffu, !active || best_k != 0xffffffffu)) {
+            all_done = true;
+            break;
+        }
+    }
+    if (!all_done) {
+#pragma unroll 1
+        for (uint32_t b = n_pair_blocks; b < n_blocks; ++b) {
+            flat2_block<false, ALPHA>(sc, ts.prims + b * (uint32_t)sizeof(PrimBlock2), b, o, d, t_min, ex0, ex1, best_t, best_k);
+            if (ANY_HIT && (b & 3u) == 3u && __all_sync(0xffffffffu, !active || best_k != 0xffffffffu)) break;
+        }
+    }
+    if (best_k == 0xffffffffu) return DevHit{0xffffffffu, 0u, 0.0f, 0.0f};
+    // (s, q) of the winner, same operations in the same order as the packed loop
+    const PrimRec p = load_block_prim(ts.prims + (best_k >> 1) * (uint32_t)sizeof(PrimBlock2), best_k & 1u);
+    float s, q;
+    prim_coords(p, o, d, best_t, s, q);
+    const PrimDecoded dec = prim_decode(p, s, q);
+    return DevHit{dec.gid, dec.cls, dec.u, dec.v};
+}
+
 // Every lane of the warp calls this together (`active` = the lane carries a ray); any-hit rays leave the
 // primitive loop only when the whole warp is done, which is the only exit that saves issue slots.
 template <bool ANY_HIT, int MODE, bool ALPHA>
@@ -234,26 +388,8 @@ __device__ __forceinline__ DevHit trace_dev(const LaunchParams &P, const TraceSm
     const SceneView &sc = P.scene;
     PrimHit best{active ? t_max : 0.0f, 0.0f, 0.0f, 0xffffffffu};  // an idle lane accepts nothing (t < 0 is never true for t > t_min = 0)
     constexpr bool PRIMS_SHARED = MODE != TRACE_BVH;
-    if (MODE == TRACE_FLAT) {
-        // the staged list is sorted pairs first, so neither loop decides the primitive kind per candidate
-        const uint32_t n = sc.n_prims, n_pairs = sc.n_flat_pairs;
-        bool all_done = false;
-#pragma unroll 2
-        for (uint32_t k = 0; k < n_pairs; ++k) {
-            prim_test<ALPHA, 1>(sc, load_prim<true>(ts.prims, nullptr, k), k, o, d, t_min, ex0, ex1, best);
-            if (ANY_HIT && (k & 7u) == 7u && __all_sync(0xffffffffu, !active || best.k != 0xffffffffu)) {
-                all_done = true;
-                break;
-            }
-        }
-        if (!all_done) {
-#pragma unroll 2
-            for (uint32_t k = n_pairs; k < n; ++k) {
-                prim_test<ALPHA, 2>(sc, load_prim<true>(ts.prims, nullptr, k), k, o, d, t_min, ex0, ex1, best);
-                if (ANY_HIT && (k & 7u) == 7u && __all_sync(0xffffffffu, !active || best.k != 0xffffffffu)) break;
-            }
-        }
-    } else if (active) {
+    if (MODE == TRACE_FLAT) return trace_flat2<ANY_HIT, ALPHA>(P, ts, active, o, d, t_min, t_max, ex0, ex1);
+    if (active) {
         const f3 inv_d = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
         const uint32_t n_fast = P.scene_smem_nodes;
         constexpr uint32_t kStackStride = kBlock * 4u;
@@ -763,7 +899,7 @@ int akr_b200_upload_scene(AkrContext *ctx, const AkrSceneDesc *desc) {
     ctx->render_ready = false;
     if ((rc = upload_vec(ctx, ctx->nodes, blob.nodes)) != AKR_OK) return rc;
     if ((rc = upload_vec(ctx, ctx->prims, blob.prims)) != AKR_OK) return rc;
-    if ((rc = upload_vec(ctx, ctx->flat_prims, blob.flat_prims)) != AKR_OK) return rc;
+    if ((rc = upload_vec(ctx, ctx->flat_prims, blob.flat_blocks)) != AKR_OK) return rc;
     if ((rc = upload_vec(ctx, ctx->shade, blob.shade)) != AKR_OK) return rc;
     if ((rc = upload_vec(ctx, ctx->instances, blob.instances)) != AKR_OK) return rc;
     if ((rc = upload_vec(ctx, ctx->materials, blob.materials)) != AKR_OK) return rc;
@@ -777,8 +913,9 @@ int akr_b200_upload_scene(AkrContext *ctx, const AkrSceneDesc *desc) {
     SceneView &v = ctx->scene;
     v.nodes = static_cast<const BvhNode *>(ctx->nodes.ptr);
     v.prims = static_cast<const PrimRec *>(ctx->prims.ptr);
-    v.flat_prims = blob.flat_prims.empty() ? nullptr : static_cast<const PrimRec *>(ctx->flat_prims.ptr);
-    v.n_flat_pairs = blob.n_flat_pairs;
+    v.flat_blocks = blob.flat_blocks.empty() ? nullptr : static_cast<const PrimBlock2 *>(ctx->flat_prims.ptr);
+    v.n_pair_blocks = blob.n_pair_blocks;
+    v.n_single_blocks = blob.n_single_blocks;
     v.tris = nullptr;  // the Moeller-Trumbore triangle list is host-simulation data; the kernels intersect primitives
     v.shade = static_cast<const TriShade *>(ctx->shade.ptr);
     v.instances = static_cast<const InstanceRec *>(ctx->instances.ptr);
@@ -940,7 +1077,7 @@ int akr_b200_render_pass(AkrContext *ctx, uint32_t n_spp, int blocking) {
 
     // trace schedule: flat list for tiny scenes that fit in shared memory, BVH otherwise (opts.trace_mode overrides)
     const int bvh_mode = ctx->smem_prims ? TRACE_BVH_SMEM : TRACE_BVH;
-    const bool flat_ok = ctx->scene.flat_prims != nullptr && ctx->smem_prims;
+    const bool flat_ok = ctx->scene.flat_blocks != nullptr && ctx->smem_prims;
     int trace_mode = flat_ok ? TRACE_FLAT : bvh_mode;
     if (ctx->opts.trace_mode == 1u) trace_mode = bvh_mode;
     if (ctx->opts.trace_mode == 2u && flat_ok) trace_mode = TRACE_FLAT;

@@ -52,6 +52,19 @@ struct alignas(16) PrimRec {
 };
 static_assert(sizeof(PrimRec) == 64, "PrimRec must be 64 bytes");
 
+// Flat trace mode (small scenes): the primitives transposed two by two so that one packed-FP32 instruction
+// (Blackwell FFMA2: fma.rn.f32x2) advances the test of two primitives.  Pair primitives come first, then single
+// triangles; each group is padded to an even count with a never-hit (NaN) primitive.
+struct alignas(16) PrimBlock2 {  // 128 B
+    float n[4][2];    // plane (nx, ny, nz, nw) of primitive 0 / 1
+    float r0[4][2];
+    float r1[4][2];
+    uint32_t gid[4];  // gid_a[0], gid_b[0], gid_a[1], gid_b[1]
+    uint32_t meta[2];
+    uint32_t _pad[2];
+};
+static_assert(sizeof(PrimBlock2) == 128, "PrimBlock2 must be 128 bytes");
+
 enum TriFlags : uint32_t {
     TRI_IS_LIGHT = 1u << 0,     // instance.light.valid()
     TRI_HAS_NORMALS = 1u << 1,  // per-corner normals: ns interpolated per hit
@@ -107,8 +120,8 @@ struct CameraRec {
 struct SceneView {
     const BvhNode *nodes;      // leaves address primitives: ~c = (first_prim << 3) | count
     const PrimRec *prims;      // BVH leaf order (CUDA kernels)
-    const PrimRec *flat_prims; // small scenes only: the same primitives sorted pairs first (flat trace mode), else nullptr
-    uint32_t n_flat_pairs;
+    const PrimBlock2 *flat_blocks;  // small scenes only (flat trace mode), else nullptr
+    uint32_t n_pair_blocks, n_single_blocks;
     const TriGeom *tris;       // two slots per primitive, gid 0xffffffff = empty (Moeller-Trumbore path of the host simulation)
     const TriShade *shade;
     const InstanceRec *instances;

@@ -171,21 +171,33 @@ AKR_HD PrimDecoded prim_decode(const PrimRec &p, float s, float q) {
     return r;
 }
 // One candidate: updates `best` when primitive k is hit at t in (t_min, best.t) by a triangle that is not
-// excluded.  Branch-free on purpose: every lane of a warp runs the same ~30 instructions per candidate and
-// commits with one predicate (a NaN from a parallel ray or a degenerate primitive fails every comparison).
-// KIND: 0 = decide per primitive, 1 = known pair, 2 = known single (the flat list is sorted pairs first).
+// excluded.  Branch-free on purpose: every lane of a warp runs the same instructions per candidate and commits
+// with one predicate (a NaN from a parallel ray or a degenerate primitive fails every comparison).  The
+// operation order (explicit FMAs) and the inside tests are exactly those of the packed FFMA2 loop of the flat
+// trace mode (akari_b200.cu: trace_flat2), so BVH and flat traversal compute identical (t, s, q) per primitive.
+// KIND: 0 = decide per primitive, 1 = known pair, 2 = known single.
+AKR_HD float prim_plane_t(const PrimRec &p, f3 o, f3 d) {
+    const float den = fmaf(p.n[2], d.z, fmaf(p.n[1], d.y, p.n[0] * d.x));
+    const float num = fmaf(p.n[2], o.z, fmaf(p.n[1], o.y, fmaf(p.n[0], o.x, p.n[3])));
+    return num * fast_rcp(-den);  // t = -(n.o + nw) / (n.d)
+}
+AKR_HD void prim_coords(const PrimRec &p, f3 o, f3 d, float t, float &s, float &q) {
+    const float hx = fmaf(t, d.x, o.x), hy = fmaf(t, d.y, o.y), hz = fmaf(t, d.z, o.z);
+    s = fmaf(p.r0[0], hx, fmaf(p.r0[1], hy, fmaf(p.r0[2], hz, p.r0[3])));
+    q = fmaf(p.r1[0], hx, fmaf(p.r1[1], hy, fmaf(p.r1[2], hz, p.r1[3])));
+}
+// pair: 0 <= s, q <= 1 tested as |s - 0.5| <= 0.5 and |q - 0.5| <= 0.5; single: s, q >= 0, s + q <= 1
+AKR_HD bool prim_inside(bool pair, float s, float q) {
+    return pair ? ((fabsf(s + -0.5f) <= 0.5f) & (fabsf(q + -0.5f) <= 0.5f)) : ((s >= 0.0f) & (q >= 0.0f) & (s + q <= 1.0f));
+}
 template <bool ALPHA, int KIND = 0>
 AKR_HD void prim_test(const SceneView &sc, const PrimRec &p, uint32_t k, f3 o, f3 d, float t_min, uint32_t ex0, uint32_t ex1, PrimHit &best) {
-    const float dz = p.n[0] * d.x + p.n[1] * d.y + p.n[2] * d.z;
-    const float oz = p.n[0] * o.x + p.n[1] * o.y + p.n[2] * o.z + p.n[3];
-    const float t = -oz * fast_rcp(dz);
-    const f3 hp = mk3(o.x + t * d.x, o.y + t * d.y, o.z + t * d.z);
-    const float s = p.r0[0] * hp.x + p.r0[1] * hp.y + p.r0[2] * hp.z + p.r0[3];
-    const float q = p.r1[0] * hp.x + p.r1[1] * hp.y + p.r1[2] * hp.z + p.r1[3];
+    const float t = prim_plane_t(p, o, d);
+    float s, q;
+    prim_coords(p, o, d, t, s, q);
     const bool pair = KIND == 1 ? true : (KIND == 2 ? false : p.gid_b != 0xffffffffu);
-    const float m = pair ? fmaxf(s, q) : s + q;  // pair: both <= 1; single: s + q <= 1
     const uint32_t gid = (pair & (s < q)) ? p.gid_b : p.gid_a;
-    bool ok = (t > t_min) & (t < best.t) & (fminf(s, q) >= 0.0f) & (m <= 1.0f) & (gid != ex0) & (gid != ex1);
+    bool ok = prim_inside(pair, s, q) & (t > t_min) & (t < best.t) & (gid != ex0) & (gid != ex1);
     if (ALPHA) {
         if (ok) {
             PrimDecoded dec = prim_decode(p, s, q);

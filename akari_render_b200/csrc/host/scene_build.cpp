@@ -869,11 +869,33 @@ int build_scene_blob(const AkrSceneDesc &d, HostSceneBlob &out, std::string &err
         pr.meta = hp.iu_a | (hp.iv_a << 2) | (hp.iu_b << 4) | (hp.iv_b << 6) | (cls_a << 8) | (cls_b << 10);
     }
     if (n_prims <= kFlatMaxPrims) {
-        for (const PrimRec &pr : out.prims)
-            if (pr.gid_b != 0xffffffffu) out.flat_prims.push_back(pr);
-        out.n_flat_pairs = static_cast<uint32_t>(out.flat_prims.size());
-        for (const PrimRec &pr : out.prims)
-            if (pr.gid_b == 0xffffffffu) out.flat_prims.push_back(pr);
+        PrimRec never;
+        std::memset(&never, 0, sizeof(never));
+        for (int c = 0; c < 4; ++c) never.n[c] = never.r0[c] = never.r1[c] = std::numeric_limits<float>::quiet_NaN();
+        never.gid_a = never.gid_b = 0xffffffffu;
+        std::vector<PrimRec> pairs, singles;
+        for (const PrimRec &pr : out.prims) (pr.gid_b != 0xffffffffu ? pairs : singles).push_back(pr);
+        if (pairs.size() & 1u) pairs.push_back(never);
+        if (singles.size() & 1u) singles.push_back(never);
+        out.n_pair_blocks = static_cast<uint32_t>(pairs.size() / 2);
+        out.n_single_blocks = static_cast<uint32_t>(singles.size() / 2);
+        pairs.insert(pairs.end(), singles.begin(), singles.end());
+        out.flat_blocks.resize(pairs.size() / 2);
+        for (size_t b2 = 0; b2 < out.flat_blocks.size(); ++b2) {
+            PrimBlock2 &blk = out.flat_blocks[b2];
+            std::memset(&blk, 0, sizeof(blk));
+            for (int h = 0; h < 2; ++h) {
+                const PrimRec &pr = pairs[2 * b2 + h];
+                for (int c = 0; c < 4; ++c) {
+                    blk.n[c][h] = pr.n[c];
+                    blk.r0[c][h] = pr.r0[c];
+                    blk.r1[c][h] = pr.r1[c];
+                }
+                blk.gid[2 * h] = pr.gid_a;
+                blk.gid[2 * h + 1] = pr.gid_b;
+                blk.meta[h] = pr.meta;
+            }
+        }
     }
     // flatten: breadth-first over inner nodes; a leaf root becomes an inner node with an empty second child
     auto leaf_code = [&](const BuildNode &n) { return ~static_cast<int32_t>((n.first << 3) | n.count); };
@@ -963,8 +985,9 @@ SceneView host_scene_view(const HostSceneBlob &b, const float *albedo_table) {
     std::memset(&v, 0, sizeof(v));
     v.nodes = b.nodes.data();
     v.prims = b.prims.data();
-    v.flat_prims = b.flat_prims.empty() ? nullptr : b.flat_prims.data();
-    v.n_flat_pairs = b.n_flat_pairs;
+    v.flat_blocks = b.flat_blocks.empty() ? nullptr : b.flat_blocks.data();
+    v.n_pair_blocks = b.n_pair_blocks;
+    v.n_single_blocks = b.n_single_blocks;
     v.tris = b.tris.data();
     v.shade = b.shade.data();
     v.instances = b.instances.data();

@@ -20,8 +20,8 @@ constexpr uint32_t kFlatMaxPrims = 64;  // scenes this small are traced as one f
 struct HostSceneBlob {
     std::vector<BvhNode> nodes;
     std::vector<PrimRec> prims;       // BVH leaf order (what the CUDA kernels intersect)
-    std::vector<PrimRec> flat_prims;  // scenes of <= kFlatMaxPrims primitives: the same records, pairs first (flat trace mode)
-    uint32_t n_flat_pairs = 0;
+    std::vector<PrimBlock2> flat_blocks;  // scenes of <= kFlatMaxPrims primitives: pairs first, two per block (flat trace mode)
+    uint32_t n_pair_blocks = 0, n_single_blocks = 0;
     std::vector<TriGeom> tris;        // two per primitive, same order (host simulation's Moeller-Trumbore path)
     std::vector<TriShade> shade;      // by global triangle id
     std::vector<InstanceRec> instances;
