@@ -128,6 +128,8 @@ class AkrEngineOptions(C.Structure):
         ("sort_by_material", C.c_uint32),
         ("profile_stages", C.c_uint32),
         ("trace_mode", C.c_uint32),
+        ("inline_shadow", C.c_uint32),
+        ("_reserved", C.c_uint32 * 3),
     ]
 
 

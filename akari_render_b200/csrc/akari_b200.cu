@@ -77,6 +77,7 @@ struct LaunchParams {
     uint32_t scene_smem_prims;  // 1 when all primitives are staged too
     uint32_t stack_depth;       // traversal stack entries per thread (shared memory)
     uint32_t stage_flat;        // stage the pairs-first flat list instead of the BVH-ordered primitives
+    uint32_t inline_shadow;     // flat scenes: the shade kernels trace their own shadow ray (no shadow queue traffic)
     uint32_t *dbg_first_hits;   // optional [n_film_pixels][2]
 };
 
@@ -348,11 +349,11 @@ __device__ __forceinline__ void flat2_block(const SceneView &sc, uint32_t addr, 
     best_k = ok1 ? 2u * b + 1u : best_k;
 }
 
+// returns the index of the hit primitive in the staged list (0xffffffff = none) and its distance
 template <bool ANY_HIT, bool ALPHA>
-__device__ __forceinline__ DevHit trace_flat2(const LaunchParams &P, const TraceSmem &ts, bool active, f3 o, f3 d, float t_min, float t_max, uint32_t ex0,
-                                              uint32_t ex1) {
-    const SceneView &sc = P.scene;
-    float best_t = active ? t_max : 0.0f;  // an idle lane accepts nothing
+__device__ __forceinline__ uint32_t trace_flat2_core(const SceneView &sc, const TraceSmem &ts, bool active, f3 o, f3 d, float t_min, float t_max, uint32_t ex0,
+                                                     uint32_t ex1, float &best_t) {
+    best_t = active ? t_max : 0.0f;  // an idle lane accepts nothing
     uint32_t best_k = 0xffffffffu;
     const uint32_t n_pair_blocks = sc.n_pair_blocks, n_blocks = n_pair_blocks + sc.n_single_blocks;
     bool all_done = false;
@@ -371,7 +372,15 @@ __device__ __forceinline__ DevHit trace_flat2(const LaunchParams &P, const Trace
             if (ANY_HIT && (b & 3u) == 3u && __all_sync(0xffffffffu, !active || best_k != 0xffffffffu)) break;
         }
     }
+    return best_k;
+}
+template <bool ANY_HIT, bool ALPHA>
+__device__ __forceinline__ DevHit trace_flat2(const LaunchParams &P, const TraceSmem &ts, bool active, f3 o, f3 d, float t_min, float t_max, uint32_t ex0,
+                                              uint32_t ex1) {
+    float best_t;
+    const uint32_t best_k = trace_flat2_core<ANY_HIT, ALPHA>(P.scene, ts, active, o, d, t_min, t_max, ex0, ex1, best_t);
     if (best_k == 0xffffffffu) return DevHit{0xffffffffu, 0u, 0.0f, 0.0f};
+    if (ANY_HIT) return DevHit{0u, 0u, 0.0f, 0.0f};  // occluded: which triangle does not matter
     // (s, q) of the winner, same operations in the same order as the packed loop
     const PrimRec p = load_block_prim(ts.prims + (best_k >> 1) * (uint32_t)sizeof(PrimBlock2), best_k & 1u);
     float s, q;
@@ -488,7 +497,7 @@ template <int MODE, bool ALPHA> __global__ void __launch_bounds__(kBlock) k_trac
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bar;
     const uint32_t n_cl = P.counters[depth * kCtrStride];
-    const uint32_t n_sh = P.counters[depth * kCtrStride + 1u];
+    const uint32_t n_sh = P.inline_shadow ? 0u : P.counters[depth * kCtrStride + 1u];  // inline mode: [1] only counts, shade traced them
     const uint32_t t_cl = (n_cl + 31u) >> 5, t_sh = (n_sh + 31u) >> 5;
     const uint32_t n_tasks = t_cl + t_sh;
     if (blockIdx.x * kWarpsPerBlock >= n_tasks) return;  // whole CTA has no work: skip the staging too
@@ -557,7 +566,13 @@ template <int CLS> struct ShadeLaunch {
 };
 
 // One shade kernel per material class; `CLS_ANY` (unsorted: every hit in slot order) exists for A/B runs.
-template <int CLS> __global__ void __launch_bounds__(kShadeBlock, ShadeLaunch<CLS>::kMinBlocks) k_shade(const __grid_constant__ LaunchParams P, uint32_t depth) {
+// INLINE_SHADOW (flat scenes without alpha materials): the thread that produced an NEE sample tests its shadow ray
+// itself against the staged primitive list (lock-step, no divergence) and adds the contribution; the shadow
+// queue (52 B written + 52 B read + a random 32 B accumulator update per shadow ray) disappears.
+template <int CLS, bool INLINE_SHADOW>
+__global__ void __launch_bounds__(kShadeBlock, ShadeLaunch<CLS>::kMinBlocks) k_shade(const __grid_constant__ LaunchParams P, uint32_t depth) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bar;
     uint32_t *ctr = P.counters + depth * kCtrStride;
     const uint32_t n = CLS == CLS_ANY ? ctr[0] : ctr[2u + (CLS == CLS_ANY ? 0 : CLS)];
     const uint2 *slots = CLS == CLS_ANY ? nullptr : P.cls.idx[CLS == CLS_ANY ? 0 : CLS];
@@ -565,6 +580,11 @@ template <int CLS> __global__ void __launch_bounds__(kShadeBlock, ShadeLaunch<CL
     const PathQueue &qout = P.q[(depth + 1u) & 1u];
     uint32_t *out_pair = ctr + kCtrStride;  // [0] next-depth paths, [1] shadow rays: reserved together
     const uint32_t stride = gridDim.x * blockDim.x;
+    TraceSmem ts{0u, 0u, 0u};
+    if (INLINE_SHADOW) {
+        if (blockIdx.x * blockDim.x >= n) return;  // whole CTA has no work: skip the staging too
+        ts = stage_scene(P, smem, &bar);
+    }
     // warp-uniform trip count so that every lane takes part in the ballots; the (slot, path_id) entry of the
     // next trip is fetched one trip ahead so that its latency is off the dependent chain
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -592,9 +612,15 @@ template <int CLS> __global__ void __launch_bounds__(kShadeBlock, ShadeLaunch<CL
                 }
             }
         }
+        if (INLINE_SHADOW) {
+            float t_hit;
+            const uint32_t occ = trace_flat2_core<true, false>(P.scene, ts, o.has_shadow, o.shadow.o, o.shadow.d, 0.0f, o.shadow.t_max, o.shadow.ex0,
+                                                               o.shadow.ex1, t_hit);
+            if (o.has_shadow) shadow_resolve(P.acc, o.shadow, occ != 0xffffffffu, depth + 1u);
+        }
         uint32_t ns, ss;
         warp_append2(out_pair, o.has_next, o.has_shadow, ns, ss);
-        if (o.has_shadow) {
+        if (!INLINE_SHADOW && o.has_shadow) {
             const ShadowQueue &s = P.shadow;
             st4(s.a + ss, f4{o.shadow.o.x, o.shadow.o.y, o.shadow.o.z, o.shadow.t_max});
             st4(s.b + ss, f4{o.shadow.d.x, o.shadow.d.y, o.shadow.d.z, u2f(o.shadow.ex0)});
@@ -676,7 +702,7 @@ struct AkrContext {
     uint32_t smem_nodes = 0, smem_prims = 0, smem_bytes = 0;  // smem_bytes = nodes + primitives (stacks come on top)
     uint32_t bvh_depth = 0;
     uint32_t class_mask = 0;   // shade classes present in the scene
-    int occ_trace[3] = {1, 1, 1}, occ_shade[4] = {1, 1, 1, 1};  // resident CTAs per SM, per kernel variant
+    int occ_trace[3] = {1, 1, 1}, occ_shade[4] = {1, 1, 1, 1}, occ_shade_inline[3] = {1, 1, 1};  // resident CTAs per SM, per kernel variant
 
     // render state
     bool render_ready = false;
@@ -697,7 +723,7 @@ struct AkrContext {
     AccView acc{};
     DeviceBuffer counters, totals, dbg_hits;
 
-    AkrEngineOptions opts{0, 0, 0, 0};
+    AkrEngineOptions opts{};
     AkrStats stats{};
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
     std::vector<cudaEvent_t> stage_events;
@@ -960,10 +986,15 @@ int akr_b200_upload_scene(AkrContext *ctx, const AkrSceneDesc *desc) {
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_trace[TRACE_FLAT], k_trace<TRACE_FLAT, false>, kBlock, smem_flat);
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_trace[TRACE_BVH_SMEM], k_trace<TRACE_BVH_SMEM, false>, kBlock, smem_bvh);
         }
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_shade[0], k_shade<CLS_LAMBERT>, kShadeBlock, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_shade[1], k_shade<CLS_CONDUCTOR>, kShadeBlock, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_shade[2], k_shade<CLS_GENERAL>, kShadeBlock, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_shade[3], k_shade<CLS_ANY>, kShadeBlock, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_shade[0], k_shade<CLS_LAMBERT, false>, kShadeBlock, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_shade[1], k_shade<CLS_CONDUCTOR, false>, kShadeBlock, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_shade[2], k_shade<CLS_GENERAL, false>, kShadeBlock, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_shade[3], k_shade<CLS_ANY, false>, kShadeBlock, 0);
+        const size_t smem_inline = (size_t)ctx->smem_nodes * sizeof(BvhNode) + blob.flat_blocks.size() * sizeof(PrimBlock2);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_shade_inline[0], k_shade<CLS_LAMBERT, true>, kShadeBlock, smem_inline);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_shade_inline[1], k_shade<CLS_CONDUCTOR, true>, kShadeBlock, smem_inline);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_shade_inline[2], k_shade<CLS_GENERAL, true>, kShadeBlock, smem_inline);
+        for (int &o : ctx->occ_shade_inline) o = std::max(o, 1);
         for (int &o : ctx->occ_trace) o = std::max(o, 1);
         for (int &o : ctx->occ_shade) o = std::max(o, 1);
     }
@@ -1082,7 +1113,12 @@ int akr_b200_render_pass(AkrContext *ctx, uint32_t n_spp, int blocking) {
     if (ctx->opts.trace_mode == 1u) trace_mode = bvh_mode;
     if (ctx->opts.trace_mode == 2u && flat_ok) trace_mode = TRACE_FLAT;
     P.stage_flat = trace_mode == TRACE_FLAT ? 1u : 0u;
-    const size_t trace_smem = ctx->smem_bytes + (trace_mode != TRACE_FLAT ? (size_t)P.stack_depth * kBlock * sizeof(int32_t) : 0);
+    // shadow rays inside the shade kernels: flat mode, no stochastic alpha, per-class kernels; opts.inline_shadow = 2 turns it off
+    P.inline_shadow = (trace_mode == TRACE_FLAT && !ctx->scene.any_alpha && ctx->opts.sort_by_material != 2u && ctx->opts.inline_shadow != 2u) ? 1u : 0u;
+    // shared memory: staged nodes + (flat mode: the padded PrimBlock2 list | BVH modes: primitives + per-thread stacks)
+    const size_t node_smem = (size_t)ctx->smem_nodes * sizeof(BvhNode);
+    const size_t flat_smem = node_smem + (size_t)(ctx->scene.n_pair_blocks + ctx->scene.n_single_blocks) * sizeof(PrimBlock2);
+    const size_t trace_smem = trace_mode == TRACE_FLAT ? flat_smem : ctx->smem_bytes + (size_t)P.stack_depth * kBlock * sizeof(int32_t);
     if (trace_smem > kSmemMax) return fail(ctx, AKR_ERR_UNSUPPORTED, "BVH too deep for the shared-memory traversal stack");
     const bool binned = ctx->opts.sort_by_material != 2u;
     const bool alpha = ctx->scene.any_alpha != 0u;
@@ -1134,6 +1170,10 @@ int akr_b200_render_pass(AkrContext *ctx, uint32_t n_spp, int blocking) {
             const uint32_t n_paths = n_pix * k;
             AKR_LAUNCH(0, k_raygen, grid_for(ctx, n_paths, 8), 0, P);
             const int g_trace = grid_for(ctx, n_paths, ctx->occ_trace[trace_mode]);
+            auto shade_grid_inline = [&](int variant) {
+                uint32_t need = (n_paths + kShadeBlock - 1) / kShadeBlock, capn = (uint32_t)(ctx->sm_count * ctx->occ_shade_inline[variant]);
+                return (int)std::max(1u, std::min(need, capn));
+            };
             auto shade_grid = [&](int variant) {
                 uint32_t need = (n_paths + kShadeBlock - 1) / kShadeBlock, capn = (uint32_t)(ctx->sm_count * ctx->occ_shade[variant]);
                 return (int)std::max(1u, std::min(need, capn));
@@ -1150,12 +1190,19 @@ int akr_b200_render_pass(AkrContext *ctx, uint32_t n_spp, int blocking) {
                     else AKR_LAUNCH(1, (k_trace<TRACE_BVH, false>), g_trace, trace_smem, P, depth);
                 }
                 if (!binned) {
-                    AKR_LAUNCH_B(6, k_shade<CLS_ANY>, shade_grid(3), kShadeBlock, 0, P, depth);
+                    AKR_LAUNCH_B(6, (k_shade<CLS_ANY, false>), shade_grid(3), kShadeBlock, 0, P, depth);
                     continue;
                 }
-                if (class_mask & (1u << CLS_LAMBERT)) AKR_LAUNCH_B(2, k_shade<CLS_LAMBERT>, shade_grid(0), kShadeBlock, 0, P, depth);
-                if (class_mask & (1u << CLS_CONDUCTOR)) AKR_LAUNCH_B(3, k_shade<CLS_CONDUCTOR>, shade_grid(1), kShadeBlock, 0, P, depth);
-                if (class_mask & (1u << CLS_GENERAL)) AKR_LAUNCH_B(6, k_shade<CLS_GENERAL>, shade_grid(2), kShadeBlock, 0, P, depth);
+                if (P.inline_shadow) {
+                    const size_t sm = flat_smem;  // nodes + the staged flat list
+                    if (class_mask & (1u << CLS_LAMBERT)) AKR_LAUNCH_B(2, (k_shade<CLS_LAMBERT, true>), shade_grid_inline(0), kShadeBlock, sm, P, depth);
+                    if (class_mask & (1u << CLS_CONDUCTOR)) AKR_LAUNCH_B(3, (k_shade<CLS_CONDUCTOR, true>), shade_grid_inline(1), kShadeBlock, sm, P, depth);
+                    if (class_mask & (1u << CLS_GENERAL)) AKR_LAUNCH_B(6, (k_shade<CLS_GENERAL, true>), shade_grid_inline(2), kShadeBlock, sm, P, depth);
+                    continue;
+                }
+                if (class_mask & (1u << CLS_LAMBERT)) AKR_LAUNCH_B(2, (k_shade<CLS_LAMBERT, false>), shade_grid(0), kShadeBlock, 0, P, depth);
+                if (class_mask & (1u << CLS_CONDUCTOR)) AKR_LAUNCH_B(3, (k_shade<CLS_CONDUCTOR, false>), shade_grid(1), kShadeBlock, 0, P, depth);
+                if (class_mask & (1u << CLS_GENERAL)) AKR_LAUNCH_B(6, (k_shade<CLS_GENERAL, false>), shade_grid(2), kShadeBlock, 0, P, depth);
             }
             AKR_LAUNCH(4, k_accumulate, grid_for(ctx, n_pix, 8), 0, P);
             k_fold_counters<<<1, 128, 0, ctx->stream>>>(P.counters, static_cast<unsigned long long *>(ctx->totals.ptr), ctx->rp.max_depth + 2u);

@@ -131,6 +131,7 @@ def main():
     ap.add_argument("--wave", type=int, default=1 << 26, help="paths in flight per wave (0 = engine default of 4 Mi)")
     ap.add_argument("--trace-mode", type=int, default=0, help="0 auto, 1 BVH, 2 flat list")
     ap.add_argument("--sort", type=int, default=0, help="0/1 per-class shade kernels, 2 one generic shade kernel")
+    ap.add_argument("--inline-shadow", type=int, default=0, help="0 auto (shade traces its own shadow ray on flat scenes), 2 off")
     ap.add_argument("--profile-stages", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     args = ap.parse_args()
@@ -162,7 +163,7 @@ def main():
     my_rows = tile[1] - tile[0]
     stream = torch.cuda.current_stream().cuda_stream
     pt = akr.PathTracer(local_rank, stream=stream)
-    eng = dict(wave_size=args.wave, sort_by_material=args.sort, trace_mode=args.trace_mode)
+    eng = dict(wave_size=args.wave, sort_by_material=args.sort, trace_mode=args.trace_mode, inline_shadow=args.inline_shadow)
     pt.set_engine_options(profile_stages=1 if args.profile_stages else 0, **eng)
     pt.upload_scene(scene)
     max_rows = max_band_rows(HEIGHT, world)

@@ -253,6 +253,9 @@ typedef struct AkrEngineOptions {
     uint32_t profile_stages;        /* record per-stage CUDA-event times (adds syncs)           */
     uint32_t trace_mode;            /* 0 = auto, 1 = BVH traversal, 2 = flat triangle list (only
                                      * honoured when every triangle fits in shared memory)       */
+    uint32_t inline_shadow;         /* 0 = auto (shade kernels trace their own shadow ray when the
+                                     * flat list is in use), 2 = off (always use the shadow queue) */
+    uint32_t _reserved[3];
 } AkrEngineOptions;
 int akr_b200_set_engine_options(AkrContext *ctx, const AkrEngineOptions *opts);
 
