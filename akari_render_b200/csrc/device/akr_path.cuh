@@ -233,6 +233,11 @@ AKR_HD void acc_add(const AccView &acc, uint32_t id, f3 c) {
     f4 l = ld4(acc.l + id);
     st4(acc.l + id, f4{l.x + c.x, l.y + c.y, l.z + c.z, 0.0f});
 }
+AKR_HD void acc_set_lb(const AccView &acc, uint32_t id, f3 l) {  // depth 0: radiance = base_replay_throughput = l
+    st4(acc.l + id, f4{l.x, l.y, l.z, 0.0f});
+    st4(acc.b + id, f4{l.x, l.y, l.z, 0.0f});
+}
+AKR_HD void acc_snap_b(const AccView &acc, uint32_t id) { st4(acc.b + id, ld4(acc.l + id)); }  // base_replay_throughput = radiance
 
 // ---- a ray that left the scene: hit_envmap = (0, 0) (pt.rs:226-228,381-396) -----------------------------
 // add_radiance(beta * 0): a NaN/inf throughput poisons the sample exactly as in the reference; a finite
@@ -247,9 +252,9 @@ AKR_HD void miss_body(const RenderParams &rp, uint32_t depth, f3 beta, uint32_t 
 
 // `depth` = path depth when the ray was cast (0 for camera rays).  `hit` is a real hit (misses end in
 // miss_body).  CLS is the shade class of the hit material (CLS_ANY: decide per call).
-template <int CLS>
+template <int CLS, class Acc>
 AKR_HD ShadeOut shade_body(const SceneView &sc, const CornerAttribs &ca, const SamplerTables &tab, const RenderParams &rp, const WaveInfo &wave,
-                           uint32_t depth, const PathState &ps, HitRec hit, const AccView &acc) {
+                           uint32_t depth, const PathState &ps, HitRec hit, Acc &acc) {
     ShadeOut out;
     out.has_shadow = false;
     out.has_next = false;
@@ -283,8 +288,7 @@ AKR_HD ShadeOut shade_body(const SceneView &sc, const CornerAttribs &ca, const S
         if (depth == 0u) {
             // radiance starts at 0; base_replay_throughput = radiance (pt.rs:415-417)
             f3 l = (dbg_on || rp.debug_depth == 0) ? splat3(0.0f) + c : splat3(0.0f);
-            st4(acc.l + id, f4{l.x, l.y, l.z, 0.0f});
-            st4(acc.b + id, f4{l.x, l.y, l.z, 0.0f});
+            acc_set_lb(acc, id, l);
         } else if (dbg_on || depth == (uint32_t)rp.debug_depth) {
             if (c.x != 0.0f || c.y != 0.0f || c.z != 0.0f) acc_add(acc, id, c);
         }
@@ -390,13 +394,13 @@ AKR_HD ShadeOut shade_body(const SceneView &sc, const CornerAttribs &ca, const S
 
 // ---- stage: shadow (pt.rs:504-513) ----------------------------------------------------------------------------
 // `depth1` = depth after the increment of the bounce that produced the item.
-AKR_HD void shadow_resolve(const AccView &acc, const ShadowItem &it, bool occluded, uint32_t depth1) {
+template <class Acc> AKR_HD void shadow_resolve(Acc &acc, const ShadowItem &it, bool occluded, uint32_t depth1) {
     uint32_t id = it.path_id;
     if (!occluded) {
         f3 c = it.contrib;
         if (c.x != 0.0f || c.y != 0.0f || c.z != 0.0f) acc_add(acc, id, c);
     }
-    if (depth1 == 1u) st4(acc.b + id, ld4(acc.l + id));  // base_replay_throughput = radiance (pt.rs:510-512)
+    if (depth1 == 1u) acc_snap_b(acc, id);  // base_replay_throughput = radiance (pt.rs:510-512)
 }
 
 // ---- stage: accumulate (pt.rs:871-876 + film.rs:196-229) -------------------------------------------------------
