@@ -267,6 +267,18 @@ def main():
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
+    # measured DRAM traffic of the dominant stage, per launch: dram__bytes_read.sum + dram__bytes_write.sum from the committed
+    # ncu launch list of this same command at 64 spp (profiles/launches_current.json <- tools/ncu_summary.py list)
+    traffic, traffic_src = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "launches_current.json")))
+        pref = "k_shade" if dom.startswith("k_shade") else "k_trace"
+        ks = [v for k, v in tj.items() if k.startswith(pref)]
+        if ks:
+            traffic = sum(v["dram_read"] + v["dram_write"] for v in ks) / sum(v["launches"] for v in ks)
+            traffic_src = "profiles/launches_current.json (ncu, cold-cache, per launch)"
+    except Exception:
+        pass
     achieved = (dom_bytes / 1e9) / (dom_ms * 1e-3) if dom_ms > 0 else 0.0
     n_seg = st.segments / max(1, st.samples)
     s_ratio = st.shadow_rays / max(1, st.segments)
@@ -297,7 +309,8 @@ def main():
             "clocks": summarize_clocks(clocks),
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(st.kernel_launches),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                         "algorithmic_bytes_per_launch": dom_bytes / max(1, dom_n),
                          "kernel": dom, "kernel_launches": dom_n, "kernel_ms": dom_ms, "kernel_algorithmic_bytes": dom_bytes,
                          "peak_source": "measured" if peaks else "fallback",
                          "pipeline_algorithmic_gbs": pipeline_gbs, "pipeline_frac": pipeline_gbs / peak,
