@@ -175,6 +175,7 @@ class PathTracer:
         self._check(self._lib.akr_b200_upload_sampler_tables(self._ctx, pmj.ctypes.data, bn.ctypes.data))
         self._scene = None
         self._tile = None
+        self._res = (0, 0)
 
     def _check(self, rc):
         if rc != 0:

@@ -81,3 +81,88 @@ def variant_nodes(scene):
     replace_with_node(scene, "floor_001", "diffuse", color=[0.6, 0.6, 0.2])
     replace_with_node(scene, "shortBox_001", "glass", color=[0.95, 0.95, 1.0], ior=1.5, roughness=0.05)
     replace_with_node(scene, "backWall_001", "emission", color=[0.4, 0.1, 0.1], strength=2.0)
+
+
+# ---- procedural clutter: a scene big enough that the BVH and the primitives live in global memory ------------------
+def _uv_sphere(cx, cy, cz, r, n_lon, n_lat):
+    """Indexed UV sphere with per-corner smooth normals and two material slots (alternating latitude bands)."""
+    import numpy as np
+    verts, idx, normals, uvs, slots = [], [], [], [], []
+    for j in range(n_lat + 1):
+        th = np.pi * j / n_lat
+        for i in range(n_lon):
+            ph = 2 * np.pi * i / n_lon
+            n = np.array([np.sin(th) * np.cos(ph), np.cos(th), np.sin(th) * np.sin(ph)])
+            verts.append(np.array([cx, cy, cz]) + r * n)
+    verts = np.array(verts, np.float32)
+    c = np.array([cx, cy, cz], np.float32)
+
+    def nrm(k):
+        v = verts[k] - c
+        return (v / np.linalg.norm(v)).astype(np.float32)
+
+    for j in range(n_lat):
+        for i in range(n_lon):
+            a = j * n_lon + i
+            b = j * n_lon + (i + 1) % n_lon
+            d = (j + 1) * n_lon + i
+            e = (j + 1) * n_lon + (i + 1) % n_lon
+            tris = []
+            if j > 0:
+                tris.append((a, b, e))
+            if j < n_lat - 1:
+                tris.append((a, e, d))
+            for t in tris:
+                idx.append(t)
+                normals.append([nrm(t[0]), nrm(t[1]), nrm(t[2])])
+                uvs.append([[i / n_lon, j / n_lat], [(i + 1) / n_lon, j / n_lat], [(i + 1) / n_lon, (j + 1) / n_lat]])
+                slots.append(j & 1)
+    return (verts, np.array(idx, np.uint32), np.array(normals, np.float32).reshape(-1, 3), np.array(uvs, np.float32).reshape(-1, 2),
+            np.array(slots, np.uint32))
+
+
+def write_clutter(tmp_path, n_lon=32, n_lat=24):
+    """cbox + six tessellated spheres (smooth per-corner normals, two materials each, one of them glass-like):
+    ~8.5 K triangles => BVH nodes and primitives exceed the shared-memory staging budget (TRACE_BVH mode)."""
+    import numpy as np
+    scene = json.load(open(os.path.join(CBOX_DIR, "scene.json")))
+    blob = bytearray(open(os.path.join(CBOX_DIR, "Scene.bin"), "rb").read())
+    scene["buffers"]["Scene"]["path"] = "Scene.bin"
+    # a glass-like and a rough-metal material derived from existing ones
+    scene["materials"]["clutter_glass"] = copy.deepcopy(scene["materials"]["shortBox_001"])
+    edit_principled(scene, "clutter_glass", transmission_weight=1.0, ior=1.45, roughness=0.1, specular_ior_level=0.5)
+    scene["materials"]["clutter_metal"] = copy.deepcopy(scene["materials"]["tallBox_001"])
+    edit_principled(scene, "clutter_metal", roughness=0.35)
+    nview = len(scene["buffer_views"])
+
+    def add_view(arr):
+        nonlocal nview
+        while len(blob) % 16:
+            blob.append(0)
+        name = f"buf_view_{nview}"
+        nview += 1
+        raw = np.ascontiguousarray(arr).tobytes()
+        scene["buffer_views"][name] = {"buffer": {"id": "Scene"}, "offset": len(blob), "length": len(raw)}
+        blob.extend(raw)
+        return {"id": name}
+
+    spheres = [(-0.55, 0.35, 0.45, 0.22), (0.45, 0.85, 0.35, 0.2), (0.0, 1.45, -0.3, 0.25), (-0.3, 1.55, 0.4, 0.15),
+               (0.6, 0.25, 0.75, 0.18), (0.1, 0.9, 0.6, 0.12)]
+    mats = [("floor_001", "clutter_metal"), ("clutter_glass", "backWall_001"), ("leftWall_001", "rightWall_001"),
+            ("clutter_metal", "clutter_glass"), ("ceiling_001", "floor_001"), ("clutter_glass", "clutter_metal")]
+    for k, (cx, cy, cz, r) in enumerate(spheres):
+        v, i, n, uv, sl = _uv_sphere(cx, cy, cz, r, n_lon, n_lat)
+        gname = f"zz_sphere_{k}_mesh"
+        scene["geometries"][gname] = {"type": "mesh", "vertices": add_view(v), "indices": add_view(i), "normals": add_view(n),
+                                      "uvs": add_view(uv), "tangents": None, "materials": add_view(sl)}
+        scene["instances"][f"zz_sphere_{k}"] = {
+            "geometry": {"id": gname},
+            "transform": {"type": "matrix", "data": [[1.0, 0.0, 0.0, 0.0], [0.0, 1.0, 0.0, 0.0], [0.0, 0.0, 1.0, 0.0], [0.0, 0.0, 0.0, 1.0]]},
+            "materials": [{"id": mats[k][0]}, {"id": mats[k][1]}]}
+    scene["buffers"]["Scene"]["length"] = len(blob)
+    d = os.path.join(str(tmp_path), "clutter")
+    os.makedirs(d, exist_ok=True)
+    open(os.path.join(d, "Scene.bin"), "wb").write(bytes(blob))
+    path = os.path.join(d, "scene.json")
+    json.dump(scene, open(path, "w"))
+    return path

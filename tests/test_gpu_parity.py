@@ -160,3 +160,57 @@ def test_full_size_frame_properties(akr, cbox, cbox_task):
     rel = np.abs(m_big - m_small) / m_small
     print(f"mean radiance 1280x720@16 {m_big} vs 320x180@256 {m_small}: rel {rel}")
     assert (rel < 0.02).all()
+
+
+def test_clutter_scene_bvh_mode(akr, oracle, tables, cbox_task, tmp_path):
+    """~8.5 K triangles: the BVH and the primitives no longer fit the shared-memory staging budget, so this runs
+    k_trace<TRACE_BVH> (top of the tree in shared memory, the rest through L1/L2), the shadow-ray queue, per-hit
+    interpolated normals, two materials per mesh and the general Principled shade kernel."""
+    import scene_variants as sv
+    w = h = 64
+    scene = akr.load_scene(sv.write_clutter(tmp_path)).set_resolution(w, h)
+    task = cbox_task(8)
+    pmj, bn = tables
+    film, st = _gpu_film(akr, scene, task)
+    ofilm, ost, _ = oracle.render(scene.desc, w, h, task.pt, task.sampler, task.filter, pmj, bn)
+    _gate(film.to_rgb(), oracle.resolve(ofilm, w * h).reshape(h, w, 3), rel_frac=1e-2, img=5e-3)
+    assert abs(int(st.segments) - int(ost.segments)) <= 2e-3 * ost.segments
+    assert abs(int(st.shadow_rays) - int(ost.shadow_rays)) <= 2e-3 * ost.shadow_rays
+
+
+def test_error_paths_and_odd_configs(akr, oracle, tables, cbox, cbox_task):
+    """Call-order and argument errors come back as status codes (never a crash), and ragged configurations render:
+    odd spp (non-power-of-two permutation length), spp_per_pass > spp, box filter, a one-row tile, a tiny wave."""
+    import ctypes as C
+    pt = akr.PathTracer(0)
+    task = cbox_task(16)
+    with pytest.raises(akr.AkariError) as e:  # begin before a scene was uploaded
+        pt.begin(task)
+    assert e.value.code == 5  # AKR_ERR_STATE
+    scene = cbox(33, 17)
+    pt.upload_scene(scene)
+    with pytest.raises(akr.AkariError) as e:  # render_pass before begin
+        pt.render_pass(1)
+    assert e.value.code == 5
+    with pytest.raises(akr.AkariError) as e:  # tile outside the sensor
+        pt.begin(task, tile=(10, 40))
+    assert e.value.code == 1  # AKR_ERR_INVALID_ARGUMENT
+    pt.begin(task)
+    with pytest.raises(akr.AkariError) as e:  # more samples than the sampler was configured for
+        pt.render_pass(17)
+    assert e.value.code == 1
+    bad = cbox_task(16)
+    bad.raw.sampler.type = 0  # independent sampler: seeded from rand::StdRng in the reference, not reproducible
+    with pytest.raises(akr.AkariError) as e:
+        pt.begin(bad)
+    assert e.value.code == 3  # AKR_ERR_UNSUPPORTED
+    pt.close()
+    odd = akr.RenderTask.from_json('{"method": {"type": "pt", "spp": 5, "max_depth": 4, "rr_depth": 1, "spp_per_pass": 64},'
+                                   ' "sampler": {"type": "pmj02bn", "seed": 9}, "film": {"filter": {"type": "box", "radius": 0.5}, "out": "x.exr"}}')
+    pmj, bn = tables
+    film, st = _gpu_film(akr, scene, odd, wave_size=1024)
+    ofilm, ost, _ = oracle.render(scene.desc, 33, 17, odd.pt, odd.sampler, odd.filter, pmj, bn)
+    _gate(film.to_rgb(), oracle.resolve(ofilm, 33 * 17).reshape(17, 33, 3), rel_frac=5e-3, img=2e-3)
+    assert st.samples == 33 * 17 * 5
+    row, _ = _gpu_film(akr, scene, odd, tile=(16, 17))
+    assert np.array_equal(row.data[:3 * 33], film.data[3 * 33 * 16:3 * 33 * 17])

@@ -191,3 +191,38 @@ def test_primitive_intersector_variants(hostsim, oracle, tables, akr, cbox_task,
     same, frac_bad, img = _gate(film, ofilm, fh, ofh, w * h, oracle)
     print(f"{variant}: first hits identical {same:.5%}; pixels over 1e-3: {frac_bad:.5%}; image rel-L2 {img:.3e}")
     assert same >= 0.999 and frac_bad <= 5e-3 and img <= 5e-3
+
+
+def test_clutter_scene_bitwise(hostsim, oracle, tables, akr, cbox_task, tmp_path):
+    """~8.5 K triangles with smooth per-corner normals and two materials per mesh: BVH over primitives (leaf ranges,
+    box padding, depth) and the per-hit shading frame against the oracle's brute-force scan, bit for bit."""
+    w = h = 40
+    scene = akr.load_scene(sv.write_clutter(tmp_path)).set_resolution(w, h)
+    task = cbox_task(8)
+    pmj, bn = tables
+    table = oracle.albedo_table()
+    ofilm, ost, ofh = oracle.render(scene.desc, w, h, task.pt, task.sampler, task.filter, pmj, bn, want_first_hits=True)
+    film, fh, st = run_hostsim(hostsim, scene, task, tables, table, w, h)
+    assert st.n_tris > 8000 and st.n_nodes > 768  # more nodes than the shared-memory staging budget holds
+    assert np.array_equal(fh, ofh)
+    assert (st.segments, st.shadow_rays) == (ost.segments, ost.shadow_rays)
+    assert np.array_equal(film, ofilm), np.abs(film - ofilm).max()
+
+
+def test_clutter_primitive_intersector(hostsim, oracle, tables, akr, cbox_task, tmp_path):
+    """Same scene through the kernels' primitive intersector (sphere quads are not parallelograms: almost all
+    primitives are single triangles; the cbox walls stay pairs)."""
+    w = h = 40
+    scene = akr.load_scene(sv.write_clutter(tmp_path)).set_resolution(w, h)
+    task = cbox_task(8)
+    pmj, bn = tables
+    table = oracle.albedo_table()
+    ofilm, ost, ofh = oracle.render(scene.desc, w, h, task.pt, task.sampler, task.filter, pmj, bn, want_first_hits=True)
+    hostsim.hostsim_set_intersector(1)
+    try:
+        film, fh, st = run_hostsim(hostsim, scene, task, tables, table, w, h)
+    finally:
+        hostsim.hostsim_set_intersector(0)
+    same, frac_bad, img = _gate(film, ofilm, fh, ofh, w * h, oracle)
+    print(f"clutter: first hits identical {same:.5%}; pixels over 1e-3: {frac_bad:.5%}; image rel-L2 {img:.3e}; pairs {st.n_pairs}/{st.n_prims}")
+    assert same >= 0.999 and frac_bad <= 5e-3 and img <= 5e-3
