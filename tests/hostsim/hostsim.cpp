@@ -145,4 +145,10 @@ int hostsim_render(const AkrSceneDesc *desc, const AkrPtConfig *cfg, const AkrSa
 
 void hostsim_make_albedo_table(float *table, uint32_t n) { make_albedo_table(table, n); }
 
+// exact-division helper of the kernels (akr_math.cuh: FastDiv): q[i], r[i] = n[i] / d, n[i] % d
+void hostsim_fastdiv(const uint32_t *n, uint32_t count, uint32_t d, uint32_t *q, uint32_t *r) {
+    FastDiv f = make_fastdiv(d);
+    for (uint32_t i = 0; i < count; ++i) q[i] = fastdiv(n[i], f, r[i]);
+}
+
 }  // extern "C"

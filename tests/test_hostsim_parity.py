@@ -226,3 +226,19 @@ def test_clutter_primitive_intersector(hostsim, oracle, tables, akr, cbox_task, 
     same, frac_bad, img = _gate(film, ofilm, fh, ofh, w * h, oracle)
     print(f"clutter: first hits identical {same:.5%}; pixels over 1e-3: {frac_bad:.5%}; image rel-L2 {img:.3e}; pairs {st.n_pairs}/{st.n_prims}")
     assert same >= 0.999 and frac_bad <= 5e-3 and img <= 5e-3
+
+
+def test_fastdiv_is_exact(hostsim):
+    """The kernels replace path_id / n_pix and pixel / width by a mul.hi estimate + one fix-up; it must be exact for
+    every 32-bit dividend and any divisor (edge divisors, powers of two, the bench's 1280 and 921600, random)."""
+    rng = np.random.default_rng(7)
+    n = np.concatenate([np.arange(0, 70000, dtype=np.uint32), rng.integers(0, 2**32, 200000, dtype=np.uint64).astype(np.uint32),
+                        np.array([2**32 - 1, 2**31, 2**31 - 1, 2**31 + 1], dtype=np.uint32)])
+    q = np.zeros_like(n)
+    r = np.zeros_like(n)
+    divisors = [1, 2, 3, 5, 7, 32, 33, 1280, 1279, 65536, 65537, 921600, 2**31 - 1, 2**31, 2**31 + 1, 2**32 - 1] + \
+        [int(x) for x in rng.integers(1, 2**32, 40, dtype=np.uint64)]
+    for d in divisors:
+        hostsim.hostsim_fastdiv(C.c_void_p(n.ctypes.data), C.c_uint32(n.size), C.c_uint32(d), C.c_void_p(q.ctypes.data), C.c_void_p(r.ctypes.data))
+        assert np.array_equal(q, (n.astype(np.uint64) // d).astype(np.uint32)), d
+        assert np.array_equal(r, (n.astype(np.uint64) % d).astype(np.uint32)), d
