@@ -81,8 +81,29 @@ struct LaunchParams {
     uint32_t *dbg_first_hits;   // optional [n_film_pixels][2]
 };
 
+// Queue records are written once and read once, gigabytes later: stream them past L2 residency (evict-first) so that
+// the L2 keeps the sampler tables, the per-triangle records and the accumulators.  AKR_STREAM_QUEUES=0 restores the
+// default policy (A/B runs).
+#ifndef AKR_STREAM_QUEUES
+#define AKR_STREAM_QUEUES 1
+#endif
+__device__ __forceinline__ f4 ldq(const f4 *p) {
+#if AKR_STREAM_QUEUES
+    const float4 v = __ldcs(reinterpret_cast<const float4 *>(p));
+    return f4{v.x, v.y, v.z, v.w};
+#else
+    return ld4(p);
+#endif
+}
+__device__ __forceinline__ void stq(f4 *p, f4 v) {
+#if AKR_STREAM_QUEUES
+    __stcs(reinterpret_cast<float4 *>(p), make_float4(v.x, v.y, v.z, v.w));
+#else
+    st4(p, v);
+#endif
+}
 __device__ __forceinline__ PathState load_path(const PathQueue &q, uint32_t i) {
-    const f4 a = ld4(q.a + i), b = ld4(q.b + i), c = ld4(q.c + i);
+    const f4 a = ldq(q.a + i), b = ldq(q.b + i), c = ldq(q.c + i);
     PathState p;
     p.o = mk3(a.x, a.y, a.z);
     p.d = mk3(a.w, b.x, b.y);
@@ -93,9 +114,9 @@ __device__ __forceinline__ PathState load_path(const PathQueue &q, uint32_t i) {
     return p;
 }
 __device__ __forceinline__ void store_path(const PathQueue &q, uint32_t i, const PathState &p) {
-    st4(q.a + i, f4{p.o.x, p.o.y, p.o.z, p.d.x});
-    st4(q.b + i, f4{p.d.y, p.d.z, u2f(p.ex), u2f(p.path_id)});
-    st4(q.c + i, f4{p.beta.x, p.beta.y, p.beta.z, p.prev_bsdf_pdf});
+    stq(q.a + i, f4{p.o.x, p.o.y, p.o.z, p.d.x});
+    stq(q.b + i, f4{p.d.y, p.d.z, u2f(p.ex), u2f(p.path_id)});
+    stq(q.c + i, f4{p.beta.x, p.beta.y, p.beta.z, p.prev_bsdf_pdf});
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -512,12 +533,12 @@ template <int MODE, bool ALPHA> __global__ void __launch_bounds__(kBlock) k_trac
             const bool active = i < n_cl;
             f4 a{0.0f, 0.0f, 0.0f, 1.0f}, b{0.0f, 0.0f, 0.0f, 0.0f};
             if (active) {
-                a = ld4(q.a + i);
-                b = ld4(q.b + i);
+                a = ldq(q.a + i);
+                b = ldq(q.b + i);
             }
             const uint32_t path_id = f2u(b.w);
             const DevHit h = trace_dev<false, MODE, ALPHA>(P, ts, active, mk3(a.x, a.y, a.z), mk3(a.w, b.x, b.y), 0.0f, 1e20f, f2u(b.z), 0xffffffffu);
-            if (active) st4(P.hits.h + i, f4{u2f(h.gid), h.u, h.v, 0.0f});
+            if (active) stq(P.hits.h + i, f4{u2f(h.gid), h.u, h.v, 0.0f});
             const bool hit = active && h.gid != 0xffffffffu;
             const uint32_t cls = P.rp.force_diffuse ? (uint32_t)CLS_LAMBERT : h.cls;
             uint32_t s0, s1;
@@ -525,7 +546,7 @@ template <int MODE, bool ALPHA> __global__ void __launch_bounds__(kBlock) k_trac
             const uint32_t s2 = warp_append(ctr + 4u, hit && cls == CLS_GENERAL);
             if (hit) P.cls.idx[cls][cls == CLS_LAMBERT ? s0 : (cls == CLS_CONDUCTOR ? s1 : s2)] = make_uint2(i, path_id);
             if (active && !hit && miss_work) {
-                const f4 c = ld4(q.c + i);
+                const f4 c = ldq(q.c + i);
                 miss_body(P.rp, depth, mk3(c.x, c.y, c.z), path_id, P.acc);
             }
         } else {
@@ -534,13 +555,13 @@ template <int MODE, bool ALPHA> __global__ void __launch_bounds__(kBlock) k_trac
             f4 a{0.0f, 0.0f, 0.0f, 0.0f}, b{1.0f, 0.0f, 0.0f, 0.0f};
             uint32_t ex1 = 0xffffffffu;
             if (active) {
-                a = ld4(P.shadow.a + i);
-                b = ld4(P.shadow.b + i);
+                a = ldq(P.shadow.a + i);
+                b = ldq(P.shadow.b + i);
                 ex1 = P.shadow.ex1[i];
             }
             const DevHit h = trace_dev<true, MODE, ALPHA>(P, ts, active, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), 0.0f, a.w, f2u(b.w), ex1);
             if (active) {
-                const f4 c = ld4(P.shadow.c + i);
+                const f4 c = ldq(P.shadow.c + i);
                 ShadowItem it;
                 it.contrib = mk3(c.x, c.y, c.z);
                 it.path_id = f2u(c.w);
@@ -599,7 +620,7 @@ __global__ void __launch_bounds__(kShadeBlock, ShadeLaunch<CLS>::kMinBlocks) k_s
         o.has_next = false;
         if (active) {
             const uint32_t i = CLS == CLS_ANY ? k : cur.x;
-            const f4 hr = ld4(P.hits.h + i);
+            const f4 hr = ldq(P.hits.h + i);
             HitRec h{f2u(hr.x), hr.y, hr.z};
             if (CLS != CLS_ANY || h.gid != 0xffffffffu) {
                 PathState ps = load_path(qin, i);
@@ -624,9 +645,9 @@ __global__ void __launch_bounds__(kShadeBlock, ShadeLaunch<CLS>::kMinBlocks) k_s
             if (o.has_shadow) shadow_resolve(P.acc, o.shadow, occ != 0xffffffffu, depth + 1u);
         } else if (o.has_shadow) {
             const ShadowQueue &s = P.shadow;
-            st4(s.a + ss, f4{o.shadow.o.x, o.shadow.o.y, o.shadow.o.z, o.shadow.t_max});
-            st4(s.b + ss, f4{o.shadow.d.x, o.shadow.d.y, o.shadow.d.z, u2f(o.shadow.ex0)});
-            st4(s.c + ss, f4{o.shadow.contrib.x, o.shadow.contrib.y, o.shadow.contrib.z, u2f(o.shadow.path_id)});
+            stq(s.a + ss, f4{o.shadow.o.x, o.shadow.o.y, o.shadow.o.z, o.shadow.t_max});
+            stq(s.b + ss, f4{o.shadow.d.x, o.shadow.d.y, o.shadow.d.z, u2f(o.shadow.ex0)});
+            stq(s.c + ss, f4{o.shadow.contrib.x, o.shadow.contrib.y, o.shadow.contrib.z, u2f(o.shadow.path_id)});
             s.ex1[ss] = o.shadow.ex1;
         }
     }

@@ -23,7 +23,7 @@ AKR_HD float bluenoise(const SamplerTables &tab, uint32_t tex, uint32_t px, uint
     // reference texel: BLUE_NOISE_TEXTURES[tex % 48][px % 128][py % 128] (sampler/mod.rs:542-550);
     // the table is transposed at upload so that consecutive px are consecutive in memory.
     uint32_t t = tex % 48u;
-    uint16_t v = tab.bn[(t * 128u + (py & 127u)) * 128u + (px & 127u)];
+    uint16_t v = AKR_RO(tab.bn[(t * 128u + (py & 127u)) * 128u + (px & 127u)]);
     return (float)v / 65535.0f;
 }
 AKR_HD float sampler_1d(const SamplerTables &tab, const RenderParams &rp, uint32_t px, uint32_t py, uint32_t sample_index, uint32_t dim) {
@@ -43,8 +43,8 @@ AKR_HD f2 sampler_2d(const SamplerTables &tab, const RenderParams &rp, uint32_t 
         index = permute_element(sample_index, rp.spp_total, rp.w_mask, hash);
     }
     uint32_t i = 65536u * (pmj_instance % 5u) + (index % 65536u);
-    float ux = (float)tab.pmj[i * 2u] * 0x1p-32f;
-    float uy = (float)tab.pmj[i * 2u + 1u] * 0x1p-32f;
+    float ux = (float)AKR_RO(tab.pmj[i * 2u]) * 0x1p-32f;
+    float uy = (float)AKR_RO(tab.pmj[i * 2u + 1u]) * 0x1p-32f;
     ux = ux + bluenoise(tab, dim, px, py);
     uy = uy + bluenoise(tab, dim + 1u, px, py);
     ux = ux - floorf(ux);
@@ -179,41 +179,42 @@ struct CornerAttribs {           // optional per-corner arrays indexed by gid * 
     const float *normals;        // [n_tris * 3][3] or nullptr
     const float *tangents;       // [n_tris * 3][3] or nullptr
 };
+AKR_HD f3 ld3g(const float *p) { return mk3(AKR_RO(p[0]), AKR_RO(p[1]), AKR_RO(p[2])); }  // read-only scene data in global memory
 AKR_HD Surface surface_from_hit(const SceneView &sc, const CornerAttribs &ca, uint32_t gid, float u, float v) {
     const TriShade &ts = sc.shade[gid];
     const InstanceRec &in = sc.instances[ts.inst];
     float w0 = 1.0f - u - v;
-    f3 v0 = ld3(ts.v0), v1 = ld3(ts.v1), v2 = ld3(ts.v2);
+    f3 v0 = ld3g(ts.v0), v1 = ld3g(ts.v1), v2 = ld3g(ts.v2);
     f3 pl = w0 * v0 + u * v1 + v * v2;
-    f3 c0 = ld3(in.m), c1 = ld3(in.m + 3), c2 = ld3(in.m + 6);
+    f3 c0 = ld3g(in.m), c1 = ld3g(in.m + 3), c2 = ld3g(in.m + 6);
     Surface s;
-    s.p = (c0 * pl.x + c1 * pl.y + c2 * pl.z) + ld3(in.t);
-    s.ng = ld3(ts.ng);
-    s.area = ts.area;
-    if (!(ts.flags & (TRI_HAS_NORMALS | TRI_HAS_TANGENTS))) {
-        s.frame = Frame{s.ng, ld3(ts.ft), ld3(ts.fs)};
+    s.p = (c0 * pl.x + c1 * pl.y + c2 * pl.z) + ld3g(in.t);
+    s.ng = ld3g(ts.ng);
+    s.area = AKR_RO(ts.area);
+    if (!(AKR_RO(ts.flags) & (TRI_HAS_NORMALS | TRI_HAS_TANGENTS))) {
+        s.frame = Frame{s.ng, ld3g(ts.ft), ld3g(ts.fs)};
         return s;
     }
     // per-hit frame: ns from interpolated corner normals (mesh.rs:594-602,620-621), tangent from the
     // tangent buffer when present (mesh.rs:558-569) else the per-triangle dp/du stored in `ft`
     f3 ns = s.ng;
-    f3 i0 = ld3(in.m_inv_t), i1 = ld3(in.m_inv_t + 3), i2 = ld3(in.m_inv_t + 6);
-    if (ts.flags & TRI_HAS_NORMALS) {
+    f3 i0 = ld3g(in.m_inv_t), i1 = ld3g(in.m_inv_t + 3), i2 = ld3g(in.m_inv_t + 6);
+    if (AKR_RO(ts.flags) & TRI_HAS_NORMALS) {
         const float *n = ca.normals + (size_t)gid * 9u;
-        f3 nl = w0 * ld3(n) + u * ld3(n + 3) + v * ld3(n + 6);
+        f3 nl = w0 * ld3g(n) + u * ld3g(n + 3) + v * ld3g(n + 6);
         ns = normalize(i0 * nl.x + i1 * nl.y + i2 * nl.z);
     }
-    f3 tt = ld3(ts.ft);
-    if (ts.flags & TRI_HAS_TANGENTS) {
+    f3 tt = ld3g(ts.ft);
+    if (AKR_RO(ts.flags) & TRI_HAS_TANGENTS) {
         const float *t = ca.tangents + (size_t)gid * 9u;
-        f3 t0 = ld3(t), t1 = ld3(t + 3), t2 = ld3(t + 6);
+        f3 t0 = ld3g(t), t1 = ld3g(t + 3), t2 = ld3g(t + 6);
         bool fin = is_finite(t0.x) && is_finite(t0.y) && is_finite(t0.z) && is_finite(t1.x) && is_finite(t1.y) && is_finite(t1.z) &&
                    is_finite(t2.x) && is_finite(t2.y) && is_finite(t2.z);
         if (fin) {
             f3 tl = normalize(w0 * t0 + u * t1 + v * t2);
             tt = c0 * tl.x + c1 * tl.y + c2 * tl.z;
         } else {
-            tt = ld3(ts.fs);  // fallback dp/du tangent is kept in `fs` for tangent-buffer meshes
+            tt = ld3g(ts.fs);  // fallback dp/du tangent is kept in `fs` for tangent-buffer meshes
         }
     }
     s.frame = (tt.x != 0.0f || tt.y != 0.0f || tt.z != 0.0f) ? frame_from_n_t(ns, tt) : frame_from_n(ns);
@@ -260,6 +261,21 @@ AKR_HD ShadeOut shade_body(const SceneView &sc, const CornerAttribs &ca, const S
     out.has_next = false;
     const uint32_t id = ps.path_id;
     const bool dbg_on = rp.debug_depth < 0;
+    const uint32_t d1 = depth + 1u;         // pt.rs:469
+    // The sampler draws of this bounce depend only on (path id, depth), so they may be issued before the hit triangle
+    // and its material are fetched (table loads in flight meanwhile).  Measured on B200: helps the register-roomier
+    // conductor / general kernels (6.7 -> 6.5 ms), costs the 64-register Lambert kernel 3 % => decided per class.
+    constexpr bool kDrawFirst = CLS != CLS_LAMBERT;
+    const PathCoord pc = path_coord(rp, wave, id);
+    const uint32_t dim0 = bounce_first_dim(d1, rp.rr_depth);
+    float ul0 = 0.0f, ub0 = 0.0f;
+    f2 ul12{0.0f, 0.0f}, ub12{0.0f, 0.0f};
+    if (kDrawFirst) {
+        ul0 = sampler_1d(tab, rp, pc.px, pc.py, pc.sample_index, dim0);
+        ul12 = sampler_2d(tab, rp, pc.px, pc.py, pc.sample_index, dim0 + 1u);
+        ub0 = sampler_1d(tab, rp, pc.px, pc.py, pc.sample_index, dim0 + 3u);
+        ub12 = sampler_2d(tab, rp, pc.px, pc.py, pc.sample_index, dim0 + 4u);
+    }
     const TriShade &ts = sc.shade[hit.gid];
     const Material &mat = sc.materials[ts.mat];
     Surface si = surface_from_hit(sc, ca, hit.gid, hit.u, hit.v);
@@ -294,14 +310,13 @@ AKR_HD ShadeOut shade_body(const SceneView &sc, const CornerAttribs &ca, const S
         }
     }
     if (depth >= rp.max_depth) return out;  // pt.rs:466-468
-    const uint32_t d1 = depth + 1u;         // pt.rs:469
-    PathCoord pc = path_coord(rp, wave, id);
-    const uint32_t dim0 = bounce_first_dim(d1, rp.rr_depth);
     // u_direct = next_3d, u_bsdf = next_3d — both are always drawn (pt.rs:471-481)
-    float ul0 = sampler_1d(tab, rp, pc.px, pc.py, pc.sample_index, dim0);
-    f2 ul12 = sampler_2d(tab, rp, pc.px, pc.py, pc.sample_index, dim0 + 1u);
-    float ub0 = sampler_1d(tab, rp, pc.px, pc.py, pc.sample_index, dim0 + 3u);
-    f2 ub12 = sampler_2d(tab, rp, pc.px, pc.py, pc.sample_index, dim0 + 4u);
+    if (!kDrawFirst) {
+        ul0 = sampler_1d(tab, rp, pc.px, pc.py, pc.sample_index, dim0);
+        ul12 = sampler_2d(tab, rp, pc.px, pc.py, pc.sample_index, dim0 + 1u);
+        ub0 = sampler_1d(tab, rp, pc.px, pc.py, pc.sample_index, dim0 + 3u);
+        ub12 = sampler_2d(tab, rp, pc.px, pc.py, pc.sample_index, dim0 + 4u);
+    }
 
     // sample_light (pt.rs:170-209) -> LightAggregate::sample_direct -> AreaLight::sample_direct (light/area.rs:51-107)
     bool dl_valid = false;
