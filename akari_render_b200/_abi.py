@@ -129,7 +129,8 @@ class AkrEngineOptions(C.Structure):
         ("profile_stages", C.c_uint32),
         ("trace_mode", C.c_uint32),
         ("inline_shadow", C.c_uint32),
-        ("_reserved", C.c_uint32 * 3),
+        ("smem_node_kb", C.c_uint32),
+        ("_reserved", C.c_uint32 * 2),
     ]
 
 

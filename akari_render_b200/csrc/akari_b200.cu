@@ -32,6 +32,7 @@ constexpr uint32_t kMaxDepthSlots = 66;           // counters for depth 0 .. 64 
 //   [0] paths entering depth d (raygen for d = 0, else the survivors of shade(d - 1))
 //   [1] shadow rays produced by shade(d - 1), traced together with [0] by trace(d)
 //   [2 + c] hits of shade class c found by trace(d)
+//   [5] / [6] next closest-hit / shadow ray handed out by the dynamic-fetch BVH trace kernel
 // [0]/[1] and [2]/[3] are 8-byte aligned pairs, so one 64-bit atomic reserves slots in two queues at once.
 constexpr uint32_t kCtrStride = 8;
 constexpr uint32_t kSmemSceneBudget = 48 * 1024;  // bytes of BVH nodes + triangles staged per CTA
@@ -571,6 +572,167 @@ template <int MODE, bool ALPHA> __global__ void __launch_bounds__(kBlock) k_trac
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// BVH scenes: persistent warps with dynamic ray fetch (Aila & Laine's "persistent while-while")
+// ------------------------------------------------------------------------------------------------
+// Incoherent rays leave a BVH at very different times; with one fixed ray per lane the warp idles until its slowest
+// lane is done (ncu on the 8.5 K-triangle test scene: 8.5 of 32 lanes active).  Here a warp keeps per-lane traversal
+// state, advances all lanes by a bounded number of node visits, and whenever fewer than AKR_REFILL_BELOW lanes still
+// carry a live ray it retires the finished ones (hit record, class binning / shadow resolve, warp-aggregated) and
+// hands the free lanes new rays from a global counter (counter block words [5] closest-hit, [6] shadow).
+#ifndef AKR_REFILL_BELOW
+#define AKR_REFILL_BELOW 24
+#endif
+#ifndef AKR_SEGMENT_STEPS
+#define AKR_SEGMENT_STEPS 12
+#endif
+
+template <bool ANY_HIT, bool SMEM_ALL, bool ALPHA>
+__device__ __forceinline__ void bvh_phase(const LaunchParams &P, const TraceSmem &ts, uint32_t depth, uint32_t n_items, uint32_t *fetch) {
+    if (n_items == 0u) return;
+    const SceneView &sc = P.scene;
+    const PathQueue &q = P.q[depth & 1u];
+    uint32_t *ctr = P.counters + depth * kCtrStride;
+    const uint32_t lane = threadIdx.x & 31u, below = (1u << lane) - 1u;
+    const bool miss_work = depth != 0u && (P.rp.debug_depth < 0 || depth == (uint32_t)P.rp.debug_depth);
+    const uint32_t n_fast = P.scene_smem_nodes;
+    constexpr uint32_t kStackStride = kBlock * 4u;
+    // per-lane ray + traversal state
+    bool have = false, done = false;
+    uint32_t slot = 0u, path_id = 0u, ex0 = 0xffffffffu, ex1 = 0xffffffffu;
+    f3 o = splat3(0.0f), d = mk3(1.0f, 0.0f, 0.0f), inv_d = splat3(0.0f);
+    PrimHit best{0.0f, 0.0f, 0.0f, 0xffffffffu};
+    int32_t node = 0;
+    uint32_t sp = ts.stack;
+    bool exhausted = false;  // warp-uniform: the global counter ran past the queue
+    while (true) {
+        const uint32_t busy = __ballot_sync(0xffffffffu, have && !done);
+        if (busy == 0u || (!exhausted && __popc(busy) < AKR_REFILL_BELOW)) {
+            // ---- retire the finished lanes (all lanes take part in the ballots) ----
+            const bool fin = have && done;
+            if (!ANY_HIT) {
+                DevHit h{0xffffffffu, 0u, 0.0f, 0.0f};
+                if (fin && best.k != 0xffffffffu) {
+                    const PrimDecoded dec = prim_decode(load_prim<SMEM_ALL>(ts.prims, sc.prims, best.k), best.s, best.q);
+                    h = DevHit{dec.gid, dec.cls, dec.u, dec.v};
+                }
+                if (fin) stq(P.hits.h + slot, f4{u2f(h.gid), h.u, h.v, 0.0f});
+                const bool hit = fin && h.gid != 0xffffffffu;
+                const uint32_t cls = P.rp.force_diffuse ? (uint32_t)CLS_LAMBERT : h.cls;
+                uint32_t s0, s1;
+                warp_append2(ctr + 2u, hit && cls == CLS_LAMBERT, hit && cls == CLS_CONDUCTOR, s0, s1);
+                const uint32_t s2 = warp_append(ctr + 4u, hit && cls == CLS_GENERAL);
+                if (hit) P.cls.idx[cls][cls == CLS_LAMBERT ? s0 : (cls == CLS_CONDUCTOR ? s1 : s2)] = make_uint2(slot, path_id);
+                if (fin && !hit && miss_work) {
+                    const f4 c = ldq(q.c + slot);
+                    miss_body(P.rp, depth, mk3(c.x, c.y, c.z), path_id, P.acc);
+                }
+            } else if (fin) {
+                const f4 c = ldq(P.shadow.c + slot);
+                ShadowItem it;
+                it.contrib = mk3(c.x, c.y, c.z);
+                it.path_id = f2u(c.w);
+                shadow_resolve(P.acc, it, best.k != 0xffffffffu, depth);  // produced at depth - 1: depth1 = depth
+            }
+            have = have && !done;
+            // ---- hand new rays to the free lanes ----
+            if (!exhausted) {
+                const bool need = !have;
+                const uint32_t m = __ballot_sync(0xffffffffu, need);
+                uint32_t base = 0u;
+                if (lane == 0u) base = atomicAdd(fetch, (uint32_t)__popc(m));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                const uint32_t idx = base + (uint32_t)__popc(m & below);
+                if (need && idx < n_items) {
+                    float t_max;
+                    if (!ANY_HIT) {
+                        const f4 a = ldq(q.a + idx), b = ldq(q.b + idx);
+                        o = mk3(a.x, a.y, a.z);
+                        d = mk3(a.w, b.x, b.y);
+                        ex0 = f2u(b.z);
+                        ex1 = 0xffffffffu;
+                        path_id = f2u(b.w);
+                        t_max = 1e20f;
+                    } else {
+                        const f4 a = ldq(P.shadow.a + idx), b = ldq(P.shadow.b + idx);
+                        o = mk3(a.x, a.y, a.z);
+                        d = mk3(b.x, b.y, b.z);
+                        t_max = a.w;
+                        ex0 = f2u(b.w);
+                        ex1 = P.shadow.ex1[idx];
+                    }
+                    inv_d = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+                    best = PrimHit{t_max, 0.0f, 0.0f, 0xffffffffu};
+                    slot = idx;
+                    node = 0;  // the root is always an inner node
+                    sp = ts.stack;
+                    have = true;
+                    done = false;
+                }
+                exhausted = base + (uint32_t)__popc(m) >= n_items;
+            }
+            if (__ballot_sync(0xffffffffu, have) == 0u) break;
+        }
+        // ---- advance every live lane by a bounded number of visits ----
+        if (have && !done) {
+            int budget = AKR_SEGMENT_STEPS;
+            while (true) {
+                while (node >= 0 && budget > 0) {
+                    --budget;
+                    BvhNode n;
+                    if (SMEM_ALL || (uint32_t)node < n_fast) n = load_node<true>(ts.nodes, nullptr, (uint32_t)node);
+                    else n = load_node<false>(0u, sc.nodes, (uint32_t)node);
+                    float tn0, tn1;
+                    const bool h0 = box_test(n.lo0, n.hi0, o, inv_d, 0.0f, best.t, tn0);
+                    const bool h1 = box_test(n.lo1, n.hi1, o, inv_d, 0.0f, best.t, tn1);
+                    const int32_t c0 = n.c0, c1 = n.c1;
+                    if (h0 && h1) {
+                        const bool swap = tn1 < tn0;
+                        sts32(sp, swap ? c0 : c1);
+                        sp += kStackStride;
+                        node = swap ? c1 : c0;
+                    } else if (h0) {
+                        node = c0;
+                    } else if (h1) {
+                        node = c1;
+                    } else {
+                        if (sp == ts.stack) {
+                            done = true;
+                            break;
+                        }
+                        sp -= kStackStride;
+                        node = lds32(sp);
+                    }
+                }
+                if (done || node >= 0) break;  // finished, or out of budget in the middle of a descent
+                const uint32_t leaf = (uint32_t)(~node);
+                const uint32_t first = leaf >> 3, count = leaf & 7u;
+                for (uint32_t k = 0; k < count; ++k)
+                    prim_test<ALPHA>(sc, load_prim<SMEM_ALL>(ts.prims, sc.prims, first + k), first + k, o, d, 0.0f, ex0, ex1, best);
+                if ((ANY_HIT && best.k != 0xffffffffu) || sp == ts.stack) {
+                    done = true;
+                    break;
+                }
+                sp -= kStackStride;
+                node = lds32(sp);
+                if (--budget <= 0) break;
+            }
+        }
+    }
+}
+
+template <bool SMEM_ALL, bool ALPHA> __global__ void __launch_bounds__(kBlock) k_trace_bvh(const __grid_constant__ LaunchParams P, uint32_t depth) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bar;
+    uint32_t *ctr = P.counters + depth * kCtrStride;
+    const uint32_t n_cl = ctr[0];
+    const uint32_t n_sh = P.inline_shadow ? 0u : ctr[1];
+    if (blockIdx.x * kBlock >= n_cl + n_sh) return;  // more CTAs than rays: skip the staging too
+    const TraceSmem ts = stage_scene(P, smem, &bar);
+    bvh_phase<false, SMEM_ALL, ALPHA>(P, ts, depth, n_cl, ctr + 5u);
+    bvh_phase<true, SMEM_ALL, ALPHA>(P, ts, depth, n_sh, ctr + 6u);
+}
+
 // resident CTAs per SM the shade kernels are compiled for (register budget = 65536 / (256 * n)); tuned on B200
 #ifndef AKR_SHADE_MINB_LAMBERT
 #define AKR_SHADE_MINB_LAMBERT 4
@@ -724,6 +886,7 @@ struct AkrContext {
     uint32_t smem_nodes = 0, smem_prims = 0, smem_bytes = 0;  // smem_bytes = nodes + primitives (stacks come on top)
     uint32_t bvh_depth = 0;
     uint32_t class_mask = 0;   // shade classes present in the scene
+    int occ_trace_dyn = 1;  // k_trace_bvh (dynamic fetch)
     int occ_trace[3] = {1, 1, 1}, occ_shade[4] = {1, 1, 1, 1}, occ_shade_inline[3] = {1, 1, 1};  // resident CTAs per SM, per kernel variant
 
     // render state
@@ -869,6 +1032,10 @@ int akr_b200_create(int device_ordinal, AkrContext **out_ctx) {
         delete ctx;
         return AKR_ERR_CUDA;
     }
+    cudaFuncSetAttribute(k_trace_bvh<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
+    cudaFuncSetAttribute(k_trace_bvh<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
+    cudaFuncSetAttribute(k_trace_bvh<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
+    cudaFuncSetAttribute(k_trace_bvh<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
     cudaFuncSetAttribute(k_trace<TRACE_BVH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
     cudaFuncSetAttribute(k_trace<TRACE_FLAT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
     cudaFuncSetAttribute(k_trace<TRACE_BVH_SMEM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
@@ -987,10 +1154,18 @@ int akr_b200_upload_scene(AkrContext *ctx, const AkrSceneDesc *desc) {
         if (m.type == MAT_PRINCIPLED && (m.lobes & (LOBE_COAT | LOBE_SPECULAR))) ctx->scene_needs_table = true;
     // shared-memory staging plan: top of the BVH first, then all primitives if they still fit
     const uint32_t tri_bytes = v.n_prims * (uint32_t)sizeof(PrimRec);
-    ctx->smem_nodes = std::min(v.n_nodes, kSmemSceneBudget / (uint32_t)sizeof(BvhNode));
-    uint32_t used = ctx->smem_nodes * (uint32_t)sizeof(BvhNode);
-    ctx->smem_prims = (ctx->smem_nodes == v.n_nodes && used + tri_bytes <= kSmemSceneBudget) ? 1u : 0u;
-    if (ctx->smem_prims) used += tri_bytes;
+    // whole scene in shared memory when it fits the budget; otherwise only the top of the tree (breadth-first order)
+    // so that several CTAs stay resident per SM — the deeper nodes and the primitives come through L1/L2
+    uint32_t used = v.n_nodes * (uint32_t)sizeof(BvhNode);
+    ctx->smem_prims = (used + tri_bytes <= kSmemSceneBudget) ? 1u : 0u;
+    if (ctx->smem_prims) {
+        ctx->smem_nodes = v.n_nodes;
+        used += tri_bytes;
+    } else {
+        const uint32_t top_bytes = (ctx->opts.smem_node_kb ? ctx->opts.smem_node_kb : 16u) * 1024u;
+        ctx->smem_nodes = std::min(v.n_nodes, std::min(top_bytes, kSmemSceneBudget) / (uint32_t)sizeof(BvhNode));
+        used = ctx->smem_nodes * (uint32_t)sizeof(BvhNode);
+    }
     ctx->smem_bytes = used;
     ctx->bvh_depth = blob.bvh_depth;
     ctx->class_mask = 0;
@@ -1017,6 +1192,17 @@ int akr_b200_upload_scene(AkrContext *ctx, const AkrSceneDesc *desc) {
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_shade_inline[1], k_shade<CLS_CONDUCTOR, true>, kShadeBlock, smem_inline);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_shade_inline[2], k_shade<CLS_GENERAL, true>, kShadeBlock, smem_inline);
         for (int &o : ctx->occ_shade_inline) o = std::max(o, 1);
+        {
+            const bool all = ctx->smem_prims != 0;
+            if (blob.any_alpha) {
+                if (all) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_trace_dyn, k_trace_bvh<true, true>, kBlock, smem_bvh);
+                else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_trace_dyn, k_trace_bvh<false, true>, kBlock, smem_bvh);
+            } else {
+                if (all) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_trace_dyn, k_trace_bvh<true, false>, kBlock, smem_bvh);
+                else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_trace_dyn, k_trace_bvh<false, false>, kBlock, smem_bvh);
+            }
+            ctx->occ_trace_dyn = std::max(ctx->occ_trace_dyn, 1);
+        }
         for (int &o : ctx->occ_trace) o = std::max(o, 1);
         for (int &o : ctx->occ_shade) o = std::max(o, 1);
     }
@@ -1132,7 +1318,7 @@ int akr_b200_render_pass(AkrContext *ctx, uint32_t n_spp, int blocking) {
     const int bvh_mode = ctx->smem_prims ? TRACE_BVH_SMEM : TRACE_BVH;
     const bool flat_ok = ctx->scene.flat_blocks != nullptr && ctx->smem_prims;
     int trace_mode = flat_ok ? TRACE_FLAT : bvh_mode;
-    if (ctx->opts.trace_mode == 1u) trace_mode = bvh_mode;
+    if (ctx->opts.trace_mode == 1u || ctx->opts.trace_mode == 3u) trace_mode = bvh_mode;
     if (ctx->opts.trace_mode == 2u && flat_ok) trace_mode = TRACE_FLAT;
     P.stage_flat = trace_mode == TRACE_FLAT ? 1u : 0u;
     // shadow rays inside the shade kernels: flat mode, no stochastic alpha, per-class kernels; opts.inline_shadow = 2 turns it off
@@ -1142,6 +1328,7 @@ int akr_b200_render_pass(AkrContext *ctx, uint32_t n_spp, int blocking) {
     const size_t flat_smem = node_smem + (size_t)(ctx->scene.n_pair_blocks + ctx->scene.n_single_blocks) * sizeof(PrimBlock2);
     const size_t trace_smem = trace_mode == TRACE_FLAT ? flat_smem : ctx->smem_bytes + (size_t)P.stack_depth * kBlock * sizeof(int32_t);
     if (trace_smem > kSmemMax) return fail(ctx, AKR_ERR_UNSUPPORTED, "BVH too deep for the shared-memory traversal stack");
+    const bool dynamic_fetch = trace_mode != TRACE_FLAT && ctx->opts.trace_mode != 3u;  // trace_mode 3 = BVH with one fixed ray per lane (A/B)
     const bool binned = ctx->opts.sort_by_material != 2u;
     const bool alpha = ctx->scene.any_alpha != 0u;
     const uint32_t class_mask = ctx->rp.force_diffuse ? (1u << CLS_LAMBERT) : ctx->class_mask;
@@ -1204,6 +1391,15 @@ int akr_b200_render_pass(AkrContext *ctx, uint32_t n_spp, int blocking) {
                 if (trace_mode == TRACE_FLAT) {
                     if (alpha) AKR_LAUNCH(1, (k_trace<TRACE_FLAT, true>), g_trace, trace_smem, P, depth);
                     else AKR_LAUNCH(1, (k_trace<TRACE_FLAT, false>), g_trace, trace_smem, P, depth);
+                } else if (dynamic_fetch) {
+                    const int g_dyn = grid_for(ctx, n_paths, ctx->occ_trace_dyn);
+                    if (trace_mode == TRACE_BVH_SMEM) {
+                        if (alpha) AKR_LAUNCH(1, (k_trace_bvh<true, true>), g_dyn, trace_smem, P, depth);
+                        else AKR_LAUNCH(1, (k_trace_bvh<true, false>), g_dyn, trace_smem, P, depth);
+                    } else {
+                        if (alpha) AKR_LAUNCH(1, (k_trace_bvh<false, true>), g_dyn, trace_smem, P, depth);
+                        else AKR_LAUNCH(1, (k_trace_bvh<false, false>), g_dyn, trace_smem, P, depth);
+                    }
                 } else if (trace_mode == TRACE_BVH_SMEM) {
                     if (alpha) AKR_LAUNCH(1, (k_trace<TRACE_BVH_SMEM, true>), g_trace, trace_smem, P, depth);
                     else AKR_LAUNCH(1, (k_trace<TRACE_BVH_SMEM, false>), g_trace, trace_smem, P, depth);

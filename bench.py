@@ -131,9 +131,12 @@ def main():
     ap.add_argument("--wave", type=int, default=1 << 26, help="paths in flight per wave (0 = engine default of 4 Mi)")
     ap.add_argument("--trace-mode", type=int, default=0, help="0 auto, 1 BVH, 2 flat list")
     ap.add_argument("--sort", type=int, default=0, help="0/1 per-class shade kernels, 2 one generic shade kernel")
+    ap.add_argument("--smem-node-kb", type=int, default=0, help="BVH scenes: KiB of top-of-tree nodes staged per CTA (0 = default)")
     ap.add_argument("--inline-shadow", type=int, default=0, help="0 auto (shade traces its own shadow ray on flat scenes), 2 off")
     ap.add_argument("--profile-stages", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--scene", default="cbox", choices=["cbox", "clutter"],
+                    help="cbox = the BASELINE workload; clutter = cbox + 8.5 K-triangle spheres (BVH / divergence stress, not the headline)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -151,7 +154,13 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    scene = akr.load_scene(os.path.join(ROOT, "scenes", "cbox", "scene.json")).set_resolution(WIDTH, HEIGHT)
+    scene_path = os.path.join(ROOT, "scenes", "cbox", "scene.json")
+    if args.scene == "clutter":  # generated on the fly by the test-suite's scene generator (experiments only)
+        import tempfile
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import scene_variants
+        scene_path = scene_variants.write_clutter(tempfile.mkdtemp(prefix=f"akr_clutter_{rank}_"))
+    scene = akr.load_scene(scene_path).set_resolution(WIDTH, HEIGHT)
     task = akr.RenderTask.from_file(os.path.join(ROOT, "scenes", "cbox", "pt.json"))
     task.pt.spp = args.spp
     spp = args.spp
@@ -163,7 +172,7 @@ def main():
     my_rows = tile[1] - tile[0]
     stream = torch.cuda.current_stream().cuda_stream
     pt = akr.PathTracer(local_rank, stream=stream)
-    eng = dict(wave_size=args.wave, sort_by_material=args.sort, trace_mode=args.trace_mode, inline_shadow=args.inline_shadow)
+    eng = dict(wave_size=args.wave, sort_by_material=args.sort, trace_mode=args.trace_mode, inline_shadow=args.inline_shadow, smem_node_kb=args.smem_node_kb)
     pt.set_engine_options(profile_stages=1 if args.profile_stages else 0, **eng)
     pt.upload_scene(scene)
     max_rows = max_band_rows(HEIGHT, world)
@@ -289,7 +298,7 @@ def main():
     # Timed window = the oracle's own render loop (AkrOracleStats.seconds), the window the reference times itself
     # (Instant around each dispatch, pt.rs:1126-1157): scene preparation and the Python binding are excluded.
     cpu = None
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and args.scene == "cbox":  # (the oracle brute-forces every triangle: only the headline scene is timed)
         from oracle import binding as oracle
         cores = best_cpu_threads(oracle, scene, task, pmj, bn)
         _, ost, _ = oracle.render(scene.desc, WIDTH, HEIGHT, task.pt, task.sampler, task.filter, pmj, bn, spp_begin=0, spp_end=1, threads=cores)
@@ -305,7 +314,7 @@ def main():
             "metric": "path samples/sec on cbox 1280x720", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(spp, world, args.wave, args.trace_mode, args.sort),
+            "config": dict(workload_config(spp, world, args.wave, args.trace_mode, args.sort), **({"scene": args.scene} if args.scene != "cbox" else {})),
             "clocks": summarize_clocks(clocks),
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(st.kernel_launches),

@@ -251,11 +251,14 @@ typedef struct AkrEngineOptions {
     uint32_t sort_by_material;      /* 0 = default (hits binned per shade class, one shade kernel
                                      * per class), 1 = same, 2 = off (one generic shade kernel)  */
     uint32_t profile_stages;        /* record per-stage CUDA-event times (adds syncs)           */
-    uint32_t trace_mode;            /* 0 = auto, 1 = BVH traversal, 2 = flat triangle list (only
-                                     * honoured when every triangle fits in shared memory)       */
+    uint32_t trace_mode;            /* 0 = auto, 1 = BVH traversal (persistent warps, dynamic ray fetch),
+                                     * 2 = flat primitive list (only honoured when every primitive fits
+                                     * in shared memory), 3 = BVH traversal with one fixed ray per lane  */
     uint32_t inline_shadow;         /* 0 = auto (shade kernels trace their own shadow ray when the
                                      * flat list is in use), 2 = off (always use the shadow queue) */
-    uint32_t _reserved[3];
+    uint32_t smem_node_kb;          /* BVH scenes that do not fit in shared memory: KiB of top-of-tree nodes each
+                                     * CTA stages (0 = default 16); read by akr_b200_upload_scene              */
+    uint32_t _reserved[2];
 } AkrEngineOptions;
 int akr_b200_set_engine_options(AkrContext *ctx, const AkrEngineOptions *opts);
 
