@@ -226,7 +226,8 @@ template <bool SHARED> __device__ __forceinline__ BvhNode load_node(uint32_t s_n
 // Stages nodes[0 .. n_nodes) and (optionally) all primitives behind `smem` with one TMA bulk copy each.
 __device__ __forceinline__ TraceSmem stage_scene(const LaunchParams &P, unsigned char *smem, uint64_t *bar) {
     const uint32_t node_bytes = P.scene_smem_nodes * (uint32_t)sizeof(BvhNode);
-    const uint32_t tri_bytes = P.stage_flat ? (P.scene.n_pair_blocks + P.scene.n_single_blocks) * (uint32_t)sizeof(PrimBlock2)
+    const uint32_t tri_bytes = P.stage_flat ? (P.scene.n_pair_blocks + P.scene.n_single_blocks + P.scene.n_occ_pair_blocks + P.scene.n_occ_single_blocks) *
+                                                  (uint32_t)sizeof(PrimBlock2)
                                             : (P.scene_smem_prims ? P.scene.n_prims * (uint32_t)sizeof(PrimRec) : 0u);
     BvhNode *s_nodes = reinterpret_cast<BvhNode *>(smem);
     PrimRec *s_tris = reinterpret_cast<PrimRec *>(smem + node_bytes);
@@ -377,10 +378,13 @@ __device__ __forceinline__ uint32_t trace_flat2_core(const SceneView &sc, const 
                                                      uint32_t ex1, float &best_t) {
     best_t = active ? t_max : 0.0f;  // an idle lane accepts nothing
     uint32_t best_k = 0xffffffffu;
-    const uint32_t n_pair_blocks = sc.n_pair_blocks, n_blocks = n_pair_blocks + sc.n_single_blocks;
+    // closest-hit rays walk the complete list, any-hit rays the occluder-only list staged right behind it
+    const uint32_t b0 = ANY_HIT ? sc.n_pair_blocks + sc.n_single_blocks : 0u;
+    const uint32_t n_pair_blocks = b0 + (ANY_HIT ? sc.n_occ_pair_blocks : sc.n_pair_blocks);
+    const uint32_t n_blocks = n_pair_blocks + (ANY_HIT ? sc.n_occ_single_blocks : sc.n_single_blocks);
     bool all_done = false;
 #pragma unroll 1
-    for (uint32_t b = 0; b < n_pair_blocks; ++b) {
+    for (uint32_t b = b0; b < n_pair_blocks; ++b) {
         flat2_block<true, ALPHA>(sc, ts.prims + b * (uint32_t)sizeof(PrimBlock2), b, o, d, t_min, ex0, ex1, best_t, best_k);
         if (ANY_HIT && (b & 3u) == 3u && __all_sync(0xffffffffu, !active || best_k != 0xffffffffu)) {
             all_done = true;
@@ -1131,6 +1135,8 @@ int akr_b200_upload_scene(AkrContext *ctx, const AkrSceneDesc *desc) {
     v.flat_blocks = blob.flat_blocks.empty() ? nullptr : static_cast<const PrimBlock2 *>(ctx->flat_prims.ptr);
     v.n_pair_blocks = blob.n_pair_blocks;
     v.n_single_blocks = blob.n_single_blocks;
+    v.n_occ_pair_blocks = blob.n_occ_pair_blocks;
+    v.n_occ_single_blocks = blob.n_occ_single_blocks;
     v.tris = nullptr;  // the Moeller-Trumbore triangle list is host-simulation data; the kernels intersect primitives
     v.shade = static_cast<const TriShade *>(ctx->shade.ptr);
     v.instances = static_cast<const InstanceRec *>(ctx->instances.ptr);
@@ -1325,7 +1331,8 @@ int akr_b200_render_pass(AkrContext *ctx, uint32_t n_spp, int blocking) {
     P.inline_shadow = (trace_mode == TRACE_FLAT && !ctx->scene.any_alpha && ctx->opts.sort_by_material != 2u && ctx->opts.inline_shadow != 2u) ? 1u : 0u;
     // shared memory: staged nodes + (flat mode: the padded PrimBlock2 list | BVH modes: primitives + per-thread stacks)
     const size_t node_smem = (size_t)ctx->smem_nodes * sizeof(BvhNode);
-    const size_t flat_smem = node_smem + (size_t)(ctx->scene.n_pair_blocks + ctx->scene.n_single_blocks) * sizeof(PrimBlock2);
+    const size_t flat_smem = node_smem + (size_t)(ctx->scene.n_pair_blocks + ctx->scene.n_single_blocks + ctx->scene.n_occ_pair_blocks +
+                                                  ctx->scene.n_occ_single_blocks) * sizeof(PrimBlock2);
     const size_t trace_smem = trace_mode == TRACE_FLAT ? flat_smem : ctx->smem_bytes + (size_t)P.stack_depth * kBlock * sizeof(int32_t);
     if (trace_smem > kSmemMax) return fail(ctx, AKR_ERR_UNSUPPORTED, "BVH too deep for the shared-memory traversal stack");
     const bool dynamic_fetch = trace_mode != TRACE_FLAT && ctx->opts.trace_mode != 3u;  // trace_mode 3 = BVH with one fixed ray per lane (A/B)

@@ -120,8 +120,11 @@ struct CameraRec {
 struct SceneView {
     const BvhNode *nodes;      // leaves address primitives: ~c = (first_prim << 3) | count
     const PrimRec *prims;      // BVH leaf order (CUDA kernels)
-    const PrimBlock2 *flat_blocks;  // small scenes only (flat trace mode), else nullptr
-    uint32_t n_pair_blocks, n_single_blocks;
+    const PrimBlock2 *flat_blocks;  // small scenes only (flat trace mode), else nullptr: [ every primitive | occluders only ]
+    uint32_t n_pair_blocks, n_single_blocks;          // the complete list (closest-hit rays)
+    uint32_t n_occ_pair_blocks, n_occ_single_blocks;  // the occluder list behind it (any-hit rays): primitives whose plane
+                                                      // supports the whole scene (convex-hull walls) cannot block a segment
+                                                      // between two points of the scene and are left out
     const TriGeom *tris;       // two slots per primitive, gid 0xffffffff = empty (Moeller-Trumbore path of the host simulation)
     const TriShade *shade;
     const InstanceRec *instances;

@@ -873,29 +873,52 @@ int build_scene_blob(const AkrSceneDesc &d, HostSceneBlob &out, std::string &err
         std::memset(&never, 0, sizeof(never));
         for (int c = 0; c < 4; ++c) never.n[c] = never.r0[c] = never.r1[c] = std::numeric_limits<float>::quiet_NaN();
         never.gid_a = never.gid_b = 0xffffffffu;
-        std::vector<PrimRec> pairs, singles;
-        for (const PrimRec &pr : out.prims) (pr.gid_b != 0xffffffffu ? pairs : singles).push_back(pr);
-        if (pairs.size() & 1u) pairs.push_back(never);
-        if (singles.size() & 1u) singles.push_back(never);
-        out.n_pair_blocks = static_cast<uint32_t>(pairs.size() / 2);
-        out.n_single_blocks = static_cast<uint32_t>(singles.size() / 2);
-        pairs.insert(pairs.end(), singles.begin(), singles.end());
-        out.flat_blocks.resize(pairs.size() / 2);
-        for (size_t b2 = 0; b2 < out.flat_blocks.size(); ++b2) {
-            PrimBlock2 &blk = out.flat_blocks[b2];
-            std::memset(&blk, 0, sizeof(blk));
-            for (int h = 0; h < 2; ++h) {
-                const PrimRec &pr = pairs[2 * b2 + h];
-                for (int c = 0; c < 4; ++c) {
-                    blk.n[c][h] = pr.n[c];
-                    blk.r0[c][h] = pr.r0[c];
-                    blk.r1[c][h] = pr.r1[c];
-                }
-                blk.gid[2 * h] = pr.gid_a;
-                blk.gid[2 * h + 1] = pr.gid_b;
-                blk.meta[h] = pr.meta;
+        // A primitive whose plane has every vertex of the scene on one side (a wall of the scene's convex hull)
+        // can meet a segment between two scene points only at an end point, which the (0, t_max) range of a shadow
+        // ray excludes: such primitives are left out of the any-hit list.
+        auto supports_scene = [&](const PrimRec &pr) {
+            if (!(pr.n[0] == pr.n[0])) return false;  // degenerate (NaN plane)
+            const double eps = 1e-5 * static_cast<double>(diag);
+            bool pos = false, neg = false;
+            for (size_t v = 0; v < static_cast<size_t>(total_tris) * 3; ++v) {
+                const float *w = world.data() + v * 3;
+                double dist = static_cast<double>(pr.n[0]) * w[0] + static_cast<double>(pr.n[1]) * w[1] + static_cast<double>(pr.n[2]) * w[2] + pr.n[3];
+                pos |= dist > eps;
+                neg |= dist < -eps;
+                if (pos && neg) return false;
             }
-        }
+            return true;
+        };
+        auto emit_blocks = [&](const std::vector<PrimRec> &list, uint32_t &n_pair_blocks, uint32_t &n_single_blocks) {
+            std::vector<PrimRec> pairs, singles;
+            for (const PrimRec &pr : list) (pr.gid_b != 0xffffffffu ? pairs : singles).push_back(pr);
+            if (pairs.size() & 1u) pairs.push_back(never);
+            if (singles.size() & 1u) singles.push_back(never);
+            n_pair_blocks = static_cast<uint32_t>(pairs.size() / 2);
+            n_single_blocks = static_cast<uint32_t>(singles.size() / 2);
+            pairs.insert(pairs.end(), singles.begin(), singles.end());
+            for (size_t b2 = 0; b2 < pairs.size() / 2; ++b2) {
+                PrimBlock2 blk;
+                std::memset(&blk, 0, sizeof(blk));
+                for (int h = 0; h < 2; ++h) {
+                    const PrimRec &pr = pairs[2 * b2 + h];
+                    for (int c = 0; c < 4; ++c) {
+                        blk.n[c][h] = pr.n[c];
+                        blk.r0[c][h] = pr.r0[c];
+                        blk.r1[c][h] = pr.r1[c];
+                    }
+                    blk.gid[2 * h] = pr.gid_a;
+                    blk.gid[2 * h + 1] = pr.gid_b;
+                    blk.meta[h] = pr.meta;
+                }
+                out.flat_blocks.push_back(blk);
+            }
+        };
+        emit_blocks(out.prims, out.n_pair_blocks, out.n_single_blocks);
+        std::vector<PrimRec> occluders;
+        for (const PrimRec &pr : out.prims)
+            if (!supports_scene(pr)) occluders.push_back(pr);
+        emit_blocks(occluders, out.n_occ_pair_blocks, out.n_occ_single_blocks);
     }
     // flatten: breadth-first over inner nodes; a leaf root becomes an inner node with an empty second child
     auto leaf_code = [&](const BuildNode &n) { return ~static_cast<int32_t>((n.first << 3) | n.count); };
@@ -988,6 +1011,8 @@ SceneView host_scene_view(const HostSceneBlob &b, const float *albedo_table) {
     v.flat_blocks = b.flat_blocks.empty() ? nullptr : b.flat_blocks.data();
     v.n_pair_blocks = b.n_pair_blocks;
     v.n_single_blocks = b.n_single_blocks;
+    v.n_occ_pair_blocks = b.n_occ_pair_blocks;
+    v.n_occ_single_blocks = b.n_occ_single_blocks;
     v.tris = b.tris.data();
     v.shade = b.shade.data();
     v.instances = b.instances.data();

@@ -21,7 +21,8 @@ struct HostSceneBlob {
     std::vector<BvhNode> nodes;
     std::vector<PrimRec> prims;       // BVH leaf order (what the CUDA kernels intersect)
     std::vector<PrimBlock2> flat_blocks;  // scenes of <= kFlatMaxPrims primitives: pairs first, two per block (flat trace mode)
-    uint32_t n_pair_blocks = 0, n_single_blocks = 0;
+    uint32_t n_pair_blocks = 0, n_single_blocks = 0;          // complete list, then ...
+    uint32_t n_occ_pair_blocks = 0, n_occ_single_blocks = 0;  // ... the occluder-only list (any-hit rays)
     std::vector<TriGeom> tris;        // two per primitive, same order (host simulation's Moeller-Trumbore path)
     std::vector<TriShade> shade;      // by global triangle id
     std::vector<InstanceRec> instances;

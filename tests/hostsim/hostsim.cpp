@@ -25,6 +25,7 @@ struct HostsimStats {
     uint32_t n_nodes, n_tris, n_materials, n_lights, bvh_depth;
     uint32_t material_types[8];
     uint32_t n_prims, n_pairs;
+    uint32_t flat_blocks, flat_occluder_blocks;  // flat trace mode: 2-primitive blocks of the complete / occluder-only list
 };
 
 // 0: Moeller-Trumbore triangles (bit-exact twin of the oracle); 1: the CUDA kernels' primitive intersector
@@ -135,6 +136,8 @@ int hostsim_render(const AkrSceneDesc *desc, const AkrPtConfig *cfg, const AkrSa
         stats->n_tris = (uint32_t)blob.shade.size();
         stats->n_prims = (uint32_t)blob.prims.size();
         for (const PrimRec &pr : blob.prims) stats->n_pairs += pr.gid_b != 0xffffffffu ? 1u : 0u;
+        stats->flat_blocks = blob.n_pair_blocks + blob.n_single_blocks;
+        stats->flat_occluder_blocks = blob.n_occ_pair_blocks + blob.n_occ_single_blocks;
         stats->n_materials = (uint32_t)blob.materials.size();
         stats->n_lights = (uint32_t)blob.lights.size();
         stats->bvh_depth = blob.bvh_depth;

@@ -15,7 +15,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 class HostsimStats(C.Structure):
     _fields_ = [("samples", C.c_uint64), ("segments", C.c_uint64), ("shadow_rays", C.c_uint64), ("n_nodes", C.c_uint32),
                 ("n_tris", C.c_uint32), ("n_materials", C.c_uint32), ("n_lights", C.c_uint32), ("bvh_depth", C.c_uint32),
-                ("material_types", C.c_uint32 * 8), ("n_prims", C.c_uint32), ("n_pairs", C.c_uint32)]
+                ("material_types", C.c_uint32 * 8), ("n_prims", C.c_uint32), ("n_pairs", C.c_uint32),
+                ("flat_blocks", C.c_uint32), ("flat_occluder_blocks", C.c_uint32)]
 
 
 @pytest.fixture(scope="module")
@@ -165,6 +166,9 @@ def test_primitive_intersector_vs_oracle(hostsim, oracle, tables, cbox, cbox_tas
         hostsim.hostsim_set_intersector(0)
     # 14 of the 18 quads are exact parallelograms; floor, back wall, left wall and the short box top are trapezoids
     assert (st.n_tris, st.n_prims, st.n_pairs) == (36, 22, 14)
+    # flat trace mode: 7 pair blocks + 4 single blocks; the five room walls support the scene (every vertex on one side),
+    # so shadow rays only test the light + the two boxes: 11 pairs + 2 singles (short box top) -> 6 + 1 blocks
+    assert (st.flat_blocks, st.flat_occluder_blocks) == (11, 7)
     same, frac_bad, img = _gate(film, ofilm, fh, ofh, w * h, oracle)
     print(f"first hits identical {same:.5%}; pixels over 1e-3: {frac_bad:.5%}; image rel-L2 {img:.3e}")
     assert same >= 0.9999
