@@ -85,11 +85,15 @@ def test_material_variants_parity(akr, oracle, tables, cbox_task, tmp_path, vari
 
 
 @pytest.mark.parametrize("kw", [dict(use_nee=0), dict(max_depth=0), dict(max_depth=1), dict(rr_depth=0), dict(indirect_only=1),
-                                dict(force_diffuse=1), dict(debug_depth=2)])
+                                dict(force_diffuse=1), dict(debug_depth=2), dict(pixel_offset=(3, -2))])
 def test_config_knobs_parity(akr, oracle, tables, cbox, cbox_task, kw):
     """pt::Config knobs (pt.rs:916-944) through the CUDA path."""
     w = h = 64
+    kw = dict(kw)
+    off = kw.pop("pixel_offset", None)
     scene, task = cbox(w, h), cbox_task(16, **kw)
+    if off is not None:
+        task.pt.pixel_offset[0], task.pt.pixel_offset[1] = off
     pmj, bn = tables
     film, st = _gpu_film(akr, scene, task)
     ofilm, ost, _ = oracle.render(scene.desc, w, h, task.pt, task.sampler, task.filter, pmj, bn)
@@ -132,11 +136,16 @@ def test_bvh_and_flat_trace_modes_agree(akr, cbox, cbox_task):
     w = h = 128
     scene, task = cbox(w, h), cbox_task(16)
     flat, sf = _gpu_film(akr, scene, task, trace_mode=2)
-    bvh, sb = _gpu_film(akr, scene, task, trace_mode=1)
-    same = (flat.data == bvh.data).mean()
-    print(f"identical film words: {same:.6%}")
-    assert same >= 0.9999
-    assert abs(int(sf.segments) - int(sb.segments)) <= 1e-5 * sf.segments
+    for mode in (1, 3):  # 1 = persistent warps with dynamic ray fetch, 3 = one fixed ray per lane
+        bvh, sb = _gpu_film(akr, scene, task, trace_mode=mode)
+        same = (flat.data == bvh.data).mean()
+        print(f"trace_mode {mode}: identical film words: {same:.6%}")
+        assert same >= 0.9999
+        assert abs(int(sf.segments) - int(sb.segments)) <= 1e-5 * sf.segments
+    # the shadow-ray queue (trace kernel) and the inline shadow rays (shade kernels) are the same computation
+    queued, sq = _gpu_film(akr, scene, task, inline_shadow=2)
+    assert np.array_equal(queued.data, flat.data)
+    assert (sq.segments, sq.shadow_rays) == (sf.segments, sf.shadow_rays)
 
 
 def test_full_size_frame_properties(akr, cbox, cbox_task):
