@@ -22,6 +22,22 @@ struct alignas(16) BvhNode {
 };
 static_assert(sizeof(BvhNode) == 64, "BvhNode must be 64 bytes");
 
+// 4-wide node (the BVH2 collapsed two levels at a time): fewer, fatter steps per ray — half the dependent node
+// fetches and loop trips of the binary tree, and the slab tests of two children can ride on one packed FFMA2.
+// STATUS: built and validated on the host (tests: test_bvh4_collapse_bitwise) but NOT yet walked by the kernels — the
+// first device version (dynamic-fetch kernel over this tree) measured slower than the binary tree on B200 (142 vs 76 ms
+// per pass on the clutter scene: the per-lane child arrays went to local memory, the 3x deeper stack cost occupancy),
+// so k_trace_bvh keeps the binary tree for now.
+// lo[axis][child] / hi[axis][child]: children (0,1) and (2,3) are adjacent pairs.  Empty slots: lo = +inf, hi = -inf,
+// c = ~0 (a leaf of zero primitives).  Child codes as in BvhNode, inner indices refer to the Bvh4Node array.
+struct alignas(16) Bvh4Node {
+    float lo[3][4];
+    float hi[3][4];
+    int32_t c[4];
+    uint32_t _pad[4];
+};
+static_assert(sizeof(Bvh4Node) == 128, "Bvh4Node must be 128 bytes");
+
 // World-space triangle for the Moeller-Trumbore traversal, stored in primitive order (2 per PrimRec).  48 bytes.
 struct alignas(16) TriGeom {
     float v0[3];
@@ -119,6 +135,8 @@ struct CameraRec {
 
 struct SceneView {
     const BvhNode *nodes;      // leaves address primitives: ~c = (first_prim << 3) | count
+    const Bvh4Node *nodes4;    // the same tree, 4-wide (host simulation only for now; nullptr on the device)
+    uint32_t n_nodes4, bvh4_depth;
     const PrimRec *prims;      // BVH leaf order (CUDA kernels)
     const PrimBlock2 *flat_blocks;  // small scenes only (flat trace mode), else nullptr: [ every primitive | occluders only ]
     uint32_t n_pair_blocks, n_single_blocks;          // the complete list (closest-hit rays)

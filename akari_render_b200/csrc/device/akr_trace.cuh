@@ -130,6 +130,79 @@ AKR_HD HitRec trace_ray(const SceneView &sc, const TraceData &td, f3 o, f3 d, fl
     return best;
 }
 
+// Slab test of child k of a 4-wide node in the form the kernel evaluates with packed FMAs: t = plane * inv_d + ood,
+// ood = -o * inv_d (boxes are padded at build time; NaNs drop out of fminf/fmaxf).
+AKR_HD bool box4_test(const Bvh4Node &n, int k, f3 inv_d, f3 ood, float t_min, float t_max, float &t_near) {
+    float tx0 = fmaf(n.lo[0][k], inv_d.x, ood.x), tx1 = fmaf(n.hi[0][k], inv_d.x, ood.x);
+    float ty0 = fmaf(n.lo[1][k], inv_d.y, ood.y), ty1 = fmaf(n.hi[1][k], inv_d.y, ood.y);
+    float tz0 = fmaf(n.lo[2][k], inv_d.z, ood.z), tz1 = fmaf(n.hi[2][k], inv_d.z, ood.z);
+    float tn = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), t_min));
+    float tf = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fminf(fmaxf(tz0, tz1), t_max));
+    t_near = tn;
+    return tn <= tf;
+}
+// One step of the 4-wide traversal: tests the four children of `n`, returns the nearest hit child (or 0x7fffffff when
+// none is hit) and writes the other hit children to `push` (n_push of them).
+AKR_HD int32_t bvh4_step(const Bvh4Node &n, f3 inv_d, f3 ood, float t_min, float t_max, int32_t push[3], int &n_push) {
+    float tn[4];
+    bool hit[4];
+    for (int k = 0; k < 4; ++k) hit[k] = box4_test(n, k, inv_d, ood, t_min, t_max, tn[k]);
+    int best = -1;
+    for (int k = 0; k < 4; ++k)
+        if (hit[k] && (best < 0 || tn[k] < tn[best])) best = k;
+    n_push = 0;
+    if (best < 0) return 0x7fffffff;
+    for (int k = 0; k < 4; ++k)
+        if (hit[k] && k != best) push[n_push++] = n.c[k];
+    return n.c[best];
+}
+
+// Moeller-Trumbore closest / any hit over the 4-wide tree (host simulation: validates the collapsed tree bit for bit
+// against the oracle's brute-force scan; the tie rule makes the result independent of the visiting order).
+template <bool ANY_HIT>
+AKR_HD HitRec trace_ray4(const SceneView &sc, f3 o, f3 d, float t_min, float t_max, uint32_t ex0, uint32_t ex1) {
+    const TriGeom *tris = sc.tris;
+    HitRec best{0xffffffffu, 0.0f, 0.0f};
+    float best_t = t_max;
+    const f3 inv_d = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    const f3 ood = mk3(-o.x * inv_d.x, -o.y * inv_d.y, -o.z * inv_d.z);
+    int32_t stack[3 * AKR_BVH_STACK];
+    int sp = 0;
+    int32_t node = 0;
+    while (true) {
+        if (node >= 0) {
+            int32_t push[3];
+            int n_push;
+            int32_t next = bvh4_step(sc.nodes4[node], inv_d, ood, t_min, best_t, push, n_push);
+            for (int k = 0; k < n_push; ++k)
+                if (sp < 3 * AKR_BVH_STACK) stack[sp++] = push[k];
+            if (next != 0x7fffffff) {
+                node = next;
+                continue;
+            }
+        } else {
+            uint32_t leaf = (uint32_t)(~node);
+            uint32_t first = (leaf >> 3) * 2u, count = (leaf & 7u) * 2u;
+            for (uint32_t k = 0; k < count; ++k) {
+                const TriGeom &tr = tris[first + k];
+                uint32_t gid = tr.gid;
+                if (gid == 0xffffffffu || gid == ex0 || gid == ex1) continue;
+                float t, u, v;
+                if (!tri_test(tr, o, d, t_min, t_max, t, u, v)) continue;
+                bool closer = (t < best_t) || (t == best_t && gid < best.gid);
+                if (!closer) continue;
+                if (sc.any_alpha && !alpha_test(sc, gid, u, v)) continue;
+                best = HitRec{gid, u, v};
+                best_t = t;
+                if (ANY_HIT) return best;
+            }
+        }
+        if (sp == 0) break;
+        node = stack[--sp];
+    }
+    return best;
+}
+
 // ---- primitive (triangle / parallelogram pair) intersector used by the CUDA kernels -----------------
 struct PrimHit {
     float t, s, q;

@@ -959,6 +959,82 @@ int build_scene_blob(const AkrSceneDesc &d, HostSceneBlob &out, std::string &err
         }
     }
 
+    // ---- 4-wide collapse: every inner node adopts its grandchildren, largest box first, until it has 4 children ----
+    {
+        struct Wide {
+            int32_t kids[4];  // build-node indices, -1 = empty
+            uint32_t depth;
+        };
+        std::vector<Wide> wide;
+        std::vector<int32_t> wide_of(bnodes.size(), -1);
+        std::vector<int32_t> worder;  // build-node index of each wide node, breadth-first
+        auto make_wide = [&](int32_t bn) {
+            std::vector<int32_t> kids;
+            if (bnodes[bn].left < 0) {
+                kids.push_back(bn);  // a leaf root
+            } else {
+                kids = {bnodes[bn].left, bnodes[bn].right};
+                while (kids.size() < 4) {
+                    int best = -1;
+                    float best_area = -1.0f;
+                    for (size_t k = 0; k < kids.size(); ++k)
+                        if (bnodes[kids[k]].left >= 0 && bnodes[kids[k]].box.half_area() > best_area) {
+                            best = static_cast<int>(k);
+                            best_area = bnodes[kids[k]].box.half_area();
+                        }
+                    if (best < 0) break;
+                    int32_t open = kids[best];
+                    kids[best] = bnodes[open].left;
+                    kids.push_back(bnodes[open].right);
+                }
+            }
+            Wide w;
+            for (int k = 0; k < 4; ++k) w.kids[k] = k < static_cast<int>(kids.size()) ? kids[k] : -1;
+            w.depth = 0;
+            return w;
+        };
+        worder.push_back(0);
+        wide_of[0] = 0;
+        wide.push_back(make_wide(0));
+        uint32_t depth4 = 0;
+        for (size_t h = 0; h < wide.size(); ++h) {
+            for (int k = 0; k < 4; ++k) {
+                int32_t kid = wide[h].kids[k];
+                if (kid >= 0 && bnodes[kid].left >= 0) {
+                    wide_of[kid] = static_cast<int32_t>(wide.size());
+                    Wide w = make_wide(kid);
+                    w.depth = wide[h].depth + 1;
+                    depth4 = std::max(depth4, w.depth);
+                    wide.push_back(w);
+                }
+            }
+        }
+        out.bvh4_depth = depth4;
+        out.nodes4.resize(wide.size());
+        for (size_t h = 0; h < wide.size(); ++h) {
+            Bvh4Node &o = out.nodes4[h];
+            std::memset(&o, 0, sizeof(o));
+            for (int k = 0; k < 4; ++k) {
+                int32_t kid = wide[h].kids[k];
+                if (kid < 0) {
+                    for (int a = 0; a < 3; ++a) {
+                        o.lo[a][k] = std::numeric_limits<float>::infinity();
+                        o.hi[a][k] = -std::numeric_limits<float>::infinity();
+                    }
+                    o.c[k] = ~0;
+                    continue;
+                }
+                float lo[3], hi[3];
+                padded(bnodes[kid].box, lo, hi);
+                for (int a = 0; a < 3; ++a) {
+                    o.lo[a][k] = lo[a];
+                    o.hi[a][k] = hi[a];
+                }
+                o.c[k] = bnodes[kid].left >= 0 ? wide_of[kid] : leaf_code(bnodes[kid]);
+            }
+        }
+    }
+
     // ---- camera (camera/mod.rs:119-153; load.rs:172-194) ----
     {
         const AkrPerspectiveCamera &cam = d.camera;
@@ -1007,6 +1083,9 @@ SceneView host_scene_view(const HostSceneBlob &b, const float *albedo_table) {
     SceneView v;
     std::memset(&v, 0, sizeof(v));
     v.nodes = b.nodes.data();
+    v.nodes4 = b.nodes4.data();
+    v.n_nodes4 = static_cast<uint32_t>(b.nodes4.size());
+    v.bvh4_depth = b.bvh4_depth;
     v.prims = b.prims.data();
     v.flat_blocks = b.flat_blocks.empty() ? nullptr : b.flat_blocks.data();
     v.n_pair_blocks = b.n_pair_blocks;

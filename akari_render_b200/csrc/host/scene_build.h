@@ -19,6 +19,8 @@ constexpr uint32_t kFlatMaxPrims = 64;  // scenes this small are traced as one f
 
 struct HostSceneBlob {
     std::vector<BvhNode> nodes;
+    std::vector<Bvh4Node> nodes4;     // the BVH collapsed to 4-wide nodes, breadth-first
+    uint32_t bvh4_depth = 0;
     std::vector<PrimRec> prims;       // BVH leaf order (what the CUDA kernels intersect)
     std::vector<PrimBlock2> flat_blocks;  // scenes of <= kFlatMaxPrims primitives: pairs first, two per block (flat trace mode)
     uint32_t n_pair_blocks = 0, n_single_blocks = 0;          // complete list, then ...

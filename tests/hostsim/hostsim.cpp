@@ -26,9 +26,11 @@ struct HostsimStats {
     uint32_t material_types[8];
     uint32_t n_prims, n_pairs;
     uint32_t flat_blocks, flat_occluder_blocks;  // flat trace mode: 2-primitive blocks of the complete / occluder-only list
+    uint32_t n_nodes4, bvh4_depth;
 };
 
-// 0: Moeller-Trumbore triangles (bit-exact twin of the oracle); 1: the CUDA kernels' primitive intersector
+// 0: Moeller-Trumbore triangles over the binary BVH (bit-exact twin of the oracle); 1: the CUDA kernels' primitive
+// intersector; 2: Moeller-Trumbore triangles over the 4-wide BVH (validates the collapsed tree)
 static thread_local int g_use_prims = 0;
 void hostsim_set_intersector(int use_prims) { g_use_prims = use_prims; }
 
@@ -90,8 +92,9 @@ int hostsim_render(const AkrSceneDesc *desc, const AkrPtConfig *cfg, const AkrSa
         for (uint32_t depth = 0; depth <= rp.max_depth && !cur.empty(); ++depth) {
             std::vector<HitRec> hits(cur.size());
             for (size_t i = 0; i < cur.size(); ++i)
-                hits[i] = g_use_prims ? trace_ray_prims<false>(sc, cur[i].o, cur[i].d, 0.0f, 1e20f, cur[i].ex, 0xffffffffu)
-                                      : trace_ray<false>(sc, td, cur[i].o, cur[i].d, 0.0f, 1e20f, cur[i].ex, 0xffffffffu);
+                hits[i] = g_use_prims == 1   ? trace_ray_prims<false>(sc, cur[i].o, cur[i].d, 0.0f, 1e20f, cur[i].ex, 0xffffffffu)
+                          : g_use_prims == 2 ? trace_ray4<false>(sc, cur[i].o, cur[i].d, 0.0f, 1e20f, cur[i].ex, 0xffffffffu)
+                                             : trace_ray<false>(sc, td, cur[i].o, cur[i].d, 0.0f, 1e20f, cur[i].ex, 0xffffffffu);
             segments += cur.size();
             if (depth == 0 && first_hits && spp_begin == wave.s0)
                 for (size_t i = 0; i < cur.size(); ++i) {
@@ -119,8 +122,9 @@ int hostsim_render(const AkrSceneDesc *desc, const AkrPtConfig *cfg, const AkrSa
             }
             shadows += shq.size();
             for (const ShadowItem &it : shq) {
-                HitRec h = g_use_prims ? trace_ray_prims<true>(sc, it.o, it.d, 0.0f, it.t_max, it.ex0, it.ex1)
-                                       : trace_ray<true>(sc, td, it.o, it.d, 0.0f, it.t_max, it.ex0, it.ex1);
+                HitRec h = g_use_prims == 1   ? trace_ray_prims<true>(sc, it.o, it.d, 0.0f, it.t_max, it.ex0, it.ex1)
+                           : g_use_prims == 2 ? trace_ray4<true>(sc, it.o, it.d, 0.0f, it.t_max, it.ex0, it.ex1)
+                                              : trace_ray<true>(sc, td, it.o, it.d, 0.0f, it.t_max, it.ex0, it.ex1);
                 shadow_resolve(av, it, h.gid != 0xffffffffu, depth + 1u);
             }
             cur.swap(next);
@@ -136,6 +140,8 @@ int hostsim_render(const AkrSceneDesc *desc, const AkrPtConfig *cfg, const AkrSa
         stats->n_tris = (uint32_t)blob.shade.size();
         stats->n_prims = (uint32_t)blob.prims.size();
         for (const PrimRec &pr : blob.prims) stats->n_pairs += pr.gid_b != 0xffffffffu ? 1u : 0u;
+        stats->n_nodes4 = (uint32_t)blob.nodes4.size();
+        stats->bvh4_depth = blob.bvh4_depth;
         stats->flat_blocks = blob.n_pair_blocks + blob.n_single_blocks;
         stats->flat_occluder_blocks = blob.n_occ_pair_blocks + blob.n_occ_single_blocks;
         stats->n_materials = (uint32_t)blob.materials.size();

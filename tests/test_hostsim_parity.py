@@ -16,7 +16,7 @@ class HostsimStats(C.Structure):
     _fields_ = [("samples", C.c_uint64), ("segments", C.c_uint64), ("shadow_rays", C.c_uint64), ("n_nodes", C.c_uint32),
                 ("n_tris", C.c_uint32), ("n_materials", C.c_uint32), ("n_lights", C.c_uint32), ("bvh_depth", C.c_uint32),
                 ("material_types", C.c_uint32 * 8), ("n_prims", C.c_uint32), ("n_pairs", C.c_uint32),
-                ("flat_blocks", C.c_uint32), ("flat_occluder_blocks", C.c_uint32)]
+                ("flat_blocks", C.c_uint32), ("flat_occluder_blocks", C.c_uint32), ("n_nodes4", C.c_uint32), ("bvh4_depth", C.c_uint32)]
 
 
 @pytest.fixture(scope="module")
@@ -246,3 +246,24 @@ def test_fastdiv_is_exact(hostsim):
         hostsim.hostsim_fastdiv(C.c_void_p(n.ctypes.data), C.c_uint32(n.size), C.c_uint32(d), C.c_void_p(q.ctypes.data), C.c_void_p(r.ctypes.data))
         assert np.array_equal(q, (n.astype(np.uint64) // d).astype(np.uint32)), d
         assert np.array_equal(r, (n.astype(np.uint64) % d).astype(np.uint32)), d
+
+
+@pytest.mark.parametrize("which", ["cbox", "clutter"])
+def test_bvh4_collapse_bitwise(hostsim, oracle, tables, akr, cbox, cbox_task, tmp_path, which):
+    """The 4-wide tree (binary BVH collapsed two levels at a time, what the dynamic-fetch kernel walks) visits exactly
+    the candidates a brute-force scan accepts: Moeller-Trumbore over it reproduces the oracle bit for bit."""
+    w = h = 40
+    scene = cbox(w, h) if which == "cbox" else akr.load_scene(sv.write_clutter(tmp_path)).set_resolution(w, h)
+    task = cbox_task(8)
+    pmj, bn = tables
+    table = oracle.albedo_table()
+    ofilm, ost, ofh = oracle.render(scene.desc, w, h, task.pt, task.sampler, task.filter, pmj, bn, want_first_hits=True)
+    hostsim.hostsim_set_intersector(2)
+    try:
+        film, fh, st = run_hostsim(hostsim, scene, task, tables, table, w, h)
+    finally:
+        hostsim.hostsim_set_intersector(0)
+    assert 0 < st.n_nodes4 < st.n_nodes and st.bvh4_depth <= st.bvh_depth
+    assert np.array_equal(fh, ofh)
+    assert (st.segments, st.shadow_rays) == (ost.segments, ost.shadow_rays)
+    assert np.array_equal(film, ofilm)
