@@ -333,4 +333,38 @@ AKR_HD HitRec trace_ray_prims(const SceneView &sc, f3 o, f3 d, float t_min, floa
     return HitRec{dec.gid, dec.u, dec.v};
 }
 
+// Reference walk over the staged flat lists (PrimBlock2, akr_scene.cuh): closest-hit rays test the complete list,
+// any-hit rays the occluder-only list behind it — what akari_b200.cu: trace_flat2 does with packed FMAs.  Used by the
+// host simulation to check the block layout and that leaving out the scene-supporting primitives never changes an
+// occlusion result.
+AKR_HD PrimRec block_prim(const PrimBlock2 &b, uint32_t h) {
+    PrimRec p;
+    for (int c = 0; c < 4; ++c) {
+        p.n[c] = b.n[c][h];
+        p.r0[c] = b.r0[c][h];
+        p.r1[c] = b.r1[c][h];
+    }
+    p.gid_a = b.gid[2u * h];
+    p.gid_b = b.gid[2u * h + 1u];
+    p.meta = b.meta[h];
+    p._pad = 0u;
+    return p;
+}
+template <bool ANY_HIT>
+AKR_HD HitRec trace_flat_ref(const SceneView &sc, f3 o, f3 d, float t_min, float t_max, uint32_t ex0, uint32_t ex1) {
+    const uint32_t b0 = ANY_HIT ? sc.n_pair_blocks + sc.n_single_blocks : 0u;
+    const uint32_t nb = ANY_HIT ? sc.n_occ_pair_blocks + sc.n_occ_single_blocks : sc.n_pair_blocks + sc.n_single_blocks;
+    PrimHit best{t_max, 0.0f, 0.0f, 0xffffffffu};
+    for (uint32_t b = b0; b < b0 + nb; ++b)
+        for (uint32_t h = 0; h < 2u; ++h) {
+            const PrimRec p = block_prim(sc.flat_blocks[b], h);
+            if (sc.any_alpha) prim_test<true>(sc, p, 2u * b + h, o, d, t_min, ex0, ex1, best);
+            else prim_test<false>(sc, p, 2u * b + h, o, d, t_min, ex0, ex1, best);
+            if (ANY_HIT && best.k != 0xffffffffu) return HitRec{0u, 0.0f, 0.0f};
+        }
+    if (best.k == 0xffffffffu) return HitRec{0xffffffffu, 0.0f, 0.0f};
+    PrimDecoded dec = prim_decode(block_prim(sc.flat_blocks[best.k >> 1], best.k & 1u), best.s, best.q);
+    return HitRec{dec.gid, dec.u, dec.v};
+}
+
 }  // namespace akr

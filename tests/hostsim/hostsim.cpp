@@ -30,7 +30,8 @@ struct HostsimStats {
 };
 
 // 0: Moeller-Trumbore triangles over the binary BVH (bit-exact twin of the oracle); 1: the CUDA kernels' primitive
-// intersector; 2: Moeller-Trumbore triangles over the 4-wide BVH (validates the collapsed tree)
+// intersector; 2: Moeller-Trumbore triangles over the 4-wide BVH (validates the collapsed tree); 3: the primitive
+// intersector over the staged flat lists (complete list for closest hits, occluder-only list for shadow rays)
 static thread_local int g_use_prims = 0;
 void hostsim_set_intersector(int use_prims) { g_use_prims = use_prims; }
 
@@ -44,6 +45,10 @@ int hostsim_render(const AkrSceneDesc *desc, const AkrPtConfig *cfg, const AkrSa
     if (rc != AKR_OK) {
         g_err = err;
         return rc;
+    }
+    if (g_use_prims == 3 && blob.flat_blocks.empty()) {
+        g_err = "scene too large for the flat trace mode";
+        return AKR_ERR_UNSUPPORTED;
     }
     if (scfg->type != AKR_SAMPLER_PMJ02BN) {
         g_err = "pmj02bn only";
@@ -94,6 +99,7 @@ int hostsim_render(const AkrSceneDesc *desc, const AkrPtConfig *cfg, const AkrSa
             for (size_t i = 0; i < cur.size(); ++i)
                 hits[i] = g_use_prims == 1   ? trace_ray_prims<false>(sc, cur[i].o, cur[i].d, 0.0f, 1e20f, cur[i].ex, 0xffffffffu)
                           : g_use_prims == 2 ? trace_ray4<false>(sc, cur[i].o, cur[i].d, 0.0f, 1e20f, cur[i].ex, 0xffffffffu)
+                          : g_use_prims == 3 ? trace_flat_ref<false>(sc, cur[i].o, cur[i].d, 0.0f, 1e20f, cur[i].ex, 0xffffffffu)
                                              : trace_ray<false>(sc, td, cur[i].o, cur[i].d, 0.0f, 1e20f, cur[i].ex, 0xffffffffu);
             segments += cur.size();
             if (depth == 0 && first_hits && spp_begin == wave.s0)
@@ -124,6 +130,7 @@ int hostsim_render(const AkrSceneDesc *desc, const AkrPtConfig *cfg, const AkrSa
             for (const ShadowItem &it : shq) {
                 HitRec h = g_use_prims == 1   ? trace_ray_prims<true>(sc, it.o, it.d, 0.0f, it.t_max, it.ex0, it.ex1)
                            : g_use_prims == 2 ? trace_ray4<true>(sc, it.o, it.d, 0.0f, it.t_max, it.ex0, it.ex1)
+                           : g_use_prims == 3 ? trace_flat_ref<true>(sc, it.o, it.d, 0.0f, it.t_max, it.ex0, it.ex1)
                                               : trace_ray<true>(sc, td, it.o, it.d, 0.0f, it.t_max, it.ex0, it.ex1);
                 shadow_resolve(av, it, h.gid != 0xffffffffu, depth + 1u);
             }

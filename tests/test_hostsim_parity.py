@@ -267,3 +267,26 @@ def test_bvh4_collapse_bitwise(hostsim, oracle, tables, akr, cbox, cbox_task, tm
     assert np.array_equal(fh, ofh)
     assert (st.segments, st.shadow_rays) == (ost.segments, ost.shadow_rays)
     assert np.array_equal(film, ofilm)
+
+
+@pytest.mark.parametrize("variant", [None, "principled_mix", "nodes"])
+def test_flat_lists_and_occluder_list_change_nothing(hostsim, tables, akr, oracle, cbox, cbox_task, tmp_path, variant):
+    """Flat trace mode data: the transposed two-primitive blocks hold the same primitives as the BVH leaves, and the
+    shorter any-hit list (scene-supporting hull walls left out) never changes an occlusion result: the film is
+    bit-identical to the BVH walk over all primitives (same per-primitive arithmetic)."""
+    w = h = 64
+    scene = cbox(w, h) if variant is None else akr.load_scene(sv.write_variant(tmp_path, variant, getattr(sv, "variant_" + variant))).set_resolution(w, h)
+    task = cbox_task(16)
+    table = oracle.albedo_table()
+    films = {}
+    for mode in (1, 3):
+        hostsim.hostsim_set_intersector(mode)
+        try:
+            films[mode] = run_hostsim(hostsim, scene, task, tables, table, w, h)
+        finally:
+            hostsim.hostsim_set_intersector(0)
+    (f1, h1, s1), (f3, h3, s3) = films[1], films[3]
+    assert s3.flat_occluder_blocks < s3.flat_blocks
+    assert (s1.segments, s1.shadow_rays) == (s3.segments, s3.shadow_rays)
+    same = (f1 == f3).mean()
+    assert np.array_equal(h1, h3) and same >= 0.99999, same  # only an exact distance tie could pick another primitive
