@@ -226,10 +226,15 @@ def main():
 
     # ---- e2e: host buffers in, host film out ----
     pmj, bn = akr.sampler_tables()
-    film_host = np.empty(7 * WIDTH * my_rows, dtype=np.float32)
+    # host buffers of the end-to-end leg live in PINNED memory (true async DMA): the sampler tables going in, the film coming out
+    pmj_pin = torch.from_numpy(pmj.view(np.int32)).pin_memory()
+    bn_pin = torch.from_numpy(bn.view(np.int16)).pin_memory()
+    pmj_h, bn_h = pmj_pin.numpy().view(np.uint32), bn_pin.numpy().view(np.uint16)
+    film_pin = torch.empty(7 * WIDTH * my_rows, dtype=torch.float32).pin_memory()
+    film_host = film_pin.numpy()
 
     def step_e2e():
-        pt.upload_sampler_tables(pmj, bn)
+        pt.upload_sampler_tables(pmj_h, bn_h)
         pt.upload_scene(scene)
         pt.begin(task, tile)
         done = 0
