@@ -1,14 +1,22 @@
 // akari_b200.cu — wavefront path-tracing kernels (sm_100a) and the C-ABI of include/akari_b200.h.
 //
-// Pipeline per wave of W paths (all state SoA in HBM, queues compacted with warp ballots):
+// Pipeline per wave of W paths (state = structure-of-arrays of 16-byte records in HBM):
 //
-//   k_raygen -> [ k_intersect -> k_shade -> k_shadow ] x (max_depth + 1) -> k_accumulate
+//   k_raygen -> [ trace(d) -> k_shade<class>(d) for every shade class present ] for d = 0 .. max_depth -> k_accumulate
 //
-// Every kernel is a persistent grid-stride kernel sized to the SM count; queue lengths live in
-// device memory, so a whole pass is enqueued without a single host round trip.  The scene's BVH and
-// triangles are staged into shared memory with one TMA bulk copy (cp.async.bulk + mbarrier) per CTA.
-// There is no tensor-core work on this path (no dense contraction exists in a path tracer) and no
-// CPU fallback: every entry point fails with AKR_ERR_CUDA when no device is usable.
+//   trace(d), small scenes (<= 64 primitives): k_trace<TRACE_FLAT> — every lane tests every primitive of a list staged in
+//                shared memory, two primitives per packed FP32 instruction (FFMA2); the shade kernels then also trace
+//                their own shadow ray inline (k_shade<CLS, true>), so no shadow queue exists.
+//   trace(d), BVH scenes: k_trace_bvh — persistent warps with dynamic ray fetch over a BVH2 (top of the tree in shared
+//                memory), closest-hit rays of depth d and the shadow rays shade(d - 1) queued.
+//   k_trace<TRACE_BVH*> keeps the one-fixed-ray-per-lane BVH walk for A/B runs (engine option trace_mode = 3).
+//
+// Hits are binned by the shade class of their material (warp-aggregated 64-bit atomics) and one shade kernel is
+// compiled per class.  Every kernel is a persistent grid-stride kernel sized SM count x resident CTAs; queue lengths
+// live in device memory, so a whole pass is enqueued without a host round trip.  Scene data is staged into shared
+// memory with one TMA bulk copy (cp.async.bulk + mbarrier) per CTA.  There is no tensor-core work on this path (no
+// dense contraction exists in a path tracer) and no CPU fallback: every entry point fails with AKR_ERR_CUDA when no
+// device is usable.
 #include "../../include/akari_b200.h"
 #include "device/akr_path.cuh"
 #include "host/scene_build.h"
