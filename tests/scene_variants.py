@@ -117,13 +117,24 @@ def _uv_sphere(cx, cy, cz, r, n_lon, n_lat):
                 normals.append([nrm(t[0]), nrm(t[1]), nrm(t[2])])
                 uvs.append([[i / n_lon, j / n_lat], [(i + 1) / n_lon, j / n_lat], [(i + 1) / n_lon, (j + 1) / n_lat]])
                 slots.append(j & 1)
-    return (verts, np.array(idx, np.uint32), np.array(normals, np.float32).reshape(-1, 3), np.array(uvs, np.float32).reshape(-1, 2),
-            np.array(slots, np.uint32))
+    idx = np.array(idx, np.uint32)
+    # per-corner tangents dp/dphi (mesh.rs:558-569); poles have a zero-length derivative -> use the x axis there
+    tang = np.zeros((len(idx) * 3, 3), np.float32)
+    for t, tri in enumerate(idx):
+        for k in range(3):
+            v = verts[tri[k]] - c
+            tv = np.array([-v[2], 0.0, v[0]], np.float32)
+            n2 = float(np.dot(tv, tv))
+            tang[3 * t + k] = tv / np.sqrt(n2) if n2 > 1e-12 else np.array([1.0, 0.0, 0.0], np.float32)
+    return (verts, idx, np.array(normals, np.float32).reshape(-1, 3), np.array(uvs, np.float32).reshape(-1, 2),
+            np.array(slots, np.uint32), tang)
 
 
 def write_clutter(tmp_path, n_lon=32, n_lat=24):
-    """cbox + six tessellated spheres (smooth per-corner normals, two materials each, one of them glass-like):
-    ~8.5 K triangles => BVH nodes and primitives exceed the shared-memory staging budget (TRACE_BVH mode)."""
+    """cbox + six tessellated spheres: smooth per-corner normals (one faceted), two materials each (glass-like, rough
+    metal, Lambert), tangent buffers on two of them (one with non-finite entries -> fallback), one instance with a
+    rotation * non-uniform scale, one mirrored.  ~8.5 K triangles => BVH nodes and primitives exceed the shared-memory
+    staging budget (TRACE_BVH mode)."""
     import numpy as np
     scene = json.load(open(os.path.join(CBOX_DIR, "scene.json")))
     blob = bytearray(open(os.path.join(CBOX_DIR, "Scene.bin"), "rb").read())
@@ -151,13 +162,26 @@ def write_clutter(tmp_path, n_lon=32, n_lat=24):
     mats = [("floor_001", "clutter_metal"), ("clutter_glass", "backWall_001"), ("leftWall_001", "rightWall_001"),
             ("clutter_metal", "clutter_glass"), ("ceiling_001", "floor_001"), ("clutter_glass", "clutter_metal")]
     for k, (cx, cy, cz, r) in enumerate(spheres):
-        v, i, n, uv, sl = _uv_sphere(cx, cy, cz, r, n_lon, n_lat)
+        v, i, n, uv, sl, tg = _uv_sphere(cx, cy, cz, r, n_lon, n_lat)
         gname = f"zz_sphere_{k}_mesh"
-        scene["geometries"][gname] = {"type": "mesh", "vertices": add_view(v), "indices": add_view(i), "normals": add_view(n),
-                                      "uvs": add_view(uv), "tangents": None, "materials": add_view(sl)}
+        tangents = None
+        if k in (1, 2):  # tangent buffers (mesh.rs:558-569); sphere 2 has non-finite entries -> the dp/du fallback
+            if k == 2:
+                tg = tg.copy()
+                tg[::7, 1] = np.nan
+            tangents = add_view(tg)
+        normals = None if k == 4 else add_view(n)  # one faceted sphere: geometric normals, uv-derived tangent frame
+        scene["geometries"][gname] = {"type": "mesh", "vertices": add_view(v), "indices": add_view(i), "normals": normals,
+                                      "uvs": add_view(uv), "tangents": tangents, "materials": add_view(sl)}
+        xf = [[1.0, 0.0, 0.0, 0.0], [0.0, 1.0, 0.0, 0.0], [0.0, 0.0, 1.0, 0.0], [0.0, 0.0, 0.0, 1.0]]
+        if k == 3:  # rotation about z * non-uniform scale + translation: inverse-transpose normals, det area scaling (mesh.rs:608-628)
+            ca, sa = float(np.cos(0.5)), float(np.sin(0.5))
+            xf = [[1.2 * ca, -0.7 * sa, 0.0, 0.25], [1.2 * sa, 0.7 * ca, 0.0, -0.55], [0.0, 0.0, 0.9, 0.1], [0.0, 0.0, 0.0, 1.0]]
+        if k == 5:  # mirrored instance (negative determinant)
+            xf = [[-1.0, 0.0, 0.0, 0.2], [0.0, 1.0, 0.0, 0.0], [0.0, 0.0, 1.0, 0.0], [0.0, 0.0, 0.0, 1.0]]
         scene["instances"][f"zz_sphere_{k}"] = {
             "geometry": {"id": gname},
-            "transform": {"type": "matrix", "data": [[1.0, 0.0, 0.0, 0.0], [0.0, 1.0, 0.0, 0.0], [0.0, 0.0, 1.0, 0.0], [0.0, 0.0, 0.0, 1.0]]},
+            "transform": {"type": "matrix", "data": xf},
             "materials": [{"id": mats[k][0]}, {"id": mats[k][1]}]}
     scene["buffers"]["Scene"]["length"] = len(blob)
     d = os.path.join(str(tmp_path), "clutter")
