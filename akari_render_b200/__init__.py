@@ -206,8 +206,8 @@ class PathTracer:
         self._scene = scene
         self._res = scene.resolution
 
-    def set_engine_options(self, wave_size=0, sort_by_material=0, profile_stages=0, trace_mode=0, inline_shadow=0, smem_node_kb=0):
-        o = AkrEngineOptions(wave_size, sort_by_material, profile_stages, trace_mode, inline_shadow, smem_node_kb)
+    def set_engine_options(self, wave_size=0, profile_stages=0, trace_mode=0, fused=0, smem_node_kb=0, aov_mask=0):
+        o = AkrEngineOptions(wave_size, 0, profile_stages, trace_mode, fused, smem_node_kb, aov_mask)
         self._check(self._lib.akr_b200_set_engine_options(self._ctx, C.byref(o)))
 
     # ---- rendering ----

@@ -125,12 +125,13 @@ class AkrStats(C.Structure):
 class AkrEngineOptions(C.Structure):
     _fields_ = [
         ("wave_size", C.c_uint32),
-        ("sort_by_material", C.c_uint32),
+        ("_unused0", C.c_uint32),
         ("profile_stages", C.c_uint32),
         ("trace_mode", C.c_uint32),
-        ("inline_shadow", C.c_uint32),
+        ("fused", C.c_uint32),
         ("smem_node_kb", C.c_uint32),
-        ("_reserved", C.c_uint32 * 2),
+        ("aov_mask", C.c_uint32),
+        ("_reserved", C.c_uint32 * 1),
     ]
 
 

@@ -1,22 +1,27 @@
 // akari_b200.cu — wavefront path-tracing kernels (sm_100a) and the C-ABI of include/akari_b200.h.
 //
-// Pipeline per wave of W paths (state = structure-of-arrays of 16-byte records in HBM):
+// Two pipelines per wave of W paths (state = structure-of-arrays of 16-byte records in HBM):
 //
-//   k_raygen -> [ trace(d) -> k_shade<class>(d) for every shade class present ] for d = 0 .. max_depth -> k_accumulate
+// FUSED (small scenes: <= 64 primitives, no stochastic alpha — cbox):
+//   k_raygen_fused -> [ k_bounce<class>(d) for every shade class present ] for d = 0 .. max_depth - 1 -> k_accumulate
+//   One kernel per (depth, shade class) does a whole bounce: shade, the NEE shadow ray, the continuation ray and the
+//   emitter term of the hit it finds (akr_path.cuh: bounce_fused).  Both rays are tested against the primitive list
+//   staged in shared memory, two primitives per packed FP32 instruction (FFMA2), every lane in lock step.  Path
+//   records (hit + throughput + radiance, 64 B) stream through per-class queues: each warp pulls its next 32 records
+//   into shared memory with 1-D TMA bulk copies (cp.async.bulk + mbarrier, double buffered) while it works on the
+//   current ones, and appends survivors to the queue of the class of the NEXT hit with warp-aggregated atomics.
+//   There is no hit queue, no shadow queue, no (slot, path id) indirection and no accumulator read-modify-write.
 //
-//   trace(d), small scenes (<= 64 primitives): k_trace<TRACE_FLAT> — every lane tests every primitive of a list staged in
-//                shared memory, two primitives per packed FP32 instruction (FFMA2); the shade kernels then also trace
-//                their own shadow ray inline (k_shade<CLS, true>), so no shadow queue exists.
-//   trace(d), BVH scenes: k_trace_bvh — persistent warps with dynamic ray fetch over a BVH2 (top of the tree in shared
-//                memory), closest-hit rays of depth d and the shadow rays shade(d - 1) queued.
-//   k_trace<TRACE_BVH*> keeps the one-fixed-ray-per-lane BVH walk for A/B runs (engine option trace_mode = 3).
+// QUEUED (BVH scenes, and flat scenes with alpha-tested materials):
+//   k_raygen -> [ trace(d) -> k_shade<class>(d) ] for d = 0 .. max_depth -> k_accumulate
+//   trace(d) = k_trace_bvh: persistent warps with dynamic ray fetch over a BVH2 (top of the tree in shared memory),
+//   closest-hit rays of depth d and the shadow rays shade(d - 1) queued (k_trace<TRACE_FLAT> on flat scenes).
+//   Hits are binned by the shade class of their material and one shade kernel is compiled per class.
 //
-// Hits are binned by the shade class of their material (warp-aggregated 64-bit atomics) and one shade kernel is
-// compiled per class.  Every kernel is a persistent grid-stride kernel sized SM count x resident CTAs; queue lengths
-// live in device memory, so a whole pass is enqueued without a host round trip.  Scene data is staged into shared
-// memory with one TMA bulk copy (cp.async.bulk + mbarrier) per CTA.  There is no tensor-core work on this path (no
-// dense contraction exists in a path tracer) and no CPU fallback: every entry point fails with AKR_ERR_CUDA when no
-// device is usable.
+// Every kernel is a persistent grid-stride kernel sized SM count x resident CTAs; queue lengths live in device memory,
+// so a whole pass is enqueued without a host round trip.  Scene data is staged into shared memory with one TMA bulk
+// copy per CTA.  There is no tensor-core work on this path (no dense contraction exists in a path tracer) and no CPU
+// fallback: every entry point fails with AKR_ERR_CUDA when no device is usable.
 #include "../../include/akari_b200.h"
 #include "device/akr_path.cuh"
 #include "host/scene_build.h"
@@ -67,6 +72,9 @@ struct ShadowQueue { // 52 B per shadow ray
 struct ClassQueues { // per shade class: (slot in the path queue, path_id) of the hits of that class
     uint2 *idx[CLS_COUNT];
 };
+struct RecQueue {    // fused pipeline: 64 B per path = BounceRec (akr_path.cuh), one queue per (depth parity, shade class)
+    f4 *r[4];        // (d.xyz, gid) | (u, v, path_id, -) | (beta.rgb, -) | (L.rgb, -)
+};
 
 struct LaunchParams {
     SceneView scene;
@@ -78,6 +86,7 @@ struct LaunchParams {
     HitQueue hits;
     ShadowQueue shadow;
     ClassQueues cls;
+    RecQueue cq[2][CLS_COUNT];
     AccView acc;
     uint32_t *counters;       // [kMaxDepthSlots][kCtrStride]
     float *film;
@@ -86,8 +95,7 @@ struct LaunchParams {
     uint32_t scene_smem_prims;  // 1 when all primitives are staged too
     uint32_t stack_depth;       // traversal stack entries per thread (shared memory)
     uint32_t stage_flat;        // stage the pairs-first flat list instead of the BVH-ordered primitives
-    uint32_t inline_shadow;     // flat scenes: the shade kernels trace their own shadow ray (no shadow queue traffic)
-    uint32_t *dbg_first_hits;   // optional [n_film_pixels][2]
+    uint32_t *first_hits;       // optional AOV (engine option aov_mask bit 0): [n_film_pixels][2] (inst, prim) of sample 0
 };
 
 // Queue records are written once and read once, gigabytes later: stream them past L2 residency (evict-first) so that
@@ -273,7 +281,6 @@ enum TraceMode : int { TRACE_BVH = 0, TRACE_FLAT = 1, TRACE_BVH_SMEM = 2 };
 
 // TRACE_FLAT: every lane tests every primitive in list order (shared-memory broadcast reads, no divergence,
 // no stack) — the cheapest schedule when the whole scene is a few dozen primitives.
-// TRACE_BVH : while-while traversal; lanes first descend to their next leaf together, then test leaves.
 // ---- flat mode with packed FP32 (FFMA2) ----------------------------------------------------------------
 // Blackwell issues fma.rn.f32x2: one instruction = two FP32 FMAs per lane.  The staged PrimBlock2 layout puts
 // the same coefficient of two primitives side by side, so the 16 FMAs of a primitive test advance TWO
@@ -423,65 +430,6 @@ __device__ __forceinline__ DevHit trace_flat2(const LaunchParams &P, const Trace
     return DevHit{dec.gid, dec.cls, dec.u, dec.v};
 }
 
-// Every lane of the warp calls this together (`active` = the lane carries a ray); any-hit rays leave the
-// primitive loop only when the whole warp is done, which is the only exit that saves issue slots.
-template <bool ANY_HIT, int MODE, bool ALPHA>
-__device__ __forceinline__ DevHit trace_dev(const LaunchParams &P, const TraceSmem &ts, bool active, f3 o, f3 d, float t_min, float t_max, uint32_t ex0,
-                                            uint32_t ex1) {
-    const SceneView &sc = P.scene;
-    PrimHit best{active ? t_max : 0.0f, 0.0f, 0.0f, 0xffffffffu};  // an idle lane accepts nothing (t < 0 is never true for t > t_min = 0)
-    constexpr bool PRIMS_SHARED = MODE != TRACE_BVH;
-    if (MODE == TRACE_FLAT) return trace_flat2<ANY_HIT, ALPHA>(P, ts, active, o, d, t_min, t_max, ex0, ex1);
-    if (active) {
-        const f3 inv_d = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-        const uint32_t n_fast = P.scene_smem_nodes;
-        constexpr uint32_t kStackStride = kBlock * 4u;
-        uint32_t sp = ts.stack;
-        int32_t node = 0;  // the root is always an inner node
-        while (true) {
-            bool done = false;
-            while (node >= 0) {
-                BvhNode n;
-                if (MODE == TRACE_BVH_SMEM || (uint32_t)node < n_fast) n = load_node<true>(ts.nodes, nullptr, (uint32_t)node);
-                else n = load_node<false>(0u, sc.nodes, (uint32_t)node);
-                float tn0, tn1;
-                const bool h0 = box_test(n.lo0, n.hi0, o, inv_d, t_min, best.t, tn0);
-                const bool h1 = box_test(n.lo1, n.hi1, o, inv_d, t_min, best.t, tn1);
-                const int32_t c0 = n.c0, c1 = n.c1;
-                if (h0 && h1) {
-                    const bool swap = tn1 < tn0;
-                    sts32(sp, swap ? c0 : c1);
-                    sp += kStackStride;
-                    node = swap ? c1 : c0;
-                } else if (h0) {
-                    node = c0;
-                } else if (h1) {
-                    node = c1;
-                } else {
-                    if (sp == ts.stack) {
-                        done = true;
-                        break;
-                    }
-                    sp -= kStackStride;
-                    node = lds32(sp);
-                }
-            }
-            if (done) break;
-            const uint32_t leaf = (uint32_t)(~node);
-            const uint32_t first = leaf >> 3, count = leaf & 7u;
-            for (uint32_t k = 0; k < count; ++k)
-                prim_test<ALPHA>(sc, load_prim<PRIMS_SHARED>(ts.prims, sc.prims, first + k), first + k, o, d, t_min, ex0, ex1, best);
-            if (ANY_HIT && best.k != 0xffffffffu) break;
-            if (sp == ts.stack) break;
-            sp -= kStackStride;
-            node = lds32(sp);
-        }
-    }
-    if (best.k == 0xffffffffu) return DevHit{0xffffffffu, 0u, 0.0f, 0.0f};
-    const PrimDecoded dec = prim_decode(load_prim<PRIMS_SHARED>(ts.prims, sc.prims, best.k), best.s, best.q);
-    return DevHit{dec.gid, dec.cls, dec.u, dec.v};
-}
-
 // Warp-aggregated append to TWO queues whose counters are an aligned 32-bit pair: one 64-bit atomic per
 // warp reserves both ranges (half the traffic to the hot L2 lines of per-queue atomics).
 __device__ __forceinline__ void warp_append2(uint32_t *counter_pair, bool pred0, bool pred1, uint32_t &slot0, uint32_t &slot1) {
@@ -524,14 +472,14 @@ __global__ void __launch_bounds__(kBlock) k_raygen(const __grid_constant__ Launc
     if (blockIdx.x == 0 && threadIdx.x == 0) P.counters[0] = n;
 }
 
-// One launch per depth traces BOTH ray kinds: the closest-hit rays of the paths entering `depth` and the
-// shadow rays the previous depth's shade stage produced.  Work is handed out in warp-sized tasks
-// (closest-hit tasks first, the shorter any-hit tasks fill the tail), so a warp is never mixed.
-template <int MODE, bool ALPHA> __global__ void __launch_bounds__(kBlock) k_trace(const __grid_constant__ LaunchParams P, uint32_t depth) {
+// Queued pipeline on a flat scene (alpha-tested materials, or engine option fused = 2): one launch per depth traces BOTH
+// ray kinds, the closest-hit rays of the paths entering `depth` and the shadow rays the previous depth's shade stage
+// produced.  Work is handed out in warp-sized tasks (closest-hit tasks first, the shorter any-hit tasks fill the tail).
+template <bool ALPHA> __global__ void __launch_bounds__(kBlock) k_trace_flat(const __grid_constant__ LaunchParams P, uint32_t depth) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bar;
     const uint32_t n_cl = P.counters[depth * kCtrStride];
-    const uint32_t n_sh = P.inline_shadow ? 0u : P.counters[depth * kCtrStride + 1u];  // inline mode: [1] only counts, shade traced them
+    const uint32_t n_sh = P.counters[depth * kCtrStride + 1u];
     const uint32_t t_cl = (n_cl + 31u) >> 5, t_sh = (n_sh + 31u) >> 5;
     const uint32_t n_tasks = t_cl + t_sh;
     if (blockIdx.x * kWarpsPerBlock >= n_tasks) return;  // whole CTA has no work: skip the staging too
@@ -550,7 +498,7 @@ template <int MODE, bool ALPHA> __global__ void __launch_bounds__(kBlock) k_trac
                 b = ldq(q.b + i);
             }
             const uint32_t path_id = f2u(b.w);
-            const DevHit h = trace_dev<false, MODE, ALPHA>(P, ts, active, mk3(a.x, a.y, a.z), mk3(a.w, b.x, b.y), 0.0f, 1e20f, f2u(b.z), 0xffffffffu);
+            const DevHit h = trace_flat2<false, ALPHA>(P, ts, active, mk3(a.x, a.y, a.z), mk3(a.w, b.x, b.y), 0.0f, 1e20f, f2u(b.z), 0xffffffffu);
             if (active) stq(P.hits.h + i, f4{u2f(h.gid), h.u, h.v, 0.0f});
             const bool hit = active && h.gid != 0xffffffffu;
             const uint32_t cls = P.rp.force_diffuse ? (uint32_t)CLS_LAMBERT : h.cls;
@@ -572,7 +520,7 @@ template <int MODE, bool ALPHA> __global__ void __launch_bounds__(kBlock) k_trac
                 b = ldq(P.shadow.b + i);
                 ex1 = P.shadow.ex1[i];
             }
-            const DevHit h = trace_dev<true, MODE, ALPHA>(P, ts, active, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), 0.0f, a.w, f2u(b.w), ex1);
+            const DevHit h = trace_flat2<true, ALPHA>(P, ts, active, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), 0.0f, a.w, f2u(b.w), ex1);
             if (active) {
                 const f4 c = ldq(P.shadow.c + i);
                 ShadowItem it;
@@ -738,14 +686,14 @@ template <bool SMEM_ALL, bool ALPHA> __global__ void __launch_bounds__(kBlock) k
     __shared__ uint64_t bar;
     uint32_t *ctr = P.counters + depth * kCtrStride;
     const uint32_t n_cl = ctr[0];
-    const uint32_t n_sh = P.inline_shadow ? 0u : ctr[1];
+    const uint32_t n_sh = ctr[1];
     if (blockIdx.x * kBlock >= n_cl + n_sh) return;  // more CTAs than rays: skip the staging too
     const TraceSmem ts = stage_scene(P, smem, &bar);
     bvh_phase<false, SMEM_ALL, ALPHA>(P, ts, depth, n_cl, ctr + 5u);
     bvh_phase<true, SMEM_ALL, ALPHA>(P, ts, depth, n_sh, ctr + 6u);
 }
 
-// resident CTAs per SM the shade kernels are compiled for (register budget = 65536 / (256 * n)); tuned on B200
+// resident CTAs per SM the shade / bounce kernels are compiled for (register budget = 65536 / (256 * n)); tuned on B200
 #ifndef AKR_SHADE_MINB_LAMBERT
 #define AKR_SHADE_MINB_LAMBERT 4
 #endif
@@ -756,68 +704,49 @@ template <bool SMEM_ALL, bool ALPHA> __global__ void __launch_bounds__(kBlock) k
 #define AKR_SHADE_BLOCK 256
 #endif
 constexpr int kShadeBlock = AKR_SHADE_BLOCK;
+constexpr int kShadeWarps = kShadeBlock / 32;
 template <int CLS> struct ShadeLaunch {
     static constexpr int kMinBlocks = CLS == CLS_LAMBERT ? AKR_SHADE_MINB_LAMBERT : (CLS == CLS_CONDUCTOR ? AKR_SHADE_MINB_CONDUCTOR : 1);
 };
 
-// One shade kernel per material class; `CLS_ANY` (unsorted: every hit in slot order) exists for A/B runs.
-// INLINE_SHADOW (flat scenes without alpha materials): the thread that produced an NEE sample tests its shadow ray
-// itself against the staged primitive list (lock-step, no divergence) and adds the contribution; the shadow
-// queue (52 B written + 52 B read + a random 32 B accumulator update per shadow ray) disappears.
-template <int CLS, bool INLINE_SHADOW>
-__global__ void __launch_bounds__(kShadeBlock, ShadeLaunch<CLS>::kMinBlocks) k_shade(const __grid_constant__ LaunchParams P, uint32_t depth) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ uint64_t bar;
+// Queued pipeline: one shade kernel per material class over the (slot, path id) list the trace stage binned.
+template <int CLS> __global__ void __launch_bounds__(kShadeBlock, ShadeLaunch<CLS>::kMinBlocks) k_shade(const __grid_constant__ LaunchParams P, uint32_t depth) {
     uint32_t *ctr = P.counters + depth * kCtrStride;
-    const uint32_t n = CLS == CLS_ANY ? ctr[0] : ctr[2u + (CLS == CLS_ANY ? 0 : CLS)];
-    const uint2 *slots = CLS == CLS_ANY ? nullptr : P.cls.idx[CLS == CLS_ANY ? 0 : CLS];
+    const uint32_t n = ctr[2u + CLS];
+    const uint2 *slots = P.cls.idx[CLS];
     const PathQueue &qin = P.q[depth & 1u];
     const PathQueue &qout = P.q[(depth + 1u) & 1u];
     uint32_t *out_pair = ctr + kCtrStride;  // [0] next-depth paths, [1] shadow rays: reserved together
     const uint32_t stride = gridDim.x * blockDim.x;
-    TraceSmem ts{0u, 0u, 0u};
-    if (INLINE_SHADOW) {
-        if (blockIdx.x * blockDim.x >= n) return;  // whole CTA has no work: skip the staging too
-        ts = stage_scene(P, smem, &bar);
-    }
     // warp-uniform trip count so that every lane takes part in the ballots; the (slot, path_id) entry of the
     // next trip is fetched one trip ahead so that its latency is off the dependent chain
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     uint2 ent = make_uint2(k, 0u);
-    if (CLS != CLS_ANY && k < n) ent = slots[k];
+    if (k < n) ent = slots[k];
     for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride, k += stride) {
         const bool active = k < n;
         const uint2 cur = ent;
-        if (CLS != CLS_ANY && k + stride < n) ent = slots[k + stride];
+        if (k + stride < n) ent = slots[k + stride];
         ShadeOut o;
         o.has_shadow = false;
         o.has_next = false;
         if (active) {
-            const uint32_t i = CLS == CLS_ANY ? k : cur.x;
+            const uint32_t i = cur.x;
             const f4 hr = ldq(P.hits.h + i);
             HitRec h{f2u(hr.x), hr.y, hr.z};
-            if (CLS != CLS_ANY || h.gid != 0xffffffffu) {
-                PathState ps = load_path(qin, i);
-                if (CLS != CLS_ANY) ps.path_id = cur.y;  // same value, but already in a register: the sampler loads do not wait for the record
-                o = shade_body<CLS>(P.scene, P.corners, P.tables, P.rp, P.wave, depth, ps, h, P.acc);
-                if (depth == 0u && P.dbg_first_hits && ps.path_id < P.wave.n_pix && P.wave.s0 == 0u) {
-                    uint32_t pix = P.wave.pix0 + ps.path_id;
-                    P.dbg_first_hits[2u * pix + 0u] = P.scene.shade[h.gid].inst;
-                    P.dbg_first_hits[2u * pix + 1u] = P.scene.shade[h.gid].prim;
-                }
+            PathState ps = load_path(qin, i);
+            ps.path_id = cur.y;  // same value, but already in a register: the sampler loads do not wait for the record
+            o = shade_body<CLS>(P.scene, P.corners, P.tables, P.rp, P.wave, depth, ps, h, P.acc);
+            if (depth == 0u && P.first_hits && ps.path_id < P.wave.n_pix && P.wave.s0 == 0u) {
+                uint32_t pix = P.wave.pix0 + ps.path_id;
+                P.first_hits[2u * pix + 0u] = P.scene.shade[h.gid].inst;
+                P.first_hits[2u * pix + 1u] = P.scene.shade[h.gid].prim;
             }
         }
         uint32_t ns, ss;
         warp_append2(out_pair, o.has_next, o.has_shadow, ns, ss);
-        if (o.has_next) store_path(qout, ns, o.next);  // before the inline trace: the next-path registers are dead during it
-        if (INLINE_SHADOW) {
-            float t_hit;
-            const uint32_t occ = trace_flat2_core<true, false>(P.scene, ts, o.has_shadow, o.shadow.o, o.shadow.d, 0.0f, o.shadow.t_max, o.shadow.ex0,
-                                                               o.shadow.ex1, t_hit);
-            // measured on B200: a register copy of the accumulators (one global read/write per bounce) and an L1
-            // prefetch of the next trip's records both LOSE here (register pressure at 64 regs/thread): 18.6 -> 20.5 ms
-            if (o.has_shadow) shadow_resolve(P.acc, o.shadow, occ != 0xffffffffu, depth + 1u);
-        } else if (o.has_shadow) {
+        if (o.has_next) store_path(qout, ns, o.next);
+        if (o.has_shadow) {
             const ShadowQueue &s = P.shadow;
             stq(s.a + ss, f4{o.shadow.o.x, o.shadow.o.y, o.shadow.o.z, o.shadow.t_max});
             stq(s.b + ss, f4{o.shadow.d.x, o.shadow.d.y, o.shadow.d.z, u2f(o.shadow.ex0)});
@@ -825,6 +754,140 @@ __global__ void __launch_bounds__(kShadeBlock, ShadeLaunch<CLS>::kMinBlocks) k_s
             s.ex1[ss] = o.shadow.ex1;
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused pipeline (flat scenes): k_raygen_fused, k_bounce<CLS>
+// ------------------------------------------------------------------------------------------------
+// Tracer of akr_path.cuh's fused bodies: both queries walk the primitive list staged in shared memory with the
+// packed-FP32 loop; every lane of the warp calls them together.
+struct DevTracer {
+    const SceneView &sc;
+    TraceSmem ts;
+    __device__ __forceinline__ bool occluded(bool active, f3 o, f3 d, float t_max, uint32_t ex0, uint32_t ex1) const {
+        float t;
+        return trace_flat2_core<true, false>(sc, ts, active, o, d, 0.0f, t_max, ex0, ex1, t) != 0xffffffffu;
+    }
+    __device__ __forceinline__ TraceHit closest(bool active, f3 o, f3 d, uint32_t ex0) const {
+        float best_t;
+        const uint32_t best_k = trace_flat2_core<false, false>(sc, ts, active, o, d, 0.0f, 1e20f, ex0, 0xffffffffu, best_t);
+        if (best_k == 0xffffffffu) return TraceHit{0xffffffffu, 0u, 0u, 0.0f, 0.0f};
+        // (s, q) of the winner, same operations in the same order as the packed loop
+        const PrimRec p = load_block_prim(ts.prims + (best_k >> 1) * (uint32_t)sizeof(PrimBlock2), best_k & 1u);
+        float s, q;
+        prim_coords(p, o, d, best_t, s, q);
+        const PrimDecoded dec = prim_decode(p, s, q);
+        return TraceHit{dec.gid, dec.cls, dec.light, dec.u, dec.v};
+    }
+};
+
+__device__ __forceinline__ void store_rec(const RecQueue &q, uint32_t i, const BounceRec &r) {
+    stq(q.r[0] + i, f4{r.d.x, r.d.y, r.d.z, u2f(r.gid)});
+    stq(q.r[1] + i, f4{r.u, r.v, u2f(r.path_id), 0.0f});
+    stq(q.r[2] + i, f4{r.beta.x, r.beta.y, r.beta.z, 0.0f});
+    stq(q.r[3] + i, f4{r.L.x, r.L.y, r.L.z, 0.0f});
+}
+// appends a surviving path to the queue of the shade class of the hit it goes to (depth d1)
+__device__ __forceinline__ void append_next(const LaunchParams &P, uint32_t d1, const BounceOut &r) {
+    uint32_t *ctr = P.counters + d1 * kCtrStride;
+    uint32_t s0, s1;
+    warp_append2(ctr + 2u, r.cont && r.cls == CLS_LAMBERT, r.cont && r.cls == CLS_CONDUCTOR, s0, s1);
+    const uint32_t s2 = warp_append(ctr + 4u, r.cont && r.cls == CLS_GENERAL);
+    if (r.cont) store_rec(P.cq[d1 & 1u][r.cls], r.cls == CLS_LAMBERT ? s0 : (r.cls == CLS_CONDUCTOR ? s1 : s2), r.next);
+}
+
+__global__ void __launch_bounds__(kBlock) k_raygen_fused(const __grid_constant__ LaunchParams P) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bar;
+    const uint32_t n = P.wave.n_pix * P.wave.n_spp;
+    if (blockIdx.x * blockDim.x >= n) return;
+    const DevTracer tr{P.scene, stage_scene(P, smem, &bar)};
+    const uint32_t stride = gridDim.x * blockDim.x;
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride, i += stride) {
+        const bool active = i < n;
+        const BounceOut r = raygen_fused(P.scene, P.corners, P.tables, P.rp, P.wave, active, i, tr, P.acc);
+        if (active && P.first_hits && i < P.wave.n_pix && P.wave.s0 == 0u) {
+            const uint32_t pix = P.wave.pix0 + i, gid = r.next.gid;
+            P.first_hits[2u * pix + 0u] = gid == 0xffffffffu ? 0xffffffffu : P.scene.shade[gid].inst;
+            P.first_hits[2u * pix + 1u] = gid == 0xffffffffu ? 0xffffffffu : P.scene.shade[gid].prim;
+        }
+        append_next(P, 0u, r);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) P.counters[0] = n;  // camera rays traced
+}
+
+// Streaming loads of the record queues bypass L2 residency (evict-first): written once, read once, gigabytes apart.
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void tma_bulk_g2s_hint(uint32_t smem_dst, const void *gsrc, uint32_t bytes, uint32_t bar, uint64_t pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_dst), "l"(gsrc),
+                 "r"(bytes), "r"(bar), "l"(pol)
+                 : "memory");
+}
+constexpr uint32_t kTileBytes = 4u * 32u * 16u;  // one warp tile: 32 records x 4 x 16 B
+
+// One bounce of every path whose current hit is of shade class CLS.  Warp w of the grid owns record tiles w, w + W, ...
+// (32 records each); lane 0 starts the TMA bulk copies of the NEXT tile into the warp's other shared-memory buffer
+// before the warp waits for the current one, so the queue reads never sit on the dependent chain.
+template <int CLS> __global__ void __launch_bounds__(kShadeBlock, ShadeLaunch<CLS>::kMinBlocks) k_bounce(const __grid_constant__ LaunchParams P, uint32_t depth) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint64_t tile_bar[kShadeWarps][2];
+    const uint32_t n = P.counters[depth * kCtrStride + 2u + CLS];
+    if (blockIdx.x * blockDim.x >= n) return;  // whole CTA has no work: skip the staging too
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    if (threadIdx.x == 0) {
+        for (int w = 0; w < kShadeWarps; ++w) {
+            mbar_init(&tile_bar[w][0], 1);
+            mbar_init(&tile_bar[w][1], 1);
+        }
+    }
+    const DevTracer tr{P.scene, stage_scene(P, smem, &bar)};  // (inits `bar`, fences the barrier inits, __syncthreads)
+    const uint32_t scene_bytes = (P.scene.n_pair_blocks + P.scene.n_single_blocks + P.scene.n_occ_pair_blocks + P.scene.n_occ_single_blocks) * (uint32_t)sizeof(PrimBlock2);
+    const uint32_t tiles = smem_u32(smem) + ((scene_bytes + 127u) & ~127u) + warp * 2u * kTileBytes;
+    const uint32_t bar0 = smem_u32(&tile_bar[warp][0]);
+    const RecQueue &qin = P.cq[depth & 1u][CLS];
+    const uint64_t pol = l2_evict_first_policy();
+    const uint32_t n_tiles = (n + 31u) >> 5, wstride = gridDim.x * kShadeWarps;
+    auto issue = [&](uint32_t tile, uint32_t buf) {
+        const uint32_t first = tile * 32u;
+        const uint32_t bytes = min(32u, n - first) * 16u;
+        const uint32_t b = bar0 + buf * 8u, dst = tiles + buf * kTileBytes;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(4u * bytes) : "memory");
+#pragma unroll
+        for (uint32_t j = 0; j < 4u; ++j) tma_bulk_g2s_hint(dst + j * 512u, qin.r[j] + first, bytes, b, pol);
+    };
+    uint32_t tile = blockIdx.x * kShadeWarps + warp;
+    if (tile < n_tiles && lane == 0u) issue(tile, 0u);
+    uint32_t n_traced = 0u, n_shadow = 0u;  // warp-uniform
+    for (uint32_t it = 0u; tile < n_tiles; tile += wstride, ++it) {
+        const uint32_t buf = it & 1u;
+        if (tile + wstride < n_tiles && lane == 0u) issue(tile + wstride, buf ^ 1u);
+        mbar_wait(&tile_bar[warp][buf], (it >> 1) & 1u);
+        const bool active = tile * 32u + lane < n;
+        const uint32_t src = tiles + buf * kTileBytes + lane * 16u;
+        const float4 r0 = lds128(src), r1 = lds128(src + 512u), r2 = lds128(src + 1024u), r3 = lds128(src + 1536u);
+        __syncwarp();  // every lane has its record in registers before lane 0 may refill this buffer (two trips from now)
+        BounceRec in;
+        in.d = mk3(r0.x, r0.y, r0.z);
+        in.gid = __float_as_uint(r0.w);
+        in.u = r1.x;
+        in.v = r1.y;
+        in.path_id = __float_as_uint(r1.z);
+        in.beta = mk3(r2.x, r2.y, r2.z);
+        in.L = mk3(r3.x, r3.y, r3.z);
+        const BounceOut r = bounce_fused<CLS>(P.scene, P.corners, P.tables, P.rp, P.wave, depth, active, in, tr, P.acc);
+        n_traced += (uint32_t)__popc(__ballot_sync(0xffffffffu, r.traced));
+        n_shadow += (uint32_t)__popc(__ballot_sync(0xffffffffu, r.shadow));
+        append_next(P, depth + 1u, r);
+    }
+    // statistics: [0] continuation rays traced (= segments of depth + 1), [1] shadow rays of this depth
+    if (lane == 0u && (n_traced | n_shadow))
+        atomicAdd(reinterpret_cast<unsigned long long *>(P.counters + (depth + 1u) * kCtrStride), (unsigned long long)n_traced | ((unsigned long long)n_shadow << 32));
 }
 
 __global__ void __launch_bounds__(kBlock) k_accumulate(const __grid_constant__ LaunchParams P) {
@@ -898,8 +961,11 @@ struct AkrContext {
     uint32_t smem_nodes = 0, smem_prims = 0, smem_bytes = 0;  // smem_bytes = nodes + primitives (stacks come on top)
     uint32_t bvh_depth = 0;
     uint32_t class_mask = 0;   // shade classes present in the scene
-    int occ_trace_dyn = 1;  // k_trace_bvh (dynamic fetch)
-    int occ_trace[3] = {1, 1, 1}, occ_shade[4] = {1, 1, 1, 1}, occ_shade_inline[3] = {1, 1, 1};  // resident CTAs per SM, per kernel variant
+    int occ_trace_dyn = 1;   // k_trace_bvh (dynamic fetch)
+    int occ_trace_flat = 1;  // k_trace_flat
+    int occ_raygen_fused = 1;
+    int occ_shade[3] = {1, 1, 1}, occ_bounce[3] = {1, 1, 1};  // resident CTAs per SM, per shade class
+    uint32_t flat_bytes = 0;  // staged PrimBlock2 lists (complete + occluder-only)
 
     // render state
     bool render_ready = false;
@@ -912,13 +978,15 @@ struct AkrContext {
 
     // wave buffers
     uint32_t wave_capacity = 0;  // paths
+    uint32_t wave_layout = 0;    // 0 = none, 1 = queued, 2 | class_mask << 8 = fused
     DeviceBuffer wave_mem;
+    RecQueue cq[2][CLS_COUNT]{};
     PathQueue q[2]{};
     HitQueue hits{};
     ShadowQueue shadow{};
     ClassQueues cls{};
     AccView acc{};
-    DeviceBuffer counters, totals, dbg_hits;
+    DeviceBuffer counters, totals, first_hits;
 
     AkrEngineOptions opts{};
     AkrStats stats{};
@@ -973,12 +1041,16 @@ int grid_for(const AkrContext *ctx, uint32_t n, int ctas_per_sm) {
     return (int)std::max(1u, std::min(need, cap));
 }
 
-int ensure_wave_buffers(AkrContext *ctx, uint32_t capacity) {
-    if (ctx->wave_capacity >= capacity && ctx->wave_mem.ptr) return AKR_OK;
-    // 16-byte records per path: two path queues (3 + 3), hits (1), shadow queue (3), accumulators (2);
-    // 4-byte words per path: shadow exclude1 (1), class (slot, path_id) lists (2 * CLS_COUNT)
+// One allocation per wave layout.  queued: two path queues (3 + 3 records of 16 B), hits (1), shadow queue (3 + one
+// word), accumulators (2), class (slot, path_id) lists (2 words per class).  fused: per shade class present two record
+// queues (4 + 4 records of 16 B: one per depth parity) and the accumulators (2).
+int ensure_wave_buffers(AkrContext *ctx, uint32_t capacity, bool fused, uint32_t class_mask) {
+    const uint32_t layout = fused ? (2u | (class_mask << 8)) : 1u;
+    if (ctx->wave_capacity >= capacity && ctx->wave_mem.ptr && ctx->wave_layout == layout) return AKR_OK;
     const size_t cap = ((size_t)capacity + 31u) & ~(size_t)31u;
-    const size_t n_vec = 3 + 3 + 1 + 3 + 2, n_word = 1 + 2 * (size_t)CLS_COUNT;
+    size_t n_classes = 0;
+    for (uint32_t c = 0; c < (uint32_t)CLS_COUNT; ++c) n_classes += (class_mask >> c) & 1u;
+    const size_t n_vec = fused ? 8 * n_classes + 2 : 3 + 3 + 1 + 3 + 2, n_word = fused ? 0 : 1 + 2 * (size_t)CLS_COUNT;
     int rc = dev_alloc(ctx, ctx->wave_mem, cap * (n_vec * 16 + n_word * 4));
     if (rc != AKR_OK) return rc;
     f4 *vbase = static_cast<f4 *>(ctx->wave_mem.ptr);
@@ -988,21 +1060,34 @@ int ensure_wave_buffers(AkrContext *ctx, uint32_t capacity) {
         voff += cap;
         return p;
     };
-    for (int k = 0; k < 2; ++k) {
-        ctx->q[k].a = take_v();
-        ctx->q[k].b = take_v();
-        ctx->q[k].c = take_v();
-    }
-    ctx->hits.h = take_v();
-    ctx->shadow.a = take_v();
-    ctx->shadow.b = take_v();
-    ctx->shadow.c = take_v();
+    std::memset(ctx->q, 0, sizeof(ctx->q));
+    std::memset(ctx->cq, 0, sizeof(ctx->cq));
+    std::memset(&ctx->hits, 0, sizeof(ctx->hits));
+    std::memset(&ctx->shadow, 0, sizeof(ctx->shadow));
+    std::memset(&ctx->cls, 0, sizeof(ctx->cls));
     ctx->acc.l = take_v();
     ctx->acc.b = take_v();
-    uint32_t *wbase = reinterpret_cast<uint32_t *>(vbase + voff);
-    for (uint32_t c = 0; c < (uint32_t)CLS_COUNT; ++c) ctx->cls.idx[c] = reinterpret_cast<uint2 *>(wbase + cap * 2 * c);
-    ctx->shadow.ex1 = wbase + cap * 2 * (size_t)CLS_COUNT;
+    if (fused) {
+        for (int k = 0; k < 2; ++k)
+            for (uint32_t c = 0; c < (uint32_t)CLS_COUNT; ++c)
+                if ((class_mask >> c) & 1u)
+                    for (int j = 0; j < 4; ++j) ctx->cq[k][c].r[j] = take_v();
+    } else {
+        for (int k = 0; k < 2; ++k) {
+            ctx->q[k].a = take_v();
+            ctx->q[k].b = take_v();
+            ctx->q[k].c = take_v();
+        }
+        ctx->hits.h = take_v();
+        ctx->shadow.a = take_v();
+        ctx->shadow.b = take_v();
+        ctx->shadow.c = take_v();
+        uint32_t *wbase = reinterpret_cast<uint32_t *>(vbase + voff);
+        for (uint32_t c = 0; c < (uint32_t)CLS_COUNT; ++c) ctx->cls.idx[c] = reinterpret_cast<uint2 *>(wbase + cap * 2 * c);
+        ctx->shadow.ex1 = wbase + cap * 2 * (size_t)CLS_COUNT;
+    }
     ctx->wave_capacity = capacity;
+    ctx->wave_layout = layout;
     return AKR_OK;
 }
 
@@ -1044,16 +1129,26 @@ int akr_b200_create(int device_ordinal, AkrContext **out_ctx) {
         delete ctx;
         return AKR_ERR_CUDA;
     }
-    cudaFuncSetAttribute(k_trace_bvh<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
-    cudaFuncSetAttribute(k_trace_bvh<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
-    cudaFuncSetAttribute(k_trace_bvh<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
-    cudaFuncSetAttribute(k_trace_bvh<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
-    cudaFuncSetAttribute(k_trace<TRACE_BVH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
-    cudaFuncSetAttribute(k_trace<TRACE_FLAT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
-    cudaFuncSetAttribute(k_trace<TRACE_BVH_SMEM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
-    cudaFuncSetAttribute(k_trace<TRACE_BVH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
-    cudaFuncSetAttribute(k_trace<TRACE_FLAT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
-    cudaFuncSetAttribute(k_trace<TRACE_BVH_SMEM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
+    {
+        cudaError_t e = cudaSuccess;
+        auto opt_in = [&](const void *fn) {
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
+        };
+        opt_in((const void *)k_trace_bvh<false, false>);
+        opt_in((const void *)k_trace_bvh<false, true>);
+        opt_in((const void *)k_trace_bvh<true, false>);
+        opt_in((const void *)k_trace_bvh<true, true>);
+        opt_in((const void *)k_trace_flat<false>);
+        opt_in((const void *)k_trace_flat<true>);
+        opt_in((const void *)k_raygen_fused);
+        opt_in((const void *)k_bounce<CLS_LAMBERT>);
+        opt_in((const void *)k_bounce<CLS_CONDUCTOR>);
+        opt_in((const void *)k_bounce<CLS_GENERAL>);
+        if (e != cudaSuccess) {  // no sm_100a image for this device, or the opt-in shared-memory size is not available
+            delete ctx;
+            return AKR_ERR_CUDA;
+        }
+    }
     if (dev_alloc(ctx, ctx->counters, kMaxDepthSlots * kCtrStride * sizeof(uint32_t)) != AKR_OK || dev_alloc(ctx, ctx->totals, 2 * sizeof(unsigned long long)) != AKR_OK) {
         delete ctx;
         return AKR_ERR_CUDA;
@@ -1070,7 +1165,7 @@ void akr_b200_destroy(AkrContext *ctx) {
     cudaDeviceSynchronize();
     for (DeviceBuffer *b : {&ctx->pmj, &ctx->bn, &ctx->albedo, &ctx->nodes, &ctx->prims, &ctx->flat_prims, &ctx->shade, &ctx->instances, &ctx->materials, &ctx->lights,
                             &ctx->alias_j, &ctx->alias_t, &ctx->alias_pdf, &ctx->corner_n, &ctx->corner_t, &ctx->film, &ctx->wave_mem, &ctx->counters,
-                            &ctx->totals, &ctx->dbg_hits})
+                            &ctx->totals, &ctx->first_hits})
         dev_free(*b);
     if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
     if (ctx->ev_stop) cudaEventDestroy(ctx->ev_stop);
@@ -1186,39 +1281,32 @@ int akr_b200_upload_scene(AkrContext *ctx, const AkrSceneDesc *desc) {
     for (const Material &m : blob.materials) ctx->class_mask |= 1u << shade_class_of(m.type);
     // resident CTAs per SM of every kernel variant with this scene's shared-memory footprint
     {
+        cudaError_t e = cudaSuccess;
+        auto occ = [&](int &out, const void *fn, int block, size_t smem) {
+            int v = 0;
+            if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, fn, block, smem);
+            out = std::max(v, 1);
+        };
         const size_t smem_bvh = used + (size_t)(blob.bvh_depth + 2u) * kBlock * sizeof(int32_t);
-        const size_t smem_flat = used;
+        ctx->flat_bytes = (uint32_t)(blob.flat_blocks.size() * sizeof(PrimBlock2));
+        const size_t smem_flat = (size_t)ctx->smem_nodes * sizeof(BvhNode) + ctx->flat_bytes;
+        const size_t smem_bounce = ((ctx->flat_bytes + 127u) & ~127u) + (size_t)kShadeWarps * 2u * kTileBytes;
+        const bool all = ctx->smem_prims != 0;
         if (blob.any_alpha) {
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_trace[TRACE_BVH], k_trace<TRACE_BVH, true>, kBlock, smem_bvh);
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_trace[TRACE_FLAT], k_trace<TRACE_FLAT, true>, kBlock, smem_flat);
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_trace[TRACE_BVH_SMEM], k_trace<TRACE_BVH_SMEM, true>, kBlock, smem_bvh);
+            occ(ctx->occ_trace_flat, (const void *)k_trace_flat<true>, kBlock, smem_flat);
+            occ(ctx->occ_trace_dyn, all ? (const void *)k_trace_bvh<true, true> : (const void *)k_trace_bvh<false, true>, kBlock, smem_bvh);
         } else {
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_trace[TRACE_BVH], k_trace<TRACE_BVH, false>, kBlock, smem_bvh);
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_trace[TRACE_FLAT], k_trace<TRACE_FLAT, false>, kBlock, smem_flat);
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_trace[TRACE_BVH_SMEM], k_trace<TRACE_BVH_SMEM, false>, kBlock, smem_bvh);
+            occ(ctx->occ_trace_flat, (const void *)k_trace_flat<false>, kBlock, smem_flat);
+            occ(ctx->occ_trace_dyn, all ? (const void *)k_trace_bvh<true, false> : (const void *)k_trace_bvh<false, false>, kBlock, smem_bvh);
         }
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_shade[0], k_shade<CLS_LAMBERT, false>, kShadeBlock, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_shade[1], k_shade<CLS_CONDUCTOR, false>, kShadeBlock, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_shade[2], k_shade<CLS_GENERAL, false>, kShadeBlock, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_shade[3], k_shade<CLS_ANY, false>, kShadeBlock, 0);
-        const size_t smem_inline = (size_t)ctx->smem_nodes * sizeof(BvhNode) + blob.flat_blocks.size() * sizeof(PrimBlock2);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_shade_inline[0], k_shade<CLS_LAMBERT, true>, kShadeBlock, smem_inline);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_shade_inline[1], k_shade<CLS_CONDUCTOR, true>, kShadeBlock, smem_inline);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_shade_inline[2], k_shade<CLS_GENERAL, true>, kShadeBlock, smem_inline);
-        for (int &o : ctx->occ_shade_inline) o = std::max(o, 1);
-        {
-            const bool all = ctx->smem_prims != 0;
-            if (blob.any_alpha) {
-                if (all) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_trace_dyn, k_trace_bvh<true, true>, kBlock, smem_bvh);
-                else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_trace_dyn, k_trace_bvh<false, true>, kBlock, smem_bvh);
-            } else {
-                if (all) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_trace_dyn, k_trace_bvh<true, false>, kBlock, smem_bvh);
-                else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_trace_dyn, k_trace_bvh<false, false>, kBlock, smem_bvh);
-            }
-            ctx->occ_trace_dyn = std::max(ctx->occ_trace_dyn, 1);
-        }
-        for (int &o : ctx->occ_trace) o = std::max(o, 1);
-        for (int &o : ctx->occ_shade) o = std::max(o, 1);
+        occ(ctx->occ_shade[0], (const void *)k_shade<CLS_LAMBERT>, kShadeBlock, 0);
+        occ(ctx->occ_shade[1], (const void *)k_shade<CLS_CONDUCTOR>, kShadeBlock, 0);
+        occ(ctx->occ_shade[2], (const void *)k_shade<CLS_GENERAL>, kShadeBlock, 0);
+        occ(ctx->occ_raygen_fused, (const void *)k_raygen_fused, kBlock, ctx->flat_bytes);
+        occ(ctx->occ_bounce[0], (const void *)k_bounce<CLS_LAMBERT>, kShadeBlock, smem_bounce);
+        occ(ctx->occ_bounce[1], (const void *)k_bounce<CLS_CONDUCTOR>, kShadeBlock, smem_bounce);
+        occ(ctx->occ_bounce[2], (const void *)k_bounce<CLS_GENERAL>, kShadeBlock, smem_bounce);
+        if (e != cudaSuccess) return fail(ctx, AKR_ERR_CUDA, std::string("cudaOccupancyMaxActiveBlocksPerMultiprocessor: ") + cudaGetErrorString(e));
     }
     ctx->scene_ready = true;
     return AKR_OK;
@@ -1285,9 +1373,13 @@ int akr_b200_begin(AkrContext *ctx, const AkrPtConfig *cfg, const AkrSamplerConf
     int rc = dev_alloc(ctx, ctx->film, (size_t)ctx->n_pixels * 7 * sizeof(float));
     if (rc != AKR_OK) return rc;
     AKR_CUDA(ctx, cudaMemsetAsync(ctx->film.ptr, 0, (size_t)ctx->n_pixels * 7 * sizeof(float), ctx->stream));  // Film::clear (film.rs:230-233)
-    rc = dev_alloc(ctx, ctx->dbg_hits, (size_t)ctx->n_pixels * 2 * sizeof(uint32_t));
-    if (rc != AKR_OK) return rc;
-    AKR_CUDA(ctx, cudaMemsetAsync(ctx->dbg_hits.ptr, 0xff, (size_t)ctx->n_pixels * 2 * sizeof(uint32_t), ctx->stream));
+    if (ctx->opts.aov_mask & AKR_AOV_FIRST_HIT_IDS) {
+        rc = dev_alloc(ctx, ctx->first_hits, (size_t)ctx->n_pixels * 2 * sizeof(uint32_t));
+        if (rc != AKR_OK) return rc;
+        AKR_CUDA(ctx, cudaMemsetAsync(ctx->first_hits.ptr, 0xff, (size_t)ctx->n_pixels * 2 * sizeof(uint32_t), ctx->stream));
+    } else {
+        dev_free(ctx->first_hits);
+    }
     AKR_CUDA(ctx, cudaMemsetAsync(ctx->counters.ptr, 0, ctx->counters.bytes, ctx->stream));
     ctx->render_ready = true;
     return AKR_OK;
@@ -1299,13 +1391,24 @@ int akr_b200_render_pass(AkrContext *ctx, uint32_t n_spp, int blocking) {
     if (n_spp == 0) return AKR_OK;
     if (ctx->spp_done + n_spp > ctx->cfg.spp) return fail(ctx, AKR_ERR_INVALID_ARGUMENT, "pass exceeds the configured spp (sampler/mod.rs:666-668)");
     AKR_CUDA(ctx, cudaSetDevice(ctx->device));
+    // trace schedule: flat list for tiny scenes that fit in shared memory, BVH otherwise (opts.trace_mode overrides)
+    const int bvh_mode = ctx->smem_prims ? TRACE_BVH_SMEM : TRACE_BVH;
+    const bool flat_ok = ctx->scene.flat_blocks != nullptr && ctx->smem_prims;
+    int trace_mode = flat_ok ? TRACE_FLAT : bvh_mode;
+    if (ctx->opts.trace_mode == 1u) trace_mode = bvh_mode;
+    if (ctx->opts.trace_mode == 2u && flat_ok) trace_mode = TRACE_FLAT;
+    const bool alpha = ctx->scene.any_alpha != 0u;
+    // fused pipeline: flat list, no stochastic alpha; opts.fused = 2 forces the queued pipeline
+    const bool fused = trace_mode == TRACE_FLAT && !alpha && ctx->opts.fused != 2u;
+    const uint32_t class_mask = ctx->rp.force_diffuse ? (1u << CLS_LAMBERT) : ctx->class_mask;
+
     // wave geometry: pixels x samples with pixels * samples <= capacity
     uint32_t cap = ctx->opts.wave_size ? ctx->opts.wave_size : (1u << 22);
     cap = std::max(cap, 1024u);
     uint32_t spp_chunk = std::min(n_spp, std::max(1u, cap / 32u));
     uint32_t pix_chunk = std::max(32u, (cap / spp_chunk) & ~31u);
     pix_chunk = std::min(pix_chunk, ctx->n_pixels);
-    int rc = ensure_wave_buffers(ctx, pix_chunk * spp_chunk);
+    int rc = ensure_wave_buffers(ctx, pix_chunk * spp_chunk, fused, class_mask);
     if (rc != AKR_OK) return rc;
 
     LaunchParams P;
@@ -1319,34 +1422,22 @@ int akr_b200_render_pass(AkrContext *ctx, uint32_t n_spp, int blocking) {
     P.hits = ctx->hits;
     P.shadow = ctx->shadow;
     P.cls = ctx->cls;
+    std::memcpy(P.cq, ctx->cq, sizeof(P.cq));
     P.acc = ctx->acc;
     P.counters = static_cast<uint32_t *>(ctx->counters.ptr);
     P.film = static_cast<float *>(ctx->film.ptr);
     P.n_film_pixels = ctx->n_pixels;
-    P.scene_smem_nodes = ctx->smem_nodes;
+    P.scene_smem_nodes = fused ? 0u : ctx->smem_nodes;  // the fused kernels stage the flat list only
     P.scene_smem_prims = ctx->smem_prims;
     P.stack_depth = ctx->bvh_depth + 2u;
-    P.dbg_first_hits = static_cast<uint32_t *>(ctx->dbg_hits.ptr);
-
-    // trace schedule: flat list for tiny scenes that fit in shared memory, BVH otherwise (opts.trace_mode overrides)
-    const int bvh_mode = ctx->smem_prims ? TRACE_BVH_SMEM : TRACE_BVH;
-    const bool flat_ok = ctx->scene.flat_blocks != nullptr && ctx->smem_prims;
-    int trace_mode = flat_ok ? TRACE_FLAT : bvh_mode;
-    if (ctx->opts.trace_mode == 1u || ctx->opts.trace_mode == 3u) trace_mode = bvh_mode;
-    if (ctx->opts.trace_mode == 2u && flat_ok) trace_mode = TRACE_FLAT;
+    P.first_hits = static_cast<uint32_t *>(ctx->first_hits.ptr);
     P.stage_flat = trace_mode == TRACE_FLAT ? 1u : 0u;
-    // shadow rays inside the shade kernels: flat mode, no stochastic alpha, per-class kernels; opts.inline_shadow = 2 turns it off
-    P.inline_shadow = (trace_mode == TRACE_FLAT && !ctx->scene.any_alpha && ctx->opts.sort_by_material != 2u && ctx->opts.inline_shadow != 2u) ? 1u : 0u;
-    // shared memory: staged nodes + (flat mode: the padded PrimBlock2 list | BVH modes: primitives + per-thread stacks)
+    // shared memory: staged nodes + (flat mode: the padded PrimBlock2 lists | BVH modes: primitives + per-thread stacks)
     const size_t node_smem = (size_t)ctx->smem_nodes * sizeof(BvhNode);
-    const size_t flat_smem = node_smem + (size_t)(ctx->scene.n_pair_blocks + ctx->scene.n_single_blocks + ctx->scene.n_occ_pair_blocks +
-                                                  ctx->scene.n_occ_single_blocks) * sizeof(PrimBlock2);
+    const size_t flat_smem = node_smem + ctx->flat_bytes;
     const size_t trace_smem = trace_mode == TRACE_FLAT ? flat_smem : ctx->smem_bytes + (size_t)P.stack_depth * kBlock * sizeof(int32_t);
-    if (trace_smem > kSmemMax) return fail(ctx, AKR_ERR_UNSUPPORTED, "BVH too deep for the shared-memory traversal stack");
-    const bool dynamic_fetch = trace_mode != TRACE_FLAT && ctx->opts.trace_mode != 3u;  // trace_mode 3 = BVH with one fixed ray per lane (A/B)
-    const bool binned = ctx->opts.sort_by_material != 2u;
-    const bool alpha = ctx->scene.any_alpha != 0u;
-    const uint32_t class_mask = ctx->rp.force_diffuse ? (1u << CLS_LAMBERT) : ctx->class_mask;
+    const size_t bounce_smem = ((ctx->flat_bytes + 127u) & ~127u) + (size_t)kShadeWarps * 2u * kTileBytes;
+    if (trace_smem > kSmemMax || bounce_smem > kSmemMax) return fail(ctx, AKR_ERR_UNSUPPORTED, "BVH too deep for the shared-memory traversal stack");
 
     const bool prof = ctx->opts.profile_stages != 0;
     struct StageMark {
@@ -1392,61 +1483,48 @@ int akr_b200_render_pass(AkrContext *ctx, uint32_t n_spp, int blocking) {
             const uint32_t k = std::min(spp_chunk, n_spp - s0);
             P.wave = make_wave(pix0, n_pix, s_begin + s0, k);
             const uint32_t n_paths = n_pix * k;
-            AKR_LAUNCH(0, k_raygen, grid_for(ctx, n_paths, 8), 0, P);
-            const int g_trace = grid_for(ctx, n_paths, ctx->occ_trace[trace_mode]);
-            auto shade_grid_inline = [&](int variant) {
-                uint32_t need = (n_paths + kShadeBlock - 1) / kShadeBlock, capn = (uint32_t)(ctx->sm_count * ctx->occ_shade_inline[variant]);
+            auto shade_grid = [&](int occ) {
+                uint32_t need = (n_paths + kShadeBlock - 1) / kShadeBlock, capn = (uint32_t)(ctx->sm_count * occ);
                 return (int)std::max(1u, std::min(need, capn));
             };
-            auto shade_grid = [&](int variant) {
-                uint32_t need = (n_paths + kShadeBlock - 1) / kShadeBlock, capn = (uint32_t)(ctx->sm_count * ctx->occ_shade[variant]);
-                return (int)std::max(1u, std::min(need, capn));
-            };
-            for (uint32_t depth = 0; depth <= ctx->rp.max_depth; ++depth) {
-                if (trace_mode == TRACE_FLAT) {
-                    if (alpha) AKR_LAUNCH(1, (k_trace<TRACE_FLAT, true>), g_trace, trace_smem, P, depth);
-                    else AKR_LAUNCH(1, (k_trace<TRACE_FLAT, false>), g_trace, trace_smem, P, depth);
-                } else if (dynamic_fetch) {
-                    const int g_dyn = grid_for(ctx, n_paths, ctx->occ_trace_dyn);
-                    if (trace_mode == TRACE_BVH_SMEM) {
-                        if (alpha) AKR_LAUNCH(1, (k_trace_bvh<true, true>), g_dyn, trace_smem, P, depth);
-                        else AKR_LAUNCH(1, (k_trace_bvh<true, false>), g_dyn, trace_smem, P, depth);
+            if (fused) {
+                AKR_LAUNCH(0, k_raygen_fused, grid_for(ctx, n_paths, ctx->occ_raygen_fused), ctx->flat_bytes, P);
+                for (uint32_t depth = 0; depth < ctx->rp.max_depth; ++depth) {
+                    if (class_mask & (1u << CLS_LAMBERT)) AKR_LAUNCH_B(2, (k_bounce<CLS_LAMBERT>), shade_grid(ctx->occ_bounce[0]), kShadeBlock, bounce_smem, P, depth);
+                    if (class_mask & (1u << CLS_CONDUCTOR)) AKR_LAUNCH_B(3, (k_bounce<CLS_CONDUCTOR>), shade_grid(ctx->occ_bounce[1]), kShadeBlock, bounce_smem, P, depth);
+                    if (class_mask & (1u << CLS_GENERAL)) AKR_LAUNCH_B(6, (k_bounce<CLS_GENERAL>), shade_grid(ctx->occ_bounce[2]), kShadeBlock, bounce_smem, P, depth);
+                }
+            } else {
+                AKR_LAUNCH(0, k_raygen, grid_for(ctx, n_paths, 8), 0, P);
+                for (uint32_t depth = 0; depth <= ctx->rp.max_depth; ++depth) {
+                    if (trace_mode == TRACE_FLAT) {
+                        const int g_trace = grid_for(ctx, n_paths, ctx->occ_trace_flat);
+                        if (alpha) AKR_LAUNCH(1, (k_trace_flat<true>), g_trace, trace_smem, P, depth);
+                        else AKR_LAUNCH(1, (k_trace_flat<false>), g_trace, trace_smem, P, depth);
                     } else {
-                        if (alpha) AKR_LAUNCH(1, (k_trace_bvh<false, true>), g_dyn, trace_smem, P, depth);
-                        else AKR_LAUNCH(1, (k_trace_bvh<false, false>), g_dyn, trace_smem, P, depth);
+                        const int g_dyn = grid_for(ctx, n_paths, ctx->occ_trace_dyn);
+                        if (trace_mode == TRACE_BVH_SMEM) {
+                            if (alpha) AKR_LAUNCH(1, (k_trace_bvh<true, true>), g_dyn, trace_smem, P, depth);
+                            else AKR_LAUNCH(1, (k_trace_bvh<true, false>), g_dyn, trace_smem, P, depth);
+                        } else {
+                            if (alpha) AKR_LAUNCH(1, (k_trace_bvh<false, true>), g_dyn, trace_smem, P, depth);
+                            else AKR_LAUNCH(1, (k_trace_bvh<false, false>), g_dyn, trace_smem, P, depth);
+                        }
                     }
-                } else if (trace_mode == TRACE_BVH_SMEM) {
-                    if (alpha) AKR_LAUNCH(1, (k_trace<TRACE_BVH_SMEM, true>), g_trace, trace_smem, P, depth);
-                    else AKR_LAUNCH(1, (k_trace<TRACE_BVH_SMEM, false>), g_trace, trace_smem, P, depth);
-                } else {
-                    if (alpha) AKR_LAUNCH(1, (k_trace<TRACE_BVH, true>), g_trace, trace_smem, P, depth);
-                    else AKR_LAUNCH(1, (k_trace<TRACE_BVH, false>), g_trace, trace_smem, P, depth);
+                    if (class_mask & (1u << CLS_LAMBERT)) AKR_LAUNCH_B(2, (k_shade<CLS_LAMBERT>), shade_grid(ctx->occ_shade[0]), kShadeBlock, 0, P, depth);
+                    if (class_mask & (1u << CLS_CONDUCTOR)) AKR_LAUNCH_B(3, (k_shade<CLS_CONDUCTOR>), shade_grid(ctx->occ_shade[1]), kShadeBlock, 0, P, depth);
+                    if (class_mask & (1u << CLS_GENERAL)) AKR_LAUNCH_B(6, (k_shade<CLS_GENERAL>), shade_grid(ctx->occ_shade[2]), kShadeBlock, 0, P, depth);
                 }
-                if (!binned) {
-                    AKR_LAUNCH_B(6, (k_shade<CLS_ANY, false>), shade_grid(3), kShadeBlock, 0, P, depth);
-                    continue;
-                }
-                if (P.inline_shadow) {
-                    const size_t sm = flat_smem;  // nodes + the staged flat list
-                    if (class_mask & (1u << CLS_LAMBERT)) AKR_LAUNCH_B(2, (k_shade<CLS_LAMBERT, true>), shade_grid_inline(0), kShadeBlock, sm, P, depth);
-                    if (class_mask & (1u << CLS_CONDUCTOR)) AKR_LAUNCH_B(3, (k_shade<CLS_CONDUCTOR, true>), shade_grid_inline(1), kShadeBlock, sm, P, depth);
-                    if (class_mask & (1u << CLS_GENERAL)) AKR_LAUNCH_B(6, (k_shade<CLS_GENERAL, true>), shade_grid_inline(2), kShadeBlock, sm, P, depth);
-                    continue;
-                }
-                if (class_mask & (1u << CLS_LAMBERT)) AKR_LAUNCH_B(2, (k_shade<CLS_LAMBERT, false>), shade_grid(0), kShadeBlock, 0, P, depth);
-                if (class_mask & (1u << CLS_CONDUCTOR)) AKR_LAUNCH_B(3, (k_shade<CLS_CONDUCTOR, false>), shade_grid(1), kShadeBlock, 0, P, depth);
-                if (class_mask & (1u << CLS_GENERAL)) AKR_LAUNCH_B(6, (k_shade<CLS_GENERAL, false>), shade_grid(2), kShadeBlock, 0, P, depth);
             }
             AKR_LAUNCH(4, k_accumulate, grid_for(ctx, n_pix, 8), 0, P);
-            k_fold_counters<<<1, 128, 0, ctx->stream>>>(P.counters, static_cast<unsigned long long *>(ctx->totals.ptr), ctx->rp.max_depth + 2u);
-            count_launch(5);
+            AKR_LAUNCH_B(5, k_fold_counters, 1, 128, 0, P.counters, static_cast<unsigned long long *>(ctx->totals.ptr), ctx->rp.max_depth + 2u);
             ctx->stats.samples += n_paths;
         }
     }
 #undef AKR_LAUNCH
 #undef AKR_LAUNCH_B
-    AKR_CUDA(ctx, cudaEventRecord(ctx->ev_stop, ctx->stream));
     AKR_CUDA(ctx, cudaGetLastError());
+    AKR_CUDA(ctx, cudaEventRecord(ctx->ev_stop, ctx->stream));
     ctx->spp_done += n_spp;
     if (blocking || prof) {
         AKR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1548,10 +1626,11 @@ int akr_b200_reset_stats(AkrContext *ctx) {
 int akr_b200_debug_first_hits(AkrContext *ctx, uint32_t *out_inst, uint32_t *out_prim, size_t n_pixels) {
     if (!ctx || !out_inst || !out_prim) return fail(ctx, AKR_ERR_INVALID_ARGUMENT, "null argument");
     if (!ctx->render_ready || n_pixels != ctx->n_pixels) return fail(ctx, AKR_ERR_STATE, "no render / size mismatch");
+    if (!ctx->first_hits.ptr) return fail(ctx, AKR_ERR_STATE, "first-hit ids were not requested (AkrEngineOptions.aov_mask & AKR_AOV_FIRST_HIT_IDS) before akr_b200_begin");
     std::vector<uint32_t> tmp(n_pixels * 2);
     AKR_CUDA(ctx, cudaSetDevice(ctx->device));
     AKR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    AKR_CUDA(ctx, cudaMemcpy(tmp.data(), ctx->dbg_hits.ptr, tmp.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    AKR_CUDA(ctx, cudaMemcpy(tmp.data(), ctx->first_hits.ptr, tmp.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     for (size_t i = 0; i < n_pixels; ++i) {
         out_inst[i] = tmp[2 * i];
         out_prim[i] = tmp[2 * i + 1];

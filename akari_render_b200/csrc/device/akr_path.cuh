@@ -251,9 +251,52 @@ AKR_HD void miss_body(const RenderParams &rp, uint32_t depth, f3 beta, uint32_t 
     }
 }
 
+// ---- handle_surface_light (pt.rs:230-258): c = beta * (Le * w) at a hit on a light triangle, zero otherwise ----
+// `ray_o`, `ray_d`, `beta`, `prev_bsdf_pdf` describe the ray that produced the hit at path depth `depth`.
+AKR_HD f3 emitter_contrib(const SceneView &sc, const RenderParams &rp, uint32_t depth, f3 ray_o, f3 ray_d, f3 beta, float prev_bsdf_pdf,
+                          const TriShade &ts, const Material &mat, const Surface &si) {
+    f3 direct = splat3(0.0f);
+    float w = 0.0f;
+    if ((ts.flags & TRI_IS_LIGHT) && (!rp.indirect_only || depth > 1u)) {
+        f3 emission = ld3(mat.emission);  // AreaLight::le (light/area.rs:36-49)
+        direct = dot(si.ng, ray_d) < 0.0f ? emission : splat3(0.0f);
+        if (depth == 0u || !rp.use_nee) {
+            w = 1.0f;
+        } else {
+            // LightAggregate::pdf_direct (light/mod.rs:134-147), AreaLight::pdf_direct (light/area.rs:109-130)
+            const InstanceRec &in = sc.instances[ts.inst];
+            float light_choice_pdf = sc.alias_pdf[in.light_id];
+            f3 wi = si.p - ray_o;
+            float dist2 = length_squared(wi);
+            wi = wi / sqrtf(dist2);
+            float pdf = ts.prim_pdf / si.area * dist2 / fmaxf(fabsf(dot(si.ng, wi)), 1e-6f);
+            w = mis_weight(prev_bsdf_pdf, light_choice_pdf * pdf);
+        }
+    }
+    return beta * (direct * w);
+}
+// add_radiance of that contribution to a register-resident radiance (same additions as acc_set_lb / acc_add)
+AKR_HD f3 emitter_add(const RenderParams &rp, uint32_t depth, f3 L, f3 c) {
+    const bool dbg_on = rp.debug_depth < 0;
+    if (depth == 0u) return (dbg_on || rp.debug_depth == 0) ? splat3(0.0f) + c : splat3(0.0f);  // radiance starts at 0
+    if ((dbg_on || depth == (uint32_t)rp.debug_depth) && (c.x != 0.0f || c.y != 0.0f || c.z != 0.0f)) return L + c;
+    return L;
+}
+// miss_body on a register-resident radiance
+AKR_HD f3 miss_add(const RenderParams &rp, uint32_t depth, f3 beta, f3 L) {
+    const bool dbg_on = rp.debug_depth < 0;
+    if (depth != 0u && (dbg_on || depth == (uint32_t)rp.debug_depth)) {
+        f3 c = beta * (splat3(0.0f) * 0.0f);
+        if (c.x != 0.0f || c.y != 0.0f || c.z != 0.0f) return L + c;
+    }
+    return L;
+}
+
 // `depth` = path depth when the ray was cast (0 for camera rays).  `hit` is a real hit (misses end in
 // miss_body).  CLS is the shade class of the hit material (CLS_ANY: decide per call).
-template <int CLS, class Acc>
+// EMIT = false (fused pipeline): the emitter term of this hit was already added by the stage that traced the ray, so
+// ps.o / ps.prev_bsdf_pdf are not read and `acc` is not touched.
+template <int CLS, bool EMIT = true, class Acc>
 AKR_HD ShadeOut shade_body(const SceneView &sc, const CornerAttribs &ca, const SamplerTables &tab, const RenderParams &rp, const WaveInfo &wave,
                            uint32_t depth, const PathState &ps, HitRec hit, Acc &acc) {
     ShadeOut out;
@@ -281,26 +324,8 @@ AKR_HD ShadeOut shade_body(const SceneView &sc, const CornerAttribs &ca, const S
     Surface si = surface_from_hit(sc, ca, hit.gid, hit.u, hit.v);
     f3 wo = -ps.d;
     // handle_surface_light (pt.rs:230-258)
-    {
-        f3 direct = splat3(0.0f);
-        float w = 0.0f;
-        if ((ts.flags & TRI_IS_LIGHT) && (!rp.indirect_only || depth > 1u)) {
-            f3 emission = ld3(mat.emission);  // AreaLight::le (light/area.rs:36-49)
-            direct = dot(si.ng, ps.d) < 0.0f ? emission : splat3(0.0f);
-            if (depth == 0u || !rp.use_nee) {
-                w = 1.0f;
-            } else {
-                // LightAggregate::pdf_direct (light/mod.rs:134-147), AreaLight::pdf_direct (light/area.rs:109-130)
-                const InstanceRec &in = sc.instances[ts.inst];
-                float light_choice_pdf = sc.alias_pdf[in.light_id];
-                f3 wi = si.p - ps.o;
-                float dist2 = length_squared(wi);
-                wi = wi / sqrtf(dist2);
-                float pdf = ts.prim_pdf / si.area * dist2 / fmaxf(fabsf(dot(si.ng, wi)), 1e-6f);
-                w = mis_weight(ps.prev_bsdf_pdf, light_choice_pdf * pdf);
-            }
-        }
-        f3 c = ps.beta * (direct * w);
+    if (EMIT) {
+        f3 c = emitter_contrib(sc, rp, depth, ps.o, ps.d, ps.beta, ps.prev_bsdf_pdf, ts, mat, si);
         if (depth == 0u) {
             // radiance starts at 0; base_replay_throughput = radiance (pt.rs:415-417)
             f3 l = (dbg_on || rp.debug_depth == 0) ? splat3(0.0f) + c : splat3(0.0f);
@@ -416,6 +441,104 @@ template <class Acc> AKR_HD void shadow_resolve(Acc &acc, const ShadowItem &it, 
         if (c.x != 0.0f || c.y != 0.0f || c.z != 0.0f) acc_add(acc, id, c);
     }
     if (depth1 == 1u) acc_snap_b(acc, id);  // base_replay_throughput = radiance (pt.rs:510-512)
+}
+
+// ---- fused pipeline (flat scenes): one kernel per (depth, shade class) does shade + shadow ray + next ray ----------
+// The path record carries the hit the PREVIOUS stage found and the radiance so far, so a bounce reads one
+// contiguous 64-byte record and writes one: no hit queue, no (slot, path id) indirection, no per-bounce accumulator
+// read-modify-write.  The emitter term of a hit (pt.rs:230-258) is evaluated by the stage that traced the ray — it has
+// the ray origin and the BSDF pdf in registers — which is why neither is part of the record.  Additions to the
+// radiance happen in the reference order: emitter(d), NEE(d), emitter(d + 1), ...
+struct BounceRec {     // 13 words, stored as 4 x 16 B
+    f3 d;              // direction of the ray that produced the hit (wo = -d)
+    uint32_t gid;      // hit triangle
+    float u, v;
+    uint32_t path_id;
+    f3 beta;
+    f3 L;              // radiance so far, emitter term of this hit included
+};
+struct TraceHit {      // result of a closest-hit query; gid 0xffffffff = miss
+    uint32_t gid, cls, light;
+    float u, v;
+};
+struct BounceOut {
+    bool cont;         // the path goes on: `next` enters depth + 1 in shade class `cls`
+    bool shadow;       // a shadow ray was traced (statistics)
+    bool traced;       // a continuation ray was traced (statistics)
+    uint32_t cls;
+    BounceRec next;
+};
+// A Tracer answers `occluded(active, o, d, t_max, ex0, ex1)` and `closest(active, o, d, ex0)`; on the device both are
+// warp-collective (every lane calls, `active` says whether it carries a ray), so the bodies below never return early.
+template <class Tracer>
+AKR_HD BounceOut continue_path(const SceneView &sc, const CornerAttribs &ca, const RenderParams &rp, uint32_t depth1, bool active, bool has_next,
+                               const PathState &nx, f3 L, Tracer &tr, const AccView &acc) {
+    BounceOut r;
+    r.shadow = false;
+    r.traced = has_next;
+    const TraceHit h = tr.closest(has_next, nx.o, nx.d, nx.ex);
+    r.cont = has_next && h.gid != 0xffffffffu;
+    r.cls = rp.force_diffuse ? (uint32_t)CLS_LAMBERT : h.cls;
+    if (has_next && !r.cont) L = miss_add(rp, depth1, nx.beta, L);
+    if (r.cont && h.light) {  // (a hit that is no light adds beta * 0 * 0: nothing, also at depth 0 where radiance = 0 + c)
+        const TriShade &ts = sc.shade[h.gid];
+        const Surface si = surface_from_hit(sc, ca, h.gid, h.u, h.v);
+        L = emitter_add(rp, depth1, L, emitter_contrib(sc, rp, depth1, nx.o, nx.d, nx.beta, nx.prev_bsdf_pdf, ts, sc.materials[ts.mat], si));
+    }
+    if (depth1 >= rp.max_depth) r.cont = false;  // pt.rs:466-468: the emitter term is all that happens at the last hit
+    if (active && !r.cont) st4(acc.l + nx.path_id, f4{L.x, L.y, L.z, 0.0f});  // the path ends here: its radiance is final
+    r.next.d = nx.d;
+    r.next.gid = h.gid;
+    r.next.u = h.u;
+    r.next.v = h.v;
+    r.next.path_id = nx.path_id;
+    r.next.beta = nx.beta;
+    r.next.L = L;
+    return r;
+}
+// raygen + camera ray + emitter term of the first hit
+template <class Tracer>
+AKR_HD BounceOut raygen_fused(const SceneView &sc, const CornerAttribs &ca, const SamplerTables &tab, const RenderParams &rp, const WaveInfo &wave, bool active,
+                              uint32_t path_id, Tracer &tr, const AccView &acc) {
+    PathState ps;
+    ps.o = splat3(0.0f);
+    ps.d = mk3(1.0f, 0.0f, 0.0f);
+    ps.ex = 0xffffffffu;
+    ps.beta = splat3(1.0f);
+    ps.prev_bsdf_pdf = 0.0f;
+    ps.path_id = path_id;
+    if (active) ps = raygen_body(sc, tab, rp, wave, path_id);
+    BounceOut r = continue_path(sc, ca, rp, 0u, active, active, ps, splat3(0.0f), tr, acc);
+    // base_replay_throughput of a path that ends at depth 0 (miss: 0; max_depth = 0: the emitter term, pt.rs:415-417)
+    if (active && !r.cont) st4(acc.b + path_id, f4{r.next.L.x, r.next.L.y, r.next.L.z, 0.0f});
+    return r;
+}
+// one bounce of one path whose hit is of shade class CLS
+template <int CLS, class Tracer>
+AKR_HD BounceOut bounce_fused(const SceneView &sc, const CornerAttribs &ca, const SamplerTables &tab, const RenderParams &rp, const WaveInfo &wave, uint32_t depth,
+                              bool active, const BounceRec &in, Tracer &tr, const AccView &acc) {
+    ShadeOut o = ShadeOut();
+    f3 L = in.L;
+    if (active) {
+        PathState ps;
+        ps.o = splat3(0.0f);
+        ps.d = in.d;
+        ps.ex = 0xffffffffu;
+        ps.beta = in.beta;
+        ps.prev_bsdf_pdf = 0.0f;
+        ps.path_id = in.path_id;
+        o = shade_body<CLS, false>(sc, ca, tab, rp, wave, depth, ps, HitRec{in.gid, in.u, in.v}, acc);
+        o.next.path_id = in.path_id;
+    }
+    const bool occluded = tr.occluded(o.has_shadow, o.shadow.o, o.shadow.d, o.shadow.t_max, o.shadow.ex0, o.shadow.ex1);
+    if (o.has_shadow && !occluded) {  // shadow_resolve (pt.rs:504-513)
+        const f3 c = o.shadow.contrib;
+        if (c.x != 0.0f || c.y != 0.0f || c.z != 0.0f) L = L + c;
+    }
+    if (active && depth == 0u) st4(acc.b + in.path_id, f4{L.x, L.y, L.z, 0.0f});  // base_replay_throughput = radiance (pt.rs:415-417,510-512)
+    BounceOut r = continue_path(sc, ca, rp, depth + 1u, active, o.has_next, o.next, L, tr, acc);
+    r.shadow = o.has_shadow;
+    return r;
 }
 
 // ---- stage: accumulate (pt.rs:871-876 + film.rs:196-229) -------------------------------------------------------

@@ -63,7 +63,7 @@ struct alignas(16) PrimRec {
     float r0[4];
     float r1[4];
     uint32_t gid_a, gid_b;  // gid_b == 0xffffffff: single triangle
-    uint32_t meta;          // bits 0-1 iu_a, 2-3 iv_a, 4-5 iu_b, 6-7 iv_b, 8-9 cls_a, 10-11 cls_b
+    uint32_t meta;          // bits 0-1 iu_a, 2-3 iv_a, 4-5 iu_b, 6-7 iv_b, 8-9 cls_a, 10-11 cls_b, 12 light_a, 13 light_b
     uint32_t _pad;
 };
 static_assert(sizeof(PrimRec) == 64, "PrimRec must be 64 bytes");

@@ -211,6 +211,7 @@ struct PrimHit {
 struct PrimDecoded {
     uint32_t gid, cls;
     float u, v;
+    uint32_t light;  // the triangle belongs to a mesh light
 };
 AKR_HD float fast_rcp(float x) {
 #if defined(__CUDA_ARCH__)
@@ -227,6 +228,7 @@ AKR_HD PrimDecoded prim_decode(const PrimRec &p, float s, float q) {
     if (p.gid_b == 0xffffffffu) {
         r.gid = p.gid_a;
         r.cls = (p.meta >> 8) & 3u;
+        r.light = (p.meta >> 12) & 1u;
         r.u = s;
         r.v = q;
         return r;
@@ -239,6 +241,7 @@ AKR_HD PrimDecoded prim_decode(const PrimRec &p, float s, float q) {
     const uint32_t iu = m & 3u, iv = (m >> 2) & 3u;
     r.gid = half ? p.gid_b : p.gid_a;
     r.cls = (half ? (p.meta >> 10) : (p.meta >> 8)) & 3u;
+    r.light = (half ? (p.meta >> 13) : (p.meta >> 12)) & 1u;
     r.u = iu == 0u ? w0 : (iu == 1u ? w1 : w2);
     r.v = iv == 0u ? w0 : (iv == 1u ? w1 : w2);
     return r;

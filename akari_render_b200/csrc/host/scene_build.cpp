@@ -866,7 +866,9 @@ int build_scene_blob(const AkrSceneDesc &d, HostSceneBlob &out, std::string &err
         }
         uint32_t cls_a = shade_class_of(out.materials[out.shade[hp.gid_a].mat].type);
         uint32_t cls_b = hp.gid_b == 0xffffffffu ? 0u : shade_class_of(out.materials[out.shade[hp.gid_b].mat].type);
-        pr.meta = hp.iu_a | (hp.iv_a << 2) | (hp.iu_b << 4) | (hp.iv_b << 6) | (cls_a << 8) | (cls_b << 10);
+        uint32_t light_a = (out.shade[hp.gid_a].flags & TRI_IS_LIGHT) ? 1u : 0u;
+        uint32_t light_b = (hp.gid_b != 0xffffffffu && (out.shade[hp.gid_b].flags & TRI_IS_LIGHT)) ? 1u : 0u;
+        pr.meta = hp.iu_a | (hp.iv_a << 2) | (hp.iu_b << 4) | (hp.iv_b << 6) | (cls_a << 8) | (cls_b << 10) | (light_a << 12) | (light_b << 13);
     }
     if (n_prims <= kFlatMaxPrims) {
         PrimRec never;

@@ -58,10 +58,10 @@ def summarize_clocks(samples):
     return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons}
 
 
-def workload_config(spp, world, wave, trace_mode, sort):
+def workload_config(spp, world, wave, trace_mode):
     return {"workload": f"cbox 1280x720 @ {spp}spp, pmj02bn seed 0, gaussian r=1.5, max_depth 12, rr_depth 5, 64 spp/pass",
             "parallelism": f"image rows x{world}", "l2": "working set (wave state) > L2; no inter-step reuse (film cleared each step)",
-            "wave_paths": wave or (1 << 22), "trace_mode": trace_mode, "sort": sort}
+            "wave_paths": wave or (1 << 22), "trace_mode": trace_mode}
 
 
 REF_SPP_PER_STEP = 4
@@ -111,7 +111,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "path samples/sec on cbox 1280x720", "value": value, "unit": "samples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(1, args.steps), "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(SPP, args.gpus, args.wave, args.trace_mode, args.sort),
+        "config": workload_config(SPP, args.gpus, args.wave, args.trace_mode),
         "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port",
                          "sample": f"{args.steps} steps x {REF_SPP_PER_STEP} of the 1024 spp of the full 1280x720 frame = {samples} samples, "
                                    f"{secs:.1f} s; CPU oracle (restatement of the reference's -d cpu path) on {cores} threads = the fastest "
@@ -130,9 +130,8 @@ def main():
     ap.add_argument("--spp", type=int, default=SPP, help="override for quick experiments (the reported config is 1024)")
     ap.add_argument("--wave", type=int, default=1 << 26, help="paths in flight per wave (0 = engine default of 4 Mi)")
     ap.add_argument("--trace-mode", type=int, default=0, help="0 auto, 1 BVH, 2 flat list")
-    ap.add_argument("--sort", type=int, default=0, help="0/1 per-class shade kernels, 2 one generic shade kernel")
     ap.add_argument("--smem-node-kb", type=int, default=0, help="BVH scenes: KiB of top-of-tree nodes staged per CTA (0 = default)")
-    ap.add_argument("--inline-shadow", type=int, default=0, help="0 auto (shade traces its own shadow ray on flat scenes), 2 off")
+    ap.add_argument("--fused", type=int, default=0, help="0 auto (fused bounce kernels on flat scenes), 2 off (trace stage + shade stage + queues)")
     ap.add_argument("--profile-stages", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--scene", default="cbox", choices=["cbox", "clutter"],
@@ -172,7 +171,7 @@ def main():
     my_rows = tile[1] - tile[0]
     stream = torch.cuda.current_stream().cuda_stream
     pt = akr.PathTracer(local_rank, stream=stream)
-    eng = dict(wave_size=args.wave, sort_by_material=args.sort, trace_mode=args.trace_mode, inline_shadow=args.inline_shadow, smem_node_kb=args.smem_node_kb)
+    eng = dict(wave_size=args.wave, trace_mode=args.trace_mode, fused=args.fused, smem_node_kb=args.smem_node_kb)
     pt.set_engine_options(profile_stages=1 if args.profile_stages else 0, **eng)
     pt.upload_scene(scene)
     max_rows = max_band_rows(HEIGHT, world)
@@ -319,7 +318,7 @@ def main():
             "metric": "path samples/sec on cbox 1280x720", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(workload_config(spp, world, args.wave, args.trace_mode, args.sort), **({"scene": args.scene} if args.scene != "cbox" else {})),
+            "config": dict(workload_config(spp, world, args.wave, args.trace_mode), **({"scene": args.scene} if args.scene != "cbox" else {})),
             "clocks": summarize_clocks(clocks),
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(st.kernel_launches),

@@ -246,23 +246,28 @@ int akr_b200_get_stats(AkrContext *ctx, AkrStats *out);
 int akr_b200_reset_stats(AkrContext *ctx);
 
 /* Tunables of the wavefront engine (not part of the reference surface). */
+enum {
+    AKR_AOV_FIRST_HIT_IDS = 1u << 0   /* (instance, primitive) of the first hit of sample 0 of every pixel */
+};
 typedef struct AkrEngineOptions {
     uint32_t wave_size;             /* paths in flight per wave; 0 = default                    */
-    uint32_t sort_by_material;      /* 0 = default (hits binned per shade class, one shade kernel
-                                     * per class), 1 = same, 2 = off (one generic shade kernel)  */
+    uint32_t _unused0;              /* (was sort_by_material; hits are always binned per shade class) */
     uint32_t profile_stages;        /* record per-stage CUDA-event times (adds syncs)           */
     uint32_t trace_mode;            /* 0 = auto, 1 = BVH traversal (persistent warps, dynamic ray fetch),
                                      * 2 = flat primitive list (only honoured when every primitive fits
-                                     * in shared memory), 3 = BVH traversal with one fixed ray per lane  */
-    uint32_t inline_shadow;         /* 0 = auto (shade kernels trace their own shadow ray when the
-                                     * flat list is in use), 2 = off (always use the shadow queue) */
+                                     * in shared memory)                                                  */
+    uint32_t fused;                 /* 0 = auto (flat scenes without alpha-tested materials run the fused
+                                     * bounce kernels: shade + shadow ray + next ray in one kernel per depth
+                                     * and shade class), 2 = off (always trace stage + shade stage + queues) */
     uint32_t smem_node_kb;          /* BVH scenes that do not fit in shared memory: KiB of top-of-tree nodes each
                                      * CTA stages (0 = default 16); read by akr_b200_upload_scene              */
-    uint32_t _reserved[2];
+    uint32_t aov_mask;              /* AKR_AOV_* outputs to record; read by akr_b200_begin                    */
+    uint32_t _reserved[1];
 } AkrEngineOptions;
 int akr_b200_set_engine_options(AkrContext *ctx, const AkrEngineOptions *opts);
 
-/* Debug taps for parity tests: first-hit (inst, prim) per pixel of sample 0 and path lengths. */
+/* AKR_AOV_FIRST_HIT_IDS: first-hit (inst, prim) per pixel of sample 0 (0xffffffff = miss); AKR_ERR_STATE when the
+ * output was not requested before akr_b200_begin. */
 int akr_b200_debug_first_hits(AkrContext *ctx, uint32_t *out_inst, uint32_t *out_prim, size_t n_pixels);
 
 #ifdef __cplusplus

@@ -14,6 +14,23 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+# Measured parity figures (per-pixel / image relative L2, ray-count deltas ...) are collected here and printed in the
+# terminal summary, so that a passing `pytest -q` run still shows the numbers next to the bounds they were checked against.
+_MEASURED = []
+
+
+def measured(line):
+    _MEASURED.append(line)
+    print(line)
+
+
+def pytest_terminal_summary(terminalreporter):
+    if _MEASURED:
+        terminalreporter.write_sep("-", "measured parity figures (value <= asserted bound)")
+        for line in _MEASURED:
+            terminalreporter.write_line(line)
+
+
 @pytest.fixture(scope="session", autouse=True)
 def _built():
     """Build every native component once (no-op when the .so files are current)."""

@@ -15,6 +15,33 @@
 
 using namespace akr;
 
+static thread_local int g_use_prims = 0;
+static thread_local int g_fused = 0;
+
+namespace {
+template <bool ANY_HIT> HitRec host_trace(const SceneView &sc, const TraceData &td, f3 o, f3 d, float t_max, uint32_t ex0, uint32_t ex1) {
+    return g_use_prims == 1   ? trace_ray_prims<ANY_HIT>(sc, o, d, 0.0f, t_max, ex0, ex1)
+           : g_use_prims == 2 ? trace_ray4<ANY_HIT>(sc, o, d, 0.0f, t_max, ex0, ex1)
+           : g_use_prims == 3 ? trace_flat_ref<ANY_HIT>(sc, o, d, 0.0f, t_max, ex0, ex1)
+                              : trace_ray<ANY_HIT>(sc, td, o, d, 0.0f, t_max, ex0, ex1);
+}
+struct HostTracer {  // the Tracer of akr_path.cuh's fused bodies, one ray at a time
+    const SceneView &sc;
+    const TraceData &td;
+    bool occluded(bool active, f3 o, f3 d, float t_max, uint32_t ex0, uint32_t ex1) const {
+        return active && host_trace<true>(sc, td, o, d, t_max, ex0, ex1).gid != 0xffffffffu;
+    }
+    TraceHit closest(bool active, f3 o, f3 d, uint32_t ex0) const {
+        TraceHit t{0xffffffffu, 0u, 0u, 0.0f, 0.0f};
+        if (!active) return t;
+        const HitRec h = host_trace<false>(sc, td, o, d, 1e20f, ex0, 0xffffffffu);
+        if (h.gid == 0xffffffffu) return t;
+        const TriShade &ts = sc.shade[h.gid];
+        return TraceHit{h.gid, shade_class_of(sc.materials[ts.mat].type), (ts.flags & TRI_IS_LIGHT) ? 1u : 0u, h.u, h.v};
+    }
+};
+}  // namespace
+
 extern "C" {
 
 static thread_local std::string g_err;
@@ -32,8 +59,12 @@ struct HostsimStats {
 // 0: Moeller-Trumbore triangles over the binary BVH (bit-exact twin of the oracle); 1: the CUDA kernels' primitive
 // intersector; 2: Moeller-Trumbore triangles over the 4-wide BVH (validates the collapsed tree); 3: the primitive
 // intersector over the staged flat lists (complete list for closest hits, occluder-only list for shadow rays)
-static thread_local int g_use_prims = 0;
 void hostsim_set_intersector(int use_prims) { g_use_prims = use_prims; }
+// 0: queued pipeline (trace stage + shade stage + shadow queue, what BVH scenes run); 1: fused pipeline (one stage per
+// depth and shade class does shade + shadow ray + next ray on records that carry hit and radiance: akr_path.cuh
+// bounce_fused, what flat scenes run)
+void hostsim_set_pipeline(int fused) { g_fused = fused; }
+
 
 
 int hostsim_render(const AkrSceneDesc *desc, const AkrPtConfig *cfg, const AkrSamplerConfig *scfg, const AkrFilterConfig *filter,
@@ -90,6 +121,45 @@ int hostsim_render(const AkrSceneDesc *desc, const AkrPtConfig *cfg, const AkrSa
     for (uint32_t pix0 = 0; pix0 < n_pixels; pix0 += wave_pixels) {
         WaveInfo wave = make_wave(pix0, std::min(wave_pixels, n_pixels - pix0), spp_begin, k);
         const uint32_t n_paths = wave.n_pix * wave.n_spp;
+        if (g_fused) {
+            // every path writes its radiance and its base_replay_throughput exactly once: start from a sentinel to prove it
+            const float kUnset = -7777.0f;
+            std::vector<f4> acc(2u * (size_t)n_paths, f4{kUnset, kUnset, kUnset, kUnset});
+            AccView av{acc.data(), acc.data() + n_paths};
+            HostTracer tr{sc, td};
+            std::vector<BounceRec> cur[CLS_COUNT], next[CLS_COUNT];
+            for (uint32_t i = 0; i < n_paths; ++i) {
+                BounceOut r = raygen_fused(sc, ca, tab, rp, wave, true, i, tr, av);
+                ++segments;
+                if (first_hits && spp_begin == wave.s0 && i < wave.n_pix) {
+                    uint32_t pix = wave.pix0 + i, gid = r.next.gid;
+                    first_hits[2 * pix + 0] = gid == 0xffffffffu ? 0xffffffffu : sc.shade[gid].inst;
+                    first_hits[2 * pix + 1] = gid == 0xffffffffu ? 0xffffffffu : sc.shade[gid].prim;
+                }
+                if (r.cont) cur[r.cls].push_back(r.next);
+            }
+            for (uint32_t depth = 0; depth < rp.max_depth; ++depth) {
+                for (uint32_t c = 0; c < (uint32_t)CLS_COUNT; ++c) {
+                    for (const BounceRec &rec : cur[c]) {
+                        BounceOut r = c == CLS_LAMBERT     ? bounce_fused<CLS_LAMBERT>(sc, ca, tab, rp, wave, depth, true, rec, tr, av)
+                                      : c == CLS_CONDUCTOR ? bounce_fused<CLS_CONDUCTOR>(sc, ca, tab, rp, wave, depth, true, rec, tr, av)
+                                                           : bounce_fused<CLS_GENERAL>(sc, ca, tab, rp, wave, depth, true, rec, tr, av);
+                        shadows += r.shadow ? 1u : 0u;
+                        segments += r.traced ? 1u : 0u;
+                        if (r.cont) next[r.cls].push_back(r.next);
+                    }
+                    cur[c].clear();
+                }
+                for (uint32_t c = 0; c < (uint32_t)CLS_COUNT; ++c) cur[c].swap(next[c]);
+            }
+            for (const f4 &v : acc)
+                if (v.x == kUnset && v.w == kUnset) {
+                    g_err = "fused pipeline: a path never wrote its accumulators";
+                    return AKR_ERR_STATE;
+                }
+            for (uint32_t p = 0; p < wave.n_pix; ++p) accumulate_body(av, wave, p, film_7n, n_pixels);
+            continue;
+        }
         std::vector<f4> acc(2u * (size_t)n_paths, f4{0.0f, 0.0f, 0.0f, 0.0f});  // raygen zeroes the accumulators
         AccView av{acc.data(), acc.data() + n_paths};
         std::vector<PathState> cur(n_paths), next;

@@ -11,13 +11,14 @@ ulp and, rarely, a path flips topology (an edge, a Russian-roulette or a hemisph
 import numpy as np
 import pytest
 
-from conftest import image_rel_l2, rel_l2_per_pixel
+from conftest import image_rel_l2, measured, rel_l2_per_pixel
 
 pytestmark = pytest.mark.gpu
 
 
 def _render_pair(akr, oracle, tables, scene, task, w, h, **kw):
     pt = akr.PathTracer(0)
+    pt.set_engine_options(aov_mask=1)  # AKR_AOV_FIRST_HIT_IDS
     film = pt.render(scene, task, **kw)
     st = pt.stats()
     fh = pt.first_hits()
@@ -42,7 +43,8 @@ def test_cbox_256_16spp_parity(akr, oracle, tables, cbox, cbox_task):
     b = oracle.resolve(ofilm, n).reshape(h, w, 3)
     rel = rel_l2_per_pixel(a, b)
     frac_bad = float((rel > 1e-3).mean())
-    print(f"pixels over 1e-3: {frac_bad:.5%}; image rel-L2 {image_rel_l2(a, b):.3e}; max {rel.max():.3e}")
+    measured(f"cbox 256x256@16: first hits equal {same_hits.mean():.6f} (>= 0.9999); pixels over 1e-3: {frac_bad:.3e} (<= 1e-3); "
+             f"image rel-L2 {image_rel_l2(a, b):.3e} (<= 1e-3); segments gpu/oracle {st.segments}/{ost.segments}")
     assert frac_bad <= 1e-3
     assert image_rel_l2(a, b) <= 1e-3
     assert abs(int(st.segments) - int(ost.segments)) <= 1e-4 * ost.segments
@@ -50,11 +52,13 @@ def test_cbox_256_16spp_parity(akr, oracle, tables, cbox, cbox_task):
     assert st.samples == ost.samples == n * 16
 
 
-def _gate(a, b, rel_frac=1e-3, img=1e-3):
+def _gate(a, b, rel_frac=1e-3, img=1e-3, what=""):
+    """Stated tolerance: at most `rel_frac` of the pixels differ by more than 1e-3 (per-pixel relative L2) and the
+    image-level relative L2 is at most `img`.  Where a test passes bounds above 1e-3 it says why."""
     rel = rel_l2_per_pixel(a, b)
     frac_bad = float((rel > 1e-3).mean())
     i = image_rel_l2(a, b)
-    print(f"pixels over 1e-3: {frac_bad:.5%}; image rel-L2 {i:.3e}")
+    measured(f"{what}: pixels over 1e-3: {frac_bad:.3e} (<= {rel_frac:g}); image rel-L2 {i:.3e} (<= {img:g})")
     assert frac_bad <= rel_frac and i <= img, (frac_bad, i)
 
 
@@ -80,7 +84,7 @@ def test_material_variants_parity(akr, oracle, tables, cbox_task, tmp_path, vari
     pmj, bn = tables
     film, st = _gpu_film(akr, scene, task)
     ofilm, ost, _ = oracle.render(scene.desc, w, h, task.pt, task.sampler, task.filter, pmj, bn)
-    _gate(film.to_rgb(), oracle.resolve(ofilm, w * h).reshape(h, w, 3), rel_frac=5e-3, img=5e-3)
+    _gate(film.to_rgb(), oracle.resolve(ofilm, w * h).reshape(h, w, 3), rel_frac=5e-3, img=5e-3, what=f"variant {variant} 96x96@16")
     assert abs(int(st.segments) - int(ost.segments)) <= 1e-3 * ost.segments
 
 
@@ -97,7 +101,7 @@ def test_config_knobs_parity(akr, oracle, tables, cbox, cbox_task, kw):
     pmj, bn = tables
     film, st = _gpu_film(akr, scene, task)
     ofilm, ost, _ = oracle.render(scene.desc, w, h, task.pt, task.sampler, task.filter, pmj, bn)
-    _gate(film.to_rgb(), oracle.resolve(ofilm, w * h).reshape(h, w, 3), rel_frac=3e-3, img=2e-3)
+    _gate(film.to_rgb(), oracle.resolve(ofilm, w * h).reshape(h, w, 3), rel_frac=3e-3, img=2e-3, what=f"knob {kw or off} 64x64@16")
     assert abs(int(st.segments) - int(ost.segments)) <= 1e-3 * max(1, ost.segments)
     assert abs(int(st.shadow_rays) - int(ost.shadow_rays)) <= 1e-3 * max(1, ost.shadow_rays)
 
@@ -110,10 +114,14 @@ def test_waves_tiles_and_engine_modes_compose_bitwise(akr, cbox, cbox_task):
     ref, st = _gpu_film(akr, scene, task)
     small, _ = _gpu_film(akr, scene, task, wave_size=4096)
     assert np.array_equal(small.data, ref.data)
-    # the generic (unsorted) shade kernel is a different instantiation (other FMA contractions): tolerance, not bits
-    unsorted, su = _gpu_film(akr, scene, task, sort_by_material=2)
-    _gate(unsorted.to_rgb(), ref.to_rgb())
-    assert abs(int(su.segments) - int(st.segments)) <= 1e-4 * st.segments
+    # the queued pipeline (trace stage + shade stage + shadow queue) is a different instantiation of the same bodies
+    # (other FMA contractions): tolerance, not bits
+    queued, sq = _gpu_film(akr, scene, task, fused=2)
+    _gate(queued.to_rgb(), ref.to_rgb(), what="queued vs fused pipeline, cbox 160x90@16")
+    assert abs(int(sq.segments) - int(st.segments)) <= 1e-4 * st.segments
+    assert abs(int(sq.shadow_rays) - int(st.shadow_rays)) <= 1e-4 * st.shadow_rays
+    small_q, _ = _gpu_film(akr, scene, task, fused=2, wave_size=4096)
+    assert np.array_equal(small_q.data, queued.data)
     n = w * h
     top, _ = _gpu_film(akr, scene, task, tile=(0, 31))
     bot, _ = _gpu_film(akr, scene, task, tile=(31, h))
@@ -131,21 +139,16 @@ def test_waves_tiles_and_engine_modes_compose_bitwise(akr, cbox, cbox_task):
 
 
 def test_bvh_and_flat_trace_modes_agree(akr, cbox, cbox_task):
-    """BVH traversal and the flat primitive list test the same primitives with the same arithmetic; only exact
-    distance ties could resolve differently."""
+    """BVH traversal (persistent warps with dynamic ray fetch) and the flat primitive list test the same primitives with
+    the same arithmetic; only exact distance ties could resolve differently.  Both through the queued pipeline."""
     w = h = 128
     scene, task = cbox(w, h), cbox_task(16)
-    flat, sf = _gpu_film(akr, scene, task, trace_mode=2)
-    for mode in (1, 3):  # 1 = persistent warps with dynamic ray fetch, 3 = one fixed ray per lane
-        bvh, sb = _gpu_film(akr, scene, task, trace_mode=mode)
-        same = (flat.data == bvh.data).mean()
-        print(f"trace_mode {mode}: identical film words: {same:.6%}")
-        assert same >= 0.9999
-        assert abs(int(sf.segments) - int(sb.segments)) <= 1e-5 * sf.segments
-    # the shadow-ray queue (trace kernel) and the inline shadow rays (shade kernels) are the same computation
-    queued, sq = _gpu_film(akr, scene, task, inline_shadow=2)
-    assert np.array_equal(queued.data, flat.data)
-    assert (sq.segments, sq.shadow_rays) == (sf.segments, sf.shadow_rays)
+    flat, sf = _gpu_film(akr, scene, task, trace_mode=2, fused=2)
+    bvh, sb = _gpu_film(akr, scene, task, trace_mode=1)
+    same = (flat.data == bvh.data).mean()
+    measured(f"BVH vs flat trace (queued pipeline), cbox 128x128@16: identical film words {same:.6f} (>= 0.9999)")
+    assert same >= 0.9999
+    assert abs(int(sf.segments) - int(sb.segments)) <= 1e-5 * sf.segments
 
 
 def test_full_size_frame_properties(akr, cbox, cbox_task):
@@ -182,7 +185,7 @@ def test_clutter_scene_bvh_mode(akr, oracle, tables, cbox_task, tmp_path):
     pmj, bn = tables
     film, st = _gpu_film(akr, scene, task)
     ofilm, ost, _ = oracle.render(scene.desc, w, h, task.pt, task.sampler, task.filter, pmj, bn)
-    _gate(film.to_rgb(), oracle.resolve(ofilm, w * h).reshape(h, w, 3), rel_frac=1e-2, img=5e-3)
+    _gate(film.to_rgb(), oracle.resolve(ofilm, w * h).reshape(h, w, 3), rel_frac=1e-2, img=5e-3, what="clutter 64x64@8 (BVH, queued)")
     assert abs(int(st.segments) - int(ost.segments)) <= 2e-3 * ost.segments
     assert abs(int(st.shadow_rays) - int(ost.shadow_rays)) <= 2e-3 * ost.shadow_rays
 
@@ -219,7 +222,61 @@ def test_error_paths_and_odd_configs(akr, oracle, tables, cbox, cbox_task):
     pmj, bn = tables
     film, st = _gpu_film(akr, scene, odd, wave_size=1024)
     ofilm, ost, _ = oracle.render(scene.desc, 33, 17, odd.pt, odd.sampler, odd.filter, pmj, bn)
-    _gate(film.to_rgb(), oracle.resolve(ofilm, 33 * 17).reshape(17, 33, 3), rel_frac=5e-3, img=2e-3)
+    _gate(film.to_rgb(), oracle.resolve(ofilm, 33 * 17).reshape(17, 33, 3), rel_frac=5e-3, img=2e-3, what="odd config 33x17@5 box filter")
     assert st.samples == 33 * 17 * 5
     row, _ = _gpu_film(akr, scene, odd, tile=(16, 17))
     assert np.array_equal(row.data[:3 * 33], film.data[3 * 33 * 16:3 * 33 * 17])
+
+
+def test_headline_config_parity_1280x720_sampler_length_1024(akr, oracle, tables, cbox, cbox_task):
+    """BASELINE config C2 itself: 1280x720 with the task's sampler permutation length 1024 (w_mask 1023, power-of-two
+    reciprocal path of sampler_1d).  The first 16 of the 1024 samples per pixel on the GPU (begin(spp = 1024) + one
+    16-spp pass, the wave size bench.py uses) against the oracle rendering the same sample range."""
+    w, h = 1280, 720
+    scene, task = cbox(w, h), cbox_task(1024)
+    pt = akr.PathTracer(0)
+    pt.set_engine_options(wave_size=1 << 26)
+    pt.upload_scene(scene)
+    pt.begin(task)
+    pt.render_pass(16, blocking=True)
+    film = pt.download_film()
+    rgb_dev = pt.resolve_rgb()
+    st = pt.stats()
+    pt.close()
+    pmj, bn = tables
+    ofilm, ost, _ = oracle.render(scene.desc, w, h, task.pt, task.sampler, task.filter, pmj, bn, spp_begin=0, spp_end=16)
+    n = w * h
+    assert np.array_equal(film.data[6 * n:], np.full(n, 16.0, np.float32))
+    ref = oracle.resolve(ofilm, n).reshape(h, w, 3)
+    _gate(film.to_rgb(), ref, what="C2 cbox 1280x720, sampler length 1024, samples 0..15")
+    # Film::copy_to_rgba_image on the device (k_resolve_film) == the oracle's resolve of the same film, bit for bit
+    assert np.array_equal(rgb_dev, oracle.resolve(film.data, n).reshape(h, w, 3))
+    assert np.array_equal(rgb_dev, film.to_rgb())
+    ds, dh = abs(int(st.segments) - int(ost.segments)) / ost.segments, abs(int(st.shadow_rays) - int(ost.shadow_rays)) / ost.shadow_rays
+    measured(f"C2 ray counts: segments rel diff {ds:.2e}, shadow rays rel diff {dh:.2e} (<= 1e-4)")
+    assert ds <= 1e-4 and dh <= 1e-4
+
+
+def test_resolve_film_device_rgba_and_tiles(akr, oracle, cbox, cbox_task):
+    """akr_b200_resolve_film[_device] (the call bench.py times and gathers): RGB and RGBA layouts, whole frame and a row
+    band, against oracle.resolve of the downloaded film."""
+    import torch
+    w, h = 96, 54
+    scene, task = cbox(w, h), cbox_task(8)
+    pt = akr.PathTracer(0)
+    pt.upload_scene(scene)
+    for tile in (None, (10, 31)):
+        pt.begin(task, tile)
+        pt.render_pass(8, blocking=True)
+        film = pt.download_film()
+        rows = h if tile is None else tile[1] - tile[0]
+        ref = oracle.resolve(film.data, w * rows).reshape(rows, w, 3)
+        assert np.array_equal(pt.resolve_rgb(), ref)
+        rgba = torch.zeros((rows, w, 4), device="cuda", dtype=torch.float32)
+        pt.resolve_into_device(rgba.data_ptr(), rgba.numel(), rgba=True)
+        pt.synchronize()
+        got = rgba.cpu().numpy()
+        assert np.array_equal(got[..., :3], ref) and (got[..., 3] == 1.0).all()
+        with pytest.raises(akr.AkariError):  # wrong size
+            pt.resolve_into_device(rgba.data_ptr(), rgba.numel() - 4, rgba=True)
+    pt.close()

@@ -19,11 +19,15 @@ class HostsimStats(C.Structure):
                 ("flat_blocks", C.c_uint32), ("flat_occluder_blocks", C.c_uint32), ("n_nodes4", C.c_uint32), ("bvh4_depth", C.c_uint32)]
 
 
-@pytest.fixture(scope="module")
-def hostsim():
+@pytest.fixture(scope="module", params=["queued", "fused"])
+def hostsim(request):
+    """Both pipelines of the engine: `queued` (trace stage / shade stage / shadow queue: BVH scenes) and `fused` (one
+    stage per depth and shade class on records that carry hit + radiance: flat scenes, akr_path.cuh bounce_fused)."""
     lib = C.CDLL(os.path.join(HERE, "hostsim", "libhostsim.so"))
     lib.hostsim_last_error.restype = C.c_char_p
-    return lib
+    lib.hostsim_set_pipeline(1 if request.param == "fused" else 0)
+    yield lib
+    lib.hostsim_set_pipeline(0)
 
 
 def run_hostsim(lib, scene, task, tables, table, w, h, y0=0, y1=None, s0=0, s1=None, wave_pixels=0):
