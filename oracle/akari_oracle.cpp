@@ -22,6 +22,7 @@
 // -ffp-contract=off so every f32 operation is a single IEEE operation (Rust never contracts).
 // ============================================================================================
 #include "../include/akari_b200.h"
+#include "chi2_tables.h"
 
 #include <algorithm>
 #include <atomic>
@@ -1860,6 +1861,23 @@ void akr_oracle_bsdf_sample(int kind, const float *color3, float roughness, floa
     SampleWi s = with_tap(t, [&](const auto &c) { return c.sample_wi(v3(wo3[0], wo3[1], wo3[2]), u_select, V2{u0, u1}); });
     wi3_out[0] = s.wi.x; wi3_out[1] = s.wi.y; wi3_out[2] = s.wi.z;
     *valid_out = s.valid ? 1 : 0;
+}
+
+// The two tables of the reference's chi-square test (akari_test.rs:31-112) for one tap closure and one wo: observed
+// histogram of sample_wi directions and expected counts from the integrated pdf (chi2_tables.h).
+void akr_oracle_bsdf_chi2_tables(int kind, const float *color3, float roughness, float eta, const float *wo3, uint64_t n_samples, uint64_t seed,
+                                 uint32_t theta_res, uint32_t phi_res, uint32_t *hist_out, double *expected_out) {
+    TapClosure t{kind, v3(color3[0], color3[1], color3[2]), roughness, eta};
+    const V3 wo = v3(wo3[0], wo3[1], wo3[2]);
+    chi2::histogram(
+        [&](float us, float u0, float u1, chi2::Dir &wi) {
+            SampleWi s = with_tap(t, [&](const auto &c) { return c.sample_wi(wo, us, V2{u0, u1}); });
+            wi = chi2::Dir{s.wi.x, s.wi.y, s.wi.z};
+            return s.valid;
+        },
+        n_samples, seed, theta_res, phi_res, hist_out, 0);
+    chi2::expected([&](chi2::Dir wi) { return with_tap(t, [&](const auto &c) { return c.evaluate(wo, v3(wi.x, wi.y, wi.z)); }).pdf; }, n_samples, theta_res,
+                   phi_res, expected_out, 0);
 }
 
 // Deterministic re-derivation of the `ggx_dielectric_s` table (svm/surface/precompute.rs:56-94,

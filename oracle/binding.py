@@ -66,6 +66,8 @@ def lib():
         l.akr_oracle_bsdf_eval.restype = None
         l.akr_oracle_bsdf_sample.argtypes = [C.c_int, vp, C.c_float, C.c_float, vp, C.c_float, C.c_float, C.c_float, vp, vp]
         l.akr_oracle_bsdf_sample.restype = None
+        l.akr_oracle_bsdf_chi2_tables.argtypes = [C.c_int, vp, C.c_float, C.c_float, vp, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, vp, vp]
+        l.akr_oracle_bsdf_chi2_tables.restype = None
         l.akr_oracle_make_albedo_table.argtypes = [vp, C.c_uint32]
         l.akr_oracle_make_albedo_table.restype = None
         _lib = l
@@ -122,3 +124,14 @@ def resolve(film, n_pixels):
     out = np.zeros(n_pixels * 3, dtype=np.float32)
     lib().akr_oracle_resolve(_ptr(film), n_pixels, _ptr(out))
     return out
+
+
+def bsdf_chi2_tables(kind, color, roughness, eta, wo, n_samples, seed, theta_res, phi_res):
+    """(observed histogram u32[theta_res * phi_res], expected counts f64[...]) of one tap closure for one wo
+    (akari_test.rs:31-112).  kind: 0 diffuse, 1 GGX reflection, 2 GGX transmission, 3 GGX conductor."""
+    color = np.asarray(color, np.float32)
+    wo = np.asarray(wo, np.float32)
+    hist = np.zeros(theta_res * phi_res, np.uint32)
+    exp = np.zeros(theta_res * phi_res, np.float64)
+    lib().akr_oracle_bsdf_chi2_tables(kind, _ptr(color), roughness, eta, _ptr(wo), n_samples, seed, theta_res, phi_res, _ptr(hist), _ptr(exp))
+    return hist, exp

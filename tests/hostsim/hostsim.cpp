@@ -7,6 +7,7 @@
 // akari_render_b200/ links or loads this file.
 #include "../../akari_render_b200/csrc/device/akr_path.cuh"
 #include "../../akari_render_b200/csrc/host/scene_build.h"
+#include "../../oracle/chi2_tables.h"
 
 #include <cstdio>
 #include <cstring>
@@ -230,6 +231,46 @@ int hostsim_render(const AkrSceneDesc *desc, const AkrPtConfig *cfg, const AkrSa
 }
 
 void hostsim_make_albedo_table(float *table, uint32_t n) { make_albedo_table(table, n); }
+
+// Chi-square tables (oracle/chi2_tables.h, methodology of akari_test.rs:31-112) of the DEVICE closures: the constant-folded
+// Material of instance `inst`'s first triangle, evaluated through closure_sample_wi / closure_eval (akr_bsdf.cuh) in an
+// identity shading frame, with the template instantiation the kernels use for that material's shade class.
+int hostsim_bsdf_chi2_tables(const AkrSceneDesc *desc, uint32_t inst, const float *albedo_table, const float *wo3, uint64_t n_samples, uint64_t seed,
+                             uint32_t theta_res, uint32_t phi_res, uint32_t *hist_out, double *expected_out, uint32_t *material_type_out) {
+    HostSceneBlob blob;
+    std::string err;
+    int rc = build_scene_blob(*desc, blob, err);
+    if (rc != AKR_OK) {
+        g_err = err;
+        return rc;
+    }
+    if (inst >= blob.instances.size()) {
+        g_err = "no such instance";
+        return AKR_ERR_INVALID_ARGUMENT;
+    }
+    const Material m = blob.materials[blob.shade[blob.instances[inst].tri_offset].mat];
+    if (material_type_out) *material_type_out = m.type;
+    const ClosureFrames cf = make_closure_frames(m, frame_identity(), mk3(0.0f, 0.0f, 1.0f));
+    const f3 wo = mk3(wo3[0], wo3[1], wo3[2]);
+    const uint32_t cls = shade_class_of(m.type);
+    auto sample = [&](float us, float u0, float u1, chi2::Dir &wi) {
+        BsdfDir s = cls == CLS_LAMBERT     ? closure_sample_wi<CLS_LAMBERT>(m, albedo_table, cf, wo, us, f2{u0, u1})
+                    : cls == CLS_CONDUCTOR ? closure_sample_wi<CLS_CONDUCTOR>(m, albedo_table, cf, wo, us, f2{u0, u1})
+                                           : closure_sample_wi<CLS_GENERAL>(m, albedo_table, cf, wo, us, f2{u0, u1});
+        wi = chi2::Dir{s.wi.x, s.wi.y, s.wi.z};
+        return s.valid;
+    };
+    auto pdf = [&](chi2::Dir w) {
+        const f3 wi = mk3(w.x, w.y, w.z);
+        return (cls == CLS_LAMBERT     ? closure_eval<CLS_LAMBERT>(m, albedo_table, cf, wo, wi)
+                : cls == CLS_CONDUCTOR ? closure_eval<CLS_CONDUCTOR>(m, albedo_table, cf, wo, wi)
+                                       : closure_eval<CLS_GENERAL>(m, albedo_table, cf, wo, wi))
+            .pdf;
+    };
+    chi2::histogram(sample, n_samples, seed, theta_res, phi_res, hist_out, 0);
+    chi2::expected(pdf, n_samples, theta_res, phi_res, expected_out, 0);
+    return AKR_OK;
+}
 
 // exact-division helper of the kernels (akr_math.cuh: FastDiv): q[i], r[i] = n[i] / d, n[i] % d
 void hostsim_fastdiv(const uint32_t *n, uint32_t count, uint32_t d, uint32_t *q, uint32_t *r) {

@@ -190,3 +190,53 @@ def write_clutter(tmp_path, n_lon=32, n_lat=24):
     path = os.path.join(d, "scene.json")
     json.dump(scene, open(path, "w"))
     return path
+
+
+# ---- white furnace: a closed, uniformly emitting Lambert cube around the camera ----------------------------------------
+def write_furnace(tmp_path, albedo=0.5, emission=1.0, half=2.0):
+    """Closed cube (inward-facing normals) centred on the cbox camera: every surface point emits `emission` and reflects
+    Lambert `albedo`.  Radiance seen along any path of at most D bounces is emission * sum_{k=0..D} albedo^k."""
+    import numpy as np
+    scene = json.load(open(os.path.join(CBOX_DIR, "scene.json")))
+    mat = copy.deepcopy(scene["materials"]["floor_001"])
+    scene["materials"] = {"furnace": mat}
+    edit_principled(scene, "furnace", base_color=[albedo] * 3, emission_color=[1.0, 1.0, 1.0], emission_strength=float(emission))
+    c = np.array([0.0, 1.0, 9.0], np.float32)  # camera position in the scene's y-up frame (SURVEY A.1)
+    v = np.array([[x, y, z] for x in (-1, 1) for y in (-1, 1) for z in (-1, 1)], np.float32) * half + c
+    # faces as quads wound so that (v1 - v0) x (v2 - v0) points INTO the cube (emission is one-sided, light/area.rs:44-48)
+    quads = [(0, 1, 3, 2), (4, 6, 7, 5), (0, 4, 5, 1), (2, 3, 7, 6), (0, 2, 6, 4), (1, 5, 7, 3)]
+    tris = []
+    for q in quads:
+        a, b, d, e = q
+        n = np.cross(v[b] - v[a], v[d] - v[a])
+        if np.dot(n, c - v[a]) < 0:  # flip to face the centre
+            b, e = e, b
+        tris += [(a, b, d), (a, d, e)]
+    idx = np.array(tris, np.uint32)
+    uvs = np.tile(np.array([[0, 0], [1, 0], [1, 1]], np.float32), (len(tris), 1))
+    blob = bytearray()
+    views = {}
+
+    def add_view(arr):
+        while len(blob) % 16:
+            blob.append(0)
+        name = f"buf_view_{len(views)}"
+        raw = np.ascontiguousarray(arr).tobytes()
+        views[name] = {"buffer": {"id": "Scene"}, "offset": len(blob), "length": len(raw)}
+        blob.extend(raw)
+        return {"id": name}
+
+    scene["geometries"] = {"furnace_mesh": {"type": "mesh", "vertices": add_view(v), "indices": add_view(idx), "normals": None, "uvs": add_view(uvs),
+                                             "tangents": None, "materials": add_view(np.zeros(1, np.uint32))}}
+    scene["instances"] = {"furnace": {"geometry": {"id": "furnace_mesh"},
+                                      "transform": {"type": "matrix", "data": [[1.0, 0, 0, 0], [0, 1.0, 0, 0], [0, 0, 1.0, 0], [0, 0, 0, 1.0]]},
+                                      "materials": [{"id": "furnace"}]}}
+    scene["lights"] = {}
+    scene["buffer_views"] = views
+    scene["buffers"] = {"Scene": {"type": "path", "path": "Scene.bin", "length": len(blob)}}
+    d = os.path.join(str(tmp_path), "furnace")
+    os.makedirs(d, exist_ok=True)
+    open(os.path.join(d, "Scene.bin"), "wb").write(bytes(blob))
+    path = os.path.join(d, "scene.json")
+    json.dump(scene, open(path, "w"))
+    return path

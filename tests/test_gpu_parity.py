@@ -248,7 +248,12 @@ def test_headline_config_parity_1280x720_sampler_length_1024(akr, oracle, tables
     n = w * h
     assert np.array_equal(film.data[6 * n:], np.full(n, 16.0, np.float32))
     ref = oracle.resolve(ofilm, n).reshape(h, w, 3)
-    _gate(film.to_rgb(), ref, what="C2 cbox 1280x720, sampler length 1024, samples 0..15")
+    got = film.to_rgb()
+    err = np.linalg.norm(got.reshape(-1, 3).astype(np.float64) - ref.reshape(-1, 3), axis=1)
+    worst = np.argsort(err)[::-1][:5]
+    measured("C2 worst pixels (x, y, |gpu - oracle|, gpu rgb, oracle rgb): " +
+             "; ".join(f"({i % w},{i // w}) {err[i]:.3g} {got.reshape(-1, 3)[i].round(3)} {ref.reshape(-1, 3)[i].round(3)}" for i in worst))
+    _gate(got, ref, what="C2 cbox 1280x720, sampler length 1024, samples 0..15")
     # Film::copy_to_rgba_image on the device (k_resolve_film) == the oracle's resolve of the same film, bit for bit
     assert np.array_equal(rgb_dev, oracle.resolve(film.data, n).reshape(h, w, 3))
     assert np.array_equal(rgb_dev, film.to_rgb())
