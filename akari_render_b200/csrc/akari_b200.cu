@@ -698,7 +698,7 @@ template <bool SMEM_ALL, bool ALPHA> __global__ void __launch_bounds__(kBlock) k
 #define AKR_SHADE_MINB_LAMBERT 4
 #endif
 #ifndef AKR_SHADE_MINB_CONDUCTOR
-#define AKR_SHADE_MINB_CONDUCTOR 3
+#define AKR_SHADE_MINB_CONDUCTOR 2
 #endif
 #ifndef AKR_SHADE_BLOCK
 #define AKR_SHADE_BLOCK 256

@@ -180,24 +180,15 @@ struct CornerAttribs {           // optional per-corner arrays indexed by gid * 
     const float *tangents;       // [n_tris * 3][3] or nullptr
 };
 AKR_HD f3 ld3g(const float *p) { return mk3(AKR_RO(p[0]), AKR_RO(p[1]), AKR_RO(p[2])); }  // read-only scene data in global memory
-AKR_HD Surface surface_from_hit(const SceneView &sc, const CornerAttribs &ca, uint32_t gid, float u, float v) {
+// per-hit frame of a triangle with per-corner normals / tangents: ns from interpolated corner normals
+// (mesh.rs:594-602,620-621), tangent from the tangent buffer when present (mesh.rs:558-569) else the per-triangle dp/du
+// stored in `ft`
+AKR_HD Frame surface_frame_interpolated(const SceneView &sc, const CornerAttribs &ca, uint32_t gid, float u, float v, f3 ng) {
     const TriShade &ts = sc.shade[gid];
     const InstanceRec &in = sc.instances[ts.inst];
     float w0 = 1.0f - u - v;
-    f3 v0 = ld3g(ts.v0), v1 = ld3g(ts.v1), v2 = ld3g(ts.v2);
-    f3 pl = w0 * v0 + u * v1 + v * v2;
     f3 c0 = ld3g(in.m), c1 = ld3g(in.m + 3), c2 = ld3g(in.m + 6);
-    Surface s;
-    s.p = (c0 * pl.x + c1 * pl.y + c2 * pl.z) + ld3g(in.t);
-    s.ng = ld3g(ts.ng);
-    s.area = AKR_RO(ts.area);
-    if (!(AKR_RO(ts.flags) & (TRI_HAS_NORMALS | TRI_HAS_TANGENTS))) {
-        s.frame = Frame{s.ng, ld3g(ts.ft), ld3g(ts.fs)};
-        return s;
-    }
-    // per-hit frame: ns from interpolated corner normals (mesh.rs:594-602,620-621), tangent from the
-    // tangent buffer when present (mesh.rs:558-569) else the per-triangle dp/du stored in `ft`
-    f3 ns = s.ng;
+    f3 ns = ng;
     f3 i0 = ld3g(in.m_inv_t), i1 = ld3g(in.m_inv_t + 3), i2 = ld3g(in.m_inv_t + 6);
     if (AKR_RO(ts.flags) & TRI_HAS_NORMALS) {
         const float *n = ca.normals + (size_t)gid * 9u;
@@ -217,7 +208,21 @@ AKR_HD Surface surface_from_hit(const SceneView &sc, const CornerAttribs &ca, ui
             tt = ld3g(ts.fs);  // fallback dp/du tangent is kept in `fs` for tangent-buffer meshes
         }
     }
-    s.frame = (tt.x != 0.0f || tt.y != 0.0f || tt.z != 0.0f) ? frame_from_n_t(ns, tt) : frame_from_n(ns);
+    return (tt.x != 0.0f || tt.y != 0.0f || tt.z != 0.0f) ? frame_from_n_t(ns, tt) : frame_from_n(ns);
+}
+AKR_HD Surface surface_from_hit(const SceneView &sc, const CornerAttribs &ca, uint32_t gid, float u, float v) {
+    const TriShade &ts = sc.shade[gid];
+    const InstanceRec &in = sc.instances[ts.inst];
+    float w0 = 1.0f - u - v;
+    f3 v0 = ld3g(ts.v0), v1 = ld3g(ts.v1), v2 = ld3g(ts.v2);
+    f3 pl = w0 * v0 + u * v1 + v * v2;
+    f3 c0 = ld3g(in.m), c1 = ld3g(in.m + 3), c2 = ld3g(in.m + 6);
+    Surface s;
+    s.p = (c0 * pl.x + c1 * pl.y + c2 * pl.z) + ld3g(in.t);
+    s.ng = ld3g(ts.ng);
+    s.area = AKR_RO(ts.area);
+    if (!(AKR_RO(ts.flags) & (TRI_HAS_NORMALS | TRI_HAS_TANGENTS))) s.frame = Frame{s.ng, ld3g(ts.ft), ld3g(ts.fs)};
+    else s.frame = surface_frame_interpolated(sc, ca, gid, u, v, s.ng);
     return s;
 }
 
@@ -308,7 +313,7 @@ AKR_HD ShadeOut shade_body(const SceneView &sc, const CornerAttribs &ca, const S
     // The sampler draws of this bounce depend only on (path id, depth), so they may be issued before the hit triangle
     // and its material are fetched (table loads in flight meanwhile).  Measured on B200: helps the register-roomier
     // conductor / general kernels (6.7 -> 6.5 ms), costs the 64-register Lambert kernel 3 % => decided per class.
-    constexpr bool kDrawFirst = CLS != CLS_LAMBERT;
+    constexpr bool kDrawFirst = CLS != CLS_LAMBERT;  // (measured again with the fused kernels: 23.5 vs 22.4 ms per pass for Lambert)
     const PathCoord pc = path_coord(rp, wave, id);
     const uint32_t dim0 = bounce_first_dim(d1, rp.rr_depth);
     float ul0 = 0.0f, ub0 = 0.0f;
