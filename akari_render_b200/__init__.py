@@ -211,11 +211,21 @@ class PathTracer:
         self._check(self._lib.akr_b200_set_engine_options(self._ctx, C.byref(o)))
 
     # ---- rendering ----
+    def _set_tile(self, tile):
+        """tile: None (whole sensor), (y0, y1) (contiguous band) or (y0, y1, block_rows, n_shards, shard) (interleaved)."""
+        if tile is None:
+            self._tile = AkrTile(0, self._res[1], 0, 0, 0, 0)
+            return None
+        t = tuple(tile) + (0, 0, 0)[: 5 - len(tile)] if len(tile) < 5 else tuple(tile)
+        self._tile = AkrTile(t[0], t[1], t[2], t[3], t[4], 0)
+        return self._tile
+
+    @property
+    def tile_rows(self):
+        return int(self._lib.akr_b200_tile_rows(C.byref(self._tile)))
+
     def begin(self, task, tile=None):
-        t = None
-        if tile is not None:
-            t = AkrTile(tile[0], tile[1])
-        self._tile = tile if tile is not None else (0, self._res[1])
+        t = self._set_tile(tile)
         self._check(self._lib.akr_b200_begin(self._ctx, C.byref(task.raw.pt), C.byref(task.raw.sampler), C.byref(task.raw.filter),
                                              C.byref(t) if t is not None else None))
 
@@ -223,12 +233,11 @@ class PathTracer:
         self._check(self._lib.akr_b200_render_pass(self._ctx, n_spp, 1 if blocking else 0))
 
     def render(self, scene, task, tile=None):
-        """pt::render (pt.rs:1161-1172): uploads `scene` when it is not the resident one, renders all passes
-        and returns the Film (host copy)."""
-        if scene is not None and scene is not self._scene:
+        """pt::render (pt.rs:1161-1172): uploads `scene` when it is not the resident one (or its resolution changed),
+        renders all passes and returns the Film (host copy)."""
+        if scene is not None and (scene is not self._scene or scene.resolution != self._res):
             self.upload_scene(scene)
-        t = AkrTile(tile[0], tile[1]) if tile is not None else None
-        self._tile = tile if tile is not None else (0, self._res[1])
+        t = self._set_tile(tile)
         self._check(self._lib.akr_b200_render_pt(self._ctx, C.byref(task.raw.pt), C.byref(task.raw.sampler), C.byref(task.raw.filter),
                                                  C.byref(t) if t is not None else None))
         return self.download_film()
@@ -237,14 +246,14 @@ class PathTracer:
         self._check(self._lib.akr_b200_synchronize(self._ctx))
 
     def download_film(self):
-        rows = self._tile[1] - self._tile[0]
+        rows = self.tile_rows
         n = self._res[0] * rows
         out = np.empty(7 * n, dtype=np.float32)
         self._check(self._lib.akr_b200_download_film(self._ctx, out.ctypes.data, out.size))
         return Film(out, self._res[0], rows)
 
     def resolve_rgb(self):
-        rows = self._tile[1] - self._tile[0]
+        rows = self.tile_rows
         out = np.empty((rows, self._res[0], 3), dtype=np.float32)
         self._check(self._lib.akr_b200_resolve_film(self._ctx, out.ctypes.data, out.size, 0))
         return out
@@ -253,7 +262,7 @@ class PathTracer:
         self._check(self._lib.akr_b200_resolve_film_device(self._ctx, C.c_void_p(device_ptr), n_floats, 1 if rgba else 0))
 
     def first_hits(self):
-        rows = self._tile[1] - self._tile[0]
+        rows = self.tile_rows
         n = self._res[0] * rows
         inst = np.empty(n, dtype=np.uint32)
         prim = np.empty(n, dtype=np.uint32)

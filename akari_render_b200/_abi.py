@@ -107,7 +107,8 @@ class AkrFilterConfig(C.Structure):
 
 
 class AkrTile(C.Structure):
-    _fields_ = [("y0", C.c_uint32), ("y1", C.c_uint32)]
+    _fields_ = [("y0", C.c_uint32), ("y1", C.c_uint32), ("block_rows", C.c_uint32), ("n_shards", C.c_uint32), ("shard", C.c_uint32),
+                ("_pad", C.c_uint32)]
 
 
 class AkrStats(C.Structure):
@@ -119,6 +120,7 @@ class AkrStats(C.Structure):
         ("gpu_ms", C.c_double),
         ("gpu_ms_kernel", C.c_double * 8),
         ("launches_kernel", C.c_uint64 * 8),
+        ("shaded_hits", C.c_uint64),
     ]
 
 
@@ -160,7 +162,7 @@ CUDA_SYMBOLS = [
     "akr_b200_begin", "akr_b200_render_pass", "akr_b200_render_pt", "akr_b200_synchronize",
     "akr_b200_download_film", "akr_b200_resolve_film", "akr_b200_resolve_film_device",
     "akr_b200_get_stats", "akr_b200_reset_stats", "akr_b200_set_engine_options",
-    "akr_b200_debug_first_hits",
+    "akr_b200_debug_first_hits", "akr_b200_tile_rows",
 ]
 
 
@@ -217,7 +219,9 @@ def load_cuda_lib():
     lib.akr_b200_reset_stats.argtypes = [vp]
     lib.akr_b200_set_engine_options.argtypes = [vp, C.POINTER(AkrEngineOptions)]
     lib.akr_b200_debug_first_hits.argtypes = [vp, vp, vp, C.c_size_t]
+    lib.akr_b200_tile_rows.argtypes = [C.POINTER(AkrTile)]
+    lib.akr_b200_tile_rows.restype = C.c_uint32
     for name in CUDA_SYMBOLS:
-        if name not in ("akr_b200_destroy", "akr_b200_last_error"):
+        if name not in ("akr_b200_destroy", "akr_b200_last_error", "akr_b200_tile_rows"):
             getattr(lib, name).restype = C.c_int
     return lib

@@ -898,13 +898,15 @@ __global__ void __launch_bounds__(kBlock) k_accumulate(const __grid_constant__ L
 // folds the per-depth counters of one wave into the 64-bit totals and clears them for the next wave
 __global__ void k_fold_counters(uint32_t *counters, unsigned long long *totals, uint32_t n_depth) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
-        unsigned long long seg = 0, sh = 0;
+        unsigned long long seg = 0, sh = 0, hits = 0;
         for (uint32_t d = 0; d < n_depth; ++d) {
             seg += counters[d * kCtrStride];
             sh += counters[d * kCtrStride + 1u];
+            hits += (unsigned long long)counters[d * kCtrStride + 2u] + counters[d * kCtrStride + 3u] + counters[d * kCtrStride + 4u];
         }
         totals[0] += seg;
         totals[1] += sh;
+        totals[2] += hits;
     }
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < n_depth * kCtrStride; i += blockDim.x) counters[i] = 0u;
@@ -1149,7 +1151,7 @@ int akr_b200_create(int device_ordinal, AkrContext **out_ctx) {
             return AKR_ERR_CUDA;
         }
     }
-    if (dev_alloc(ctx, ctx->counters, kMaxDepthSlots * kCtrStride * sizeof(uint32_t)) != AKR_OK || dev_alloc(ctx, ctx->totals, 2 * sizeof(unsigned long long)) != AKR_OK) {
+    if (dev_alloc(ctx, ctx->counters, kMaxDepthSlots * kCtrStride * sizeof(uint32_t)) != AKR_OK || dev_alloc(ctx, ctx->totals, 4 * sizeof(unsigned long long)) != AKR_OK) {
         delete ctx;
         return AKR_ERR_CUDA;
     }
@@ -1329,12 +1331,19 @@ int akr_b200_begin(AkrContext *ctx, const AkrPtConfig *cfg, const AkrSamplerConf
     if (filter->type != AKR_FILTER_BOX && filter->type != AKR_FILTER_GAUSSIAN) return fail(ctx, AKR_ERR_INVALID_ARGUMENT, "unknown filter");
     AKR_CUDA(ctx, cudaSetDevice(ctx->device));
     const uint32_t width = ctx->scene.camera.width, height = ctx->scene.camera.height;
-    uint32_t y0 = 0, y1 = height;
+    uint32_t y0 = 0, y1 = height, t_block = 1, t_shards = 1, t_shard = 0;
     if (tile) {
         y0 = tile->y0;
         y1 = tile->y1;
+        if (tile->n_shards > 1u) {
+            t_block = tile->block_rows ? tile->block_rows : 1u;
+            t_shards = tile->n_shards;
+            t_shard = tile->shard;
+        }
     }
-    if (y0 >= y1 || y1 > height) return fail(ctx, AKR_ERR_INVALID_ARGUMENT, "bad tile");
+    if (y0 >= y1 || y1 > height || t_shard >= t_shards) return fail(ctx, AKR_ERR_INVALID_ARGUMENT, "bad tile");
+    const uint32_t tile_rows = interleaved_tile_rows(y0, y1, t_block, t_shards, t_shard);
+    if (tile_rows == 0u) return fail(ctx, AKR_ERR_INVALID_ARGUMENT, "bad tile: the shard owns no row");
     if (ctx->scene_needs_table) {
         int rc = ensure_albedo_table(ctx);
         if (rc != AKR_OK) return rc;
@@ -1364,11 +1373,14 @@ int akr_b200_begin(AkrContext *ctx, const AkrPtConfig *cfg, const AkrSamplerConf
     rp.width = width;
     rp.height = height;
     rp.y0 = y0;
+    rp.tile_block = t_block;
+    rp.tile_shards = t_shards;
+    rp.tile_shard = t_shard;
     finish_render_params(rp);
     ctx->cfg = *cfg;
     ctx->tile_y0 = y0;
     ctx->tile_y1 = y1;
-    ctx->n_pixels = width * (y1 - y0);
+    ctx->n_pixels = width * tile_rows;
     ctx->spp_done = 0;
     int rc = dev_alloc(ctx, ctx->film, (size_t)ctx->n_pixels * 7 * sizeof(float));
     if (rc != AKR_OK) return rc;
@@ -1602,14 +1614,20 @@ int akr_b200_resolve_film(AkrContext *ctx, float *out_host, size_t n_floats, int
     return rc;
 }
 
+uint32_t akr_b200_tile_rows(const AkrTile *tile) {
+    if (!tile) return 0u;
+    return interleaved_tile_rows(tile->y0, tile->y1, tile->block_rows, tile->n_shards, tile->shard);
+}
+
 int akr_b200_get_stats(AkrContext *ctx, AkrStats *out) {
     if (!ctx || !out) return fail(ctx, AKR_ERR_INVALID_ARGUMENT, "null argument");
     AKR_CUDA(ctx, cudaSetDevice(ctx->device));
     AKR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    unsigned long long t[2] = {0, 0};
+    unsigned long long t[3] = {0, 0, 0};
     AKR_CUDA(ctx, cudaMemcpy(t, ctx->totals.ptr, sizeof(t), cudaMemcpyDeviceToHost));
     ctx->stats.segments = t[0];
     ctx->stats.shadow_rays = t[1];
+    ctx->stats.shaded_hits = t[2];
     *out = ctx->stats;
     return AKR_OK;
 }

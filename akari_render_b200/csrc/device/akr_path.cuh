@@ -85,6 +85,11 @@ AKR_HD PathCoord path_coord(const RenderParams &rp, const WaveInfo &w, uint32_t 
     uint32_t s_local = fastdiv(path_id, w.n_pix_div, p_local);
     uint32_t pix = w.pix0 + p_local;
     uint32_t row = fastdiv(pix, rp.width_div, col);
+    if (rp.tile_shards > 1u) {  // interleaved tile: local row -> sensor row
+        uint32_t within;
+        const uint32_t blk = fastdiv(row, rp.tile_block_div, within);
+        row = (blk * rp.tile_shards + rp.tile_shard) * rp.tile_block + within;
+    }
     return PathCoord{col, rp.y0 + row, w.s0 + s_local, pix};
 }
 

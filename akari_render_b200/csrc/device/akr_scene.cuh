@@ -174,15 +174,31 @@ struct RenderParams {  // pt::Config + sampler + filter, resolved for one pass
     float filter_radius;
     uint32_t width, height;  // full sensor
     uint32_t y0;             // first row of this context's tile
+    uint32_t tile_block, tile_shards, tile_shard;  // interleaved tile (AkrTile): local row -> y0 + ((row / block) * shards + shard) * block + row % block
     // derived (finish_render_params)
     FastDiv width_div;       // pixel -> (row, column)
+    FastDiv tile_block_div;
     uint32_t spp_pow2;       // spp_total is a power of two: x / spp == x * inv_spp exactly
     float inv_spp;
 };
 inline void finish_render_params(RenderParams &rp) {
     rp.width_div = make_fastdiv(rp.width);
+    if (rp.tile_block == 0u) rp.tile_block = 1u;
+    if (rp.tile_shards == 0u) rp.tile_shards = 1u;
+    rp.tile_block_div = make_fastdiv(rp.tile_block);
     rp.spp_pow2 = (rp.spp_total & (rp.spp_total - 1u)) == 0u ? 1u : 0u;
     rp.inv_spp = 1.0f / (float)rp.spp_total;
+}
+
+// rows of [y0, y1) that belong to one interleaved shard (AkrTile semantics)
+inline uint32_t interleaved_tile_rows(uint32_t y0, uint32_t y1, uint32_t block, uint32_t shards, uint32_t shard) {
+    if (y1 <= y0) return 0u;
+    if (shards <= 1u) return y1 - y0;
+    if (block == 0u) block = 1u;
+    const uint32_t span = y1 - y0, n_blocks = (span + block - 1u) / block;
+    uint32_t rows = 0u;
+    for (uint32_t b = shard; b < n_blocks; b += shards) rows += (b + 1u) * block <= span ? block : span - b * block;
+    return rows;
 }
 
 }  // namespace akr

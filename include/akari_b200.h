@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define AKR_B200_ABI_VERSION 1u
+#define AKR_B200_ABI_VERSION 2u
 
 /* ---- status codes -------------------------------------------------------------------------- */
 enum {
@@ -172,10 +172,17 @@ typedef struct AkrFilterConfig {
     float radius;
 } AkrFilterConfig;
 
-/* Image-plane shard rendered by this context: rows [y0, y1) of the full sensor.
- * The sampler is keyed by absolute pixel coordinates, so any tiling yields the same image.     */
+/* Image-plane shard rendered by this context: rows [y0, y1) of the full sensor, or — when n_shards > 1 —
+ * every n_shards-th block of `block_rows` rows of that range: row y belongs to shard ((y - y0) / block_rows) % n_shards.
+ * Interleaving spreads expensive image regions over all GPUs (contiguous bands leave the band with the light source
+ * 8 % more work on cbox).  The film of the context holds only its own rows, packed in increasing y.  The sampler is
+ * keyed by absolute pixel coordinates, so any tiling yields the same image.  block_rows = 0 means 1.               */
 typedef struct AkrTile {
     uint32_t y0, y1;
+    uint32_t block_rows;            /* rows per interleaved block (ignored when n_shards <= 1)  */
+    uint32_t n_shards;              /* 0 or 1: the contiguous band [y0, y1)                      */
+    uint32_t shard;                 /* which of the n_shards interleaved sets, < n_shards        */
+    uint32_t _pad;
 } AkrTile;
 
 typedef struct AkrStats {
@@ -188,6 +195,7 @@ typedef struct AkrStats {
                                      * 2 shade/Lambert, 3 shade/conductor, 4 accumulate, 5 misc,
                                      * 6 shade/general (or the unsorted shade kernel)                */
     uint64_t launches_kernel[8];
+    uint64_t shaded_hits;           /* hits that went through a shade / bounce kernel (segments minus misses) */
 } AkrStats;
 
 typedef struct AkrContext AkrContext;
@@ -233,7 +241,10 @@ int akr_b200_render_pt(AkrContext *ctx, const AkrPtConfig *cfg, const AkrSampler
 int akr_b200_synchronize(AkrContext *ctx);
 
 /* Film in the reference layout (film.rs:66-76,88-93): f32[3N] sum rgb*w | f32[3N] splat | f32[N]
- * sum w, N = width * tile_rows, pixel index x + (y - y0) * width.  Caller-allocated host buffer. */
+ * sum w, N = width * tile_rows, pixel index x + local_row * width with the tile's rows packed in increasing y
+ * (local_row = y - y0 for a contiguous band).  Caller-allocated host buffer.
+ * akr_b200_tile_rows: number of rows of `tile` on a sensor of any width (host helper, no device needed). */
+uint32_t akr_b200_tile_rows(const AkrTile *tile);
 int akr_b200_download_film(AkrContext *ctx, float *out_7n, size_t n_floats);
 
 /* Film::copy_to_rgba_image(hdr) (film.rs:120-148): rgb/weight (+splat*scale); writes

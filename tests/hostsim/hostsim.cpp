@@ -18,6 +18,7 @@ using namespace akr;
 
 static thread_local int g_use_prims = 0;
 static thread_local int g_fused = 0;
+static thread_local uint32_t g_tile_block = 1, g_tile_shards = 1, g_tile_shard = 0;  // interleaved tile (AkrTile semantics)
 
 namespace {
 template <bool ANY_HIT> HitRec host_trace(const SceneView &sc, const TraceData &td, f3 o, f3 d, float t_max, uint32_t ex0, uint32_t ex1) {
@@ -65,6 +66,12 @@ void hostsim_set_intersector(int use_prims) { g_use_prims = use_prims; }
 // depth and shade class does shade + shadow ray + next ray on records that carry hit and radiance: akr_path.cuh
 // bounce_fused, what flat scenes run)
 void hostsim_set_pipeline(int fused) { g_fused = fused; }
+// rows [y0, y1) of hostsim_render are then the rows of shard `shard` of `n_shards` interleaved sets of `block_rows`-row blocks
+void hostsim_set_tile_interleave(uint32_t block_rows, uint32_t n_shards, uint32_t shard) {
+    g_tile_block = block_rows ? block_rows : 1u;
+    g_tile_shards = n_shards ? n_shards : 1u;
+    g_tile_shard = shard;
+}
 
 
 
@@ -113,8 +120,11 @@ int hostsim_render(const AkrSceneDesc *desc, const AkrPtConfig *cfg, const AkrSa
     rp.width = desc->camera.width;
     rp.height = desc->camera.height;
     rp.y0 = y0;
+    rp.tile_block = g_tile_block;
+    rp.tile_shards = g_tile_shards;
+    rp.tile_shard = g_tile_shard;
     finish_render_params(rp);
-    const uint32_t rows = y1 - y0;
+    const uint32_t rows = interleaved_tile_rows(y0, y1, g_tile_block, g_tile_shards, g_tile_shard);
     const uint32_t n_pixels = rp.width * rows;
     const uint32_t k = spp_end - spp_begin;
     if (wave_pixels == 0) wave_pixels = n_pixels;

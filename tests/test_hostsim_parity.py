@@ -30,11 +30,11 @@ def hostsim(request):
     lib.hostsim_set_pipeline(0)
 
 
-def run_hostsim(lib, scene, task, tables, table, w, h, y0=0, y1=None, s0=0, s1=None, wave_pixels=0):
+def run_hostsim(lib, scene, task, tables, table, w, h, y0=0, y1=None, s0=0, s1=None, wave_pixels=0, n_rows=None):
     pmj, bn = tables
     y1 = h if y1 is None else y1
     s1 = task.pt.spp if s1 is None else s1
-    n = w * (y1 - y0)
+    n = w * ((y1 - y0) if n_rows is None else n_rows)  # n_rows: rows of an interleaved tile (hostsim_set_tile_interleave)
     film = np.zeros(7 * n, np.float32)
     fh = np.zeros((n, 2), np.uint32)
     st = HostsimStats()
@@ -120,6 +120,25 @@ def test_config_knobs_bitwise(hostsim, oracle, tables, cbox, cbox_task, kw):
     film, _, st = run_hostsim(hostsim, scene, task, tables, table, w, h)
     assert (st.segments, st.shadow_rays) == (ost.segments, ost.shadow_rays)
     assert np.array_equal(film, ofilm)
+
+
+def test_interleaved_tiles_compose_bitwise(hostsim, oracle, tables, cbox, cbox_task):
+    """Interleaved row blocks (AkrTile block_rows / n_shards / shard): the rows a shard renders are bit-identical to the
+    same rows of the whole frame, for block heights that do and do not divide the frame."""
+    w, h = 24, 22
+    scene, task = cbox(w, h), cbox_task(8)
+    table = oracle.albedo_table()
+    ref, _, _ = run_hostsim(hostsim, scene, task, tables, table, w, h)
+    ref_rgb = ref[:3 * w * h].reshape(h, w, 3)
+    try:
+        for block, shards in ((1, 2), (4, 3), (5, 2), (8, 4)):
+            for shard in range(shards):
+                rows = [y for y in range(h) if (y // block) % shards == shard]
+                hostsim.hostsim_set_tile_interleave(block, shards, shard)
+                film, _, _ = run_hostsim(hostsim, scene, task, tables, table, w, h, n_rows=len(rows))
+                assert np.array_equal(film[:3 * w * len(rows)].reshape(len(rows), w, 3), ref_rgb[rows])
+    finally:
+        hostsim.hostsim_set_tile_interleave(1, 1, 0)
 
 
 def test_box_filter_and_odd_spp(hostsim, oracle, tables, cbox, akr):
