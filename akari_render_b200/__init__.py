@@ -134,6 +134,14 @@ class RenderTask:
     def out(self):
         return self.raw.out.decode()
 
+    @property
+    def method(self):
+        return "aov" if self.raw.method == 1 else "pt"
+
+    @property
+    def aov(self):
+        return self.raw.aov
+
 
 class Film:
     """Reference film layout (film.rs:66-76): f32 | rgb 3N | splat 3N | weight N |."""
@@ -240,6 +248,15 @@ class PathTracer:
         t = self._set_tile(tile)
         self._check(self._lib.akr_b200_render_pt(self._ctx, C.byref(task.raw.pt), C.byref(task.raw.sampler), C.byref(task.raw.filter),
                                                  C.byref(t) if t is not None else None))
+        return self.download_film()
+
+    def render_aov(self, scene, task, tile=None):
+        """aov::render (aov.rs:175-185): the `aov` method of `task` (RenderTask with method type "aov")."""
+        if scene is not None and (scene is not self._scene or scene.resolution != self._res):
+            self.upload_scene(scene)
+        t = self._set_tile(tile)
+        self._check(self._lib.akr_b200_render_aov(self._ctx, C.byref(task.raw.aov), C.byref(task.raw.sampler), C.byref(task.raw.filter),
+                                                  C.byref(t) if t is not None else None))
         return self.download_film()
 
     def synchronize(self):

@@ -137,12 +137,21 @@ class AkrEngineOptions(C.Structure):
     ]
 
 
+class AkrAovConfig(C.Structure):
+    _fields_ = [("spp", C.c_uint32), ("aov", C.c_uint32), ("remap", C.c_uint32), ("_pad", C.c_uint32)]
+
+
+AOV_NAMES = ["ns", "ng", "tangent", "bitangent", "albedo", "roughness"]  # AKR_AOV_* order (aov.rs:9-22)
+
+
 class AkrRenderTask(C.Structure):
     _fields_ = [
         ("pt", AkrPtConfig),
         ("sampler", AkrSamplerConfig),
         ("filter", AkrFilterConfig),
         ("out", C.c_char * 512),
+        ("method", C.c_uint32),
+        ("aov", AkrAovConfig),
     ]
 
 
@@ -159,7 +168,7 @@ HOST_SYMBOLS = [
 CUDA_SYMBOLS = [
     "akr_b200_create", "akr_b200_destroy", "akr_b200_last_error", "akr_b200_set_stream",
     "akr_b200_upload_sampler_tables", "akr_b200_upload_albedo_table", "akr_b200_upload_scene",
-    "akr_b200_begin", "akr_b200_render_pass", "akr_b200_render_pt", "akr_b200_synchronize",
+    "akr_b200_begin", "akr_b200_render_pass", "akr_b200_render_pt", "akr_b200_render_aov", "akr_b200_synchronize",
     "akr_b200_download_film", "akr_b200_resolve_film", "akr_b200_resolve_film_device",
     "akr_b200_get_stats", "akr_b200_reset_stats", "akr_b200_set_engine_options",
     "akr_b200_debug_first_hits", "akr_b200_tile_rows",
@@ -211,6 +220,7 @@ def load_cuda_lib():
     lib.akr_b200_render_pass.argtypes = [vp, C.c_uint32, C.c_int]
     lib.akr_b200_render_pt.argtypes = [vp, C.POINTER(AkrPtConfig), C.POINTER(AkrSamplerConfig),
                                        C.POINTER(AkrFilterConfig), C.POINTER(AkrTile)]
+    lib.akr_b200_render_aov.argtypes = [vp, C.POINTER(AkrAovConfig), C.POINTER(AkrSamplerConfig), C.POINTER(AkrFilterConfig), C.POINTER(AkrTile)]
     lib.akr_b200_synchronize.argtypes = [vp]
     lib.akr_b200_download_film.argtypes = [vp, vp, C.c_size_t]
     lib.akr_b200_resolve_film.argtypes = [vp, vp, C.c_size_t, C.c_int]

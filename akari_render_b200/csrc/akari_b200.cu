@@ -95,6 +95,7 @@ struct LaunchParams {
     uint32_t scene_smem_prims;  // 1 when all primitives are staged too
     uint32_t stack_depth;       // traversal stack entries per thread (shared memory)
     uint32_t stage_flat;        // stage the pairs-first flat list instead of the BVH-ordered primitives
+    uint32_t aov, aov_remap;    // k_aov: which AKR_AOV_* quantity, v -> v * 0.5 + 0.5
     uint32_t *first_hits;       // optional AOV (engine option aov_mask bit 0): [n_film_pixels][2] (inst, prim) of sample 0
 };
 
@@ -890,6 +891,22 @@ template <int CLS> __global__ void __launch_bounds__(kShadeBlock, ShadeLaunch<CL
         atomicAdd(reinterpret_cast<unsigned long long *>(P.counters + (depth + 1u) * kCtrStride), (unsigned long long)n_traced | ((unsigned long long)n_shadow << 32));
 }
 
+// The `aov` method (aov.rs:96-155) after raygen + one trace stage: the first-hit quantity of every camera sample goes to
+// both accumulators (radiance == base_replay_throughput, so k_accumulate's indirect clamp is a no-op and its NaN removal
+// is Film::add_sample's).  Misses keep the zeros raygen wrote.
+__global__ void __launch_bounds__(kBlock) k_aov(const __grid_constant__ LaunchParams P) {
+    const uint32_t n = P.wave.n_pix * P.wave.n_spp;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const f4 hr = ldq(P.hits.h + i);
+        if (f2u(hr.x) == 0xffffffffu) continue;
+        const f4 a = ldq(P.q[0].a + i), b = ldq(P.q[0].b + i);
+        const f3 c = aov_body(P.scene, P.corners, P.tables, P.rp, P.wave, P.aov, P.aov_remap != 0u, f2u(b.w), mk3(a.w, b.x, b.y), HitRec{f2u(hr.x), hr.y, hr.z});
+        st4(P.acc.l + f2u(b.w), f4{c.x, c.y, c.z, 0.0f});
+        st4(P.acc.b + f2u(b.w), f4{c.x, c.y, c.z, 0.0f});
+    }
+}
+
 __global__ void __launch_bounds__(kBlock) k_accumulate(const __grid_constant__ LaunchParams P) {
     const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < P.wave.n_pix; p += stride) accumulate_body(P.acc, P.wave, p, P.film, P.n_film_pixels);
@@ -990,6 +1007,8 @@ struct AkrContext {
     AccView acc{};
     DeviceBuffer counters, totals, first_hits;
 
+    int aov_mode = -1;        // >= 0: the render in progress is the `aov` method with this AKR_AOV_* output
+    uint32_t aov_remap = 0;
     AkrEngineOptions opts{};
     AkrStats stats{};
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
@@ -1394,6 +1413,7 @@ int akr_b200_begin(AkrContext *ctx, const AkrPtConfig *cfg, const AkrSamplerConf
     }
     AKR_CUDA(ctx, cudaMemsetAsync(ctx->counters.ptr, 0, ctx->counters.bytes, ctx->stream));
     ctx->render_ready = true;
+    ctx->aov_mode = -1;
     return AKR_OK;
 }
 
@@ -1411,7 +1431,8 @@ int akr_b200_render_pass(AkrContext *ctx, uint32_t n_spp, int blocking) {
     if (ctx->opts.trace_mode == 2u && flat_ok) trace_mode = TRACE_FLAT;
     const bool alpha = ctx->scene.any_alpha != 0u;
     // fused pipeline: flat list, no stochastic alpha; opts.fused = 2 forces the queued pipeline
-    const bool fused = trace_mode == TRACE_FLAT && !alpha && ctx->opts.fused != 2u;
+    const bool aov = ctx->aov_mode >= 0;  // the aov method runs raygen + one trace stage of the queued pipeline + k_aov
+    const bool fused = trace_mode == TRACE_FLAT && !alpha && ctx->opts.fused != 2u && !aov;
     const uint32_t class_mask = ctx->rp.force_diffuse ? (1u << CLS_LAMBERT) : ctx->class_mask;
 
     // wave geometry: pixels x samples with pixels * samples <= capacity
@@ -1443,6 +1464,8 @@ int akr_b200_render_pass(AkrContext *ctx, uint32_t n_spp, int blocking) {
     P.scene_smem_prims = ctx->smem_prims;
     P.stack_depth = ctx->bvh_depth + 2u;
     P.first_hits = static_cast<uint32_t *>(ctx->first_hits.ptr);
+    P.aov = aov ? (uint32_t)ctx->aov_mode : 0u;
+    P.aov_remap = ctx->aov_remap;
     P.stage_flat = trace_mode == TRACE_FLAT ? 1u : 0u;
     // shared memory: staged nodes + (flat mode: the padded PrimBlock2 lists | BVH modes: primitives + per-thread stacks)
     const size_t node_smem = (size_t)ctx->smem_nodes * sizeof(BvhNode);
@@ -1508,7 +1531,7 @@ int akr_b200_render_pass(AkrContext *ctx, uint32_t n_spp, int blocking) {
                 }
             } else {
                 AKR_LAUNCH(0, k_raygen, grid_for(ctx, n_paths, 8), 0, P);
-                for (uint32_t depth = 0; depth <= ctx->rp.max_depth; ++depth) {
+                for (uint32_t depth = 0; depth <= (aov ? 0u : ctx->rp.max_depth); ++depth) {
                     if (trace_mode == TRACE_FLAT) {
                         const int g_trace = grid_for(ctx, n_paths, ctx->occ_trace_flat);
                         if (alpha) AKR_LAUNCH(1, (k_trace_flat<true>), g_trace, trace_smem, P, depth);
@@ -1522,6 +1545,10 @@ int akr_b200_render_pass(AkrContext *ctx, uint32_t n_spp, int blocking) {
                             if (alpha) AKR_LAUNCH(1, (k_trace_bvh<false, true>), g_dyn, trace_smem, P, depth);
                             else AKR_LAUNCH(1, (k_trace_bvh<false, false>), g_dyn, trace_smem, P, depth);
                         }
+                    }
+                    if (aov) {
+                        AKR_LAUNCH(5, k_aov, grid_for(ctx, n_paths, 8), 0, P);
+                        break;
                     }
                     if (class_mask & (1u << CLS_LAMBERT)) AKR_LAUNCH_B(2, (k_shade<CLS_LAMBERT>), shade_grid(ctx->occ_shade[0]), kShadeBlock, 0, P, depth);
                     if (class_mask & (1u << CLS_CONDUCTOR)) AKR_LAUNCH_B(3, (k_shade<CLS_CONDUCTOR>), shade_grid(ctx->occ_shade[1]), kShadeBlock, 0, P, depth);
@@ -1567,6 +1594,23 @@ int akr_b200_render_pt(AkrContext *ctx, const AkrPtConfig *cfg, const AkrSampler
         cnt += cur;
     }
     return akr_b200_synchronize(ctx);
+}
+
+int akr_b200_render_aov(AkrContext *ctx, const AkrAovConfig *cfg, const AkrSamplerConfig *sampler, const AkrFilterConfig *filter, const AkrTile *tile) {
+    if (!ctx || !cfg) return fail(ctx, AKR_ERR_INVALID_ARGUMENT, "null argument");
+    if (cfg->aov > AKR_AOV_ROUGHNESS) return fail(ctx, AKR_ERR_INVALID_ARGUMENT, "unknown aov");
+    AkrPtConfig pc;
+    std::memset(&pc, 0, sizeof(pc));
+    pc.spp = cfg->spp;
+    pc.spp_per_pass = cfg->spp;  // aov.rs renders all samples in one dispatch (:160-166)
+    pc.debug_depth = -1;
+    int rc = akr_b200_begin(ctx, &pc, sampler, filter, tile);
+    if (rc != AKR_OK) return rc;
+    ctx->aov_mode = (int)cfg->aov;
+    ctx->aov_remap = cfg->remap ? 1u : 0u;
+    rc = akr_b200_render_pass(ctx, cfg->spp, 1);
+    ctx->aov_mode = -1;
+    return rc;
 }
 
 int akr_b200_synchronize(AkrContext *ctx) {

@@ -477,4 +477,47 @@ template <int CLS> AKR_HD BsdfDir closure_sample_wi(const Material &m, const flo
     return BsdfDir{wi, valid};
 }
 
+// ---- Surface::albedo / emission / roughness / ns (the `aov` integrator's taps, aov.rs:96-155) ---------------------
+// albedo() + emission(): PrincipledBsdfWrapper overrides both with base_color / emission (principled.rs:227-234,267-274);
+// diffuse node: reflectance * pi (diffuse.rs:56-63); glass node: Addictive mixture a.albedo + b.albedo = kt + kr
+// (mod.rs:659-675,875-882,981-988); emission node: 0 + emission (mod.rs:372-383,399-410).
+AKR_HD f3 material_albedo_plus_emission(const Material &m) {
+    if (m.wrap_inner) return ld3(m.color) + ld3(m.emission);
+    switch (m.type) {
+    case MAT_LAMBERT: return ld3(m.diffuse) * AKR_PI + splat3(0.0f);
+    case MAT_GLASS: return (ld3(m.trans_color) + ld3(m.color)) + (splat3(0.0f) + splat3(0.0f));
+    case MAT_EMISSION: return splat3(0.0f) + ld3(m.emission);
+    default: return splat3(0.0f);
+    }
+}
+// roughness(wo, u_select): walks the tree like sample_wi does and returns the roughness of the lobe it lands on
+// (mod.rs:536-553 Coated, :641-657 Mixture, :883-891 / :989-997 microfacet lobes, diffuse.rs:64-72 = 1).
+AKR_HD float material_roughness(const Material &m, const float *table, f3 wo, float u_select) {
+    if (!m.wrap_inner) {
+        if (m.type == MAT_GLASS) return tr_lobe_roughness(m.roughness_raw);  // both lobes of the mixture share the distribution
+        return 1.0f;                                                          // diffuse node, emission node (inner = None)
+    }
+    if (m.lobes & LOBE_COAT) {
+        f3 eo = splat3(1.0f) * m.coat_weight * ggx_dielectric_albedo(table, m.coat_roughness, abs_cos_theta(wo), m.coat_ior);
+        if (choose2(avg3(eo), u_select)) return tr_lobe_roughness(m.coat_roughness);
+    }
+    if (choose2(m.metallic, u_select)) return tr_lobe_roughness(m.roughness);  // Mix(bsdf1, metal): first = metal
+    if (m.lobes & LOBE_SPECULAR) {
+        f3 eo = ld3(m.spec_tint) * ggx_dielectric_albedo(table, m.roughness, abs_cos_theta(wo), m.eta_s) * m.f0;
+        if (choose2(avg3(eo), u_select)) return tr_lobe_roughness(m.roughness);
+    }
+    if (choose2(m.transmission, u_select)) return tr_lobe_roughness(m.roughness_raw);  // dielectric: either lobe, same distribution
+    return 1.0f;                                                                         // diffuse
+}
+AKR_HD float closure_roughness(const Material &m, const float *table, const ClosureFrames &c, f3 wo, float u_select) {  // mod.rs:774-783, twice
+    f3 wo_l = to_local(c.outer, wo);
+    if (c.has_inner) wo_l = to_local(c.inner, wo_l);
+    return material_roughness(m, table, wo_l, u_select);
+}
+AKR_HD f3 closure_ns(const ClosureFrames &c) {  // SurfaceClosure::ns (mod.rs:724-727), innermost ns = (0, 0, 1)
+    f3 ns = mk3(0.0f, 0.0f, 1.0f);
+    if (c.has_inner) ns = to_world(c.inner, ns);
+    return to_world(c.outer, ns);
+}
+
 }  // namespace akr

@@ -13,6 +13,7 @@
 // All paths of one stage launch are at the same depth (no path regeneration inside a wave), so the
 // depth and the sampler dimension are launch constants, not per-path state.
 #pragma once
+#include "../../../include/akari_b200.h"
 #include "akr_trace.cuh"
 
 namespace akr {
@@ -549,6 +550,28 @@ AKR_HD BounceOut bounce_fused(const SceneView &sc, const CornerAttribs &ca, cons
     BounceOut r = continue_path(sc, ca, rp, depth + 1u, active, o.has_next, o.next, L, tr, acc);
     r.shadow = o.has_shadow;
     return r;
+}
+
+// ---- the `aov` integrator (crates/akari_integrator/src/aov.rs:96-155): colour of one camera sample's first hit -----------
+// `d` is the camera ray direction; the roughness AOV draws next_1d at the dimension after the filter pair (dim 6).
+AKR_HD f3 aov_body(const SceneView &sc, const CornerAttribs &ca, const SamplerTables &tab, const RenderParams &rp, const WaveInfo &wave, uint32_t aov,
+                   bool remap, uint32_t path_id, f3 d, HitRec hit) {
+    const TriShade &ts = sc.shade[hit.gid];
+    const Material &mat = sc.materials[ts.mat];
+    const Surface si = surface_from_hit(sc, ca, hit.gid, hit.u, hit.v);
+    const f3 wo = -d;
+    f3 v;
+    if (aov == AKR_AOV_SHADING_NORMAL) v = closure_ns(make_closure_frames(mat, si.frame, si.ng));
+    else if (aov == AKR_AOV_GEOMETRY_NORMAL) v = si.ng;
+    else if (aov == AKR_AOV_TANGENT) v = si.frame.t;
+    else if (aov == AKR_AOV_BITANGENT) v = si.frame.s;
+    else if (aov == AKR_AOV_ALBEDO) return material_albedo_plus_emission(mat);
+    else {
+        const PathCoord pc = path_coord(rp, wave, path_id);
+        const float u = sampler_1d(tab, rp, pc.px, pc.py, pc.sample_index, 6u);
+        return splat3(1.0f) * closure_roughness(mat, sc.albedo_table, make_closure_frames(mat, si.frame, si.ng), wo, u);
+    }
+    return remap ? v * 0.5f + splat3(0.5f) : v;
 }
 
 // ---- stage: accumulate (pt.rs:871-876 + film.rs:196-229) -------------------------------------------------------

@@ -525,7 +525,21 @@ void parse_task(const akr::json::Value &root_in, AkrRenderTask *t) {
     }
     const Value &method = root->at("method");
     const std::string &type = method.at("type").string();
-    if (type != "pt") throw std::runtime_error("method '" + type + "' is outside the hot-path scope (only 'pt')");
+    if (type == "aov") {  // aov::Config (aov.rs:9-36)
+        t->method = AKR_METHOD_AOV;
+        if (method.has("spp")) t->aov.spp = method.at("spp").u32();
+        if (method.has("remap")) t->aov.remap = method.at("remap").boolean() ? 1u : 0u;
+        if (method.has("aov")) {
+            static const char *names[] = {"ns", "ng", "tangent", "bitangent", "albedo", "roughness"};
+            const std::string &a = method.at("aov").string();
+            uint32_t k = 0;
+            while (k < 6 && a != names[k]) ++k;
+            if (k == 6) throw std::runtime_error("unknown aov '" + a + "'");
+            t->aov.aov = k;
+        }
+    } else if (type != "pt") {
+        throw std::runtime_error("method '" + type + "' is outside the hot-path scope (only 'pt' and 'aov')");
+    }
     auto opt_u32 = [&](const char *k, uint32_t &dst) { if (method.has(k)) dst = method.at(k).u32(); };
     auto opt_bool = [&](const char *k, uint32_t &dst) { if (method.has(k)) dst = method.at(k).boolean() ? 1u : 0u; };
     opt_u32("spp", t->pt.spp);
@@ -708,6 +722,11 @@ void akr_host_default_task(AkrRenderTask *t) {
     t->filter.type = AKR_FILTER_GAUSSIAN;       // PixelFilter::default (film.rs:51-55)
     t->filter.radius = 1.5f;
     std::snprintf(t->out, sizeof(t->out), "out.exr");
+    t->method = AKR_METHOD_PT;
+    t->aov.spp = 256;  // aov::Config::default (aov.rs:29-36)
+    t->aov.aov = AKR_AOV_SHADING_NORMAL;
+    t->aov.remap = 1;
+    t->aov._pad = 0;
 }
 
 int akr_host_parse_method_string(const char *method_json, AkrRenderTask *out_task) {

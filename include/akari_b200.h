@@ -172,6 +172,17 @@ typedef struct AkrFilterConfig {
     float radius;
 } AkrFilterConfig;
 
+/* AOV integrator (crates/akari_integrator/src/aov.rs:9-36): what is written to the film for the first hit of every
+ * camera sample instead of radiance.  `remap` maps the vector outputs v -> v * 0.5 + 0.5 (aov.rs:101-127). */
+enum { AKR_AOV_SHADING_NORMAL = 0, AKR_AOV_GEOMETRY_NORMAL = 1, AKR_AOV_TANGENT = 2, AKR_AOV_BITANGENT = 3,
+       AKR_AOV_ALBEDO = 4, AKR_AOV_ROUGHNESS = 5 };
+typedef struct AkrAovConfig {
+    uint32_t spp;                   /* default 256 */
+    uint32_t aov;                   /* AKR_AOV_*, default shading normal */
+    uint32_t remap;                 /* bool, default true */
+    uint32_t _pad;
+} AkrAovConfig;
+
 /* Image-plane shard rendered by this context: rows [y0, y1) of the full sensor, or — when n_shards > 1 —
  * every n_shards-th block of `block_rows` rows of that range: row y belongs to shard ((y - y0) / block_rows) % n_shards.
  * Interleaving spreads expensive image regions over all GPUs (contiguous bands leave the band with the light source
@@ -237,6 +248,11 @@ int akr_b200_render_pass(AkrContext *ctx, uint32_t n_spp, int blocking);
 /* Convenience: begin + ceil(spp/spp_per_pass) passes, blocking.  == pt::render (pt.rs:1161-1172). */
 int akr_b200_render_pt(AkrContext *ctx, const AkrPtConfig *cfg, const AkrSamplerConfig *sampler,
                        const AkrFilterConfig *filter, const AkrTile *tile);
+
+/* The `aov` method (aov.rs:52-185): spp camera samples per pixel, the chosen first-hit quantity (shading / geometric
+ * normal, tangent, bitangent, albedo + emission, lobe roughness) accumulated into the film like radiance.  Blocking. */
+int akr_b200_render_aov(AkrContext *ctx, const AkrAovConfig *cfg, const AkrSamplerConfig *sampler,
+                        const AkrFilterConfig *filter, const AkrTile *tile);
 
 int akr_b200_synchronize(AkrContext *ctx);
 

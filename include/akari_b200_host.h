@@ -34,13 +34,16 @@ const AkrSceneDesc *akr_host_scene_desc(const AkrHostScene *scene);
 /* Camera::set_resolution (camera/mod.rs:54-65) — BASELINE configs override the sensor size. */
 int akr_host_scene_set_resolution(AkrHostScene *scene, uint32_t width, uint32_t height);
 
-/* RenderTask / RenderConfig (lib.rs:57-109): one `{method:{type:"pt",...}, sampler, film}` entry.
- * Only `type: "pt"` is in scope; other methods return AKR_ERR_UNSUPPORTED. */
+/* RenderTask / RenderConfig (lib.rs:57-109): one `{method:{type:"pt"|"aov",...}, sampler, film}` entry.
+ * `pt` (pt.rs:916-944) and `aov` (aov.rs:23-36) are in scope; other methods return AKR_ERR_UNSUPPORTED. */
+enum { AKR_METHOD_PT = 0, AKR_METHOD_AOV = 1 };
 typedef struct AkrRenderTask {
     AkrPtConfig pt;
     AkrSamplerConfig sampler;
     AkrFilterConfig filter;
     char out[512];                  /* film.out */
+    uint32_t method;                /* AKR_METHOD_* */
+    AkrAovConfig aov;               /* valid when method == AKR_METHOD_AOV */
 } AkrRenderTask;
 int akr_host_parse_method_file(const char *method_json_path, AkrRenderTask *out_task);
 int akr_host_parse_method_string(const char *method_json, AkrRenderTask *out_task);

@@ -578,6 +578,9 @@ struct DiffuseBsdf {  // diffuse.rs:13-80
         return {wi, true};
     }
     Color emission(V3) const { return v3s(0.0f); }
+    Color albedo(V3) const { return reflectance * PI; }  // diffuse.rs:56-63
+    float roughness(V3, float) const { return 1.0f; }    // diffuse.rs:64-72
+    V3 ns() const { return v3(0, 0, 1); }
 };
 
 struct FresnelDielectric {  // mod.rs:1166-1175
@@ -616,6 +619,9 @@ template <class Fresnel> struct MicrofacetReflection {  // mod.rs:820-900
         return {wi, FrameFn::same_hemisphere(wo, wi)};
     }
     Color emission(V3) const { return v3s(0.0f); }
+    Color albedo(V3) const { return color; }                          // mod.rs:875-882
+    float roughness(V3, float) const { return dist.roughness(); }    // mod.rs:883-891
+    V3 ns() const { return v3(0, 0, 1); }
 };
 
 struct MicrofacetTransmission {  // mod.rs:902-1006
@@ -657,6 +663,9 @@ struct MicrofacetTransmission {  // mod.rs:902-1006
         return {r.wt, valid};
     }
     Color emission(V3) const { return v3s(0.0f); }
+    Color albedo(V3) const { return color; }                          // mod.rs:981-988
+    float roughness(V3, float) const { return dist.roughness(); }    // mod.rs:989-997
+    V3 ns() const { return v3(0, 0, 1); }
 };
 
 enum class Blend { Addictive, Mix };
@@ -689,6 +698,18 @@ template <class A, class B, class FracFn> struct BsdfMixture {
         if (mode == Blend::Addictive) return a.emission(wo) + b.emission(wo);
         return a.emission(wo) * (1.0f - fr) + b.emission(wo) * fr;
     }
+    Color albedo(V3 wo) const {  // mod.rs:659-675
+        float fr = frac(wo);
+        if (mode == Blend::Addictive) return a.albedo(wo) + b.albedo(wo);
+        return a.albedo(wo) * (1.0f - fr) + b.albedo(wo) * fr;
+    }
+    float roughness(V3 wo, float u_select) const {  // mod.rs:641-657
+        float fr = frac(wo);
+        ChoiceU c = weighted_discrete_choice2_and_remap(fr, 1u, 0u, u_select);
+        if (c.i == 0) return a.roughness(wo, c.u);
+        return b.roughness(wo, c.u);
+    }
+    V3 ns() const { return a.ns(); }  // mod.rs:575-577
 };
 // CoatedBsdf (mod.rs:476-567).  EFn: Color(V3 w)
 template <class Top, class Bottom, class EFn> struct CoatedBsdf {
@@ -718,6 +739,17 @@ template <class Top, class Bottom, class EFn> struct CoatedBsdf {
         Color eo = e_top(wo);
         return top.emission(wo) * eo + bottom.emission(wo) * (v3s(1.0f) - eo);
     }
+    Color albedo(V3 wo) const {  // mod.rs:523-535
+        Color eo = e_top(wo);
+        return top.albedo(wo) * eo + bottom.albedo(wo) * (v3s(1.0f) - eo);
+    }
+    float roughness(V3 wo, float u_select) const {  // mod.rs:536-553
+        Color eo = e_top(wo);
+        ChoiceU c = weighted_discrete_choice2_and_remap(avg(eo), 0u, 1u, u_select);
+        if (c.i == 0) return top.roughness(wo, c.u);
+        return bottom.roughness(wo, c.u);
+    }
+    V3 ns() const { return bottom.ns(); }  // mod.rs:482-484
 };
 template <class Inner> struct ScaledBsdf {  // mod.rs:412-475 (weight is wo-independent in principled.rs:190-193)
     Inner inner;
@@ -728,6 +760,9 @@ template <class Inner> struct ScaledBsdf {  // mod.rs:412-475 (weight is wo-inde
     }
     SampleWi sample_wi(V3 wo, float us, V2 u) const { return inner.sample_wi(wo, us, u); }
     Color emission(V3 wo) const { return inner.emission(wo) * weight; }
+    Color albedo(V3 wo) const { return inner.albedo(wo) * weight; }           // mod.rs:446-454
+    float roughness(V3 wo, float us) const { return inner.roughness(wo, us); }  // mod.rs:456-464
+    V3 ns() const { return inner.ns(); }
 };
 template <class Inner> struct EmissiveSurface {  // mod.rs:330-411, inner = Some
     Inner inner;
@@ -735,19 +770,28 @@ template <class Inner> struct EmissiveSurface {  // mod.rs:330-411, inner = Some
     Eval evaluate(V3 wo, V3 wi) const { return inner.evaluate(wo, wi); }
     SampleWi sample_wi(V3 wo, float us, V2 u) const { return inner.sample_wi(wo, us, u); }
     Color emission(V3 wo) const { return emission_ + inner.emission(wo); }
+    Color albedo(V3 wo) const { return inner.albedo(wo); }                       // mod.rs:372-383
+    float roughness(V3 wo, float us) const { return inner.roughness(wo, us); }  // mod.rs:385-397
+    V3 ns() const { return inner.ns(); }                                         // mod.rs:338-342
 };
 struct EmissionOnly {  // EmissiveSurface { inner: None } (svm/mod.rs:124-133)
     Color emission_;
     Eval evaluate(V3, V3) const { return {v3s(0.0f), 0.0f}; }
     SampleWi sample_wi(V3, float, V2) const { return {v3s(0.0f), false}; }
     Color emission(V3) const { return emission_; }
+    Color albedo(V3) const { return v3s(0.0f); }          // mod.rs:372-383 (inner = None)
+    float roughness(V3, float) const { return 1.0f; }     // mod.rs:385-397
+    V3 ns() const { return v3(0, 0, 1); }
 };
 template <class Inner> struct PrincipledBsdfWrapper {  // principled.rs:218-275
     Inner inner;
-    Color albedo, emission_;
+    Color albedo_c, emission_;
     Eval evaluate(V3 wo, V3 wi) const { return inner.evaluate(wo, wi); }
     SampleWi sample_wi(V3 wo, float us, V2 u) const { return inner.sample_wi(wo, us, u); }
     Color emission(V3) const { return emission_; }
+    Color albedo(V3) const { return albedo_c; }                                 // principled.rs:227-234
+    float roughness(V3 wo, float us) const { return inner.roughness(wo, us); }  // principled.rs:257-265
+    V3 ns() const { return v3(0, 0, 1); }                                        // principled.rs:224-226
 };
 // SurfaceClosure (mod.rs:697-816)
 template <class Inner> struct SurfaceClosure {
@@ -772,6 +816,9 @@ template <class Inner> struct SurfaceClosure {
         return {wi, valid};
     }
     Color emission(V3 wo) const { return inner.emission(to_local(frame, wo)); }
+    Color albedo(V3 wo) const { return inner.albedo(to_local(frame, wo)); }                           // mod.rs:766-773
+    float roughness(V3 wo, float us) const { return inner.roughness(to_local(frame, wo), us); }      // mod.rs:774-783
+    V3 ns() const { return to_world(frame, inner.ns()); }                                             // mod.rs:724-727
 };
 struct BsdfSample {  // mod.rs:34-51
     V3 wi;
@@ -1741,6 +1788,70 @@ int akr_oracle_render(const AkrSceneDesc *scene, const AkrPtConfig *cfg, const A
         stats->threads = static_cast<uint32_t>(n_threads);
         stats->n_lights = static_cast<uint32_t>(sc.lights.size());
     }
+    return AKR_OK;
+}
+
+// The `aov` integrator (crates/akari_integrator/src/aov.rs:52-185): per camera sample the chosen first-hit quantity is
+// added to the film (remove_nan, weight 1) instead of radiance.  Single pass over samples [0, cfg->spp).
+int akr_oracle_render_aov(const AkrSceneDesc *scene, const AkrAovConfig *cfg, const AkrSamplerConfig *sampler_cfg, const AkrFilterConfig *filter,
+                          const uint32_t *pmj02bn, const uint16_t *bluenoise, const float *albedo_table, uint32_t y0, uint32_t y1, float *film_7n) {
+    if (!scene || !cfg || !sampler_cfg || !filter || !pmj02bn || !bluenoise || !albedo_table || !film_7n) {
+        g_err = "null argument";
+        return AKR_ERR_INVALID_ARGUMENT;
+    }
+    if (sampler_cfg->type != AKR_SAMPLER_PMJ02BN || cfg->spp == 0 || cfg->spp > AKR_PMJ02BN_SAMPLES || cfg->aov > AKR_AOV_ROUGHNESS) {
+        g_err = "unsupported aov configuration";
+        return AKR_ERR_UNSUPPORTED;
+    }
+    Scene sc;
+    if (!prepare_scene(sc, scene, albedo_table)) {
+        g_err = sc.error;
+        return AKR_ERR_UNSUPPORTED;
+    }
+    const uint32_t width = sc.camera.width, height = sc.camera.height;
+    if (y1 > height || y0 >= y1) {
+        g_err = "bad tile";
+        return AKR_ERR_INVALID_ARGUMENT;
+    }
+    uint32_t w = cfg->spp - 1;
+    w |= w >> 1; w |= w >> 2; w |= w >> 4; w |= w >> 8; w |= w >> 16;
+    const uint32_t rows = y1 - y0;
+    const size_t n = static_cast<size_t>(width) * rows;
+    Tables tab{pmj02bn, bluenoise};
+    auto remap = [&](V3 v) { return cfg->remap ? v * 0.5f + v3s(0.5f) : v; };
+    for (uint32_t r = 0; r < rows; ++r)
+        for (uint32_t x = 0; x < width; ++x) {
+            const uint32_t y = y0 + r;
+            Pmj02BnSampler sampler{tab, static_cast<uint32_t>(sampler_cfg->seed), 0, x, y, UINT32_MAX, cfg->spp, w};
+            const size_t i = static_cast<size_t>(x) + static_cast<size_t>(r) * width;
+            for (uint32_t s = 0; s < cfg->spp; ++s) {
+                sampler.start();
+                Ray ray = generate_ray(sc, *filter, x, y, sampler);
+                Hit hit = trace_closest(sc, ray);
+                Color color = v3s(0.0f);
+                if (hit.hit) {
+                    SurfaceInteraction si = surface_interaction(sc, hit.inst, hit.prim, hit.bary);
+                    const V3 wo = -ray.d;
+                    switch (cfg->aov) {
+                    case AKR_AOV_SHADING_NORMAL: color = remap(with_surface_closure(sc, si, false, [&](const auto &c) { return c.ns(); })); break;
+                    case AKR_AOV_GEOMETRY_NORMAL: color = remap(si.ng); break;
+                    case AKR_AOV_TANGENT: color = remap(si.frame.t); break;
+                    case AKR_AOV_BITANGENT: color = remap(si.frame.s); break;
+                    case AKR_AOV_ALBEDO: color = with_surface_closure(sc, si, false, [&](const auto &c) { return c.albedo(wo) + c.emission(wo); }); break;
+                    default: {
+                        const float u = sampler.next_1d();
+                        color = v3s(1.0f) * with_surface_closure(sc, si, false, [&](const auto &c) { return c.roughness(wo, u); });
+                    }
+                    }
+                }
+                if (has_nan(color)) color = v3s(0.0f);
+                color = color * 1.0f;
+                film_7n[i * 3 + 0] += color.x;
+                film_7n[i * 3 + 1] += color.y;
+                film_7n[i * 3 + 2] += color.z;
+                film_7n[6 * n + i] += 1.0f;
+            }
+        }
     return AKR_OK;
 }
 

@@ -45,6 +45,8 @@ def lib():
         l.akr_oracle_render.argtypes = [vp, vp, vp, vp, vp, vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                         C.c_int, vp, vp, C.POINTER(AkrOracleStats)]
         l.akr_oracle_render.restype = C.c_int
+        l.akr_oracle_render_aov.argtypes = [vp, vp, vp, vp, vp, vp, vp, C.c_uint32, C.c_uint32, vp]
+        l.akr_oracle_render_aov.restype = C.c_int
         l.akr_oracle_resolve.argtypes = [vp, C.c_size_t, vp]
         l.akr_oracle_resolve.restype = None
         l.akr_oracle_xxhash32_4.argtypes = [C.c_uint32] * 4
@@ -135,3 +137,17 @@ def bsdf_chi2_tables(kind, color, roughness, eta, wo, n_samples, seed, theta_res
     exp = np.zeros(theta_res * phi_res, np.float64)
     lib().akr_oracle_bsdf_chi2_tables(kind, _ptr(color), roughness, eta, _ptr(wo), n_samples, seed, theta_res, phi_res, _ptr(hist), _ptr(exp))
     return hist, exp
+
+
+def render_aov(scene_desc_ptr, width, height, aov_cfg, sampler_cfg, filter_cfg, pmj, bn, table=None, y0=0, y1=None):
+    """The `aov` integrator (aov.rs) with the oracle.  Returns the film (7n float32)."""
+    if y1 is None:
+        y1 = height
+    if table is None:
+        table = albedo_table()
+    film = np.zeros(7 * width * (y1 - y0), dtype=np.float32)
+    rc = lib().akr_oracle_render_aov(C.cast(scene_desc_ptr, C.c_void_p), C.byref(aov_cfg), C.byref(sampler_cfg), C.byref(filter_cfg), _ptr(pmj), _ptr(bn),
+                                     _ptr(table), y0, y1, _ptr(film))
+    if rc != 0:
+        raise RuntimeError(f"oracle aov render failed ({rc}): {lib().akr_oracle_last_error().decode()}")
+    return film

@@ -240,6 +240,53 @@ int hostsim_render(const AkrSceneDesc *desc, const AkrPtConfig *cfg, const AkrSa
     return AKR_OK;
 }
 
+// The `aov` method through the kernels' bodies: raygen_body, the chosen intersector, aov_body, accumulate_body.
+int hostsim_render_aov(const AkrSceneDesc *desc, const AkrAovConfig *cfg, const AkrSamplerConfig *scfg, const AkrFilterConfig *filter, const uint32_t *pmj,
+                       const uint16_t *bn, const float *albedo_table, uint32_t y0, uint32_t y1, float *film_7n) {
+    HostSceneBlob blob;
+    std::string err;
+    int rc = build_scene_blob(*desc, blob, err);
+    if (rc != AKR_OK) {
+        g_err = err;
+        return rc;
+    }
+    std::vector<uint16_t> bnt(48u * 128u * 128u);
+    transpose_bluenoise(bn, bnt.data());
+    SceneView sc = host_scene_view(blob, albedo_table);
+    CornerAttribs ca{blob.corner_normals.empty() ? nullptr : blob.corner_normals.data(), blob.corner_tangents.empty() ? nullptr : blob.corner_tangents.data()};
+    SamplerTables tab{pmj, bnt.data()};
+    TraceData td{nullptr, sc.nodes, sc.tris, 0u};
+    RenderParams rp;
+    std::memset(&rp, 0, sizeof(rp));
+    rp.spp_total = cfg->spp;
+    uint32_t w = cfg->spp - 1;
+    w |= w >> 1; w |= w >> 2; w |= w >> 4; w |= w >> 8; w |= w >> 16;
+    rp.w_mask = w;
+    rp.seed = (uint32_t)scfg->seed;
+    rp.debug_depth = -1;
+    rp.filter_type = filter->type;
+    rp.filter_radius = filter->radius;
+    rp.width = desc->camera.width;
+    rp.height = desc->camera.height;
+    rp.y0 = y0;
+    finish_render_params(rp);
+    const uint32_t n_pixels = rp.width * (y1 - y0);
+    WaveInfo wave = make_wave(0, n_pixels, 0, cfg->spp);
+    const uint32_t n_paths = wave.n_pix * wave.n_spp;
+    std::vector<f4> acc(2u * (size_t)n_paths, f4{0.0f, 0.0f, 0.0f, 0.0f});
+    AccView av{acc.data(), acc.data() + n_paths};
+    for (uint32_t i = 0; i < n_paths; ++i) {
+        PathState ps = raygen_body(sc, tab, rp, wave, i);
+        HitRec h = host_trace<false>(sc, td, ps.o, ps.d, 1e20f, 0xffffffffu, 0xffffffffu);
+        if (h.gid == 0xffffffffu) continue;
+        f3 c = aov_body(sc, ca, tab, rp, wave, cfg->aov, cfg->remap != 0u, i, ps.d, h);
+        av.l[i] = f4{c.x, c.y, c.z, 0.0f};
+        av.b[i] = f4{c.x, c.y, c.z, 0.0f};
+    }
+    for (uint32_t p = 0; p < wave.n_pix; ++p) accumulate_body(av, wave, p, film_7n, n_pixels);
+    return AKR_OK;
+}
+
 void hostsim_make_albedo_table(float *table, uint32_t n) { make_albedo_table(table, n); }
 
 // Chi-square tables (oracle/chi2_tables.h, methodology of akari_test.rs:31-112) of the DEVICE closures: the constant-folded
