@@ -81,6 +81,9 @@ class AkrSceneDesc(C.Structure):
         ("shader_data", C.POINTER(C.c_uint8)),
         ("shader_data_size", C.c_size_t),
         ("camera", AkrPerspectiveCamera),
+        ("images", C.c_void_p),
+        ("n_images", C.c_uint32),
+        ("_pad", C.c_uint32),
     ]
 
 

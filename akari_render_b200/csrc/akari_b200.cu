@@ -972,7 +972,8 @@ struct AkrContext {
     bool albedo_ready = false;
 
     // scene
-    DeviceBuffer nodes, prims, flat_prims, shade, instances, materials, lights, alias_j, alias_t, alias_pdf, corner_n, corner_t;
+    DeviceBuffer nodes, prims, flat_prims, shade, instances, materials, lights, alias_j, alias_t, alias_pdf, corner_n, corner_t, corner_uv;
+    DeviceBuffer svm_nodes, svm_kind_first, svm_data, textures, texels;
     SceneView scene{};
     CornerAttribs corners{};
     bool scene_ready = false;
@@ -1185,7 +1186,8 @@ void akr_b200_destroy(AkrContext *ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     for (DeviceBuffer *b : {&ctx->pmj, &ctx->bn, &ctx->albedo, &ctx->nodes, &ctx->prims, &ctx->flat_prims, &ctx->shade, &ctx->instances, &ctx->materials, &ctx->lights,
-                            &ctx->alias_j, &ctx->alias_t, &ctx->alias_pdf, &ctx->corner_n, &ctx->corner_t, &ctx->film, &ctx->wave_mem, &ctx->counters,
+                            &ctx->alias_j, &ctx->alias_t, &ctx->alias_pdf, &ctx->corner_n, &ctx->corner_t, &ctx->corner_uv, &ctx->svm_nodes,
+                            &ctx->svm_kind_first, &ctx->svm_data, &ctx->textures, &ctx->texels, &ctx->film, &ctx->wave_mem, &ctx->counters,
                             &ctx->totals, &ctx->first_hits})
         dev_free(*b);
     if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
@@ -1252,6 +1254,17 @@ int akr_b200_upload_scene(AkrContext *ctx, const AkrSceneDesc *desc) {
     if ((rc = upload_vec(ctx, ctx->alias_pdf, blob.alias_pdf)) != AKR_OK) return rc;
     if ((rc = upload_vec(ctx, ctx->corner_n, blob.corner_normals)) != AKR_OK) return rc;
     if ((rc = upload_vec(ctx, ctx->corner_t, blob.corner_tangents)) != AKR_OK) return rc;
+    if ((rc = upload_vec(ctx, ctx->corner_uv, blob.corner_uvs)) != AKR_OK) return rc;
+    if ((rc = upload_vec(ctx, ctx->svm_nodes, blob.svm_nodes)) != AKR_OK) return rc;
+    if ((rc = upload_vec(ctx, ctx->svm_kind_first, blob.svm_kind_first)) != AKR_OK) return rc;
+    if ((rc = upload_vec(ctx, ctx->svm_data, blob.svm_data)) != AKR_OK) return rc;
+    if ((rc = upload_vec(ctx, ctx->texels, blob.texels)) != AKR_OK) return rc;
+    {  // texture records: byte offsets into the texel blob become device pointers
+        std::vector<TextureRec> recs = blob.textures;
+        for (TextureRec &tr : recs) tr.texels = static_cast<const uint8_t *>(ctx->texels.ptr) + reinterpret_cast<size_t>(tr.texels);
+        if ((rc = upload_vec(ctx, ctx->textures, recs)) != AKR_OK) return rc;
+        AKR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // recs is a local
+    }
     AKR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // blob is a local
     SceneView &v = ctx->scene;
     v.nodes = static_cast<const BvhNode *>(ctx->nodes.ptr);
@@ -1277,6 +1290,14 @@ int akr_b200_upload_scene(AkrContext *ctx, const AkrSceneDesc *desc) {
     v.n_lights = (uint32_t)blob.lights.size();
     v.any_alpha = blob.any_alpha;
     v.camera = blob.camera;
+    v.svm.nodes = static_cast<const AkrSvmNode *>(ctx->svm_nodes.ptr);
+    v.svm.kind_first = static_cast<const uint32_t *>(ctx->svm_kind_first.ptr);
+    v.svm.data = static_cast<const uint8_t *>(ctx->svm_data.ptr);
+    v.svm.textures = static_cast<const TextureRec *>(ctx->textures.ptr);
+    v.svm.n_kinds = (uint32_t)blob.svm_kind_first.size() - 1u;
+    v.svm.n_textures = (uint32_t)blob.textures.size();
+    v.svm.data_size = (uint32_t)blob.svm_data.size();
+    v.corner_uvs = blob.corner_uvs.empty() ? nullptr : static_cast<const float *>(ctx->corner_uv.ptr);
     ctx->corners.normals = blob.corner_normals.empty() ? nullptr : static_cast<const float *>(ctx->corner_n.ptr);
     ctx->corners.tangents = blob.corner_tangents.empty() ? nullptr : static_cast<const float *>(ctx->corner_t.ptr);
     ctx->scene_needs_table = false;
@@ -1299,7 +1320,7 @@ int akr_b200_upload_scene(AkrContext *ctx, const AkrSceneDesc *desc) {
     ctx->smem_bytes = used;
     ctx->bvh_depth = blob.bvh_depth;
     ctx->class_mask = 0;
-    for (const Material &m : blob.materials) ctx->class_mask |= 1u << shade_class_of(m.type);
+    for (const Material &m : blob.materials) ctx->class_mask |= 1u << shade_class_of(m);
     // resident CTAs per SM of every kernel variant with this scene's shared-memory footprint
     {
         cudaError_t e = cudaSuccess;

@@ -31,7 +31,7 @@ enum MaterialLobes : uint32_t {
     LOBE_BASE = 1u << 5,          // metallic < 1 - eps (the non-metal branch is evaluated)
 };
 
-struct Material {  // 56 words
+struct Material {  // 48 words
     uint32_t type;
     uint32_t lobes;
     float color[3];        // base colour (principled) / reflectance*pi (diffuse) / kr (glass)
@@ -53,8 +53,12 @@ struct Material {  // 56 words
     uint32_t has_normal;   // normal != (0,0,0)
     uint32_t wrap_inner;   // 1 when the shader is a Principled node: it wraps itself in a second
                            // SurfaceClosure with the normal-map frame (principled.rs:208-214)
-    uint32_t _pad;
+    uint32_t dynamic;      // some input depends on the hit (image texture / texture coordinates): the record holds the
+                           // evaluation at uv = (0, 0) and is re-evaluated per hit from (shader_kind, data_offset), akr_svm.cuh
+    uint32_t shader_kind, data_offset;  // ShaderRef (svm/mod.rs:213-219)
+    uint32_t _pad[3];
 };
+static_assert(sizeof(Material) == 192, "Material is 48 words");
 
 // Shade classes: the trace stage bins every hit by the class of its material and one shade kernel is
 // compiled per class, so a warp never interleaves Lambert, conductor and full-tree code (the
@@ -63,6 +67,8 @@ enum ShadeClass : uint32_t { CLS_LAMBERT = 0, CLS_CONDUCTOR = 1, CLS_GENERAL = 2
 AKR_HD uint32_t shade_class_of(uint32_t material_type) {
     return material_type == MAT_LAMBERT ? (uint32_t)CLS_LAMBERT : (material_type == MAT_CONDUCTOR ? (uint32_t)CLS_CONDUCTOR : (uint32_t)CLS_GENERAL);
 }
+// a texture-driven material can be any type at any hit: it always takes the general kernel
+AKR_HD uint32_t shade_class_of(const Material &m) { return m.dynamic ? (uint32_t)CLS_GENERAL : shade_class_of(m.type); }
 
 struct BsdfEval {
     f3 f;

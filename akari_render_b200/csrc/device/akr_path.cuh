@@ -331,7 +331,14 @@ AKR_HD ShadeOut shade_body(const SceneView &sc, const CornerAttribs &ca, const S
         ub12 = sampler_2d(tab, rp, pc.px, pc.py, pc.sample_index, dim0 + 4u);
     }
     const TriShade &ts = sc.shade[hit.gid];
-    const Material &mat = sc.materials[ts.mat];
+    const Material *matp = &sc.materials[ts.mat];
+    Material dyn;
+    if ((CLS == CLS_GENERAL || CLS == CLS_ANY) && matp->dynamic) {  // texture-driven inputs: the reference's per-dispatch evaluation (eval.rs:364-380)
+        dyn = *matp;
+        svm_eval<false, false>(sc.svm, matp->shader_kind, matp->data_offset, hit_uv(sc, hit.gid, hit.u, hit.v, false), dyn, nullptr);
+        matp = &dyn;
+    }
+    const Material &mat = *matp;
     Surface si = surface_from_hit(sc, ca, hit.gid, hit.u, hit.v);
     f3 wo = -ps.d;
     // handle_surface_light (pt.rs:230-258)
@@ -557,7 +564,14 @@ AKR_HD BounceOut bounce_fused(const SceneView &sc, const CornerAttribs &ca, cons
 AKR_HD f3 aov_body(const SceneView &sc, const CornerAttribs &ca, const SamplerTables &tab, const RenderParams &rp, const WaveInfo &wave, uint32_t aov,
                    bool remap, uint32_t path_id, f3 d, HitRec hit) {
     const TriShade &ts = sc.shade[hit.gid];
-    const Material &mat = sc.materials[ts.mat];
+    const Material *matp = &sc.materials[ts.mat];
+    Material dyn;
+    if (matp->dynamic) {
+        dyn = *matp;
+        svm_eval<false, false>(sc.svm, matp->shader_kind, matp->data_offset, hit_uv(sc, hit.gid, hit.u, hit.v, false), dyn, nullptr);
+        matp = &dyn;
+    }
+    const Material &mat = *matp;
     const Surface si = surface_from_hit(sc, ca, hit.gid, hit.u, hit.v);
     const f3 wo = -d;
     f3 v;

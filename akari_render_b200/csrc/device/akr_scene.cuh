@@ -9,7 +9,7 @@
 // shared memory by a TMA bulk copy at kernel start; larger scenes keep the top of the BVH in shared
 // memory and the rest in L2.
 #pragma once
-#include "akr_bsdf.cuh"
+#include "akr_svm.cuh"
 
 namespace akr {
 
@@ -152,6 +152,8 @@ struct SceneView {
     const float *alias_t;
     const float *alias_pdf;
     const float *albedo_table; // 16^3
+    SvmView svm;               // shader programs + constants + textures (texture-driven materials and alpha tests only)
+    const float *corner_uvs;   // [n_tris * 3][2] per-corner texture coordinates, or nullptr when no material needs them
     uint32_t n_nodes, n_prims, n_tris, n_instances, n_materials, n_lights;
     uint32_t any_alpha;        // some material has alpha < 1
     CameraRec camera;

@@ -50,11 +50,28 @@ AKR_HD bool box_test(const float *lo, const float *hi, f3 o, f3 inv_d, float t_m
     return tn <= tf;
 }
 
-// scene.rs:49-86 for constant-alpha materials: pass if alpha >= 1 or alpha > hash / 2^32
+// Texture coordinates of a hit (mesh.rs:534-546): interpolated per-corner uvs, or the default corners (0,0), (1,0), (1,0.1).
+// `for_alpha_test`: the default third corner is (0, 0.1) in surface_interaction_for_alpha_test (mesh.rs:456-467) — preserved.
+AKR_HD f2 hit_uv(const SceneView &sc, uint32_t gid, float u, float v, bool for_alpha_test) {
+    float a[2] = {0.0f, 0.0f}, b[2] = {1.0f, 0.0f}, c[2] = {for_alpha_test ? 0.0f : 1.0f, 0.1f};
+    if ((sc.shade[gid].flags & TRI_HAS_UVS) && sc.corner_uvs) {
+        const float *p = sc.corner_uvs + (size_t)gid * 6u;
+        a[0] = p[0]; a[1] = p[1]; b[0] = p[2]; b[1] = p[3]; c[0] = p[4]; c[1] = p[5];
+    }
+    const float w = 1.0f - u - v;
+    return f2{w * a[0] + u * b[0] + v * c[0], w * a[1] + u * b[1] + v * c[1]};
+}
+// scene.rs:49-86: pass if alpha >= 1 or alpha > hash / 2^32; alpha = Surface::alpha() of the material in SvmEvalMode::Alpha
 AKR_HD bool alpha_test(const SceneView &sc, uint32_t gid, float u, float v) {
     const TriShade &ts = sc.shade[gid];
     if (!(ts.flags & TRI_ALPHA)) return true;
-    float alpha = sc.materials[ts.mat].alpha;
+    const Material &mat = sc.materials[ts.mat];
+    float alpha = mat.alpha;
+    if (mat.dynamic) {
+        Material tmp;
+        svm_eval<true, false>(sc.svm, mat.shader_kind, mat.data_offset, hit_uv(sc, gid, u, v, true), tmp, nullptr);
+        alpha = tmp.alpha;
+    }
     uint32_t h = xxhash32_4(ts.inst, ts.prim, f2u(u), f2u(v));
     float hf = (float)h * (float)(1.0 / 4294967295.0);
     return (alpha >= 1.0f) || (alpha > hf);

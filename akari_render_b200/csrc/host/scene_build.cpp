@@ -15,225 +15,24 @@ namespace akr {
 namespace {
 
 // ---------------------------------------------------------------------------------------------
-// SVM constant folding (svm/eval.rs:97-269 for the constant node set)
+// SVM: every material's node program is evaluated once here with the evaluator the kernels use (akr_svm.cuh).  A
+// program without hit-dependent nodes folds to constants; a texture-driven one keeps its ShaderRef for per-hit evaluation.
 // ---------------------------------------------------------------------------------------------
-struct Val {
-    enum K { None, F, F3, F4, ColorAlpha, Closure } k = None;
-    float f = 0.0f;
-    float v[4] = {0, 0, 0, 0};
-};
-
-float as_float(const Val &v) { return v.k == Val::F ? v.f : v.v[0]; }  // eval_float_auto_convert (eval.rs:327-343)
-void as_float3(const Val &v, float out[3]) {                             // eval_float3_auto_convert (eval.rs:311-326)
-    if (v.k == Val::F3 || v.k == Val::F4) {
-        out[0] = v.v[0];
-        out[1] = v.v[1];
-        out[2] = v.v[2];
-    } else {
-        out[0] = v.f;
-        out[1] = 0.0f;
-        out[2] = 0.0f;
-    }
-}
-
-// Gulbrandsen parametrisation (svm/surface/mod.rs:1040-1052), per channel
-void artistic_to_conductor(float c, float g, float &n, float &k) {
-    float r = std::fmin(std::fmax(c, 0.0f), 0.99f);
-    float r_sqrt = std::sqrt(r);
-    float n_min = (1.0f - r) / (1.0f + r);
-    float n_max = (1.0f + r_sqrt) / (1.0f - r_sqrt);
-    n = g * (n_min - n_max) + n_max;  // n_max.lerp(n_min, g)
-    float k2 = ((n + 1.0f) * (n + 1.0f) * r - (n - 1.0f) * (n - 1.0f)) / (1.0f - r);
-    k2 = std::fmax(k2, 0.0f);
-    k = std::sqrt(k2);
-}
-float ior_from_f0(float f0) {  // mod.rs:1090-1094
-    float s = std::sqrt(std::fmin(std::fmax(f0, 0.0f), 0.99f));
-    return (1.0f + s) / (1.0f - s);
-}
-float f0_from_ior(float ior) {  // mod.rs:1095-1098
-    float f = (ior - 1.0f) / (ior + 1.0f);
-    return f * f;
-}
-
-int fold_material(const AkrSceneDesc &d, AkrShaderRef ref, Material &m, std::string &err) {
-    if (ref.shader_kind >= d.n_shader_kinds) {
-        err = "shader_kind out of range";
+int fold_material(const SvmView &svm, AkrShaderRef ref, Material &m, std::string &err) {
+    std::memset(&m, 0, sizeof(m));
+    bool dynamic = false;
+    int rc = svm_eval<false, true>(svm, ref.shader_kind, ref.data_offset, f2{0.0f, 0.0f}, m, &dynamic);
+    if (rc == SVM_BAD_PROGRAM) {
+        err = "malformed shader program (kind / constant offset / node reference / input type out of range)";
         return AKR_ERR_INVALID_ARGUMENT;
     }
-    const AkrShaderKind &kind = d.shader_kinds[ref.shader_kind];
-    if (kind.n_nodes == 0 || kind.n_nodes > 256) {
-        err = "shader kind has an unsupported node count";
+    if (rc != SVM_OK) {
+        err = "shader uses an SVM op or colour space outside the implemented scope, or has more than 64 nodes";
         return AKR_ERR_UNSUPPORTED;
     }
-    std::vector<Val> vals(kind.n_nodes);
-    auto rd = [&](uint32_t off, float &dst) -> bool {
-        size_t o = static_cast<size_t>(ref.data_offset) + off;
-        if (o + 4 > d.shader_data_size) return false;
-        std::memcpy(&dst, d.shader_data + o, 4);
-        return true;
-    };
-    std::memset(&m, 0, sizeof(m));
-    m.alpha = 1.0f;
-    m.type = MAT_EMISSION;
-    bool have_closure = false;
-    for (uint32_t i = 0; i < kind.n_nodes; ++i) {
-        const AkrSvmNode &n = kind.nodes[i];
-        for (uint32_t k = 0; k < n.n_args; ++k) {
-            bool is_ref = !(n.op == AKR_SVM_FLOAT || n.op == AKR_SVM_FLOAT3 || (n.op == AKR_SVM_RGB_TEX && k == 1));
-            if (is_ref && n.a[k] >= i) {
-                err = "SVM node refers to a later node";
-                return AKR_ERR_INVALID_ARGUMENT;
-            }
-        }
-        Val &r = vals[i];
-        switch (n.op) {
-        case AKR_SVM_FLOAT:
-            r.k = Val::F;
-            if (!rd(n.a[0], r.f)) {
-                err = "constant offset out of range";
-                return AKR_ERR_INVALID_ARGUMENT;
-            }
-            break;
-        case AKR_SVM_FLOAT3:
-            r.k = Val::F3;
-            if (!rd(n.a[0], r.v[0]) || !rd(n.a[0] + 4, r.v[1]) || !rd(n.a[0] + 8, r.v[2])) {
-                err = "constant offset out of range";
-                return AKR_ERR_INVALID_ARGUMENT;
-            }
-            break;
-        case AKR_SVM_RGB_TEX:  // eval.rs:127-136; sRGB -> sRGB working space is the identity (texture/mod.rs:9-31)
-            if (n.a[1] != 1u) {
-                err = "rgb node in a non-sRGB colour space is not supported";
-                return AKR_ERR_UNSUPPORTED;
-            }
-            r.k = Val::F4;
-            r.v[0] = vals[n.a[0]].v[0];
-            r.v[1] = vals[n.a[0]].v[1];
-            r.v[2] = vals[n.a[0]].v[2];
-            r.v[3] = 1.0f;
-            break;
-        case AKR_SVM_SPECTRAL_UPLIFT:  // eval.rs:160-180 (RGB pass-through)
-            r.k = Val::ColorAlpha;
-            std::memcpy(r.v, vals[n.a[0]].v, sizeof(r.v));
-            break;
-        case AKR_SVM_DIFFUSE_BSDF: {  // diffuse.rs:82-104
-            const Val &c = vals[n.a[0]];
-            r.k = Val::Closure;
-            m.type = MAT_LAMBERT;
-            m.wrap_inner = 0;
-            for (int c3 = 0; c3 < 3; ++c3) {
-                m.color[c3] = c.v[c3];
-                m.diffuse[c3] = c.v[c3] * AKR_FRAC_1_PI;
-            }
-            m.alpha = c.v[3];
-            have_closure = true;
-            break;
-        }
-        case AKR_SVM_EMISSION: {  // svm/mod.rs:124-133
-            const Val &c = vals[n.a[0]];
-            float s = vals[n.a[1]].f;
-            r.k = Val::Closure;
-            m.type = MAT_EMISSION;
-            for (int c3 = 0; c3 < 3; ++c3) m.emission[c3] = c.v[c3] * s;
-            have_closure = true;
-            break;
-        }
-        case AKR_SVM_GLASS_BSDF: {  // glass.rs:13-45
-            r.k = Val::Closure;
-            m.type = MAT_GLASS;
-            for (int c3 = 0; c3 < 3; ++c3) {
-                m.color[c3] = vals[n.a[0]].v[c3];
-                m.trans_color[c3] = vals[n.a[1]].v[c3];
-            }
-            m.roughness_raw = vals[n.a[2]].f;
-            m.roughness = m.roughness_raw;
-            m.eta = vals[n.a[3]].f;
-            have_closure = true;
-            break;
-        }
-        case AKR_SVM_PRINCIPLED_BSDF: {  // principled.rs:23-49
-            if (n.n_args != 25) {
-                err = "principled node needs 25 inputs";
-                return AKR_ERR_INVALID_ARGUMENT;
-            }
-            r.k = Val::Closure;
-            auto col = [&](uint32_t k, float out[3]) {
-                const Val &c = vals[n.a[k]];
-                out[0] = c.v[0];
-                out[1] = c.v[1];
-                out[2] = c.v[2];
-            };
-            auto flt = [&](uint32_t k) { return as_float(vals[n.a[k]]); };
-            col(AKR_P_BASE_COLOR, m.color);
-            m.alpha = vals[n.a[AKR_P_BASE_COLOR]].v[3];
-            float em[3];
-            col(AKR_P_EMISSION_COLOR, em);
-            float es = flt(AKR_P_EMISSION_STRENGTH);
-            for (int c3 = 0; c3 < 3; ++c3) {
-                m.emission[c3] = em[c3] * es;
-                m.diffuse[c3] = m.color[c3] * AKR_FRAC_1_PI;
-                m.trans_color[c3] = std::sqrt(m.color[c3]);
-            }
-            m.metallic = flt(AKR_P_METALLIC);
-            m.roughness = flt(AKR_P_ROUGHNESS);
-            m.roughness_raw = vals[n.a[AKR_P_ROUGHNESS]].f;
-            m.eta = flt(AKR_P_IOR);
-            m.transmission = flt(AKR_P_TRANSMISSION_WEIGHT);
-            float level = flt(AKR_P_SPECULAR_IOR_LEVEL);
-            col(AKR_P_SPECULAR_TINT, m.spec_tint);
-            // specular layer (principled.rs:55-61)
-            float eta_s = m.eta;
-            float f0 = f0_from_ior(eta_s);
-            if (level != 0.5f) {
-                f0 *= 2.0f * level;
-                eta_s = ior_from_f0(f0);
-            }
-            m.f0 = f0;
-            m.eta_s = eta_s;
-            m.coat_weight = flt(AKR_P_COAT_WEIGHT);
-            m.coat_roughness = flt(AKR_P_COAT_ROUGHNESS);
-            m.coat_ior = flt(AKR_P_COAT_IOR);
-            float tint[3];
-            col(AKR_P_COAT_TINT, tint);
-            for (int c3 = 0; c3 < 3; ++c3) m.coat_scale[c3] = m.coat_weight * (tint[c3] - 1.0f) + 1.0f;  // white.lerp(tint, w)
-            for (int c3 = 0; c3 < 3; ++c3) artistic_to_conductor(m.color[c3], m.spec_tint[c3], m.metal_n[c3], m.metal_k[c3]);
-            float nrm[3];
-            as_float3(vals[n.a[AKR_P_NORMAL]], nrm);
-            m.normal[0] = -nrm[0];
-            m.normal[1] = -nrm[1];
-            m.normal[2] = nrm[2];
-            m.has_normal = (m.normal[0] != 0.0f || m.normal[1] != 0.0f || m.normal[2] != 0.0f) ? 1u : 0u;
-            m.wrap_inner = 1;
-            const float EPS = 1e-4f;  // BsdfMixture::EPS
-            uint32_t lobes = 0;
-            bool spec_zero = (m.f0 == 0.0f) || (m.spec_tint[0] == 0.0f && m.spec_tint[1] == 0.0f && m.spec_tint[2] == 0.0f);
-            if (m.coat_weight != 0.0f) lobes |= LOBE_COAT;
-            if (!spec_zero) lobes |= LOBE_SPECULAR;
-            if (m.metallic < 1.0f - EPS) lobes |= LOBE_BASE;
-            if (m.metallic > EPS) lobes |= LOBE_METAL;
-            if ((lobes & LOBE_BASE) && m.transmission < 1.0f - EPS) lobes |= LOBE_DIFFUSE;
-            if ((lobes & LOBE_BASE) && m.transmission > EPS) lobes |= LOBE_TRANSMISSION;
-            m.lobes = lobes;
-            // exact reductions (see akr_bsdf.cuh header): only when the mix fractions are exactly 0 / 1
-            if (!(lobes & LOBE_COAT) && m.metallic == 0.0f && !(lobes & LOBE_SPECULAR) && m.transmission == 0.0f) m.type = MAT_LAMBERT;
-            else if (!(lobes & LOBE_COAT) && m.metallic == 1.0f) m.type = MAT_CONDUCTOR;
-            else m.type = MAT_PRINCIPLED;
-            have_closure = true;
-            break;
-        }
-        case AKR_SVM_MATERIAL_OUTPUT:
-            r.k = Val::Closure;
-            break;
-        default:
-            err = "SVM op " + std::to_string(n.op) + " is outside the implemented hot-path scope";
-            return AKR_ERR_UNSUPPORTED;
-        }
-    }
-    if (!have_closure) {
-        err = "shader has no surface closure";
-        return AKR_ERR_INVALID_ARGUMENT;
-    }
+    m.dynamic = dynamic ? 1u : 0u;
+    m.shader_kind = ref.shader_kind;
+    m.data_offset = ref.data_offset;
     return AKR_OK;
 }
 
@@ -458,6 +257,47 @@ int build_scene_blob(const AkrSceneDesc &d, HostSceneBlob &out, std::string &err
         return AKR_ERR_INVALID_ARGUMENT;
     }
     out = HostSceneBlob{};
+    // ---- shader virtual machine tables ----
+    out.svm_kind_first.push_back(0u);
+    for (uint32_t k = 0; k < d.n_shader_kinds; ++k) {
+        const AkrShaderKind &kind = d.shader_kinds[k];
+        if (kind.n_nodes && !kind.nodes) {
+            err = "shader kind without nodes";
+            return AKR_ERR_INVALID_ARGUMENT;
+        }
+        out.svm_nodes.insert(out.svm_nodes.end(), kind.nodes, kind.nodes + kind.n_nodes);
+        out.svm_kind_first.push_back(static_cast<uint32_t>(out.svm_nodes.size()));
+    }
+    out.svm_data.assign(d.shader_data, d.shader_data + d.shader_data_size);
+    for (uint32_t t = 0; t < d.n_images; ++t) {
+        const AkrImage &img = d.images[t];
+        if (!img.texels || img.width == 0 || img.height == 0 || img.texel_format > AKR_TEXEL_RGBA32F || img.address > AKR_ADDRESS_EDGE || img.filter > AKR_FILTER_LINEAR) {
+            err = "bad image";
+            return AKR_ERR_INVALID_ARGUMENT;
+        }
+        while (out.texels.size() % 16) out.texels.push_back(0);
+        TextureRec tr{};
+        tr.texels = reinterpret_cast<const void *>(out.texels.size());  // byte offset, patched below / by the uploader
+        tr.width = img.width;
+        tr.height = img.height;
+        tr.texel_format = img.texel_format;
+        tr.address = img.address;
+        tr.filter = img.filter;
+        const size_t bytes = static_cast<size_t>(img.width) * img.height * (img.texel_format == AKR_TEXEL_RGBA8 ? 4 : 16);
+        const uint8_t *src = static_cast<const uint8_t *>(img.texels);
+        out.texels.insert(out.texels.end(), src, src + bytes);
+        out.textures.push_back(tr);
+    }
+    std::vector<TextureRec> host_textures = out.textures;
+    for (TextureRec &tr : host_textures) tr.texels = out.texels.data() + reinterpret_cast<size_t>(tr.texels);
+    SvmView svm{};
+    svm.nodes = out.svm_nodes.data();
+    svm.kind_first = out.svm_kind_first.data();
+    svm.data = out.svm_data.data();
+    svm.textures = host_textures.data();
+    svm.n_kinds = d.n_shader_kinds;
+    svm.n_textures = d.n_images;
+    svm.data_size = static_cast<uint32_t>(out.svm_data.size());
     // ---- materials: one record per distinct ShaderRef ----
     std::map<std::pair<uint32_t, uint32_t>, uint32_t> mat_index;
     auto material_of = [&](AkrShaderRef ref, uint32_t &idx) -> int {
@@ -468,7 +308,8 @@ int build_scene_blob(const AkrSceneDesc &d, HostSceneBlob &out, std::string &err
             return AKR_OK;
         }
         Material m;
-        int rc = fold_material(d, ref, m, err);
+        int rc = fold_material(svm, ref, m, err);
+        if (rc == AKR_OK && m.dynamic) out.any_dynamic = 1;
         if (rc != AKR_OK) return rc;
         idx = static_cast<uint32_t>(out.materials.size());
         out.materials.push_back(m);
@@ -494,6 +335,14 @@ int build_scene_blob(const AkrSceneDesc &d, HostSceneBlob &out, std::string &err
         return AKR_ERR_INVALID_ARGUMENT;
     }
     out.shade.resize(total_tris);
+    for (uint32_t i = 0; i < d.n_instances; ++i)  // every material is evaluated up front: per-corner uvs are kept only for texture-driven ones
+        for (uint32_t k = 0; k < d.instances[i].n_materials; ++k) {
+            uint32_t idx;
+            int rc = material_of(d.instances[i].materials[k], idx);
+            if (rc != AKR_OK) return rc;
+        }
+    out.textures_host = host_textures;
+    if (out.any_dynamic) out.corner_uvs.assign(static_cast<size_t>(total_tris) * 6, 0.0f);
     if (any_normals) out.corner_normals.assign(static_cast<size_t>(total_tris) * 9, 0.0f);
     if (any_tangents) out.corner_tangents.assign(static_cast<size_t>(total_tris) * 9, 0.0f);
     std::vector<float> world(static_cast<size_t>(total_tris) * 9);  // v0,v1,v2 world per gid
@@ -602,7 +451,7 @@ int build_scene_blob(const AkrSceneDesc &d, HostSceneBlob &out, std::string &err
             if (g.normals) flags |= TRI_HAS_NORMALS;
             if (g.tangents) flags |= TRI_HAS_TANGENTS;
             if (g.uvs) flags |= TRI_HAS_UVS;
-            if (!(out.materials[ts.mat].alpha >= 1.0f)) {
+            if (!(out.materials[ts.mat].alpha >= 1.0f) || out.materials[ts.mat].dynamic) {  // (a texture-driven alpha is only known per hit)
                 flags |= TRI_ALPHA;
                 out.any_alpha = 1;
             }
@@ -617,6 +466,7 @@ int build_scene_blob(const AkrSceneDesc &d, HostSceneBlob &out, std::string &err
                 st3(ts.ft, tt);  // world dp/du tangent
                 st3(ts.fs, tt);  // fallback when the tangent buffer holds non-finite values
             }
+            if (g.uvs && !out.corner_uvs.empty()) std::memcpy(out.corner_uvs.data() + static_cast<size_t>(gid) * 6, g.uvs + static_cast<size_t>(p) * 6, 24);
             if (g.normals) std::memcpy(out.corner_normals.data() + static_cast<size_t>(gid) * 9, g.normals + static_cast<size_t>(p) * 9, 36);
             if (g.tangents) std::memcpy(out.corner_tangents.data() + static_cast<size_t>(gid) * 9, g.tangents + static_cast<size_t>(p) * 9, 36);
             // world-space vertices for traversal
@@ -826,7 +676,7 @@ int build_scene_blob(const AkrSceneDesc &d, HostSceneBlob &out, std::string &err
         st3(tg.v0, w0);
         st3(tg.e1, w1 - w0);
         st3(tg.e2, w2 - w0);
-        tg.cls = shade_class_of(out.materials[out.shade[gid].mat].type);
+        tg.cls = shade_class_of(out.materials[out.shade[gid].mat]);
     };
     for (uint32_t k = 0; k < n_prims; ++k) {
         const HostPrim &hp = hprims[btris[k].index];
@@ -864,8 +714,8 @@ int build_scene_blob(const AkrSceneDesc &d, HostSceneBlob &out, std::string &err
             pr.r0[3] = static_cast<float>(r0w);
             pr.r1[3] = static_cast<float>(r1w);
         }
-        uint32_t cls_a = shade_class_of(out.materials[out.shade[hp.gid_a].mat].type);
-        uint32_t cls_b = hp.gid_b == 0xffffffffu ? 0u : shade_class_of(out.materials[out.shade[hp.gid_b].mat].type);
+        uint32_t cls_a = shade_class_of(out.materials[out.shade[hp.gid_a].mat]);
+        uint32_t cls_b = hp.gid_b == 0xffffffffu ? 0u : shade_class_of(out.materials[out.shade[hp.gid_b].mat]);
         uint32_t light_a = (out.shade[hp.gid_a].flags & TRI_IS_LIGHT) ? 1u : 0u;
         uint32_t light_b = (hp.gid_b != 0xffffffffu && (out.shade[hp.gid_b].flags & TRI_IS_LIGHT)) ? 1u : 0u;
         pr.meta = hp.iu_a | (hp.iv_a << 2) | (hp.iu_b << 4) | (hp.iv_b << 6) | (cls_a << 8) | (cls_b << 10) | (light_a << 12) | (light_b << 13);
@@ -1103,6 +953,14 @@ SceneView host_scene_view(const HostSceneBlob &b, const float *albedo_table) {
     v.alias_t = b.alias_t.data();
     v.alias_pdf = b.alias_pdf.data();
     v.albedo_table = albedo_table;
+    v.svm.nodes = b.svm_nodes.data();
+    v.svm.kind_first = b.svm_kind_first.data();
+    v.svm.data = b.svm_data.data();
+    v.svm.textures = b.textures_host.empty() ? nullptr : b.textures_host.data();
+    v.svm.n_kinds = static_cast<uint32_t>(b.svm_kind_first.size() - 1);
+    v.svm.n_textures = static_cast<uint32_t>(b.textures_host.size());
+    v.svm.data_size = static_cast<uint32_t>(b.svm_data.size());
+    v.corner_uvs = b.corner_uvs.empty() ? nullptr : b.corner_uvs.data();
     v.n_nodes = static_cast<uint32_t>(b.nodes.size());
     v.n_prims = static_cast<uint32_t>(b.prims.size());
     v.n_tris = static_cast<uint32_t>(b.shade.size());

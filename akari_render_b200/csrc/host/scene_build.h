@@ -34,6 +34,15 @@ struct HostSceneBlob {
     std::vector<float> alias_t, alias_pdf;
     std::vector<float> corner_normals;   // [n_tris * 9] or empty
     std::vector<float> corner_tangents;  // [n_tris * 9] or empty
+    std::vector<float> corner_uvs;       // [n_tris * 6] or empty (only when a texture-driven material exists)
+    // shader virtual machine tables (akr_svm.cuh): programs of every kind, constant blob, textures
+    std::vector<AkrSvmNode> svm_nodes;
+    std::vector<uint32_t> svm_kind_first;
+    std::vector<uint8_t> svm_data;
+    std::vector<TextureRec> textures;    // .texels = byte offset into `texels` (patched to a pointer by whoever owns the copy)
+    std::vector<uint8_t> texels;
+    std::vector<TextureRec> textures_host;  // the same records with .texels pointing into `texels` (host-side evaluation)
+    uint32_t any_dynamic = 0;            // some material is texture-driven
     CameraRec camera{};
     uint32_t any_alpha = 0;
     uint32_t bvh_depth = 0;

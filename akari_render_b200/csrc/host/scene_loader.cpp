@@ -9,8 +9,12 @@
 #include "../../../include/akari_b200_host.h"
 #include "json.hpp"
 
+#include <zlib.h>
+
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
+#include <functional>
 #include <cstring>
 #include <fstream>
 #include <map>
@@ -201,9 +205,141 @@ bool same_bytecode(const std::vector<AkrSvmNode> &a, const std::vector<AkrSvmNod
     return true;
 }
 
+// (image, sampler) -> texture index: what SceneLoader::preload collects into the bindless heap (load.rs:494-529,611-646)
+using ImageResolver = std::function<uint32_t(const akr::json::Value &image)>;
+
+// ---- image decoding (load.rs:550-610) ---------------------------------------------------------------------------------
+// raw float: width * height * channels f32, missing channels filled with 0 (alpha: 1), NOT flipped (load.rs:556-588);
+// png: decoded, flipped vertically, converted to RGBA8 (load.rs:590-603).  jpeg / tiff / dds / exr need decoders this host
+// does not carry (the Rust host uses the `image` crate): rejected with AKR_ERR_UNSUPPORTED.
+uint8_t paeth(uint8_t a, uint8_t b, uint8_t c) {
+    int p = (int)a + (int)b - (int)c, pa = std::abs(p - a), pb = std::abs(p - b), pc = std::abs(p - c);
+    return (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
+}
+uint32_t be32(const uint8_t *p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
+void decode_png(const uint8_t *data, size_t len, uint32_t &width, uint32_t &height, std::vector<uint8_t> &rgba8) {
+    static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+    if (len < 8 || std::memcmp(data, sig, 8) != 0) throw std::runtime_error("png: bad signature");
+    size_t pos = 8;
+    uint32_t bit_depth = 0, color_type = 0, interlace = 0;
+    std::vector<uint8_t> idat, palette, trns;
+    bool have_ihdr = false;
+    while (pos + 12 <= len) {
+        const uint32_t clen = be32(data + pos);
+        const std::string type(reinterpret_cast<const char *>(data + pos + 4), 4);
+        if (pos + 12 + clen > len) throw std::runtime_error("png: truncated chunk");
+        const uint8_t *body = data + pos + 8;
+        if (type == "IHDR") {
+            width = be32(body);
+            height = be32(body + 4);
+            bit_depth = body[8];
+            color_type = body[9];
+            interlace = body[12];
+            have_ihdr = true;
+        } else if (type == "PLTE") {
+            palette.assign(body, body + clen);
+        } else if (type == "tRNS") {
+            trns.assign(body, body + clen);
+        } else if (type == "IDAT") {
+            idat.insert(idat.end(), body, body + clen);
+        } else if (type == "IEND") {
+            break;
+        }
+        pos += 12 + clen;
+    }
+    if (!have_ihdr || width == 0 || height == 0) throw std::runtime_error("png: no IHDR");
+    if (interlace != 0) throw std::runtime_error("png: interlaced images are not supported");
+    if (bit_depth != 8 && bit_depth != 16) throw std::runtime_error("png: only 8 / 16 bits per channel are supported");
+    uint32_t ch;
+    switch (color_type) {
+    case 0: ch = 1; break;
+    case 2: ch = 3; break;
+    case 3: ch = 1; break;
+    case 4: ch = 2; break;
+    case 6: ch = 4; break;
+    default: throw std::runtime_error("png: bad colour type");
+    }
+    if (color_type == 3 && bit_depth != 8) throw std::runtime_error("png: palette images must be 8 bit");
+    const size_t bpp = (size_t)ch * bit_depth / 8, stride = (size_t)width * bpp;
+    std::vector<uint8_t> raw((stride + 1) * height);
+    uLongf out_len = static_cast<uLongf>(raw.size());
+    if (uncompress(raw.data(), &out_len, idat.data(), static_cast<uLong>(idat.size())) != Z_OK || out_len != raw.size())
+        throw std::runtime_error("png: inflate failed");
+    std::vector<uint8_t> img(stride * height);
+    for (uint32_t y = 0; y < height; ++y) {
+        const uint8_t filter = raw[y * (stride + 1)];
+        const uint8_t *src = raw.data() + y * (stride + 1) + 1;
+        uint8_t *dst = img.data() + y * stride;
+        const uint8_t *up = y ? dst - stride : nullptr;
+        for (size_t x = 0; x < stride; ++x) {
+            const uint8_t a = x >= bpp ? dst[x - bpp] : 0, b = up ? up[x] : 0, c = (up && x >= bpp) ? up[x - bpp] : 0;
+            uint8_t v = src[x];
+            switch (filter) {
+            case 0: break;
+            case 1: v = static_cast<uint8_t>(v + a); break;
+            case 2: v = static_cast<uint8_t>(v + b); break;
+            case 3: v = static_cast<uint8_t>(v + ((a + b) >> 1)); break;
+            case 4: v = static_cast<uint8_t>(v + paeth(a, b, c)); break;
+            default: throw std::runtime_error("png: bad filter type");
+            }
+            dst[x] = v;
+        }
+    }
+    rgba8.resize((size_t)width * height * 4);
+    for (uint32_t y = 0; y < height; ++y) {
+        const uint32_t fy = height - 1 - y;  // DynamicImage::flipv (load.rs:590)
+        for (uint32_t x = 0; x < width; ++x) {
+            const uint8_t *px = img.data() + y * stride + x * bpp;
+            auto sample = [&](uint32_t c) -> uint8_t { return bit_depth == 8 ? px[c] : px[2 * c]; };  // 16 -> 8 bit: high byte (to_rgba8)
+            uint8_t r, g, b, a = 255;
+            if (color_type == 3) {
+                const uint32_t i = px[0];
+                if (3 * i + 2 >= palette.size()) throw std::runtime_error("png: palette index out of range");
+                r = palette[3 * i];
+                g = palette[3 * i + 1];
+                b = palette[3 * i + 2];
+                if (i < trns.size()) a = trns[i];
+            } else if (ch <= 2) {
+                r = g = b = sample(0);
+                if (ch == 2) a = sample(1);
+            } else {
+                r = sample(0);
+                g = sample(1);
+                b = sample(2);
+                if (ch == 4) a = sample(3);
+            }
+            uint8_t *o = rgba8.data() + ((size_t)fy * width + x) * 4;
+            o[0] = r; o[1] = g; o[2] = b; o[3] = a;
+        }
+    }
+}
+void decode_image(const std::string &format, const uint8_t *bytes, size_t len, uint32_t width, uint32_t height, uint32_t channels, AkrImage &img,
+                  std::vector<uint8_t> &texels) {
+    if (channels == 0 || channels > 4) throw std::runtime_error("Invalid number of channels: " + std::to_string(channels));
+    if (format == "float") {
+        if (len != (size_t)width * height * channels * 4) throw std::runtime_error("float image: buffer length does not match width * height * channels * 4");
+        img.texel_format = AKR_TEXEL_RGBA32F;
+        img.width = width;
+        img.height = height;
+        std::vector<float> rgba((size_t)width * height * 4);
+        const float *src = reinterpret_cast<const float *>(bytes);
+        std::vector<float> tmp((size_t)width * height * channels);
+        std::memcpy(tmp.data(), src, len);
+        for (size_t i = 0; i < (size_t)width * height; ++i)
+            for (uint32_t c = 0; c < 4; ++c) rgba[i * 4 + c] = c < channels ? tmp[i * channels + c] : (c == 3 ? 1.0f : 0.0f);
+        texels.resize(rgba.size() * 4);
+        std::memcpy(texels.data(), rgba.data(), texels.size());
+    } else if (format == "png") {
+        img.texel_format = AKR_TEXEL_RGBA8;
+        decode_png(bytes, len, img.width, img.height, texels);
+    } else {
+        throw std::runtime_error("image format '" + format + "' needs a decoder this host does not carry (png and raw float are implemented)");
+    }
+}
+
 class ShaderCompiler {
   public:
-    explicit ShaderCompiler(const akr::json::Value &graph) : graph_(graph), nodes_(graph.at("nodes")) {}
+    ShaderCompiler(const akr::json::Value &graph, ImageResolver images) : graph_(graph), nodes_(graph.at("nodes")), images_(std::move(images)) {}
     CompiledShader compile() {
         const std::string &kind = graph_.at("kind").string();
         if (kind != "surface") throw std::runtime_error("shader kind '" + kind + "' is not supported (compiler.rs:277-286)");
@@ -217,6 +353,7 @@ class ShaderCompiler {
   private:
     const akr::json::Value &graph_;
     const akr::json::Value &nodes_;
+    ImageResolver images_;
     std::map<std::string, uint32_t> env_;
     std::vector<AkrSvmNode> bytecode_;
     std::vector<uint8_t> data_;
@@ -229,6 +366,11 @@ class ShaderCompiler {
         return static_cast<uint32_t>(off);
     }
     uint32_t push_f32(float v) { return push_bytes(&v, 4, 4); }
+    uint32_t push_u32(uint32_t v) { return push_bytes(&v, 4, 4); }
+    uint32_t opt_ref(const akr::json::Value &node, const char *field) {
+        if (!node.has(field) || node.at(field).is_null()) return AKR_SVM_NONE;
+        return ref(node, field);
+    }
     uint32_t push_float3(const float v[3]) {
         // luisa Float3: 16-byte size and alignment; the pad lane is zero.
         float q[4] = {v[0], v[1], v[2], 0.0f};
@@ -295,10 +437,56 @@ class ShaderCompiler {
             idx = static_cast<uint32_t>(bytecode_.size() - 1);
         } else if (type == "output") {
             idx = push(AKR_SVM_MATERIAL_OUTPUT, {ref(node, "node")});
+        } else if (type == "image") {  // compiler.rs:135-160
+            const akr::json::Value &image = node.at("image");
+            const std::string &cs = image.at("colorspace").string();
+            uint32_t cs_id;
+            if (cs == "none") cs_id = 0;  // ColorSpaceId::NONE: no gamma decode
+            else if (cs == "srgb") cs_id = 1;
+            else throw std::runtime_error("image node: colorspace '" + cs + "' is todo!() in the reference (texture/mod.rs:52-58)");
+            uint32_t tex = push_u32(images_(image));
+            uint32_t uv = opt_ref(node, "uv");
+            idx = push(AKR_SVM_RGB_IMAGE_TEX, {tex, cs_id, uv});
+        } else if (type == "texcoords") {
+            idx = push(AKR_SVM_TEX_COORDS, {});
+        } else if (type == "extract") {  // compiler.rs:272-276
+            uint32_t n = ref(node, "node");
+            const std::string &f = node.at("field").string();
+            uint32_t fid;
+            if (f == "uv") fid = AKR_SVM_FIELD_UV;
+            else if (f == "Red") fid = AKR_SVM_FIELD_RED;
+            else if (f == "Green") fid = AKR_SVM_FIELD_GREEN;
+            else if (f == "Blue") fid = AKR_SVM_FIELD_BLUE;
+            else throw std::runtime_error("extract node: unknown field '" + f + "'");
+            idx = push(AKR_SVM_EXTRACT_FIELD, {n, fid});
+        } else if (type == "mapping") {  // compiler.rs:288-304
+            uint32_t v = ref(node, "vector");
+            uint32_t loc = ref(node, "location");
+            uint32_t rot = ref(node, "rotation");
+            uint32_t sc = ref(node, "scale");
+            const std::string &m = node.at("mapping").string();
+            uint32_t ty;
+            if (m == "point") ty = 0;
+            else if (m == "texture") ty = 1;
+            else throw std::runtime_error("mapping node: unknown type '" + m + "'");
+            idx = push(AKR_SVM_MAPPING, {v, ty, loc, rot, sc});
+        } else if (type == "normal_map") {  // compiler.rs:305-317
+            uint32_t nrm = ref(node, "normal");
+            uint32_t st = ref(node, "strength");
+            if (node.at("space").string() != "tangent") throw std::runtime_error("normal_map: only tangent space is implemented in the reference (eval.rs:190-194)");
+            idx = push(AKR_SVM_NORMAL_MAP, {nrm, st});
+        } else if (type == "checkerboard") {  // compiler.rs:318-334
+            uint32_t v = opt_ref(node, "vector");
+            uint32_t sc = ref(node, "scale");
+            uint32_t c1 = ref(node, "color1");
+            uint32_t c2 = ref(node, "color2");
+            idx = push(AKR_SVM_CHECKERBOARD, {v, sc, c1, c2});
+        } else if (type == "separate_color") {  // compiler.rs:335-341
+            if (node.at("mode").string() != "rgb") throw std::runtime_error("separate_color: unknown mode");
+            idx = push(AKR_SVM_SEPARATE_COLOR, {ref(node, "color")});
         } else {
-            // image / checkerboard / mapping / normal_map / texcoords / extract / separate_color are
-            // SURVEY 8(f) rank 2 ("next"); float4 / noise / mix / math are todo!() in the reference.
-            throw std::runtime_error("shader node type '" + type + "' is outside the implemented hot-path scope");
+            // float4 / noise / mix / math / metal / plastic are todo!() (or unreachable) in the reference compiler
+            throw std::runtime_error("shader node type '" + type + "' is todo!() in the reference compiler (svm/compiler.rs:134,161-163,262-266,342)");
         }
         env_[id] = idx;
         return idx;
@@ -323,6 +511,8 @@ struct AkrHostScene {
     std::vector<std::vector<AkrShaderRef>> instance_materials;
     std::vector<AkrInstance> instances;
     std::vector<std::string> instance_names, geometry_names, material_names;
+    std::vector<std::vector<uint8_t>> image_texels;  // decoded RGBA8 / RGBA32F texels, one per (image, sampler) slot
+    std::vector<AkrImage> images;
     AkrSceneDesc desc{};
 
     void refresh_desc() {
@@ -359,6 +549,9 @@ struct AkrHostScene {
         desc.shader_kinds = kinds.data();
         desc.shader_data = shader_data.data();
         desc.shader_data_size = shader_data.size();
+        for (size_t i = 0; i < images.size(); ++i) images[i].texels = image_texels[i].data();
+        desc.images = images.empty() ? nullptr : images.data();
+        desc.n_images = static_cast<uint32_t>(images.size());
     }
 };
 
@@ -446,9 +639,39 @@ void load_scene_impl(const std::string &path, AkrHostScene &hs) {
     }
 
     // ---- materials -> SVM (load.rs:242-253; compiler.rs:25-46) ----
+    // image textures: one slot per distinct (buffer view, format, size, channels, extension, interpolation) (load.rs:611-646)
+    std::map<std::string, uint32_t> image_slots;
+    ImageResolver resolve_image = [&](const Value &image) -> uint32_t {
+        const std::string view_id = image.at("data").at("id").string();
+        const std::string &format = image.at("format").string();
+        const std::string &extension = image.at("extension").string();
+        const std::string &interp = image.at("interpolation").string();
+        const uint32_t width = image.at("width").u32(), height = image.at("height").u32(), channels = image.at("channels").u32();
+        const std::string key = view_id + "|" + format + "|" + extension + "|" + interp + "|" + std::to_string(width) + "x" + std::to_string(height) + "x" +
+                                std::to_string(channels);
+        auto it = image_slots.find(key);
+        if (it != image_slots.end()) return it->second;
+        AkrImage img{};
+        if (extension == "repeat") img.address = AKR_ADDRESS_REPEAT;  // load.rs:684-689
+        else if (extension == "clip") img.address = AKR_ADDRESS_ZERO;
+        else if (extension == "mirror") img.address = AKR_ADDRESS_MIRROR;
+        else if (extension == "extend") img.address = AKR_ADDRESS_EDGE;
+        else throw std::runtime_error("image: unknown extension '" + extension + "'");
+        if (interp == "nearest") img.filter = AKR_FILTER_POINT;  // load.rs:690-699 (cubic falls back to linear)
+        else if (interp == "linear" || interp == "cubic") img.filter = AKR_FILTER_LINEAR;
+        else throw std::runtime_error("image: unknown interpolation '" + interp + "'");
+        auto [bytes, len] = view_bytes(image.at("data"), 1, "image data");
+        std::vector<uint8_t> texels;
+        decode_image(format, bytes, len, width, height, channels, img, texels);
+        const uint32_t slot = static_cast<uint32_t>(hs.images.size());
+        hs.images.push_back(img);
+        hs.image_texels.push_back(std::move(texels));
+        image_slots[key] = slot;
+        return slot;
+    };
     std::map<std::string, AkrShaderRef> mat_refs;
     for (const auto &[name, mat] : root.at("materials").object()) {
-        CompiledShader cs = ShaderCompiler(mat.at("shader")).compile();
+        CompiledShader cs = ShaderCompiler(mat.at("shader"), resolve_image).compile();
         uint32_t kind = UINT32_MAX;
         for (size_t k = 0; k < hs.kind_nodes.size(); ++k)
             if (same_bytecode(hs.kind_nodes[k], cs.nodes)) {

@@ -59,8 +59,21 @@ enum {
     AKR_SVM_DIFFUSE_BSDF = 5,     /* a0 = reflectance node                                 */
     AKR_SVM_GLASS_BSDF = 6,       /* a0 = kr, a1 = kt, a2 = roughness, a3 = eta            */
     AKR_SVM_PRINCIPLED_BSDF = 7,  /* a[0..25) in the field order of SvmPrincipledBsdf      */
-    AKR_SVM_MATERIAL_OUTPUT = 8   /* a0 = surface closure node                             */
+    AKR_SVM_MATERIAL_OUTPUT = 8,  /* a0 = surface closure node                             */
+    /* texture-driven nodes (svm/compiler.rs:135-337, svm/eval.rs:137-269); AKR_SVM_NONE = "input not connected"  */
+    AKR_SVM_RGB_IMAGE_TEX = 9,    /* a0 = const offset (u32 texture index into AkrSceneDesc.images),
+                                   * a1 = colorspace id (0 = none, 1 = sRGB: decode with srgb_to_linear),
+                                   * a2 = uv node or AKR_SVM_NONE (then the hit's uv)                          */
+    AKR_SVM_NORMAL_MAP = 10,      /* a0 = normal node, a1 = strength node (tangent space only)               */
+    AKR_SVM_MAPPING = 11,         /* a0 = vector, a1 = type (0 point, 1 texture), a2 = location, a3 = rotation
+                                   * (ignored, as in the reference), a4 = scale                                */
+    AKR_SVM_EXTRACT_FIELD = 12,   /* a0 = node, a1 = field (AKR_SVM_FIELD_*)                                  */
+    AKR_SVM_TEX_COORDS = 13,      /* the hit's uv; only its field "uv" can be extracted                       */
+    AKR_SVM_CHECKERBOARD = 14,    /* a0 = vector node or AKR_SVM_NONE, a1 = scale, a2 = color1, a3 = color2  */
+    AKR_SVM_SEPARATE_COLOR = 15   /* a0 = color node; fields Red / Green / Blue                               */
 };
+#define AKR_SVM_NONE 0xffffffffu
+enum { AKR_SVM_FIELD_UV = 0, AKR_SVM_FIELD_RED = 1, AKR_SVM_FIELD_GREEN = 2, AKR_SVM_FIELD_BLUE = 3 };
 #define AKR_SVM_MAX_ARGS 25u
 
 /* Field order of a[] for AKR_SVM_PRINCIPLED_BSDF (svm/mod.rs:151-178). */
@@ -121,6 +134,21 @@ typedef struct AkrInstance {
     uint32_t _pad;
 } AkrInstance;
 
+/* ---- image textures (reference: load.rs:536-646,680-702; one entry per (image, sampler) pair = one bindless slot) ------
+ * The host decodes the file formats (png / jpeg / tiff / exr / dds / raw float, load.rs:550-610) and hands over texels:
+ * RGBA8 unorm for the 8-bit formats, RGBA32F for exr / raw float, row 0 first as stored in the texture.             */
+enum { AKR_TEXEL_RGBA8 = 0, AKR_TEXEL_RGBA32F = 1 };
+enum { AKR_ADDRESS_REPEAT = 0, AKR_ADDRESS_ZERO = 1, AKR_ADDRESS_MIRROR = 2, AKR_ADDRESS_EDGE = 3 };   /* load.rs:684-689 */
+enum { AKR_FILTER_POINT = 0, AKR_FILTER_LINEAR = 1 };                                                   /* load.rs:690-699 */
+typedef struct AkrImage {
+    const void *texels;             /* [height][width][4] u8 or f32                                */
+    uint32_t width, height;
+    uint32_t texel_format;          /* AKR_TEXEL_*                                                  */
+    uint32_t address;               /* AKR_ADDRESS_*                                                */
+    uint32_t filter;                /* AKR_FILTER_*                                                 */
+    uint32_t _pad;
+} AkrImage;
+
 /* ---- camera (reference: crates/akari_render/src/camera/mod.rs:108-153) ------------------------ */
 typedef struct AkrPerspectiveCamera {
     float c2w[16];                  /* column-major camera-to-world (load.rs:129-171)          */
@@ -143,6 +171,9 @@ typedef struct AkrSceneDesc {
     const uint8_t *shader_data;     /* constant blob, each material's block padded to 16 B      */
     size_t shader_data_size;
     AkrPerspectiveCamera camera;
+    const AkrImage *images;         /* [n_images], indexed by the u32 an AKR_SVM_RGB_IMAGE_TEX node reads */
+    uint32_t n_images;
+    uint32_t _pad;
 } AkrSceneDesc;
 
 /* ---- render configuration -------------------------------------------------------------------

@@ -866,6 +866,7 @@ struct ShaderEval {
     Color emission_only{};
     Color glass_kr{}, glass_kt{};
     float glass_eta = 1.0f, glass_roughness = 0.0f;
+    bool dynamic = false;  // some input depends on the hit (uv / image texture): re-evaluated per dispatch
 };
 struct OInstance {
     float m[16];  // column-major
@@ -877,8 +878,8 @@ struct OInstance {
     AliasTable area_sampler;
     uint32_t tri_offset;
     std::vector<ShaderEval> evals;  // evaluated constants of materials[k] (pure function of the blob)
-    std::vector<float> alphas;      // Surface::alpha() of materials[k] in SvmEvalMode::Alpha
-    bool any_alpha = false;
+    std::vector<float> alphas;      // Surface::alpha() of materials[k] in SvmEvalMode::Alpha (constant shaders)
+    bool any_alpha = false;         // some material has alpha < 1, or an alpha that depends on the hit
 };
 struct WorldTri {
     V3 v0, v1, v2;
@@ -937,7 +938,7 @@ struct Scene {
 
 // ---- SVM evaluation: literal per-dispatch interpretation (svm/eval.rs:97-269,364-380) ----------
 struct SvmValue {
-    enum Kind { None, Float, Float3, Float4, ColorAlpha, Closure } kind = None;
+    enum Kind { None, Float, Float2, Float3, Float4, ColorAlpha, Closure, TexCoords, SeparateColor } kind = None;
     float f = 0.0f;
     float v[4] = {0, 0, 0, 0};  // Float3/Float4 or ColorAlpha (rgb, alpha)
 };
@@ -948,10 +949,77 @@ float val_float_auto(const SvmValue &v) {  // eval_float_auto_convert (eval.rs:3
 }
 V3 val_float3_auto(const SvmValue &v) {  // eval_float3_auto_convert (eval.rs:311-326)
     if (v.kind == SvmValue::Float3 || v.kind == SvmValue::Float4) return v3(v.v[0], v.v[1], v.v[2]);
+    if (v.kind == SvmValue::Float2 || v.kind == SvmValue::TexCoords) return v3(v.v[0], v.v[1], 0.0f);
     return v3(v.f, 0.0f, 0.0f);
 }
+V2 val_float2_auto(const SvmValue &v) {  // eval_float2_auto_convert (eval.rs:296-310)
+    if (v.kind == SvmValue::Float) return V2{v.f, 0.0f};
+    return V2{v.v[0], v.v[1]};
+}
 
-bool eval_shader(const Scene &sc, AkrShaderRef ref, ShaderEval &out, std::string *err) {
+// ---- image textures: ASSUMED (luisa `Tex2d::sample` behind the bindless heap, eval.rs:139-147).  Normalised
+// coordinates, texel centres at (i + 0.5) / size, bilinear weights in f32, the sampler's address mode per texel. ----
+inline int wrap_texel(int i, int n, uint32_t address, bool &zero) {
+    zero = false;
+    if (i >= 0 && i < n) return i;
+    switch (address) {
+    case AKR_ADDRESS_REPEAT: {
+        int m = i % n;
+        return m < 0 ? m + n : m;
+    }
+    case AKR_ADDRESS_MIRROR: {
+        int period = 2 * n;
+        int m = i % period;
+        if (m < 0) m += period;
+        return m < n ? m : period - 1 - m;
+    }
+    case AKR_ADDRESS_EDGE: return i < 0 ? 0 : n - 1;
+    default: zero = true; return 0;
+    }
+}
+inline void fetch_texel(const AkrImage &img, int x, int y, float out[4]) {
+    bool zx, zy;
+    int ix = wrap_texel(x, static_cast<int>(img.width), img.address, zx);
+    int iy = wrap_texel(y, static_cast<int>(img.height), img.address, zy);
+    if (zx || zy) {
+        out[0] = out[1] = out[2] = out[3] = 0.0f;
+        return;
+    }
+    size_t i = (static_cast<size_t>(iy) * img.width + static_cast<size_t>(ix)) * 4;
+    if (img.texel_format == AKR_TEXEL_RGBA8) {
+        const uint8_t *t = static_cast<const uint8_t *>(img.texels) + i;
+        for (int c = 0; c < 4; ++c) out[c] = static_cast<float>(t[c]) / 255.0f;
+    } else {
+        const float *t = static_cast<const float *>(img.texels) + i;
+        for (int c = 0; c < 4; ++c) out[c] = t[c];
+    }
+}
+inline void sample_texture(const AkrImage &img, V2 uv, float out[4]) {
+    float fx = uv.x * static_cast<float>(img.width), fy = uv.y * static_cast<float>(img.height);
+    if (img.filter == AKR_FILTER_POINT) {
+        fetch_texel(img, static_cast<int>(std::floor(fx)), static_cast<int>(std::floor(fy)), out);
+        return;
+    }
+    float x = fx - 0.5f, y = fy - 0.5f;
+    float x0 = std::floor(x), y0 = std::floor(y);
+    float tx = x - x0, ty = y - y0;
+    int ix = static_cast<int>(x0), iy = static_cast<int>(y0);
+    float c00[4], c10[4], c01[4], c11[4];
+    fetch_texel(img, ix, iy, c00);
+    fetch_texel(img, ix + 1, iy, c10);
+    fetch_texel(img, ix, iy + 1, c01);
+    fetch_texel(img, ix + 1, iy + 1, c11);
+    for (int c = 0; c < 4; ++c) {
+        float a = c00[c] * (1.0f - tx) + c10[c] * tx;
+        float b = c01[c] * (1.0f - tx) + c11[c] * tx;
+        out[c] = a * (1.0f - ty) + b * ty;
+    }
+}
+inline float srgb_to_linear1(float s) {  // color.rs:555-558
+    return s <= 0.04045f ? s / 12.92f : std::pow((s + 0.055f) / 1.055f, 2.4f);
+}
+
+bool eval_shader(const Scene &sc, AkrShaderRef ref, V2 si_uv, ShaderEval &out, std::string *err) {
     const AkrSceneDesc &d = *sc.desc;
     if (ref.shader_kind >= d.n_shader_kinds) {
         if (err) *err = "shader kind out of range";
@@ -1060,6 +1128,86 @@ bool eval_shader(const Scene &sc, AkrShaderRef ref, ShaderEval &out, std::string
         case AKR_SVM_MATERIAL_OUTPUT:
             r.kind = SvmValue::Closure;
             break;
+        case AKR_SVM_RGB_IMAGE_TEX: {  // eval.rs:137-157
+            uint32_t tex_idx;
+            std::memcpy(&tex_idx, d.shader_data + ref.data_offset + n.a[0], 4);
+            if (tex_idx >= d.n_images) {
+                if (err) *err = "texture index out of range";
+                return false;
+            }
+            V2 uv = n.a[2] != AKR_SVM_NONE ? val_float2_auto(vals[n.a[2]]) : si_uv;
+            float rgba[4];
+            sample_texture(d.images[tex_idx], uv, rgba);
+            if (n.a[1] != 0)  // rgb_gamma_correction(rgb, sRGB) = srgb_to_linear (texture/mod.rs:52-58)
+                for (int c = 0; c < 3; ++c) rgba[c] = srgb_to_linear1(rgba[c]);
+            r.kind = SvmValue::Float4;
+            for (int c = 0; c < 4; ++c) r.v[c] = rgba[c];
+            out.dynamic = true;
+            break;
+        }
+        case AKR_SVM_NORMAL_MAP: {  // eval.rs:182-196
+            V3 nv = val_float3_auto(vals[n.a[0]]);
+            V3 normal = 2.0f * nv - v3s(1.0f);
+            float strength = val_float_auto(vals[n.a[1]]);
+            if (strength != 1.0f) normal = normal * v3(strength, strength, 1.0f);
+            r.kind = SvmValue::Float3;
+            r.v[0] = normal.x;
+            r.v[1] = normal.y;
+            r.v[2] = normal.z;
+            break;
+        }
+        case AKR_SVM_MAPPING: {  // eval.rs:197-213 (rotation is a todo in the reference)
+            V3 v = val_float3_auto(vals[n.a[0]]);
+            V3 location = val_float3_auto(vals[n.a[2]]);
+            V3 scale = val_float3_auto(vals[n.a[4]]);
+            V3 o = n.a[1] == 0 ? v * scale + location : (v - location) / scale;
+            r.kind = SvmValue::Float3;
+            r.v[0] = o.x;
+            r.v[1] = o.y;
+            r.v[2] = o.z;
+            break;
+        }
+        case AKR_SVM_TEX_COORDS:  // eval.rs:225-232
+            r.kind = SvmValue::TexCoords;
+            r.v[0] = si_uv.x;
+            r.v[1] = si_uv.y;
+            out.dynamic = true;
+            break;
+        case AKR_SVM_SEPARATE_COLOR: {  // eval.rs:249-264
+            V3 c = val_float3_auto(vals[n.a[0]]);
+            r.kind = SvmValue::SeparateColor;
+            r.v[0] = c.x;
+            r.v[1] = c.y;
+            r.v[2] = c.z;
+            break;
+        }
+        case AKR_SVM_EXTRACT_FIELD: {  // eval.rs:214-224
+            const SvmValue &src = vals[n.a[0]];
+            if (src.kind == SvmValue::TexCoords && n.a[1] == AKR_SVM_FIELD_UV) {
+                r.kind = SvmValue::Float2;
+                r.v[0] = src.v[0];
+                r.v[1] = src.v[1];
+            } else if (src.kind == SvmValue::SeparateColor && n.a[1] >= AKR_SVM_FIELD_RED && n.a[1] <= AKR_SVM_FIELD_BLUE) {
+                r.kind = SvmValue::Float;
+                r.f = src.v[n.a[1] - AKR_SVM_FIELD_RED];
+            } else {
+                if (err) *err = "extract: field not found";
+                return false;
+            }
+            break;
+        }
+        case AKR_SVM_CHECKERBOARD: {  // eval.rs:233-248
+            V2 uv = n.a[0] != AKR_SVM_NONE ? val_float2_auto(vals[n.a[0]]) : si_uv;
+            if (n.a[0] == AKR_SVM_NONE) out.dynamic = true;
+            const SvmValue &c1 = vals[n.a[2]];
+            const SvmValue &c2 = vals[n.a[3]];
+            float scale = vals[n.a[1]].f;
+            int px = static_cast<int>(std::floor(uv.x * scale * 2.0f)), py = static_cast<int>(std::floor(uv.y * scale * 2.0f));
+            const SvmValue &pick = ((px + py) % 2 == 0) ? c1 : c2;
+            r.kind = SvmValue::ColorAlpha;
+            for (int c = 0; c < 4; ++c) r.v[c] = pick.v[c];
+            break;
+        }
         default:
             if (err) *err = "unsupported SVM op " + std::to_string(n.op);
             return false;
@@ -1090,7 +1238,10 @@ template <class F> auto with_surface_closure(const Scene &sc, const SurfaceInter
     }
     // SvmEvaluator::eval_shader re-reads the constant blob on every dispatch (eval.rs:364-380); the result
     // is a pure function of (kind, data_offset), evaluated once in prepare_scene with the same code.
-    const ShaderEval &ev = sc.instances[si.inst_id].evals[si.mat_index];
+    const ShaderEval &cached = sc.instances[si.inst_id].evals[si.mat_index];
+    ShaderEval per_hit;
+    if (cached.dynamic) eval_shader(sc, si.surface, si.uv, per_hit, nullptr);  // texture-driven inputs: evaluated at this hit's uv
+    const ShaderEval &ev = cached.dynamic ? per_hit : cached;
     if (ev.out_op == AKR_SVM_DIFFUSE_BSDF) {
         SurfaceClosure<DiffuseBsdf> c{DiffuseBsdf{ev.diffuse_reflectance}, si.frame, si.ng};
         return f(c);
@@ -1309,6 +1460,28 @@ inline bool alpha_test(const Scene &sc, uint32_t inst_id, uint32_t prim_id, V2 b
     const AkrMesh &g = sc.desc->meshes[inst.geom_id];
     uint32_t mat_index = (inst.flags & AKR_MESH_HAS_MULTI_MATERIALS) ? g.material_slots[prim_id] : 0u;
     float alpha = inst.alphas[mat_index];
+    if (inst.evals[mat_index].dynamic) {
+        // surface_interaction_for_alpha_test (mesh.rs:426-485): uv only; NOTE the default third corner is (0, 0.1) here
+        // and (1, 0.1) in surface_interaction (mesh.rs:456-467 vs :541-546) — preserved
+        V2 uv0, uv1, uv2;
+        uint32_t p3 = prim_id * 3;
+        if (g.uvs) {
+            uv0 = {g.uvs[2 * (p3 + 0)], g.uvs[2 * (p3 + 0) + 1]};
+            uv1 = {g.uvs[2 * (p3 + 1)], g.uvs[2 * (p3 + 1) + 1]};
+            uv2 = {g.uvs[2 * (p3 + 2)], g.uvs[2 * (p3 + 2) + 1]};
+        } else {
+            uv0 = {0.0f, 0.0f};
+            uv1 = {1.0f, 0.0f};
+            uv2 = {0.0f, 0.1f};
+        }
+        float w = 1.0f - bary.x - bary.y;
+        V2 uv{w * uv0.x + bary.x * uv1.x + bary.y * uv2.x, w * uv0.y + bary.x * uv1.y + bary.y * uv2.y};
+        ShaderEval ev;
+        eval_shader(sc, inst.materials[mat_index], uv, ev, nullptr);
+        alpha = 1.0f;  // SvmEvalMode::Alpha (principled.rs:15-22, diffuse.rs:85-92); other closures keep Surface::alpha() = 1
+        if (ev.out_op == AKR_SVM_PRINCIPLED_BSDF) alpha = ev.principled.alpha;
+        if (ev.out_op == AKR_SVM_DIFFUSE_BSDF) alpha = ev.diffuse_alpha;
+    }
     uint32_t h = xxhash32_4(inst_id, prim_id, f2u(bary.x), f2u(bary.y));
     float hf = static_cast<float>(h) * static_cast<float>(1.0 / static_cast<double>(UINT32_MAX));
     return (alpha >= 1.0f) || (alpha > hf);
@@ -1386,7 +1559,7 @@ bool prepare_scene(Scene &sc, const AkrSceneDesc *desc, const float *albedo_tabl
         o.alphas.assign(in.n_materials, 1.0f);
         for (uint32_t k = 0; k < in.n_materials; ++k) {
             std::string err;
-            if (!eval_shader(sc, in.materials[k], o.evals[k], &err)) {
+            if (!eval_shader(sc, in.materials[k], V2{0.0f, 0.0f}, o.evals[k], &err)) {
                 sc.error = err;
                 return false;
             }
@@ -1394,7 +1567,7 @@ bool prepare_scene(Scene &sc, const AkrSceneDesc *desc, const float *albedo_tabl
             // the reflectance colour (diffuse.rs:85-92); emission / glass keep Surface::alpha() = 1 (mod.rs:54-56)
             if (o.evals[k].out_op == AKR_SVM_PRINCIPLED_BSDF) o.alphas[k] = o.evals[k].principled.alpha;
             if (o.evals[k].out_op == AKR_SVM_DIFFUSE_BSDF) o.alphas[k] = o.evals[k].diffuse_alpha;
-            if (!(o.alphas[k] >= 1.0f)) o.any_alpha = true;
+            if (!(o.alphas[k] >= 1.0f) || o.evals[k].dynamic) o.any_alpha = true;
         }
     }
     // mesh lights (load.rs:312-415): per-triangle power = mean over 16 samples of max(emission) * area.

@@ -39,7 +39,7 @@ struct HostTracer {  // the Tracer of akr_path.cuh's fused bodies, one ray at a 
         const HitRec h = host_trace<false>(sc, td, o, d, 1e20f, ex0, 0xffffffffu);
         if (h.gid == 0xffffffffu) return t;
         const TriShade &ts = sc.shade[h.gid];
-        return TraceHit{h.gid, shade_class_of(sc.materials[ts.mat].type), (ts.flags & TRI_IS_LIGHT) ? 1u : 0u, h.u, h.v};
+        return TraceHit{h.gid, shade_class_of(sc.materials[ts.mat]), (ts.flags & TRI_IS_LIGHT) ? 1u : 0u, h.u, h.v};
     }
 };
 }  // namespace
@@ -200,7 +200,7 @@ int hostsim_render(const AkrSceneDesc *desc, const AkrPtConfig *cfg, const AkrSa
                     continue;
                 }
                 // bin by shade class like the trace kernel does; each class runs its own specialisation
-                uint32_t cls = rp.force_diffuse ? (uint32_t)CLS_LAMBERT : shade_class_of(sc.materials[sc.shade[hits[i].gid].mat].type);
+                uint32_t cls = rp.force_diffuse ? (uint32_t)CLS_LAMBERT : shade_class_of(sc.materials[sc.shade[hits[i].gid].mat]);
                 ShadeOut o = cls == CLS_LAMBERT     ? shade_body<CLS_LAMBERT>(sc, ca, tab, rp, wave, depth, cur[i], hits[i], av)
                              : cls == CLS_CONDUCTOR ? shade_body<CLS_CONDUCTOR>(sc, ca, tab, rp, wave, depth, cur[i], hits[i], av)
                                                     : shade_body<CLS_GENERAL>(sc, ca, tab, rp, wave, depth, cur[i], hits[i], av);
@@ -309,7 +309,7 @@ int hostsim_bsdf_chi2_tables(const AkrSceneDesc *desc, uint32_t inst, const floa
     if (material_type_out) *material_type_out = m.type;
     const ClosureFrames cf = make_closure_frames(m, frame_identity(), mk3(0.0f, 0.0f, 1.0f));
     const f3 wo = mk3(wo3[0], wo3[1], wo3[2]);
-    const uint32_t cls = shade_class_of(m.type);
+    const uint32_t cls = shade_class_of(m);
     auto sample = [&](float us, float u0, float u1, chi2::Dir &wi) {
         BsdfDir s = cls == CLS_LAMBERT     ? closure_sample_wi<CLS_LAMBERT>(m, albedo_table, cf, wo, us, f2{u0, u1})
                     : cls == CLS_CONDUCTOR ? closure_sample_wi<CLS_CONDUCTOR>(m, albedo_table, cf, wo, us, f2{u0, u1})

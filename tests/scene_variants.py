@@ -240,3 +240,161 @@ def write_furnace(tmp_path, albedo=0.5, emission=1.0, half=2.0):
     path = os.path.join(d, "scene.json")
     json.dump(scene, open(path, "w"))
     return path
+
+
+# ---- texture-driven materials: image textures (raw float + png), mapping, checkerboard, normal map, separate colour, alpha ----
+def _png_bytes(rgba):
+    """Minimal PNG writer (8-bit RGBA, filter type 0..4 cycled per row so that the decoder's un-filtering is exercised)."""
+    import struct
+    import zlib
+    import numpy as np
+    h, w, _ = rgba.shape
+    raw = bytearray()
+    prev = np.zeros((w, 4), np.int32)
+    for y in range(h):
+        cur = rgba[y].astype(np.int32)
+        ft = y % 5
+        left = np.vstack([np.zeros((1, 4), np.int32), cur[:-1]])
+        upleft = np.vstack([np.zeros((1, 4), np.int32), prev[:-1]])
+        if ft == 0:
+            enc = cur
+        elif ft == 1:
+            enc = cur - left
+        elif ft == 2:
+            enc = cur - prev
+        elif ft == 3:
+            enc = cur - ((left + prev) >> 1)
+        else:
+            p = left + prev - upleft
+            pa, pb, pc = np.abs(p - left), np.abs(p - prev), np.abs(p - upleft)
+            pred = np.where((pa <= pb) & (pa <= pc), left, np.where(pb <= pc, prev, upleft))
+            enc = cur - pred
+        raw.append(ft)
+        raw.extend((enc & 0xFF).astype(np.uint8).tobytes())
+        prev = cur
+
+    def chunk(tag, data):
+        c = struct.pack(">I", len(data)) + tag + data
+        return c + struct.pack(">I", zlib.crc32(tag + data) & 0xFFFFFFFF)
+    return b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 6, 0, 0, 0)) + chunk(b"IDAT", zlib.compress(bytes(raw), 6)) + chunk(b"IEND", b"")
+
+
+def write_textured(tmp_path, alpha_cutout=True):
+    """cbox with texture-driven Principled inputs on every wall and both boxes:
+      floor      base colour = raw-float RGBA image (repeat, linear), mesh uvs
+      backWall   base colour = sRGB png through texcoords -> extract(uv) -> mapping(point, scale 3, offset) (mirror, nearest)
+      leftWall   base colour = checkerboard(scale 4) of two rgb colours
+      rightWall  normal = normal_map(raw-float RGB image, strength 0.7), base colour constant
+      shortBox   base colour = png with an alpha channel (0 / 0.5 / 1 patches): stochastic alpha-tested traversal (clip address mode)
+      tallBox    roughness = extract(Red) of separate_color(float image), metallic 1
+    """
+    import numpy as np
+    scene = json.load(open(os.path.join(CBOX_DIR, "scene.json")))
+    blob = bytearray(open(os.path.join(CBOX_DIR, "Scene.bin"), "rb").read())
+    scene["buffers"]["Scene"]["path"] = "Scene.bin"
+    nview = len(scene["buffer_views"])
+
+    def add_view(raw):
+        nonlocal nview
+        while len(blob) % 16:
+            blob.append(0)
+        name = f"buf_view_{nview}"
+        nview += 1
+        scene["buffer_views"][name] = {"buffer": {"id": "Scene"}, "offset": len(blob), "length": len(raw)}
+        blob.extend(raw)
+        return {"id": name}
+
+    rng = np.random.default_rng(7)
+
+    # the fixture's uv buffers are all zero except on the short box: give every mesh a planar per-face parametrisation
+    # (drop the triangle's dominant normal axis, normalise by the mesh bounds) so that textures actually vary
+    def view_array(ref, dtype, cols):
+        v = scene["buffer_views"][ref["id"]]
+        return np.frombuffer(bytes(blob[v["offset"]:v["offset"] + v["length"]]), dtype).reshape(-1, cols)
+    for gname, g in scene["geometries"].items():
+        verts, idx = view_array(g["vertices"], np.float32, 3), view_array(g["indices"], np.uint32, 3)
+        lo, ext = verts.min(axis=0), np.maximum(verts.max(axis=0) - verts.min(axis=0), 1e-6)
+        uvs = np.zeros((len(idx) * 3, 2), np.float32)
+        for t, tri in enumerate(idx):
+            n = np.abs(np.cross(verts[tri[1]] - verts[tri[0]], verts[tri[2]] - verts[tri[0]]))
+            keep = [a for a in range(3) if a != int(np.argmax(n))]
+            for k in range(3):
+                q = (verts[tri[k]] - lo) / ext
+                uvs[3 * t + k] = (q[keep[0]], q[keep[1]])
+        g["uvs"] = add_view(uvs.tobytes())
+
+    def image(arr, fmt, colorspace, extension, interpolation):
+        h, w, c = arr.shape
+        raw = np.ascontiguousarray(arr, np.float32).tobytes() if fmt == "float" else _png_bytes(arr)
+        return {"data": add_view(raw), "format": fmt, "colorspace": colorspace, "extension": extension, "interpolation": interpolation,
+                "width": w, "height": h, "channels": c}
+
+    def graph_of(material):
+        g = scene["materials"][material]["shader"]
+        return g, g["nodes"], _principled_name(g)
+
+    def rgb_const(nodes, name, value):
+        nodes[name + "_rgb"] = {"type": "rgb", "value": list(value), "colorspace": "srgb"}
+        nodes[name] = {"type": "spectral_uplift", "rgb": {"id": name + "_rgb"}}
+        return {"id": name}
+
+    # floor: raw float RGBA (3 channels + alpha 1), bilinear, repeat
+    g, nodes, p = graph_of("floor_001")
+    tex = (0.15 + 0.7 * rng.random((8, 8, 3))).astype(np.float32)
+    nodes["tex"] = {"type": "image", "image": image(tex, "float", "none", "repeat", "linear"), "uv": None}
+    nodes["tex_up"] = {"type": "spectral_uplift", "rgb": {"id": "tex"}}
+    nodes[p]["base_color"] = {"id": "tex_up"}
+    # backWall: sRGB png, nearest, mirror, uv through texcoords -> extract -> mapping
+    g, nodes, p = graph_of("backWall_001")
+    png = (rng.random((16, 12, 4)) * 255).astype(np.uint8)
+    png[..., 3] = 255
+    nodes["tc"] = {"type": "texcoords"}
+    nodes["uv"] = {"type": "extract", "node": {"id": "tc"}, "field": "uv"}
+    nodes["m_loc"] = {"type": "float3", "value": [0.25, -0.4, 0.0]}
+    nodes["m_rot"] = {"type": "float3", "value": [0.0, 0.0, 0.0]}
+    nodes["m_scale"] = {"type": "float3", "value": [3.0, 2.0, 1.0]}
+    nodes["map"] = {"type": "mapping", "vector": {"id": "uv"}, "mapping": "point", "location": {"id": "m_loc"}, "rotation": {"id": "m_rot"},
+                    "scale": {"id": "m_scale"}}
+    nodes["tex"] = {"type": "image", "image": image(png, "png", "srgb", "mirror", "nearest"), "uv": {"id": "map"}}
+    nodes["tex_up"] = {"type": "spectral_uplift", "rgb": {"id": "tex"}}
+    nodes[p]["base_color"] = {"id": "tex_up"}
+    # leftWall: checkerboard
+    g, nodes, p = graph_of("leftWall_001")
+    nodes["cb_scale"] = {"type": "float", "value": 4.0}
+    nodes["cb"] = {"type": "checkerboard", "vector": None, "scale": {"id": "cb_scale"}, "color1": rgb_const(nodes, "cb1", [0.63, 0.065, 0.05]),
+                   "color2": rgb_const(nodes, "cb2", [0.9, 0.9, 0.2])}
+    nodes[p]["base_color"] = {"id": "cb"}
+    # rightWall: normal map from a float image
+    g, nodes, p = graph_of("rightWall_001")
+    nm = np.zeros((6, 6, 3), np.float32)
+    nm[..., 0] = 0.5 + 0.25 * rng.standard_normal((6, 6)).clip(-1, 1)
+    nm[..., 1] = 0.5 + 0.25 * rng.standard_normal((6, 6)).clip(-1, 1)
+    nm[..., 2] = 0.9
+    nodes["nm_tex"] = {"type": "image", "image": image(nm, "float", "none", "extend", "linear"), "uv": None}
+    nodes["nm_strength"] = {"type": "float", "value": 0.7}
+    nodes["nm"] = {"type": "normal_map", "normal": {"id": "nm_tex"}, "strength": {"id": "nm_strength"}, "space": "tangent"}
+    nodes[p]["normal"] = {"id": "nm"}
+    # shortBox: png with alpha patches, clip
+    if alpha_cutout:
+        g, nodes, p = graph_of("shortBox_001")
+        cut = np.zeros((8, 8, 4), np.uint8)
+        cut[..., :3] = (rng.random((8, 8, 3)) * 200 + 40).astype(np.uint8)
+        cut[..., 3] = rng.choice(np.array([0, 128, 255], np.uint8), size=(8, 8))
+        nodes["tex"] = {"type": "image", "image": image(cut, "png", "srgb", "clip", "linear"), "uv": None}
+        nodes["tex_up"] = {"type": "spectral_uplift", "rgb": {"id": "tex"}}
+        nodes[p]["base_color"] = {"id": "tex_up"}
+    # tallBox: roughness from the red channel of a float image
+    g, nodes, p = graph_of("tallBox_001")
+    rough = np.zeros((4, 4, 3), np.float32)
+    rough[..., 0] = 0.1 + 0.5 * rng.random((4, 4))
+    nodes["r_tex"] = {"type": "image", "image": image(rough, "float", "none", "repeat", "linear"), "uv": None}
+    nodes["r_sep"] = {"type": "separate_color", "mode": "rgb", "color": {"id": "r_tex"}}
+    nodes["r_red"] = {"type": "extract", "node": {"id": "r_sep"}, "field": "Red"}
+    nodes[p]["roughness"] = {"id": "r_red"}
+    scene["buffers"]["Scene"]["length"] = len(blob)
+    d = os.path.join(str(tmp_path), "textured_alpha" if alpha_cutout else "textured")
+    os.makedirs(d, exist_ok=True)
+    open(os.path.join(d, "Scene.bin"), "wb").write(bytes(blob))
+    path = os.path.join(d, "scene.json")
+    json.dump(scene, open(path, "w"))
+    return path

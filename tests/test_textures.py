@@ -1,0 +1,177 @@
+"""Texture-driven shading: image textures (raw float + png), texcoords / extract / mapping, checkerboard,
+normal map, separate colour, and the stochastic alpha test of the traversal (scene.rs:49-86) that only texture alpha
+channels can trigger.  CPU: host loader, the kernels' bodies (tests/hostsim, both pipelines) bit for bit against the
+oracle's per-dispatch SVM interpreter.  GPU: the CUDA path against the oracle at the stated tolerance."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+import scene_variants as sv
+from conftest import image_rel_l2, measured, rel_l2_per_pixel
+from test_hostsim_parity import run_hostsim
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+class AkrImage(C.Structure):
+    _fields_ = [("texels", C.c_void_p), ("width", C.c_uint32), ("height", C.c_uint32), ("texel_format", C.c_uint32), ("address", C.c_uint32),
+                ("filter", C.c_uint32), ("_pad", C.c_uint32)]
+
+
+def _images(scene):
+    d = scene.desc.contents
+    arr = C.cast(d.images, C.POINTER(AkrImage))
+    return [arr[i] for i in range(d.n_images)]
+
+
+def test_loader_decodes_png_and_float_images(akr, tmp_path):
+    """png: every filter type, flipped vertically like DynamicImage::flipv (load.rs:590), RGBA8; raw float: channels
+    padded to RGBA with alpha 1, not flipped (load.rs:556-588); sampler modes mapped as load.rs:680-702."""
+    path = sv.write_textured(tmp_path)
+    scene = akr.load_scene(path)
+    sj = json.load(open(path))
+    blob = open(os.path.join(os.path.dirname(path), "Scene.bin"), "rb").read()
+    imgs = _images(scene)
+    assert len(imgs) == 5
+    seen = 0
+    for mat in sj["materials"].values():
+        for node in mat["shader"]["nodes"].values():
+            if node["type"] != "image":
+                continue
+            im = node["image"]
+            v = sj["buffer_views"][im["data"]["id"]]
+            raw = blob[v["offset"]:v["offset"] + v["length"]]
+            match = [g for g in imgs if (g.width, g.height) == (im["width"], im["height"]) and
+                     g.address == {"repeat": 0, "clip": 1, "mirror": 2, "extend": 3}[im["extension"]] and
+                     g.filter == {"nearest": 0, "linear": 1}[im["interpolation"]] and g.texel_format == (1 if im["format"] == "float" else 0)]
+            assert len(match) == 1
+            g = match[0]
+            n = g.width * g.height * 4
+            if im["format"] == "float":
+                got = np.ctypeslib.as_array(C.cast(g.texels, C.POINTER(C.c_float)), (n,)).reshape(g.height, g.width, 4)
+                src = np.frombuffer(raw, np.float32).reshape(im["height"], im["width"], im["channels"])
+                assert np.array_equal(got[..., :im["channels"]], src) and (got[..., 3] == 1.0).all()
+            else:
+                import cv2
+                got = np.ctypeslib.as_array(C.cast(g.texels, C.POINTER(C.c_uint8)), (n,)).reshape(g.height, g.width, 4)
+                ref = cv2.imdecode(np.frombuffer(raw, np.uint8), cv2.IMREAD_UNCHANGED)  # BGRA, independent decoder
+                assert np.array_equal(got, ref[::-1, :, [2, 1, 0, 3]])
+            seen += 1
+    assert seen == 5
+
+
+def test_unsupported_nodes_and_formats_are_rejected(akr, tmp_path):
+    path = sv.write_textured(tmp_path)
+    sj = json.load(open(path))
+    bad = json.loads(json.dumps(sj))
+    bad["materials"]["floor_001"]["shader"]["nodes"]["tex"]["image"]["format"] = "jpeg"
+    p2 = os.path.join(os.path.dirname(path), "bad.json")
+    json.dump(bad, open(p2, "w"))
+    with pytest.raises(akr.AkariError):
+        akr.load_scene(p2)
+    bad = json.loads(json.dumps(sj))
+    bad["materials"]["floor_001"]["shader"]["nodes"]["n"] = {"type": "noise", "dim": 2, "scale": {"id": "cb_scale"}}
+    bad["materials"]["floor_001"]["shader"]["nodes"]["tex"]["uv"] = {"id": "n"}
+    json.dump(bad, open(p2, "w"))
+    with pytest.raises(akr.AkariError):
+        akr.load_scene(p2)
+
+
+@pytest.mark.parametrize("fused", [0, 1], ids=["queued", "fused"])
+@pytest.mark.parametrize("alpha", [True, False], ids=["alpha_cutout", "opaque"])
+def test_textured_scene_hostsim_bitwise(akr, oracle, tables, cbox_task, tmp_path, fused, alpha):
+    lib = C.CDLL(os.path.join(HERE, "hostsim", "libhostsim.so"))
+    lib.hostsim_last_error.restype = C.c_char_p
+    lib.hostsim_set_pipeline(fused)
+    try:
+        w = h = 40
+        scene = akr.load_scene(sv.write_textured(tmp_path, alpha_cutout=alpha)).set_resolution(w, h)
+        task = cbox_task(8)
+        pmj, bn = tables
+        ofilm, ost, ofh = oracle.render(scene.desc, w, h, task.pt, task.sampler, task.filter, pmj, bn, want_first_hits=True)
+        film, fh, st = run_hostsim(lib, scene, task, tables, oracle.albedo_table(), w, h)
+        assert np.array_equal(fh, ofh)
+        assert (st.segments, st.shadow_rays) == (ost.segments, ost.shadow_rays)
+        assert np.array_equal(film, ofilm)
+        # the primitive intersector (what the kernels run).  Opaque variant: the usual per-pixel gate.  Alpha cutout: the
+        # alpha test hashes the BITS of the barycentrics (scene.rs:57-63), which differ in the last place between two
+        # intersectors (as between the reference's own OptiX and Embree back ends), so every stochastic decision is
+        # redrawn: the images agree statistically, not per pixel.
+        lib.hostsim_set_intersector(1)
+        film1, fh1, _ = run_hostsim(lib, scene, task, tables, oracle.albedo_table(), w, h)
+        a, b = akr.Film(film1, w, h).to_rgb(), oracle.resolve(ofilm, w * h).reshape(h, w, 3)
+        if alpha:
+            ma, mb = a.reshape(-1, 3).mean(axis=0), b.reshape(-1, 3).mean(axis=0)
+            assert (np.abs(ma - mb) / mb < 0.05).all(), (ma, mb)
+        else:
+            assert float((rel_l2_per_pixel(a, b) > 1e-3).mean()) <= 2e-2
+    finally:
+        lib.hostsim_set_intersector(0)
+        lib.hostsim_set_pipeline(0)
+
+
+def test_alpha_cutout_changes_the_image_and_stays_unbiased_in_alpha(akr, oracle, tables, cbox_task, tmp_path):
+    """The stochastic alpha test is live: rays pass through the short box in proportion to 1 - alpha."""
+    w = h = 32
+    pmj, bn = tables
+    task = cbox_task(16)
+    a = akr.load_scene(sv.write_textured(tmp_path, alpha_cutout=True)).set_resolution(w, h)
+    b = akr.load_scene(sv.write_textured(tmp_path, alpha_cutout=False)).set_resolution(w, h)
+    fa, sa, ha = oracle.render(a.desc, w, h, task.pt, task.sampler, task.filter, pmj, bn, want_first_hits=True)
+    fb, sb, hb = oracle.render(b.desc, w, h, task.pt, task.sampler, task.filter, pmj, bn, want_first_hits=True)
+    box = 6  # instance id of the short box (BTreeMap order)
+    hits_a, hits_b = int((ha[:, 0] == box).sum()), int((hb[:, 0] == box).sum())
+    assert 0.2 * hits_b < hits_a < 0.9 * hits_b, (hits_a, hits_b)  # alpha patches are 0 / 0.5 / 1 in equal shares
+    assert not np.array_equal(fa, fb)
+
+
+@pytest.mark.gpu
+def test_textured_scene_gpu_parity(akr, oracle, tables, cbox_task, tmp_path):
+    """Opaque textured variant: per-pixel gate against the oracle."""
+    w = h = 128
+    scene = akr.load_scene(sv.write_textured(tmp_path, alpha_cutout=False)).set_resolution(w, h)
+    task = cbox_task(16)
+    pmj, bn = tables
+    pt = akr.PathTracer(0)
+    pt.set_engine_options(aov_mask=1)
+    film = pt.render(scene, task)
+    st = pt.stats()
+    fh = pt.first_hits()
+    pt.close()
+    ofilm, ost, ofh = oracle.render(scene.desc, w, h, task.pt, task.sampler, task.filter, pmj, bn, want_first_hits=True)
+    same = float(((fh[0] == ofh[:, 0]) & (fh[1] == ofh[:, 1])).mean())
+    a, b = film.to_rgb(), oracle.resolve(ofilm, w * h).reshape(h, w, 3)
+    bad = float((rel_l2_per_pixel(a, b) > 1e-3).mean())
+    img = image_rel_l2(a, b)
+    ds = abs(int(st.segments) - int(ost.segments)) / ost.segments
+    measured(f"textured cbox (opaque) 128x128@16: first hits equal {same:.5f} (>= 0.9999); pixels over 1e-3: {bad:.3e} (<= 5e-3); "
+             f"image rel-L2 {img:.3e} (<= 5e-3); segments rel diff {ds:.2e} (<= 1e-3)")
+    assert same >= 0.9999 and bad <= 5e-3 and img <= 5e-3 and ds <= 1e-3
+
+
+@pytest.mark.gpu
+def test_alpha_cutout_gpu_statistical_parity(akr, oracle, tables, cbox_task, tmp_path):
+    """Alpha-cutout variant: the alpha test hashes the bits of the barycentrics, so a different intersector redraws every
+    stochastic decision (see the hostsim test); GPU and oracle must agree in distribution: equal 8x8-block means within
+    4 standard errors, first-hit counts on the cut-out box within 3 %, ray counts within 1 %."""
+    from test_analytic_pins import _equal_means
+    w = h = 96
+    scene = akr.load_scene(sv.write_textured(tmp_path, alpha_cutout=True)).set_resolution(w, h)
+    task = cbox_task(64)
+    pmj, bn = tables
+    pt = akr.PathTracer(0)
+    pt.set_engine_options(aov_mask=1)
+    film = pt.render(scene, task)
+    st = pt.stats()
+    fh = pt.first_hits()
+    pt.close()
+    ofilm, ost, ofh = oracle.render(scene.desc, w, h, task.pt, task.sampler, task.filter, pmj, bn, want_first_hits=True)
+    _equal_means(film.to_rgb(), oracle.resolve(ofilm, w * h).reshape(h, w, 3), "textured cbox (alpha cutout) 96x96@64, GPU vs oracle")
+    box = 6
+    ga, oa = int((fh[0] == box).sum()), int((ofh[:, 0] == box).sum())
+    ds = abs(int(st.segments) - int(ost.segments)) / ost.segments
+    measured(f"alpha cutout: first hits on the cut-out box gpu/oracle {ga}/{oa} (within 10 %), segments rel diff {ds:.2e} (<= 1e-2)")
+    assert abs(ga - oa) <= 0.1 * oa and ds <= 1e-2
