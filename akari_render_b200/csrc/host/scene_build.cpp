@@ -730,11 +730,15 @@ int build_scene_blob(const AkrSceneDesc &d, HostSceneBlob &out, std::string &err
         // ray excludes: such primitives are left out of the any-hit list.
         auto supports_scene = [&](const PrimRec &pr) {
             if (!(pr.n[0] == pr.n[0])) return false;  // degenerate (NaN plane)
-            const double eps = 1e-5 * static_cast<double>(diag);
             bool pos = false, neg = false;
             for (size_t v = 0; v < static_cast<size_t>(total_tris) * 3; ++v) {
                 const float *w = world.data() + v * 3;
-                double dist = static_cast<double>(pr.n[0]) * w[0] + static_cast<double>(pr.n[1]) * w[1] + static_cast<double>(pr.n[2]) * w[2] + pr.n[3];
+                const double t0 = static_cast<double>(pr.n[0]) * w[0], t1 = static_cast<double>(pr.n[1]) * w[1], t2 = static_cast<double>(pr.n[2]) * w[2];
+                const double dist = t0 + t1 + t2 + pr.n[3];
+                // tolerance = a few f32 ulps of the terms of this very evaluation (the plane coefficients are rounded to f32, so
+                // the wall's own vertices do not evaluate to exactly 0); anything that really protrudes past the wall keeps it
+                // in the occluder list
+                const double eps = 16.0 * 1.1920929e-7 * (std::fabs(t0) + std::fabs(t1) + std::fabs(t2) + std::fabs(static_cast<double>(pr.n[3])));
                 pos |= dist > eps;
                 neg |= dist < -eps;
                 if (pos && neg) return false;

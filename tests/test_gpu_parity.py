@@ -95,7 +95,10 @@ def test_material_variants_parity(akr, oracle, tables, cbox_task, tmp_path, vari
     pmj, bn = tables
     film, st = _gpu_film(akr, scene, task)
     ofilm, ost, _ = oracle.render(scene.desc, w, h, task.pt, task.sampler, task.filter, pmj, bn)
-    _gate(film.to_rgb(), oracle.resolve(ofilm, w * h).reshape(h, w, 3), rel_frac=5e-3, img=5e-3, what=f"variant {variant} 96x96@16")
+    # principled_mix: rough dielectric transmission + coat + partial metal make more topology flips per ulp than Lambert walls
+    # (measured on B200: 2.6e-3 of the pixels, image rel-L2 2.1e-4); nodes: measured 4.3e-4 / 1.7e-5
+    frac = 5e-3 if variant == "principled_mix" else 1e-3
+    _gate(film.to_rgb(), oracle.resolve(ofilm, w * h).reshape(h, w, 3), rel_frac=frac, img=1e-3, what=f"variant {variant} 96x96@16")
     assert abs(int(st.segments) - int(ost.segments)) <= 1e-3 * ost.segments
 
 
@@ -112,7 +115,8 @@ def test_config_knobs_parity(akr, oracle, tables, cbox, cbox_task, kw):
     pmj, bn = tables
     film, st = _gpu_film(akr, scene, task)
     ofilm, ost, _ = oracle.render(scene.desc, w, h, task.pt, task.sampler, task.filter, pmj, bn)
-    _gate(film.to_rgb(), oracle.resolve(ofilm, w * h).reshape(h, w, 3), rel_frac=3e-3, img=2e-3, what=f"knob {kw or off} 64x64@16")
+    # 64x64 = 4096 pixels: one flipped path is 2.4e-4 of the pixels; measured worst (indirect_only) 1.7e-3 / image 7.5e-4
+    _gate(film.to_rgb(), oracle.resolve(ofilm, w * h).reshape(h, w, 3), rel_frac=3e-3, img=1.5e-3, what=f"knob {kw or off} 64x64@16")
     assert abs(int(st.segments) - int(ost.segments)) <= 1e-3 * max(1, ost.segments)
     assert abs(int(st.shadow_rays) - int(ost.shadow_rays)) <= 1e-3 * max(1, ost.shadow_rays)
 
@@ -204,7 +208,7 @@ def test_clutter_scene_bvh_mode(akr, oracle, tables, cbox_task, tmp_path):
     pmj, bn = tables
     film, st = _gpu_film(akr, scene, task)
     ofilm, ost, _ = oracle.render(scene.desc, w, h, task.pt, task.sampler, task.filter, pmj, bn)
-    _gate(film.to_rgb(), oracle.resolve(ofilm, w * h).reshape(h, w, 3), rel_frac=1e-2, img=5e-3, what="clutter 64x64@8 (BVH, queued)")
+    _gate(film.to_rgb(), oracle.resolve(ofilm, w * h).reshape(h, w, 3), rel_frac=1e-3, img=1e-3, what="clutter 64x64@8 (BVH, queued)")  # measured 4.9e-4 / 1.1e-4
     assert abs(int(st.segments) - int(ost.segments)) <= 2e-3 * ost.segments
     assert abs(int(st.shadow_rays) - int(ost.shadow_rays)) <= 2e-3 * ost.shadow_rays
 
@@ -241,7 +245,7 @@ def test_error_paths_and_odd_configs(akr, oracle, tables, cbox, cbox_task):
     pmj, bn = tables
     film, st = _gpu_film(akr, scene, odd, wave_size=1024)
     ofilm, ost, _ = oracle.render(scene.desc, 33, 17, odd.pt, odd.sampler, odd.filter, pmj, bn)
-    _gate(film.to_rgb(), oracle.resolve(ofilm, 33 * 17).reshape(17, 33, 3), rel_frac=5e-3, img=2e-3, what="odd config 33x17@5 box filter")
+    _gate(film.to_rgb(), oracle.resolve(ofilm, 33 * 17).reshape(17, 33, 3), rel_frac=2e-3, img=1e-3, what="odd config 33x17@5 box filter")  # 561 pixels: one flip = 1.8e-3; measured 0 / 2.5e-7
     assert st.samples == 33 * 17 * 5
     row, _ = _gpu_film(akr, scene, odd, tile=(16, 17))
     assert np.array_equal(row.data[:3 * 33], film.data[3 * 33 * 16:3 * 33 * 17])
