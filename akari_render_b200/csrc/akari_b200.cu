@@ -833,24 +833,13 @@ constexpr uint32_t kTileBytes = 4u * 32u * 16u;  // one warp tile: 32 records x 
 
 // One bounce of every path whose current hit is of shade class CLS.  Warp w of the grid owns record tiles w, w + W, ...
 // (32 records each); lane 0 starts the TMA bulk copies of the NEXT tile into the warp's other shared-memory buffer
-// before the warp waits for the current one, so the queue reads never sit on the dependent chain.
-template <int CLS> __global__ void __launch_bounds__(kShadeBlock, ShadeLaunch<CLS>::kMinBlocks) k_bounce(const __grid_constant__ LaunchParams P, uint32_t depth) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ uint64_t bar;
-    __shared__ uint64_t tile_bar[kShadeWarps][2];
+// before the warp waits for the current one, so the queue reads never sit on the dependent chain.  `it` counts the tiles
+// this warp has consumed in this launch (it selects the buffer and the mbarrier phase) and carries over from class to class.
+template <int CLS>
+__device__ __forceinline__ void bounce_phase(const LaunchParams &P, uint32_t depth, const DevTracer &tr, uint32_t tiles, uint64_t *tile_bar2, uint32_t &it) {
     const uint32_t n = P.counters[depth * kCtrStride + 2u + CLS];
-    if (blockIdx.x * blockDim.x >= n) return;  // whole CTA has no work: skip the staging too
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    if (threadIdx.x == 0) {
-        for (int w = 0; w < kShadeWarps; ++w) {
-            mbar_init(&tile_bar[w][0], 1);
-            mbar_init(&tile_bar[w][1], 1);
-        }
-    }
-    const DevTracer tr{P.scene, stage_scene(P, smem, &bar)};  // (inits `bar`, fences the barrier inits, __syncthreads)
-    const uint32_t scene_bytes = (P.scene.n_pair_blocks + P.scene.n_single_blocks + P.scene.n_occ_pair_blocks + P.scene.n_occ_single_blocks) * (uint32_t)sizeof(PrimBlock2);
-    const uint32_t tiles = smem_u32(smem) + ((scene_bytes + 127u) & ~127u) + warp * 2u * kTileBytes;
-    const uint32_t bar0 = smem_u32(&tile_bar[warp][0]);
+    const uint32_t bar0 = smem_u32(tile_bar2);
     const RecQueue &qin = P.cq[depth & 1u][CLS];
     const uint64_t pol = l2_evict_first_policy();
     const uint32_t n_tiles = (n + 31u) >> 5, wstride = gridDim.x * kShadeWarps;
@@ -863,12 +852,12 @@ template <int CLS> __global__ void __launch_bounds__(kShadeBlock, ShadeLaunch<CL
         for (uint32_t j = 0; j < 4u; ++j) tma_bulk_g2s_hint(dst + j * 512u, qin.r[j] + first, bytes, b, pol);
     };
     uint32_t tile = blockIdx.x * kShadeWarps + warp;
-    if (tile < n_tiles && lane == 0u) issue(tile, 0u);
+    if (tile < n_tiles && lane == 0u) issue(tile, it & 1u);
     uint32_t n_traced = 0u, n_shadow = 0u;  // warp-uniform
-    for (uint32_t it = 0u; tile < n_tiles; tile += wstride, ++it) {
+    for (; tile < n_tiles; tile += wstride, ++it) {
         const uint32_t buf = it & 1u;
         if (tile + wstride < n_tiles && lane == 0u) issue(tile + wstride, buf ^ 1u);
-        mbar_wait(&tile_bar[warp][buf], (it >> 1) & 1u);
+        mbar_wait(tile_bar2 + buf, (it >> 1) & 1u);
         const bool active = tile * 32u + lane < n;
         const uint32_t src = tiles + buf * kTileBytes + lane * 16u;
         const float4 r0 = lds128(src), r1 = lds128(src + 512u), r2 = lds128(src + 1024u), r3 = lds128(src + 1536u);
@@ -889,6 +878,38 @@ template <int CLS> __global__ void __launch_bounds__(kShadeBlock, ShadeLaunch<CL
     // statistics: [0] continuation rays traced (= segments of depth + 1), [1] shadow rays of this depth
     if (lane == 0u && (n_traced | n_shadow))
         atomicAdd(reinterpret_cast<unsigned long long *>(P.counters + (depth + 1u) * kCtrStride), (unsigned long long)n_traced | ((unsigned long long)n_shadow << 32));
+}
+// MASK = the shade classes this launch serves, one after the other in every CTA (bit c = class c).  Serving all classes of
+// a depth in ONE launch halves the launches per pass on cbox and lets the CTAs that run out of Lambert records start on
+// the conductor records instead of idling until the next launch: the tail of a depth is paid once, not once per class
+// (this is what limits scaling when the frame is split over 8 GPUs and every launch is short).
+template <uint32_t MASK> struct BounceLaunch {
+    static constexpr int kMinBlocks = (MASK & (1u << CLS_GENERAL)) ? 1 : ((MASK & (1u << CLS_CONDUCTOR)) ? AKR_SHADE_MINB_CONDUCTOR : AKR_SHADE_MINB_LAMBERT);
+};
+template <uint32_t MASK> __global__ void __launch_bounds__(kShadeBlock, BounceLaunch<MASK>::kMinBlocks) k_bounce(const __grid_constant__ LaunchParams P, uint32_t depth) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint64_t tile_bar[kShadeWarps][2];
+    const uint32_t *ctr = P.counters + depth * kCtrStride + 2u;
+    uint32_t n_max = 0u;
+#pragma unroll
+    for (uint32_t c = 0; c < (uint32_t)CLS_COUNT; ++c)
+        if (MASK & (1u << c)) n_max = max(n_max, ctr[c]);
+    if (blockIdx.x * blockDim.x >= n_max) return;  // whole CTA has no work in any class: skip the staging too
+    const uint32_t warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        for (int w = 0; w < kShadeWarps; ++w) {
+            mbar_init(&tile_bar[w][0], 1);
+            mbar_init(&tile_bar[w][1], 1);
+        }
+    }
+    const DevTracer tr{P.scene, stage_scene(P, smem, &bar)};  // (inits `bar`, fences the barrier inits, __syncthreads)
+    const uint32_t scene_bytes = (P.scene.n_pair_blocks + P.scene.n_single_blocks + P.scene.n_occ_pair_blocks + P.scene.n_occ_single_blocks) * (uint32_t)sizeof(PrimBlock2);
+    const uint32_t tiles = smem_u32(smem) + ((scene_bytes + 127u) & ~127u) + warp * 2u * kTileBytes;
+    uint32_t it = 0u;
+    if (MASK & (1u << CLS_LAMBERT)) bounce_phase<CLS_LAMBERT>(P, depth, tr, tiles, &tile_bar[warp][0], it);
+    if (MASK & (1u << CLS_CONDUCTOR)) bounce_phase<CLS_CONDUCTOR>(P, depth, tr, tiles, &tile_bar[warp][0], it);
+    if (MASK & (1u << CLS_GENERAL)) bounce_phase<CLS_GENERAL>(P, depth, tr, tiles, &tile_bar[warp][0], it);
 }
 
 // The `aov` method (aov.rs:96-155) after raygen + one trace stage: the first-hit quantity of every camera sample goes to
@@ -984,7 +1005,8 @@ struct AkrContext {
     int occ_trace_dyn = 1;   // k_trace_bvh (dynamic fetch)
     int occ_trace_flat = 1;  // k_trace_flat
     int occ_raygen_fused = 1;
-    int occ_shade[3] = {1, 1, 1}, occ_bounce[3] = {1, 1, 1};  // resident CTAs per SM, per shade class
+    int occ_shade[3] = {1, 1, 1};                // resident CTAs per SM, per shade class
+    int occ_bounce[5] = {1, 1, 1, 1, 1};         // k_bounce<MASK> for MASK = 1, 2, 4, 3, 7
     uint32_t flat_bytes = 0;  // staged PrimBlock2 lists (complete + occluder-only)
 
     // render state
@@ -1163,9 +1185,11 @@ int akr_b200_create(int device_ordinal, AkrContext **out_ctx) {
         opt_in((const void *)k_trace_flat<false>);
         opt_in((const void *)k_trace_flat<true>);
         opt_in((const void *)k_raygen_fused);
-        opt_in((const void *)k_bounce<CLS_LAMBERT>);
-        opt_in((const void *)k_bounce<CLS_CONDUCTOR>);
-        opt_in((const void *)k_bounce<CLS_GENERAL>);
+        opt_in((const void *)k_bounce<1u>);
+        opt_in((const void *)k_bounce<2u>);
+        opt_in((const void *)k_bounce<4u>);
+        opt_in((const void *)k_bounce<3u>);
+        opt_in((const void *)k_bounce<7u>);
         if (e != cudaSuccess) {  // no sm_100a image for this device, or the opt-in shared-memory size is not available
             delete ctx;
             return AKR_ERR_CUDA;
@@ -1345,9 +1369,11 @@ int akr_b200_upload_scene(AkrContext *ctx, const AkrSceneDesc *desc) {
         occ(ctx->occ_shade[1], (const void *)k_shade<CLS_CONDUCTOR>, kShadeBlock, 0);
         occ(ctx->occ_shade[2], (const void *)k_shade<CLS_GENERAL>, kShadeBlock, 0);
         occ(ctx->occ_raygen_fused, (const void *)k_raygen_fused, kBlock, ctx->flat_bytes);
-        occ(ctx->occ_bounce[0], (const void *)k_bounce<CLS_LAMBERT>, kShadeBlock, smem_bounce);
-        occ(ctx->occ_bounce[1], (const void *)k_bounce<CLS_CONDUCTOR>, kShadeBlock, smem_bounce);
-        occ(ctx->occ_bounce[2], (const void *)k_bounce<CLS_GENERAL>, kShadeBlock, smem_bounce);
+        occ(ctx->occ_bounce[0], (const void *)k_bounce<1u>, kShadeBlock, smem_bounce);
+        occ(ctx->occ_bounce[1], (const void *)k_bounce<2u>, kShadeBlock, smem_bounce);
+        occ(ctx->occ_bounce[2], (const void *)k_bounce<4u>, kShadeBlock, smem_bounce);
+        occ(ctx->occ_bounce[3], (const void *)k_bounce<3u>, kShadeBlock, smem_bounce);
+        occ(ctx->occ_bounce[4], (const void *)k_bounce<7u>, kShadeBlock, smem_bounce);
         if (e != cudaSuccess) return fail(ctx, AKR_ERR_CUDA, std::string("cudaOccupancyMaxActiveBlocksPerMultiprocessor: ") + cudaGetErrorString(e));
     }
     ctx->scene_ready = true;
@@ -1545,10 +1571,15 @@ int akr_b200_render_pass(AkrContext *ctx, uint32_t n_spp, int blocking) {
             };
             if (fused) {
                 AKR_LAUNCH(0, k_raygen_fused, grid_for(ctx, n_paths, ctx->occ_raygen_fused), ctx->flat_bytes, P);
+                // one launch per depth serves every shade class present (opts.fused = 3: one launch per class, for A/B runs)
+                const bool per_class = ctx->opts.fused == 3u;
                 for (uint32_t depth = 0; depth < ctx->rp.max_depth; ++depth) {
-                    if (class_mask & (1u << CLS_LAMBERT)) AKR_LAUNCH_B(2, (k_bounce<CLS_LAMBERT>), shade_grid(ctx->occ_bounce[0]), kShadeBlock, bounce_smem, P, depth);
-                    if (class_mask & (1u << CLS_CONDUCTOR)) AKR_LAUNCH_B(3, (k_bounce<CLS_CONDUCTOR>), shade_grid(ctx->occ_bounce[1]), kShadeBlock, bounce_smem, P, depth);
-                    if (class_mask & (1u << CLS_GENERAL)) AKR_LAUNCH_B(6, (k_bounce<CLS_GENERAL>), shade_grid(ctx->occ_bounce[2]), kShadeBlock, bounce_smem, P, depth);
+                    if (class_mask == 1u || (per_class && (class_mask & 1u))) AKR_LAUNCH_B(2, (k_bounce<1u>), shade_grid(ctx->occ_bounce[0]), kShadeBlock, bounce_smem, P, depth);
+                    if (class_mask == 2u || (per_class && (class_mask & 2u))) AKR_LAUNCH_B(3, (k_bounce<2u>), shade_grid(ctx->occ_bounce[1]), kShadeBlock, bounce_smem, P, depth);
+                    if (class_mask == 4u || (per_class && (class_mask & 4u))) AKR_LAUNCH_B(6, (k_bounce<4u>), shade_grid(ctx->occ_bounce[2]), kShadeBlock, bounce_smem, P, depth);
+                    if (per_class) continue;
+                    if (class_mask == 3u) AKR_LAUNCH_B(2, (k_bounce<3u>), shade_grid(ctx->occ_bounce[3]), kShadeBlock, bounce_smem, P, depth);
+                    else if (class_mask >= 5u) AKR_LAUNCH_B(6, (k_bounce<7u>), shade_grid(ctx->occ_bounce[4]), kShadeBlock, bounce_smem, P, depth);
                 }
             } else {
                 AKR_LAUNCH(0, k_raygen, grid_for(ctx, n_paths, 8), 0, P);

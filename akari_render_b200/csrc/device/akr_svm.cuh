@@ -270,11 +270,11 @@ AKR_HD int svm_eval(const SvmView &svm, uint32_t shader_kind, uint32_t data_offs
             m.wrap_inner = 0u;
             m.alpha = c.v[3];
             have_closure = true;
-            if (ALPHA_ONLY) break;
-            for (int c3 = 0; c3 < 3; ++c3) {
-                m.color[c3] = c.v[c3];
-                m.diffuse[c3] = c.v[c3] * AKR_FRAC_1_PI;
-            }
+            if (!ALPHA_ONLY)
+                for (int c3 = 0; c3 < 3; ++c3) {
+                    m.color[c3] = c.v[c3];
+                    m.diffuse[c3] = c.v[c3] * AKR_FRAC_1_PI;
+                }
             break;
         }
         case AKR_SVM_EMISSION: {  // svm/mod.rs:124-133
@@ -293,14 +293,15 @@ AKR_HD int svm_eval(const SvmView &svm, uint32_t shader_kind, uint32_t data_offs
             r.kind = SV_CLOSURE;
             m.type = MAT_GLASS;
             have_closure = true;
-            if (ALPHA_ONLY) break;
-            for (int c3 = 0; c3 < 3; ++c3) {
-                m.color[c3] = vals[n.a[0]].v[c3];
-                m.trans_color[c3] = vals[n.a[1]].v[c3];
+            if (!ALPHA_ONLY) {
+                for (int c3 = 0; c3 < 3; ++c3) {
+                    m.color[c3] = vals[n.a[0]].v[c3];
+                    m.trans_color[c3] = vals[n.a[1]].v[c3];
+                }
+                m.roughness_raw = vals[n.a[2]].v[0];
+                m.roughness = m.roughness_raw;
+                m.eta = vals[n.a[3]].v[0];
             }
-            m.roughness_raw = vals[n.a[2]].v[0];
-            m.roughness = m.roughness_raw;
-            m.eta = vals[n.a[3]].v[0];
             break;
         }
         case AKR_SVM_PRINCIPLED_BSDF: {  // principled.rs:23-49
