@@ -879,10 +879,11 @@ __device__ __forceinline__ void bounce_phase(const LaunchParams &P, uint32_t dep
     if (lane == 0u && (n_traced | n_shadow))
         atomicAdd(reinterpret_cast<unsigned long long *>(P.counters + (depth + 1u) * kCtrStride), (unsigned long long)n_traced | ((unsigned long long)n_shadow << 32));
 }
-// MASK = the shade classes this launch serves, one after the other in every CTA (bit c = class c).  Serving all classes of
-// a depth in ONE launch halves the launches per pass on cbox and lets the CTAs that run out of Lambert records start on
-// the conductor records instead of idling until the next launch: the tail of a depth is paid once, not once per class
-// (this is what limits scaling when the frame is split over 8 GPUs and every launch is short).
+// MASK = the shade classes this launch serves, one after the other in every CTA (bit c = class c).  Measured on B200:
+// serving Lambert + conductor in ONE launch per depth (half the launches, CTAs that run out of Lambert records start on
+// conductor records) is SLOWER than one launch per class — 31.0 vs 29.1 ms per pass on one GPU, 12.8 vs 13.8 G samples/s
+// on eight: the merged kernel's larger code and common register allocation cost more than the saved tails — so the
+// engine launches single-class masks; the template keeps the general form.
 template <uint32_t MASK> struct BounceLaunch {
     static constexpr int kMinBlocks = (MASK & (1u << CLS_GENERAL)) ? 1 : ((MASK & (1u << CLS_CONDUCTOR)) ? AKR_SHADE_MINB_CONDUCTOR : AKR_SHADE_MINB_LAMBERT);
 };
@@ -1006,7 +1007,7 @@ struct AkrContext {
     int occ_trace_flat = 1;  // k_trace_flat
     int occ_raygen_fused = 1;
     int occ_shade[3] = {1, 1, 1};                // resident CTAs per SM, per shade class
-    int occ_bounce[5] = {1, 1, 1, 1, 1};         // k_bounce<MASK> for MASK = 1, 2, 4, 3, 7
+    int occ_bounce[3] = {1, 1, 1};               // k_bounce<1 << class>
     uint32_t flat_bytes = 0;  // staged PrimBlock2 lists (complete + occluder-only)
 
     // render state
@@ -1188,8 +1189,6 @@ int akr_b200_create(int device_ordinal, AkrContext **out_ctx) {
         opt_in((const void *)k_bounce<1u>);
         opt_in((const void *)k_bounce<2u>);
         opt_in((const void *)k_bounce<4u>);
-        opt_in((const void *)k_bounce<3u>);
-        opt_in((const void *)k_bounce<7u>);
         if (e != cudaSuccess) {  // no sm_100a image for this device, or the opt-in shared-memory size is not available
             delete ctx;
             return AKR_ERR_CUDA;
@@ -1372,8 +1371,6 @@ int akr_b200_upload_scene(AkrContext *ctx, const AkrSceneDesc *desc) {
         occ(ctx->occ_bounce[0], (const void *)k_bounce<1u>, kShadeBlock, smem_bounce);
         occ(ctx->occ_bounce[1], (const void *)k_bounce<2u>, kShadeBlock, smem_bounce);
         occ(ctx->occ_bounce[2], (const void *)k_bounce<4u>, kShadeBlock, smem_bounce);
-        occ(ctx->occ_bounce[3], (const void *)k_bounce<3u>, kShadeBlock, smem_bounce);
-        occ(ctx->occ_bounce[4], (const void *)k_bounce<7u>, kShadeBlock, smem_bounce);
         if (e != cudaSuccess) return fail(ctx, AKR_ERR_CUDA, std::string("cudaOccupancyMaxActiveBlocksPerMultiprocessor: ") + cudaGetErrorString(e));
     }
     ctx->scene_ready = true;
@@ -1571,15 +1568,10 @@ int akr_b200_render_pass(AkrContext *ctx, uint32_t n_spp, int blocking) {
             };
             if (fused) {
                 AKR_LAUNCH(0, k_raygen_fused, grid_for(ctx, n_paths, ctx->occ_raygen_fused), ctx->flat_bytes, P);
-                // one launch per depth serves every shade class present (opts.fused = 3: one launch per class, for A/B runs)
-                const bool per_class = ctx->opts.fused == 3u;
                 for (uint32_t depth = 0; depth < ctx->rp.max_depth; ++depth) {
-                    if (class_mask == 1u || (per_class && (class_mask & 1u))) AKR_LAUNCH_B(2, (k_bounce<1u>), shade_grid(ctx->occ_bounce[0]), kShadeBlock, bounce_smem, P, depth);
-                    if (class_mask == 2u || (per_class && (class_mask & 2u))) AKR_LAUNCH_B(3, (k_bounce<2u>), shade_grid(ctx->occ_bounce[1]), kShadeBlock, bounce_smem, P, depth);
-                    if (class_mask == 4u || (per_class && (class_mask & 4u))) AKR_LAUNCH_B(6, (k_bounce<4u>), shade_grid(ctx->occ_bounce[2]), kShadeBlock, bounce_smem, P, depth);
-                    if (per_class) continue;
-                    if (class_mask == 3u) AKR_LAUNCH_B(2, (k_bounce<3u>), shade_grid(ctx->occ_bounce[3]), kShadeBlock, bounce_smem, P, depth);
-                    else if (class_mask >= 5u) AKR_LAUNCH_B(6, (k_bounce<7u>), shade_grid(ctx->occ_bounce[4]), kShadeBlock, bounce_smem, P, depth);
+                    if (class_mask & 1u) AKR_LAUNCH_B(2, (k_bounce<1u>), shade_grid(ctx->occ_bounce[0]), kShadeBlock, bounce_smem, P, depth);
+                    if (class_mask & 2u) AKR_LAUNCH_B(3, (k_bounce<2u>), shade_grid(ctx->occ_bounce[1]), kShadeBlock, bounce_smem, P, depth);
+                    if (class_mask & 4u) AKR_LAUNCH_B(6, (k_bounce<4u>), shade_grid(ctx->occ_bounce[2]), kShadeBlock, bounce_smem, P, depth);
                 }
             } else {
                 AKR_LAUNCH(0, k_raygen, grid_for(ctx, n_paths, 8), 0, P);
