@@ -416,6 +416,103 @@ __device__ __forceinline__ uint32_t trace_flat2_core(const SceneView &sc, const 
     }
     return best_k;
 }
+// Closest-hit ray A and any-hit ray B of the same lane against one PrimBlock2, the block loaded ONCE.  Two independent
+// dependency chains per trip also give the scheduler twice the instruction-level parallelism of the single-ray loop.
+template <bool PAIR, bool WITH_B>
+__device__ __forceinline__ void flat2_block_dual(uint32_t addr, uint32_t b, f3 oa, f3 da, uint32_t exa, float &best_t, uint32_t &best_k, f3 ob, f3 db, float tmax_b,
+                                                 uint32_t exb0, uint32_t exb1, bool &occluded) {
+    u64 n0, n1, n2, nw, r00, r01, r02, r0w, r10, r11, r12, r1w;
+    lds2x64(addr, n0, n1);
+    lds2x64(addr + 16u, n2, nw);
+    lds2x64(addr + 32u, r00, r01);
+    lds2x64(addr + 48u, r02, r0w);
+    lds2x64(addr + 64u, r10, r11);
+    lds2x64(addr + 80u, r12, r1w);
+    const uint4 g = lds_u4(addr + 96u);
+    auto coords = [&](f3 o, f3 d, float &t0, float &t1, float &s0, float &s1, float &q0, float &q1, u64 &s2, u64 &q2) {
+        const u64 ox2 = pk2(o.x, o.x), oy2 = pk2(o.y, o.y), oz2 = pk2(o.z, o.z);
+        const u64 dx2 = pk2(d.x, d.x), dy2 = pk2(d.y, d.y), dz2 = pk2(d.z, d.z);
+        const u64 den = fma2(n2, dz2, fma2(n1, dy2, mul2(n0, dx2)));
+        const u64 num = fma2(n2, oz2, fma2(n1, oy2, fma2(n0, ox2, nw)));
+        float den0, den1;
+        upk2(den, den0, den1);
+        const u64 t2 = mul2(num, pk2(rcp_neg(den0), rcp_neg(den1)));
+        const u64 hx = fma2(t2, dx2, ox2), hy = fma2(t2, dy2, oy2), hz = fma2(t2, dz2, oz2);
+        s2 = fma2(r00, hx, fma2(r01, hy, fma2(r02, hz, r0w)));
+        q2 = fma2(r10, hx, fma2(r11, hy, fma2(r12, hz, r1w)));
+        upk2(t2, t0, t1);
+        upk2(s2, s0, s1);
+        upk2(q2, q0, q1);
+    };
+    auto inside = [&](float s0, float s1, float q0, float q1, u64 s2, u64 q2, bool &in0, bool &in1, uint32_t &gid0, uint32_t &gid1) {
+        if (PAIR) {
+            const u64 mhalf2 = pk2(-0.5f, -0.5f);
+            float a0, a1, c0, c1;
+            upk2(add2(s2, mhalf2), a0, a1);
+            upk2(add2(q2, mhalf2), c0, c1);
+            in0 = (fabsf(a0) <= 0.5f) & (fabsf(c0) <= 0.5f);
+            in1 = (fabsf(a1) <= 0.5f) & (fabsf(c1) <= 0.5f);
+            gid0 = s0 < q0 ? g.y : g.x;
+            gid1 = s1 < q1 ? g.w : g.z;
+        } else {
+            float m0, m1;
+            upk2(add2(s2, q2), m0, m1);
+            in0 = (s0 >= 0.0f) & (q0 >= 0.0f) & (m0 <= 1.0f);
+            in1 = (s1 >= 0.0f) & (q1 >= 0.0f) & (m1 <= 1.0f);
+            gid0 = g.x;
+            gid1 = g.z;
+        }
+    };
+    {
+        float t0, t1, s0, s1, q0, q1;
+        u64 s2, q2;
+        coords(oa, da, t0, t1, s0, s1, q0, q1, s2, q2);
+        bool in0, in1;
+        uint32_t gid0, gid1;
+        inside(s0, s1, q0, q1, s2, q2, in0, in1, gid0, gid1);
+        const bool ok0 = in0 & (t0 > 0.0f) & (t0 < best_t) & (gid0 != exa);
+        best_t = ok0 ? t0 : best_t;
+        best_k = ok0 ? 2u * b : best_k;
+        const bool ok1 = in1 & (t1 > 0.0f) & (t1 < best_t) & (gid1 != exa);
+        best_t = ok1 ? t1 : best_t;
+        best_k = ok1 ? 2u * b + 1u : best_k;
+    }
+    if (WITH_B) {
+        float t0, t1, s0, s1, q0, q1;
+        u64 s2, q2;
+        coords(ob, db, t0, t1, s0, s1, q0, q1, s2, q2);
+        bool in0, in1;
+        uint32_t gid0, gid1;
+        inside(s0, s1, q0, q1, s2, q2, in0, in1, gid0, gid1);
+        occluded |= in0 & (t0 > 0.0f) & (t0 < tmax_b) & (gid0 != exb0) & (gid0 != exb1);
+        occluded |= in1 & (t1 > 0.0f) & (t1 < tmax_b) & (gid1 != exb0) & (gid1 != exb1);
+    }
+}
+// One walk over the complete staged list: closest hit of ray A (t in (0, 1e20), exclude exa) and occlusion of ray B
+// (t in (0, tmax_b), exclude exb0 / exb1).  B is only tested against the leading occluder blocks of each group.  Inactive
+// rays accept nothing (A: best_t = 0; B: tmax_b = 0).
+__device__ __forceinline__ uint32_t trace_flat2_dual(const SceneView &sc, const TraceSmem &ts, bool active_a, f3 oa, f3 da, uint32_t exa, float &best_t,
+                                                     bool active_b, f3 ob, f3 db, float tmax_b, uint32_t exb0, uint32_t exb1, bool &occluded) {
+    best_t = active_a ? 1e20f : 0.0f;
+    tmax_b = active_b ? tmax_b : 0.0f;
+    occluded = false;
+    uint32_t best_k = 0xffffffffu;
+    const uint32_t np = sc.n_pair_blocks, nps = sc.n_shadow_pair_blocks, ne = np + sc.n_single_blocks, nss = np + sc.n_shadow_single_blocks;
+#pragma unroll 1
+    for (uint32_t b = 0; b < nps; ++b)
+        flat2_block_dual<true, true>(ts.prims + b * (uint32_t)sizeof(PrimBlock2), b, oa, da, exa, best_t, best_k, ob, db, tmax_b, exb0, exb1, occluded);
+#pragma unroll 1
+    for (uint32_t b = nps; b < np; ++b)
+        flat2_block_dual<true, false>(ts.prims + b * (uint32_t)sizeof(PrimBlock2), b, oa, da, exa, best_t, best_k, ob, db, tmax_b, exb0, exb1, occluded);
+#pragma unroll 1
+    for (uint32_t b = np; b < nss; ++b)
+        flat2_block_dual<false, true>(ts.prims + b * (uint32_t)sizeof(PrimBlock2), b, oa, da, exa, best_t, best_k, ob, db, tmax_b, exb0, exb1, occluded);
+#pragma unroll 1
+    for (uint32_t b = nss; b < ne; ++b)
+        flat2_block_dual<false, false>(ts.prims + b * (uint32_t)sizeof(PrimBlock2), b, oa, da, exa, best_t, best_k, ob, db, tmax_b, exb0, exb1, occluded);
+    return best_k;
+}
+
 template <bool ANY_HIT, bool ALPHA>
 __device__ __forceinline__ DevHit trace_flat2(const LaunchParams &P, const TraceSmem &ts, bool active, f3 o, f3 d, float t_min, float t_max, uint32_t ex0,
                                               uint32_t ex1) {
@@ -765,9 +862,17 @@ template <int CLS> __global__ void __launch_bounds__(kShadeBlock, ShadeLaunch<CL
 struct DevTracer {
     const SceneView &sc;
     TraceSmem ts;
-    __device__ __forceinline__ bool occluded(bool active, f3 o, f3 d, float t_max, uint32_t ex0, uint32_t ex1) const {
-        float t;
-        return trace_flat2_core<true, false>(sc, ts, active, o, d, 0.0f, t_max, ex0, ex1, t) != 0xffffffffu;
+    // shadow ray + continuation ray of the same path in one walk over the staged list
+    __device__ __forceinline__ TraceHit trace2(bool has_shadow, f3 so, f3 sd, float st_max, uint32_t sex0, uint32_t sex1, bool &occluded, bool has_next, f3 o, f3 d,
+                                               uint32_t ex0) const {
+        float best_t;
+        const uint32_t best_k = trace_flat2_dual(sc, ts, has_next, o, d, ex0, best_t, has_shadow, so, sd, st_max, sex0, sex1, occluded);
+        if (best_k == 0xffffffffu) return TraceHit{0xffffffffu, 0u, 0u, 0.0f, 0.0f};
+        const PrimRec p = load_block_prim(ts.prims + (best_k >> 1) * (uint32_t)sizeof(PrimBlock2), best_k & 1u);
+        float s, q;
+        prim_coords(p, o, d, best_t, s, q);
+        const PrimDecoded dec = prim_decode(p, s, q);
+        return TraceHit{dec.gid, dec.cls, dec.light, dec.u, dec.v};
     }
     __device__ __forceinline__ TraceHit closest(bool active, f3 o, f3 d, uint32_t ex0) const {
         float best_t;
@@ -1297,6 +1402,8 @@ int akr_b200_upload_scene(AkrContext *ctx, const AkrSceneDesc *desc) {
     v.n_single_blocks = blob.n_single_blocks;
     v.n_occ_pair_blocks = blob.n_occ_pair_blocks;
     v.n_occ_single_blocks = blob.n_occ_single_blocks;
+    v.n_shadow_pair_blocks = blob.n_shadow_pair_blocks;
+    v.n_shadow_single_blocks = blob.n_shadow_single_blocks;
     v.tris = nullptr;  // the Moeller-Trumbore triangle list is host-simulation data; the kernels intersect primitives
     v.shade = static_cast<const TriShade *>(ctx->shade.ptr);
     v.instances = static_cast<const InstanceRec *>(ctx->instances.ptr);

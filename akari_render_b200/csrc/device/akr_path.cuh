@@ -486,15 +486,14 @@ struct BounceOut {
     uint32_t cls;
     BounceRec next;
 };
-// A Tracer answers `occluded(active, o, d, t_max, ex0, ex1)` and `closest(active, o, d, ex0)`; on the device both are
-// warp-collective (every lane calls, `active` says whether it carries a ray), so the bodies below never return early.
-template <class Tracer>
+// A Tracer answers `closest(active, o, d, ex0)` and `trace2(shadow ray, &occluded, continuation ray)`; on the device both
+// are warp-collective (every lane calls, the flags say whether it carries a ray), so the bodies below never return early.
+// `h` = closest hit of the continuation ray `nx` (gid 0xffffffff = miss)
 AKR_HD BounceOut continue_path(const SceneView &sc, const CornerAttribs &ca, const RenderParams &rp, uint32_t depth1, bool active, bool has_next,
-                               const PathState &nx, f3 L, Tracer &tr, const AccView &acc) {
+                               const PathState &nx, f3 L, const TraceHit &h, const AccView &acc) {
     BounceOut r;
     r.shadow = false;
     r.traced = has_next;
-    const TraceHit h = tr.closest(has_next, nx.o, nx.d, nx.ex);
     r.cont = has_next && h.gid != 0xffffffffu;
     r.cls = rp.force_diffuse ? (uint32_t)CLS_LAMBERT : h.cls;
     if (has_next && !r.cont) L = miss_add(rp, depth1, nx.beta, L);
@@ -526,7 +525,8 @@ AKR_HD BounceOut raygen_fused(const SceneView &sc, const CornerAttribs &ca, cons
     ps.prev_bsdf_pdf = 0.0f;
     ps.path_id = path_id;
     if (active) ps = raygen_body(sc, tab, rp, wave, path_id);
-    BounceOut r = continue_path(sc, ca, rp, 0u, active, active, ps, splat3(0.0f), tr, acc);
+    const TraceHit h = tr.closest(active, ps.o, ps.d, ps.ex);
+    BounceOut r = continue_path(sc, ca, rp, 0u, active, active, ps, splat3(0.0f), h, acc);
     // base_replay_throughput of a path that ends at depth 0 (miss: 0; max_depth = 0: the emitter term, pt.rs:415-417)
     if (active && !r.cont) st4(acc.b + path_id, f4{r.next.L.x, r.next.L.y, r.next.L.z, 0.0f});
     return r;
@@ -548,13 +548,16 @@ AKR_HD BounceOut bounce_fused(const SceneView &sc, const CornerAttribs &ca, cons
         o = shade_body<CLS, false>(sc, ca, tab, rp, wave, depth, ps, HitRec{in.gid, in.u, in.v}, acc);
         o.next.path_id = in.path_id;
     }
-    const bool occluded = tr.occluded(o.has_shadow, o.shadow.o, o.shadow.d, o.shadow.t_max, o.shadow.ex0, o.shadow.ex1);
+    // the NEE shadow ray and the continuation ray are both known here: one trace call serves both (on the device one walk
+    // over the staged primitive list, two independent dependency chains per trip)
+    bool occluded;
+    const TraceHit h = tr.trace2(o.has_shadow, o.shadow.o, o.shadow.d, o.shadow.t_max, o.shadow.ex0, o.shadow.ex1, occluded, o.has_next, o.next.o, o.next.d, o.next.ex);
     if (o.has_shadow && !occluded) {  // shadow_resolve (pt.rs:504-513)
         const f3 c = o.shadow.contrib;
         if (c.x != 0.0f || c.y != 0.0f || c.z != 0.0f) L = L + c;
     }
     if (active && depth == 0u) st4(acc.b + in.path_id, f4{L.x, L.y, L.z, 0.0f});  // base_replay_throughput = radiance (pt.rs:415-417,510-512)
-    BounceOut r = continue_path(sc, ca, rp, depth + 1u, active, o.has_next, o.next, L, tr, acc);
+    BounceOut r = continue_path(sc, ca, rp, depth + 1u, active, o.has_next, o.next, L, h, acc);
     r.shadow = o.has_shadow;
     return r;
 }

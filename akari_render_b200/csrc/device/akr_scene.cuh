@@ -143,6 +143,8 @@ struct SceneView {
     uint32_t n_occ_pair_blocks, n_occ_single_blocks;  // the occluder list behind it (any-hit rays): primitives whose plane
                                                       // supports the whole scene (convex-hull walls) cannot block a segment
                                                       // between two points of the scene and are left out
+    uint32_t n_shadow_pair_blocks, n_shadow_single_blocks;  // the complete list keeps occluders first in each group: a shadow ray
+                                                            // only needs these leading blocks (dual trace of the fused kernels)
     const TriGeom *tris;       // two slots per primitive, gid 0xffffffff = empty (Moeller-Trumbore path of the host simulation)
     const TriShade *shade;
     const InstanceRec *instances;

@@ -770,10 +770,18 @@ int build_scene_blob(const AkrSceneDesc &d, HostSceneBlob &out, std::string &err
                 out.flat_blocks.push_back(blk);
             }
         };
-        emit_blocks(out.prims, out.n_pair_blocks, out.n_single_blocks);
-        std::vector<PrimRec> occluders;
-        for (const PrimRec &pr : out.prims)
-            if (!supports_scene(pr)) occluders.push_back(pr);
+        // complete list: occluders first inside the pair group and inside the single group, so that a kernel that walks the
+        // complete list for a closest-hit ray can test a shadow ray against the leading `n_shadow_*_blocks` of each group
+        // in the same trip (akari_b200.cu: trace_flat2_dual)
+        std::vector<PrimRec> occluders, walls, ordered;
+        for (const PrimRec &pr : out.prims) (supports_scene(pr) ? walls : occluders).push_back(pr);
+        ordered = occluders;
+        ordered.insert(ordered.end(), walls.begin(), walls.end());
+        emit_blocks(ordered, out.n_pair_blocks, out.n_single_blocks);
+        uint32_t occ_pairs = 0, occ_singles = 0;
+        for (const PrimRec &pr : occluders) (pr.gid_b != 0xffffffffu ? occ_pairs : occ_singles) += 1u;
+        out.n_shadow_pair_blocks = (occ_pairs + 1u) / 2u;
+        out.n_shadow_single_blocks = (occ_singles + 1u) / 2u;
         emit_blocks(occluders, out.n_occ_pair_blocks, out.n_occ_single_blocks);
     }
     // flatten: breadth-first over inner nodes; a leaf root becomes an inner node with an empty second child
@@ -948,6 +956,8 @@ SceneView host_scene_view(const HostSceneBlob &b, const float *albedo_table) {
     v.n_single_blocks = b.n_single_blocks;
     v.n_occ_pair_blocks = b.n_occ_pair_blocks;
     v.n_occ_single_blocks = b.n_occ_single_blocks;
+    v.n_shadow_pair_blocks = b.n_shadow_pair_blocks;
+    v.n_shadow_single_blocks = b.n_shadow_single_blocks;
     v.tris = b.tris.data();
     v.shade = b.shade.data();
     v.instances = b.instances.data();

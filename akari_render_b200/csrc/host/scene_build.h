@@ -25,6 +25,7 @@ struct HostSceneBlob {
     std::vector<PrimBlock2> flat_blocks;  // scenes of <= kFlatMaxPrims primitives: pairs first, two per block (flat trace mode)
     uint32_t n_pair_blocks = 0, n_single_blocks = 0;          // complete list, then ...
     uint32_t n_occ_pair_blocks = 0, n_occ_single_blocks = 0;  // ... the occluder-only list (any-hit rays)
+    uint32_t n_shadow_pair_blocks = 0, n_shadow_single_blocks = 0;  // leading blocks of each group of the complete list that hold occluders
     std::vector<TriGeom> tris;        // two per primitive, same order (host simulation's Moeller-Trumbore path)
     std::vector<TriShade> shade;      // by global triangle id
     std::vector<InstanceRec> instances;

@@ -33,6 +33,10 @@ struct HostTracer {  // the Tracer of akr_path.cuh's fused bodies, one ray at a 
     bool occluded(bool active, f3 o, f3 d, float t_max, uint32_t ex0, uint32_t ex1) const {
         return active && host_trace<true>(sc, td, o, d, t_max, ex0, ex1).gid != 0xffffffffu;
     }
+    TraceHit trace2(bool has_shadow, f3 so, f3 sd, float st_max, uint32_t sex0, uint32_t sex1, bool &occ, bool has_next, f3 o, f3 d, uint32_t ex0) const {
+        occ = occluded(has_shadow, so, sd, st_max, sex0, sex1);
+        return closest(has_next, o, d, ex0);
+    }
     TraceHit closest(bool active, f3 o, f3 d, uint32_t ex0) const {
         TraceHit t{0xffffffffu, 0u, 0u, 0.0f, 0.0f};
         if (!active) return t;
