@@ -73,7 +73,7 @@ struct ClassQueues { // per shade class: (slot in the path queue, path_id) of th
     uint2 *idx[CLS_COUNT];
 };
 struct RecQueue {    // fused pipeline: 64 B per path = BounceRec (akr_path.cuh), one queue per (depth parity, shade class)
-    f4 *r[4];        // (d.xyz, gid) | (u, v, path_id, -) | (beta.rgb, -) | (L.rgb, -)
+    f4 *r[4];        // (d.xyz, gid) | (u, v, path_id, pixel) | (beta.rgb, sample index) | (L.rgb, -)
 };
 
 struct LaunchParams {
@@ -889,8 +889,8 @@ struct DevTracer {
 
 __device__ __forceinline__ void store_rec(const RecQueue &q, uint32_t i, const BounceRec &r) {
     stq(q.r[0] + i, f4{r.d.x, r.d.y, r.d.z, u2f(r.gid)});
-    stq(q.r[1] + i, f4{r.u, r.v, u2f(r.path_id), 0.0f});
-    stq(q.r[2] + i, f4{r.beta.x, r.beta.y, r.beta.z, 0.0f});
+    stq(q.r[1] + i, f4{r.u, r.v, u2f(r.path_id), u2f(r.pxpy)});
+    stq(q.r[2] + i, f4{r.beta.x, r.beta.y, r.beta.z, u2f(r.sample_index)});
     stq(q.r[3] + i, f4{r.L.x, r.L.y, r.L.z, 0.0f});
 }
 // appends a surviving path to the queue of the shade class of the hit it goes to (depth d1)
@@ -973,7 +973,9 @@ __device__ __forceinline__ void bounce_phase(const LaunchParams &P, uint32_t dep
         in.u = r1.x;
         in.v = r1.y;
         in.path_id = __float_as_uint(r1.z);
+        in.pxpy = __float_as_uint(r1.w);
         in.beta = mk3(r2.x, r2.y, r2.z);
+        in.sample_index = __float_as_uint(r2.w);
         in.L = mk3(r3.x, r3.y, r3.z);
         const BounceOut r = bounce_fused<CLS>(P.scene, P.corners, P.tables, P.rp, P.wave, depth, active, in, tr, P.acc);
         n_traced += (uint32_t)__popc(__ballot_sync(0xffffffffu, r.traced));
@@ -1583,7 +1585,7 @@ int akr_b200_render_pass(AkrContext *ctx, uint32_t n_spp, int blocking) {
     const bool alpha = ctx->scene.any_alpha != 0u;
     // fused pipeline: flat list, no stochastic alpha; opts.fused = 2 forces the queued pipeline
     const bool aov = ctx->aov_mode >= 0;  // the aov method runs raygen + one trace stage of the queued pipeline + k_aov
-    const bool fused = trace_mode == TRACE_FLAT && !alpha && ctx->opts.fused != 2u && !aov;
+    const bool fused = trace_mode == TRACE_FLAT && !alpha && ctx->opts.fused != 2u && !aov && ctx->rp.width <= 65535u && ctx->rp.height <= 65535u;  // (records pack the pixel as x | y << 16)
     const uint32_t class_mask = ctx->rp.force_diffuse ? (1u << CLS_LAMBERT) : ctx->class_mask;
 
     // wave geometry: pixels x samples with pixels * samples <= capacity

@@ -100,6 +100,8 @@ struct PathState {  // what survives from one bounce to the next (13 words in th
     f3 beta;
     float prev_bsdf_pdf;
     uint32_t path_id;
+    uint32_t pxpy, sample_index;  // fused pipeline only: sensor pixel (x | y << 16) and sample index, so that the sampler
+                                  // needs no path_id -> (pixel, sample) divisions per bounce (sensors up to 65535 x 65535)
 };
 struct ShadowItem {    // 13 words
     f3 o, d;
@@ -172,6 +174,8 @@ AKR_HD PathState raygen_body(const SceneView &sc, const SamplerTables &tab, cons
     ps.beta = splat3(1.0f);
     ps.prev_bsdf_pdf = 0.0f;
     ps.path_id = path_id;
+    ps.pxpy = pc.px | (pc.py << 16);
+    ps.sample_index = pc.sample_index;
     return ps;
 }
 
@@ -320,7 +324,8 @@ AKR_HD ShadeOut shade_body(const SceneView &sc, const CornerAttribs &ca, const S
     // and its material are fetched (table loads in flight meanwhile).  Measured on B200: helps the register-roomier
     // conductor / general kernels (6.7 -> 6.5 ms), costs the 64-register Lambert kernel 3 % => decided per class.
     constexpr bool kDrawFirst = CLS != CLS_LAMBERT;  // (measured again with the fused kernels: 23.5 vs 22.4 ms per pass for Lambert)
-    const PathCoord pc = path_coord(rp, wave, id);
+    // fused pipeline: the record carries (pixel, sample index); queued pipeline: recover them from the path id
+    const PathCoord pc = EMIT ? path_coord(rp, wave, id) : PathCoord{ps.pxpy & 0xffffu, ps.pxpy >> 16, ps.sample_index, 0u};
     const uint32_t dim0 = bounce_first_dim(d1, rp.rr_depth);
     float ul0 = 0.0f, ub0 = 0.0f;
     f2 ul12{0.0f, 0.0f}, ub12{0.0f, 0.0f};
@@ -467,12 +472,14 @@ template <class Acc> AKR_HD void shadow_resolve(Acc &acc, const ShadowItem &it, 
 // read-modify-write.  The emitter term of a hit (pt.rs:230-258) is evaluated by the stage that traced the ray — it has
 // the ray origin and the BSDF pdf in registers — which is why neither is part of the record.  Additions to the
 // radiance happen in the reference order: emitter(d), NEE(d), emitter(d + 1), ...
-struct BounceRec {     // 13 words, stored as 4 x 16 B
+struct BounceRec {     // 15 words, stored as 4 x 16 B
     f3 d;              // direction of the ray that produced the hit (wo = -d)
     uint32_t gid;      // hit triangle
     float u, v;
     uint32_t path_id;
+    uint32_t pxpy;     // sensor pixel x | y << 16
     f3 beta;
+    uint32_t sample_index;
     f3 L;              // radiance so far, emitter term of this hit included
 };
 struct TraceHit {      // result of a closest-hit query; gid 0xffffffff = miss
@@ -509,6 +516,8 @@ AKR_HD BounceOut continue_path(const SceneView &sc, const CornerAttribs &ca, con
     r.next.u = h.u;
     r.next.v = h.v;
     r.next.path_id = nx.path_id;
+    r.next.pxpy = nx.pxpy;
+    r.next.sample_index = nx.sample_index;
     r.next.beta = nx.beta;
     r.next.L = L;
     return r;
@@ -524,6 +533,8 @@ AKR_HD BounceOut raygen_fused(const SceneView &sc, const CornerAttribs &ca, cons
     ps.beta = splat3(1.0f);
     ps.prev_bsdf_pdf = 0.0f;
     ps.path_id = path_id;
+    ps.pxpy = 0u;
+    ps.sample_index = 0u;
     if (active) ps = raygen_body(sc, tab, rp, wave, path_id);
     const TraceHit h = tr.closest(active, ps.o, ps.d, ps.ex);
     BounceOut r = continue_path(sc, ca, rp, 0u, active, active, ps, splat3(0.0f), h, acc);
@@ -545,9 +556,13 @@ AKR_HD BounceOut bounce_fused(const SceneView &sc, const CornerAttribs &ca, cons
         ps.beta = in.beta;
         ps.prev_bsdf_pdf = 0.0f;
         ps.path_id = in.path_id;
+        ps.pxpy = in.pxpy;
+        ps.sample_index = in.sample_index;
         o = shade_body<CLS, false>(sc, ca, tab, rp, wave, depth, ps, HitRec{in.gid, in.u, in.v}, acc);
-        o.next.path_id = in.path_id;
     }
+    o.next.path_id = in.path_id;
+    o.next.pxpy = in.pxpy;
+    o.next.sample_index = in.sample_index;
     // the NEE shadow ray and the continuation ray are both known here: one trace call serves both (on the device one walk
     // over the staged primitive list, two independent dependency chains per trip)
     bool occluded;
