@@ -566,6 +566,7 @@ __global__ void __launch_bounds__(kBlock) k_raygen(const __grid_constant__ Launc
         store_path(P.q[0], i, ps);
         st4(P.acc.l + i, f4{0.0f, 0.0f, 0.0f, 0.0f});
         st4(P.acc.b + i, f4{0.0f, 0.0f, 0.0f, 0.0f});
+        P.acc.poison[i] = 0u;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) P.counters[0] = n;
 }
@@ -1202,7 +1203,7 @@ int ensure_wave_buffers(AkrContext *ctx, uint32_t capacity, bool fused, uint32_t
     const size_t cap = ((size_t)capacity + 31u) & ~(size_t)31u;
     size_t n_classes = 0;
     for (uint32_t c = 0; c < (uint32_t)CLS_COUNT; ++c) n_classes += (class_mask >> c) & 1u;
-    const size_t n_vec = fused ? 8 * n_classes + 2 : 3 + 3 + 1 + 3 + 2, n_word = fused ? 0 : 1 + 2 * (size_t)CLS_COUNT;
+    const size_t n_vec = fused ? 8 * n_classes + 2 : 3 + 3 + 1 + 3 + 2, n_word = fused ? 0 : 2 + 2 * (size_t)CLS_COUNT;
     int rc = dev_alloc(ctx, ctx->wave_mem, cap * (n_vec * 16 + n_word * 4));
     if (rc != AKR_OK) return rc;
     f4 *vbase = static_cast<f4 *>(ctx->wave_mem.ptr);
@@ -1219,6 +1220,7 @@ int ensure_wave_buffers(AkrContext *ctx, uint32_t capacity, bool fused, uint32_t
     std::memset(&ctx->cls, 0, sizeof(ctx->cls));
     ctx->acc.l = take_v();
     ctx->acc.b = take_v();
+    ctx->acc.poison = nullptr;  // fused pipeline: the radiance lives in the record, a miss adds its NaN in place
     if (fused) {
         for (int k = 0; k < 2; ++k)
             for (uint32_t c = 0; c < (uint32_t)CLS_COUNT; ++c)
@@ -1237,6 +1239,7 @@ int ensure_wave_buffers(AkrContext *ctx, uint32_t capacity, bool fused, uint32_t
         uint32_t *wbase = reinterpret_cast<uint32_t *>(vbase + voff);
         for (uint32_t c = 0; c < (uint32_t)CLS_COUNT; ++c) ctx->cls.idx[c] = reinterpret_cast<uint2 *>(wbase + cap * 2 * c);
         ctx->shadow.ex1 = wbase + cap * 2 * (size_t)CLS_COUNT;
+        ctx->acc.poison = wbase + cap * (2 * (size_t)CLS_COUNT + 1);
     }
     ctx->wave_capacity = capacity;
     ctx->wave_layout = layout;

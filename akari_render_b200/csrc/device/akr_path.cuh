@@ -116,6 +116,7 @@ struct f4 {             // 16-byte record: one vector load/store per access
 struct AccView {       // per-path radiance accumulators, indexed by path_id (not compacted); zeroed by raygen
     f4 *l;             // radiance (xyz)
     f4 *b;             // base_replay_throughput (xyz)
+    uint32_t *poison;  // queued pipeline: channels of the radiance a miss poisoned with NaN (see miss_body); zeroed by raygen
 };
 AKR_HD f4 ld4(const f4 *p) {
 #if defined(__CUDA_ARCH__)
@@ -262,7 +263,11 @@ AKR_HD void miss_body(const RenderParams &rp, uint32_t depth, f3 beta, uint32_t 
     const bool dbg_on = rp.debug_depth < 0;
     if (depth != 0u && (dbg_on || depth == (uint32_t)rp.debug_depth)) {
         f3 c = beta * (splat3(0.0f) * 0.0f);
-        if (c.x != 0.0f || c.y != 0.0f || c.z != 0.0f) acc_add(acc, id, c);
+        // c is 0 or NaN per channel.  The trace stage that finds the miss runs concurrently with the shadow rays of the same
+        // path (which read-modify-write the radiance), so the NaN is not added here: the poisoned channels are recorded and
+        // accumulate_body applies them — x + NaN = NaN whenever it is added, so the result is the reference's.
+        uint32_t mask = (c.x != 0.0f ? 1u : 0u) | (c.y != 0.0f ? 2u : 0u) | (c.z != 0.0f ? 4u : 0u);
+        if (mask) acc.poison[id] = mask;  // (one miss per path: no other writer)
     }
 }
 
@@ -617,6 +622,11 @@ AKR_HD void accumulate_body(const AccView &acc, const WaveInfo &w, uint32_t p_lo
         uint32_t id = s * w.n_pix + p_local;
         f4 l4 = ld4(acc.l + id), b4 = ld4(acc.b + id);
         f3 L = mk3(l4.x, l4.y, l4.z);
+        if (acc.poison) {  // queued pipeline: a miss with a non-finite throughput poisons the sample (pt.rs:381-396 adds beta * 0)
+            const uint32_t m = acc.poison[id];
+            const float nan = u2f(0x7fc00000u);
+            if (m) L = mk3((m & 1u) ? L.x + nan : L.x, (m & 2u) ? L.y + nan : L.y, (m & 4u) ? L.z + nan : L.z);
+        }
         f3 B = mk3(b4.x, b4.y, b4.z);
         f3 ind = L - B;  // clamp_indirect = 1000, Color::clamp -> [0, max] (pt.rs:130,871-876; color.rs:352-361)
         ind = mk3(clampf(ind.x, 0.0f, 1000.0f), clampf(ind.y, 0.0f, 1000.0f), clampf(ind.z, 0.0f, 1000.0f));

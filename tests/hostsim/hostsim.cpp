@@ -140,7 +140,7 @@ int hostsim_render(const AkrSceneDesc *desc, const AkrPtConfig *cfg, const AkrSa
             // every path writes its radiance and its base_replay_throughput exactly once: start from a sentinel to prove it
             const float kUnset = -7777.0f;
             std::vector<f4> acc(2u * (size_t)n_paths, f4{kUnset, kUnset, kUnset, kUnset});
-            AccView av{acc.data(), acc.data() + n_paths};
+            AccView av{acc.data(), acc.data() + n_paths, nullptr};
             HostTracer tr{sc, td};
             std::vector<BounceRec> cur[CLS_COUNT], next[CLS_COUNT];
             for (uint32_t i = 0; i < n_paths; ++i) {
@@ -176,7 +176,8 @@ int hostsim_render(const AkrSceneDesc *desc, const AkrPtConfig *cfg, const AkrSa
             continue;
         }
         std::vector<f4> acc(2u * (size_t)n_paths, f4{0.0f, 0.0f, 0.0f, 0.0f});  // raygen zeroes the accumulators
-        AccView av{acc.data(), acc.data() + n_paths};
+        std::vector<uint32_t> poison(n_paths, 0u);
+        AccView av{acc.data(), acc.data() + n_paths, poison.data()};
         std::vector<PathState> cur(n_paths), next;
         for (uint32_t i = 0; i < n_paths; ++i) cur[i] = raygen_body(sc, tab, rp, wave, i);
         for (uint32_t depth = 0; depth <= rp.max_depth && !cur.empty(); ++depth) {
@@ -278,7 +279,7 @@ int hostsim_render_aov(const AkrSceneDesc *desc, const AkrAovConfig *cfg, const 
     WaveInfo wave = make_wave(0, n_pixels, 0, cfg->spp);
     const uint32_t n_paths = wave.n_pix * wave.n_spp;
     std::vector<f4> acc(2u * (size_t)n_paths, f4{0.0f, 0.0f, 0.0f, 0.0f});
-    AccView av{acc.data(), acc.data() + n_paths};
+    AccView av{acc.data(), acc.data() + n_paths, nullptr};
     for (uint32_t i = 0; i < n_paths; ++i) {
         PathState ps = raygen_body(sc, tab, rp, wave, i);
         HitRec h = host_trace<false>(sc, td, ps.o, ps.d, 1e20f, 0xffffffffu, 0xffffffffu);

@@ -49,3 +49,22 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp")):
                 text = open(os.path.join(base, f), errors="ignore").read()
                 assert "oracle" not in text.replace("the oracle", "").replace("oracle's", "") or f in ("akr_math.cuh",), (f,)
+
+
+def test_write_image_exr_and_pfm_round_trip(akr, tmp_path):
+    """util::write_image for `.exr` (util/mod.rs:95-127: linear RGB f32) through the host library, read back with an
+    independent decoder (OpenCV's OpenEXR / PFM readers)."""
+    import os
+    os.environ["OPENCV_IO_ENABLE_OPENEXR"] = "1"
+    import numpy as np
+    cv2 = __import__("pytest").importorskip("cv2")
+    rgb = (np.random.default_rng(3).random((9, 13, 3)) * 4.0).astype(np.float32)
+    rgb[0, 0] = (0.0, 1e-6, 1e4)
+    for ext in ("exr", "pfm"):
+        path = str(tmp_path / f"img.{ext}")
+        akr.write_image(path, rgb)
+        back = cv2.imread(path, cv2.IMREAD_UNCHANGED)
+        if back is None and ext == "exr":
+            __import__("pytest").skip("this OpenCV build has no OpenEXR reader")
+        assert back is not None and back.dtype == np.float32 and back.shape == rgb.shape
+        assert np.array_equal(back[..., ::-1], rgb)  # OpenCV returns BGR
