@@ -1144,6 +1144,10 @@ struct AkrContext {
     AkrEngineOptions opts{};
     AkrStats stats{};
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    // fused pipeline with several shade classes: the classes of one depth are independent, so their kernels run on two
+    // streams and the second class's CTAs fill the tail of the first (fork / join with events at every depth)
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t ev_main = nullptr, ev_side = nullptr;
     std::vector<cudaEvent_t> stage_events;
 };
 
@@ -1280,7 +1284,10 @@ int akr_b200_create(int device_ordinal, AkrContext **out_ctx) {
         return AKR_ERR_CUDA;
     }
     ctx->sm_count = prop.multiProcessorCount;
-    if (cudaEventCreate(&ctx->ev_start) != cudaSuccess || cudaEventCreate(&ctx->ev_stop) != cudaSuccess) {
+    if (cudaEventCreate(&ctx->ev_start) != cudaSuccess || cudaEventCreate(&ctx->ev_stop) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_main, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_side, cudaEventDisableTiming) != cudaSuccess) {
         delete ctx;
         return AKR_ERR_CUDA;
     }
@@ -1325,6 +1332,9 @@ void akr_b200_destroy(AkrContext *ctx) {
         dev_free(*b);
     if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
     if (ctx->ev_stop) cudaEventDestroy(ctx->ev_stop);
+    if (ctx->ev_main) cudaEventDestroy(ctx->ev_main);
+    if (ctx->ev_side) cudaEventDestroy(ctx->ev_side);
+    if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
     for (cudaEvent_t e : ctx->stage_events) cudaEventDestroy(e);
     delete ctx;
 }
@@ -1680,10 +1690,34 @@ int akr_b200_render_pass(AkrContext *ctx, uint32_t n_spp, int blocking) {
             };
             if (fused) {
                 AKR_LAUNCH(0, k_raygen_fused, grid_for(ctx, n_paths, ctx->occ_raygen_fused), ctx->flat_bytes, P);
+                // Lambert on the context stream, conductor (and general) on the side stream when both exist: each depth forks
+                // after the previous depth's kernels and joins before the next (per-stage profiling keeps one stream)
+                const bool two_streams = !prof && ctx->opts.fused != 3u && (class_mask & 1u) && (class_mask & 6u);
+                cudaStream_t side = two_streams ? ctx->side_stream : ctx->stream;
                 for (uint32_t depth = 0; depth < ctx->rp.max_depth; ++depth) {
+                    if (two_streams) {  // the side stream waits for everything the context stream has enqueued so far
+                        cudaEventRecord(ctx->ev_main, ctx->stream);
+                        cudaStreamWaitEvent(side, ctx->ev_main, 0);
+                    }
                     if (class_mask & 1u) AKR_LAUNCH_B(2, (k_bounce<1u>), shade_grid(ctx->occ_bounce[0]), kShadeBlock, bounce_smem, P, depth);
-                    if (class_mask & 2u) AKR_LAUNCH_B(3, (k_bounce<2u>), shade_grid(ctx->occ_bounce[1]), kShadeBlock, bounce_smem, P, depth);
-                    if (class_mask & 4u) AKR_LAUNCH_B(6, (k_bounce<4u>), shade_grid(ctx->occ_bounce[2]), kShadeBlock, bounce_smem, P, depth);
+                    if (class_mask & 2u) {
+                        if (prof) AKR_LAUNCH_B(3, (k_bounce<2u>), shade_grid(ctx->occ_bounce[1]), kShadeBlock, bounce_smem, P, depth);
+                        else {
+                            k_bounce<2u><<<shade_grid(ctx->occ_bounce[1]), kShadeBlock, bounce_smem, side>>>(P, depth);
+                            count_launch(3);
+                        }
+                    }
+                    if (class_mask & 4u) {
+                        if (prof) AKR_LAUNCH_B(6, (k_bounce<4u>), shade_grid(ctx->occ_bounce[2]), kShadeBlock, bounce_smem, P, depth);
+                        else {
+                            k_bounce<4u><<<shade_grid(ctx->occ_bounce[2]), kShadeBlock, bounce_smem, side>>>(P, depth);
+                            count_launch(6);
+                        }
+                    }
+                    if (two_streams) {  // join: the next depth (or k_accumulate) needs both
+                        cudaEventRecord(ctx->ev_side, side);
+                        cudaStreamWaitEvent(ctx->stream, ctx->ev_side, 0);
+                    }
                 }
             } else {
                 AKR_LAUNCH(0, k_raygen, grid_for(ctx, n_paths, 8), 0, P);

@@ -316,7 +316,8 @@ typedef struct AkrEngineOptions {
                                      * in shared memory)                                                  */
     uint32_t fused;                 /* 0 = auto (flat scenes without alpha-tested materials run the fused
                                      * bounce kernels: shade + shadow ray + next ray in one kernel per depth
-                                     * and shade class), 2 = off (always trace stage + shade stage + queues) */
+                                     * and shade class), 2 = off (always trace stage + shade stage + queues),
+                                     * 3 = fused, every kernel on the context stream (no side stream; A/B runs) */
     uint32_t smem_node_kb;          /* BVH scenes that do not fit in shared memory: KiB of top-of-tree nodes each
                                      * CTA stages (0 = default 16); read by akr_b200_upload_scene              */
     uint32_t aov_mask;              /* AKR_AOV_* outputs to record; read by akr_b200_begin                    */
