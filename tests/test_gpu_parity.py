@@ -314,3 +314,34 @@ def test_resolve_film_device_rgba_and_tiles(akr, oracle, cbox, cbox_task):
         with pytest.raises(akr.AkariError):  # wrong size
             pt.resolve_into_device(rgba.data_ptr(), rgba.numel() - 4, rgba=True)
     pt.close()
+
+
+def test_api_edges_first_hit_ids_tiles_and_aov(akr, oracle, tables, cbox, cbox_task, tmp_path):
+    """Opt-in outputs and tiles outside the headline path: first-hit ids must be requested before `begin`; an interleaved
+    tile of a BVH / alpha-tested (queued-pipeline) scene and of an `aov` render equals the same rows of the whole frame."""
+    import scene_variants as sv
+    w, h = 48, 30
+    scene, task = cbox(w, h), cbox_task(4)
+    pt = akr.PathTracer(0)
+    pt.render(scene, task)
+    with pytest.raises(akr.AkariError) as e:
+        pt.first_hits()
+    assert e.value.code == 5  # AKR_ERR_STATE: not requested
+    pt.set_engine_options(aov_mask=1)
+    pt.render(scene, task)
+    inst, prim = pt.first_hits()
+    pmj, bn = tables
+    _, _, ofh = oracle.render(scene.desc, w, h, task.pt, task.sampler, task.filter, pmj, bn, want_first_hits=True)
+    assert ((inst == ofh[:, 0]) & (prim == ofh[:, 1])).mean() >= 0.999
+    tex = akr.load_scene(sv.write_textured(tmp_path, alpha_cutout=False)).set_resolution(w, h)
+    full = pt.render(tex, task)
+    rows = [y for y in range(h) if (y // 4) % 3 == 1]
+    part = pt.render(tex, task, tile=(0, h, 4, 3, 1))
+    assert part.rows == len(rows)
+    assert np.array_equal(part.data[:3 * w * len(rows)].reshape(len(rows), w, 3), full.data[:3 * w * h].reshape(h, w, 3)[rows])
+    aov = akr.RenderTask.from_json('{"method": {"type": "aov", "spp": 4, "aov": "albedo"}, "sampler": {"type": "pmj02bn", "seed": 0},'
+                                   ' "film": {"filter": {"type": "gaussian", "radius": 1.5}, "out": "a.exr"}}')
+    a_full = pt.render_aov(tex, aov)
+    a_part = pt.render_aov(tex, aov, tile=(0, h, 4, 3, 1))
+    assert np.array_equal(a_part.data[:3 * w * len(rows)].reshape(len(rows), w, 3), a_full.data[:3 * w * h].reshape(h, w, 3)[rows])
+    pt.close()
