@@ -804,12 +804,21 @@ template <bool SMEM_ALL, bool ALPHA> __global__ void __launch_bounds__(kBlock) k
 #endif
 constexpr int kShadeBlock = AKR_SHADE_BLOCK;
 constexpr int kShadeWarps = kShadeBlock / 32;
+#ifndef AKR_SHADE_MINB_GENERAL
+#define AKR_SHADE_MINB_GENERAL 2  // 128 registers, 2 CTAs per SM: measured 127 vs 166 ms per pass (1 CTA, 206 registers) on the all-Principled box
+#endif
+#ifndef AKR_GENERAL_BLOCK
+#define AKR_GENERAL_BLOCK 256
+#endif
+constexpr int kGeneralBlock = AKR_GENERAL_BLOCK;  // block size of the kernels that carry the full Principled tree
+constexpr int shade_block_of(int cls) { return cls == CLS_GENERAL ? kGeneralBlock : kShadeBlock; }
 template <int CLS> struct ShadeLaunch {
-    static constexpr int kMinBlocks = CLS == CLS_LAMBERT ? AKR_SHADE_MINB_LAMBERT : (CLS == CLS_CONDUCTOR ? AKR_SHADE_MINB_CONDUCTOR : 1);
+    static constexpr int kThreads = shade_block_of(CLS);
+    static constexpr int kMinBlocks = CLS == CLS_LAMBERT ? AKR_SHADE_MINB_LAMBERT : (CLS == CLS_CONDUCTOR ? AKR_SHADE_MINB_CONDUCTOR : AKR_SHADE_MINB_GENERAL);
 };
 
 // Queued pipeline: one shade kernel per material class over the (slot, path id) list the trace stage binned.
-template <int CLS> __global__ void __launch_bounds__(kShadeBlock, ShadeLaunch<CLS>::kMinBlocks) k_shade(const __grid_constant__ LaunchParams P, uint32_t depth) {
+template <int CLS> __global__ void __launch_bounds__(ShadeLaunch<CLS>::kThreads, ShadeLaunch<CLS>::kMinBlocks) k_shade(const __grid_constant__ LaunchParams P, uint32_t depth) {
     uint32_t *ctr = P.counters + depth * kCtrStride;
     const uint32_t n = ctr[2u + CLS];
     const uint2 *slots = P.cls.idx[CLS];
@@ -941,14 +950,14 @@ constexpr uint32_t kTileBytes = 4u * 32u * 16u;  // one warp tile: 32 records x 
 // (32 records each); lane 0 starts the TMA bulk copies of the NEXT tile into the warp's other shared-memory buffer
 // before the warp waits for the current one, so the queue reads never sit on the dependent chain.  `it` counts the tiles
 // this warp has consumed in this launch (it selects the buffer and the mbarrier phase) and carries over from class to class.
-template <int CLS>
+template <int CLS, int WARPS>
 __device__ __forceinline__ void bounce_phase(const LaunchParams &P, uint32_t depth, const DevTracer &tr, uint32_t tiles, uint64_t *tile_bar2, uint32_t &it) {
     const uint32_t n = P.counters[depth * kCtrStride + 2u + CLS];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     const uint32_t bar0 = smem_u32(tile_bar2);
     const RecQueue &qin = P.cq[depth & 1u][CLS];
     const uint64_t pol = l2_evict_first_policy();
-    const uint32_t n_tiles = (n + 31u) >> 5, wstride = gridDim.x * kShadeWarps;
+    const uint32_t n_tiles = (n + 31u) >> 5, wstride = gridDim.x * (uint32_t)WARPS;
     auto issue = [&](uint32_t tile, uint32_t buf) {
         const uint32_t first = tile * 32u;
         const uint32_t bytes = min(32u, n - first) * 16u;
@@ -957,7 +966,7 @@ __device__ __forceinline__ void bounce_phase(const LaunchParams &P, uint32_t dep
 #pragma unroll
         for (uint32_t j = 0; j < 4u; ++j) tma_bulk_g2s_hint(dst + j * 512u, qin.r[j] + first, bytes, b, pol);
     };
-    uint32_t tile = blockIdx.x * kShadeWarps + warp;
+    uint32_t tile = blockIdx.x * (uint32_t)WARPS + warp;
     if (tile < n_tiles && lane == 0u) issue(tile, it & 1u);
     uint32_t n_traced = 0u, n_shadow = 0u;  // warp-uniform
     for (; tile < n_tiles; tile += wstride, ++it) {
@@ -993,12 +1002,15 @@ __device__ __forceinline__ void bounce_phase(const LaunchParams &P, uint32_t dep
 // on eight: the merged kernel's larger code and common register allocation cost more than the saved tails — so the
 // engine launches single-class masks; the template keeps the general form.
 template <uint32_t MASK> struct BounceLaunch {
-    static constexpr int kMinBlocks = (MASK & (1u << CLS_GENERAL)) ? 1 : ((MASK & (1u << CLS_CONDUCTOR)) ? AKR_SHADE_MINB_CONDUCTOR : AKR_SHADE_MINB_LAMBERT);
+    static constexpr int kThreads = (MASK & (1u << CLS_GENERAL)) ? kGeneralBlock : kShadeBlock;
+    static constexpr int kWarps = kThreads / 32;
+    static constexpr int kMinBlocks = (MASK & (1u << CLS_GENERAL)) ? AKR_SHADE_MINB_GENERAL : ((MASK & (1u << CLS_CONDUCTOR)) ? AKR_SHADE_MINB_CONDUCTOR : AKR_SHADE_MINB_LAMBERT);
 };
-template <uint32_t MASK> __global__ void __launch_bounds__(kShadeBlock, BounceLaunch<MASK>::kMinBlocks) k_bounce(const __grid_constant__ LaunchParams P, uint32_t depth) {
+template <uint32_t MASK> __global__ void __launch_bounds__(BounceLaunch<MASK>::kThreads, BounceLaunch<MASK>::kMinBlocks) k_bounce(const __grid_constant__ LaunchParams P, uint32_t depth) {
+    constexpr int kWarps = BounceLaunch<MASK>::kWarps;
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bar;
-    __shared__ uint64_t tile_bar[kShadeWarps][2];
+    __shared__ uint64_t tile_bar[kWarps][2];
     const uint32_t *ctr = P.counters + depth * kCtrStride + 2u;
     uint32_t n_max = 0u;
 #pragma unroll
@@ -1007,7 +1019,7 @@ template <uint32_t MASK> __global__ void __launch_bounds__(kShadeBlock, BounceLa
     if (blockIdx.x * blockDim.x >= n_max) return;  // whole CTA has no work in any class: skip the staging too
     const uint32_t warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
-        for (int w = 0; w < kShadeWarps; ++w) {
+        for (int w = 0; w < kWarps; ++w) {
             mbar_init(&tile_bar[w][0], 1);
             mbar_init(&tile_bar[w][1], 1);
         }
@@ -1016,9 +1028,9 @@ template <uint32_t MASK> __global__ void __launch_bounds__(kShadeBlock, BounceLa
     const uint32_t scene_bytes = (P.scene.n_pair_blocks + P.scene.n_single_blocks + P.scene.n_occ_pair_blocks + P.scene.n_occ_single_blocks) * (uint32_t)sizeof(PrimBlock2);
     const uint32_t tiles = smem_u32(smem) + ((scene_bytes + 127u) & ~127u) + warp * 2u * kTileBytes;
     uint32_t it = 0u;
-    if (MASK & (1u << CLS_LAMBERT)) bounce_phase<CLS_LAMBERT>(P, depth, tr, tiles, &tile_bar[warp][0], it);
-    if (MASK & (1u << CLS_CONDUCTOR)) bounce_phase<CLS_CONDUCTOR>(P, depth, tr, tiles, &tile_bar[warp][0], it);
-    if (MASK & (1u << CLS_GENERAL)) bounce_phase<CLS_GENERAL>(P, depth, tr, tiles, &tile_bar[warp][0], it);
+    if (MASK & (1u << CLS_LAMBERT)) bounce_phase<CLS_LAMBERT, kWarps>(P, depth, tr, tiles, &tile_bar[warp][0], it);
+    if (MASK & (1u << CLS_CONDUCTOR)) bounce_phase<CLS_CONDUCTOR, kWarps>(P, depth, tr, tiles, &tile_bar[warp][0], it);
+    if (MASK & (1u << CLS_GENERAL)) bounce_phase<CLS_GENERAL, kWarps>(P, depth, tr, tiles, &tile_bar[warp][0], it);
 }
 
 // The `aov` method (aov.rs:96-155) after raygen + one trace stage: the first-hit quantity of every camera sample goes to
@@ -1478,6 +1490,7 @@ int akr_b200_upload_scene(AkrContext *ctx, const AkrSceneDesc *desc) {
         ctx->flat_bytes = (uint32_t)(blob.flat_blocks.size() * sizeof(PrimBlock2));
         const size_t smem_flat = (size_t)ctx->smem_nodes * sizeof(BvhNode) + ctx->flat_bytes;
         const size_t smem_bounce = ((ctx->flat_bytes + 127u) & ~127u) + (size_t)kShadeWarps * 2u * kTileBytes;
+        const size_t smem_bounce_general = ((ctx->flat_bytes + 127u) & ~127u) + (size_t)(kGeneralBlock / 32) * 2u * kTileBytes;
         const bool all = ctx->smem_prims != 0;
         if (blob.any_alpha) {
             occ(ctx->occ_trace_flat, (const void *)k_trace_flat<true>, kBlock, smem_flat);
@@ -1488,11 +1501,11 @@ int akr_b200_upload_scene(AkrContext *ctx, const AkrSceneDesc *desc) {
         }
         occ(ctx->occ_shade[0], (const void *)k_shade<CLS_LAMBERT>, kShadeBlock, 0);
         occ(ctx->occ_shade[1], (const void *)k_shade<CLS_CONDUCTOR>, kShadeBlock, 0);
-        occ(ctx->occ_shade[2], (const void *)k_shade<CLS_GENERAL>, kShadeBlock, 0);
+        occ(ctx->occ_shade[2], (const void *)k_shade<CLS_GENERAL>, kGeneralBlock, 0);
         occ(ctx->occ_raygen_fused, (const void *)k_raygen_fused, kBlock, ctx->flat_bytes);
         occ(ctx->occ_bounce[0], (const void *)k_bounce<1u>, kShadeBlock, smem_bounce);
         occ(ctx->occ_bounce[1], (const void *)k_bounce<2u>, kShadeBlock, smem_bounce);
-        occ(ctx->occ_bounce[2], (const void *)k_bounce<4u>, kShadeBlock, smem_bounce);
+        occ(ctx->occ_bounce[2], (const void *)k_bounce<4u>, kGeneralBlock, smem_bounce_general);
         if (e != cudaSuccess) return fail(ctx, AKR_ERR_CUDA, std::string("cudaOccupancyMaxActiveBlocksPerMultiprocessor: ") + cudaGetErrorString(e));
     }
     ctx->scene_ready = true;
@@ -1638,6 +1651,7 @@ int akr_b200_render_pass(AkrContext *ctx, uint32_t n_spp, int blocking) {
     const size_t flat_smem = node_smem + ctx->flat_bytes;
     const size_t trace_smem = trace_mode == TRACE_FLAT ? flat_smem : ctx->smem_bytes + (size_t)P.stack_depth * kBlock * sizeof(int32_t);
     const size_t bounce_smem = ((ctx->flat_bytes + 127u) & ~127u) + (size_t)kShadeWarps * 2u * kTileBytes;
+    const size_t bounce_smem_general = ((ctx->flat_bytes + 127u) & ~127u) + (size_t)(kGeneralBlock / 32) * 2u * kTileBytes;
     if (trace_smem > kSmemMax || bounce_smem > kSmemMax) return fail(ctx, AKR_ERR_UNSUPPORTED, "BVH too deep for the shared-memory traversal stack");
 
     const bool prof = ctx->opts.profile_stages != 0;
@@ -1684,8 +1698,8 @@ int akr_b200_render_pass(AkrContext *ctx, uint32_t n_spp, int blocking) {
             const uint32_t k = std::min(spp_chunk, n_spp - s0);
             P.wave = make_wave(pix0, n_pix, s_begin + s0, k);
             const uint32_t n_paths = n_pix * k;
-            auto shade_grid = [&](int occ) {
-                uint32_t need = (n_paths + kShadeBlock - 1) / kShadeBlock, capn = (uint32_t)(ctx->sm_count * occ);
+            auto shade_grid = [&](int occ, int block = kShadeBlock) {
+                uint32_t need = (n_paths + (uint32_t)block - 1u) / (uint32_t)block, capn = (uint32_t)(ctx->sm_count * occ);
                 return (int)std::max(1u, std::min(need, capn));
             };
             if (fused) {
@@ -1708,9 +1722,9 @@ int akr_b200_render_pass(AkrContext *ctx, uint32_t n_spp, int blocking) {
                         }
                     }
                     if (class_mask & 4u) {
-                        if (prof) AKR_LAUNCH_B(6, (k_bounce<4u>), shade_grid(ctx->occ_bounce[2]), kShadeBlock, bounce_smem, P, depth);
+                        if (prof) AKR_LAUNCH_B(6, (k_bounce<4u>), shade_grid(ctx->occ_bounce[2], kGeneralBlock), kGeneralBlock, bounce_smem_general, P, depth);
                         else {
-                            k_bounce<4u><<<shade_grid(ctx->occ_bounce[2]), kShadeBlock, bounce_smem, side>>>(P, depth);
+                            k_bounce<4u><<<shade_grid(ctx->occ_bounce[2], kGeneralBlock), kGeneralBlock, bounce_smem_general, side>>>(P, depth);
                             count_launch(6);
                         }
                     }
@@ -1742,7 +1756,7 @@ int akr_b200_render_pass(AkrContext *ctx, uint32_t n_spp, int blocking) {
                     }
                     if (class_mask & (1u << CLS_LAMBERT)) AKR_LAUNCH_B(2, (k_shade<CLS_LAMBERT>), shade_grid(ctx->occ_shade[0]), kShadeBlock, 0, P, depth);
                     if (class_mask & (1u << CLS_CONDUCTOR)) AKR_LAUNCH_B(3, (k_shade<CLS_CONDUCTOR>), shade_grid(ctx->occ_shade[1]), kShadeBlock, 0, P, depth);
-                    if (class_mask & (1u << CLS_GENERAL)) AKR_LAUNCH_B(6, (k_shade<CLS_GENERAL>), shade_grid(ctx->occ_shade[2]), kShadeBlock, 0, P, depth);
+                    if (class_mask & (1u << CLS_GENERAL)) AKR_LAUNCH_B(6, (k_shade<CLS_GENERAL>), shade_grid(ctx->occ_shade[2], kGeneralBlock), kGeneralBlock, 0, P, depth);
                 }
             }
             AKR_LAUNCH(4, k_accumulate, grid_for(ctx, n_pix, 8), 0, P);

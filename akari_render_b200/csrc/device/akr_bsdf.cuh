@@ -56,7 +56,9 @@ struct Material {  // 48 words
     uint32_t dynamic;      // some input depends on the hit (image texture / texture coordinates): the record holds the
                            // evaluation at uv = (0, 0) and is re-evaluated per hit from (shader_kind, data_offset), akr_svm.cuh
     uint32_t shader_kind, data_offset;  // ShaderRef (svm/mod.rs:213-219)
-    uint32_t _pad[3];
+    uint32_t alpha_dynamic;  // `dynamic`, and alpha itself can differ from hit to hit (a texture with alpha != 1 texels or
+                             // the zero address mode feeds the closure colour): only then traversal evaluates alpha per hit
+    uint32_t _pad[2];
 };
 static_assert(sizeof(Material) == 192, "Material is 48 words");
 
@@ -267,8 +269,7 @@ AKR_HD BsdfEval mf_transmission_eval(f3 color, float eta_in, TR a, f3 wo, f3 wi)
     }
     return BsdfEval{f, pdf};
 }
-AKR_HD BsdfDir mf_transmission_sample(float eta_in, TR a, f3 wo, f2 u) {  // mod.rs:981-993 + geometry.rs:284-303
-    f3 wh = tr_sample_wh(a, wo, u);
+AKR_HD BsdfDir mf_refract_about(float eta_in, f3 wh, f3 wo) {  // geometry.rs:284-303 on the sampled microfacet normal
     f3 n = wh;
     float cos_i = dot(wo, n);
     float eta = cos_i >= 0.0f ? eta_in : 1.0f / eta_in;
@@ -280,6 +281,9 @@ AKR_HD BsdfDir mf_transmission_sample(float eta_in, TR a, f3 wo, f2 u) {  // mod
     float cos_t = sqrtf(1.0f - sin2_t);
     f3 wt = -wo / eta + (cos_i / eta - cos_t) * n;
     return BsdfDir{wt, !same_hemisphere(wo, wt)};
+}
+AKR_HD BsdfDir mf_transmission_sample(float eta_in, TR a, f3 wo, f2 u) {  // mod.rs:981-993
+    return mf_refract_about(eta_in, tr_sample_wh(a, wo, u), wo);
 }
 
 // weighted_discrete_choice2_and_remap (sampling.rs:61-70): returns true for the first option
@@ -298,75 +302,9 @@ AKR_HD BsdfEval dielectric_eval(f3 kr, f3 kt, float eta, float rough, f3 wo, f3 
     BsdfEval eb = mf_reflection_eval<0>(kr, eta, nullptr, nullptr, a, wo, wi);
     return BsdfEval{ea.f + eb.f, lerpf(ea.pdf, eb.pdf, frac)};
 }
-AKR_HD BsdfDir dielectric_sample(float eta, float rough, f3 wo, float u_select, f2 u) {
-    TR a = tr_from_roughness(rough);
-    float frac = fr_dielectric(cos_theta(wo), eta);
-    // choice(frac, 1, 0): first -> bsdf_b (reflection)
-    if (choose2(frac, u_select)) return mf_reflection_sample(a, wo, u);
-    return mf_transmission_sample(eta, a, wo, u);
-}
 
-// ---- the Principled tree in the material-local frame (principled.rs:143-199) ----------------------
+// ---- the Principled tree in the material-local frame (principled.rs:143-199): general_eval / general_sample below ----
 AKR_HD f3 ld3(const float *p) { return mk3(p[0], p[1], p[2]); }
-
-AKR_HD BsdfEval principled_base_eval(const Material &m, const float *table, f3 wo, f3 wi) {
-    // bsdf0 = Mix(diffuse, dielectric, transmission)   (principled.rs:143-148; mod.rs:606-619)
-    const float EPS = 1e-4f;
-    float tr = m.transmission;
-    BsdfEval ea = tr < 1.0f - EPS ? diffuse_eval(ld3(m.diffuse), wo, wi) : zero_eval();
-    BsdfEval eb = tr > EPS ? dielectric_eval(ld3(m.color), ld3(m.trans_color), m.eta, m.roughness_raw, wo, wi) : zero_eval();
-    BsdfEval bottom = BsdfEval{lerp3(ea.f, eb.f, tr), lerpf(ea.pdf, eb.pdf, tr)};
-    if (!(m.lobes & LOBE_SPECULAR)) return bottom;  // CoatedBsdf with e_top == 0 and top colour == 0
-    // bsdf1 = Coated(top = specular GGX, bottom, e_top)   (principled.rs:55-80,151-168; mod.rs:486-503)
-    TR a = tr_from_roughness(m.roughness);
-    BsdfEval top = mf_reflection_eval<0>(ld3(m.spec_tint) * m.f0, m.eta_s, nullptr, nullptr, a, wo, wi);
-    f3 tint = ld3(m.spec_tint);
-    f3 eo = tint * ggx_dielectric_albedo(table, m.roughness, abs_cos_theta(wo), m.eta_s) * m.f0;
-    f3 ei = tint * ggx_dielectric_albedo(table, m.roughness, abs_cos_theta(wi), m.eta_s) * m.f0;
-    float p_top = avg3(eo);
-    float pdf = top.pdf * p_top + bottom.pdf * (1.0f - p_top);
-    f3 f = top.f + bottom.f * min3(splat3(1.0f) - eo, splat3(1.0f) - ei);
-    return BsdfEval{f, pdf};
-}
-AKR_HD BsdfDir principled_base_sample(const Material &m, const float *table, f3 wo, float u_select, f2 u) {
-    if (m.lobes & LOBE_SPECULAR) {
-        f3 eo = ld3(m.spec_tint) * ggx_dielectric_albedo(table, m.roughness, abs_cos_theta(wo), m.eta_s) * m.f0;
-        if (choose2(avg3(eo), u_select)) return mf_reflection_sample(tr_from_roughness(m.roughness), wo, u);
-    }  // else: choice with weight 0 never picks the top lobe and remaps u to (u - 0) / (1 - 0) == u
-    // Mix(diffuse, dielectric, transmission): choice(frac, 1, 0) -> first = bsdf_b (dielectric)
-    if (choose2(m.transmission, u_select)) return dielectric_sample(m.eta, m.roughness_raw, wo, u_select, u);
-    return diffuse_sample(wo, u);
-}
-
-AKR_HD BsdfEval principled_eval(const Material &m, const float *table, f3 wo, f3 wi) {
-    const float EPS = 1e-4f;
-    // bsdf2 = Mix(bsdf1, metal, metallic)   (principled.rs:131-142,170-175)
-    float mt = m.metallic;
-    BsdfEval ea = mt < 1.0f - EPS ? principled_base_eval(m, table, wo, wi) : zero_eval();
-    BsdfEval eb = mt > EPS ? mf_reflection_eval<1>(splat3(1.0f), 0.0f, m.metal_n, m.metal_k, tr_from_roughness(m.roughness), wo, wi) : zero_eval();
-    BsdfEval e2 = BsdfEval{lerp3(ea.f, eb.f, mt), lerpf(ea.pdf, eb.pdf, mt)};
-    // EmissiveSurface: pass-through; ScaledBsdf(weight = lerp(1, coat_tint, coat_weight))  (principled.rs:178-193)
-    BsdfEval scaled = BsdfEval{e2.f * ld3(m.coat_scale), e2.pdf};
-    if (!(m.lobes & LOBE_COAT)) return scaled;
-    // bsdf4 = Coated(top = clearcoat GGX, bottom = scaled, e_top)   (principled.rs:81-98,183-199)
-    TR a = tr_from_roughness(m.coat_roughness);
-    BsdfEval top = mf_reflection_eval<0>(splat3(1.0f) * m.coat_weight, m.coat_ior, nullptr, nullptr, a, wo, wi);
-    f3 eo = splat3(1.0f) * m.coat_weight * ggx_dielectric_albedo(table, m.coat_roughness, abs_cos_theta(wo), m.coat_ior);
-    f3 ei = splat3(1.0f) * m.coat_weight * ggx_dielectric_albedo(table, m.coat_roughness, abs_cos_theta(wi), m.coat_ior);
-    float p_top = avg3(eo);
-    float pdf = top.pdf * p_top + scaled.pdf * (1.0f - p_top);
-    f3 f = top.f + scaled.f * min3(splat3(1.0f) - eo, splat3(1.0f) - ei);
-    return BsdfEval{f, pdf};
-}
-AKR_HD BsdfDir principled_sample(const Material &m, const float *table, f3 wo, float u_select, f2 u) {
-    if (m.lobes & LOBE_COAT) {
-        f3 eo = splat3(1.0f) * m.coat_weight * ggx_dielectric_albedo(table, m.coat_roughness, abs_cos_theta(wo), m.coat_ior);
-        if (choose2(avg3(eo), u_select)) return mf_reflection_sample(tr_from_roughness(m.coat_roughness), wo, u);
-    }
-    // Mix(bsdf1, metal, metallic): choice(frac, 1, 0) -> first = metal
-    if (choose2(m.metallic, u_select)) return mf_reflection_sample(tr_from_roughness(m.roughness), wo, u);
-    return principled_base_sample(m, table, wo, u_select, u);
-}
 
 // SurfaceClosure::check_wo_wi_valid (mod.rs:706-718)
 AKR_HD bool check_wo_wi_valid(f3 ns, f3 ng, f3 wo, f3 wi) {
@@ -407,27 +345,105 @@ AKR_HD float albedo_table_cell(uint32_t cell, uint32_t n) {
 }
 
 // ---- material dispatch in the material-local frame -----------------------------------------------
+// The general class (every material type in one kernel) keeps ONE copy of each building block: the leaves a material
+// needs are evaluated first — diffuse, dielectric (GGX transmission + reflection), metal (GGX with complex Fresnel) —
+// and then combined by type.  The arithmetic per leaf and per combination is the reference's, operation for operation;
+// what changes against a per-type switch of fully inlined trees is the code size (the general kernels were 19 K
+// instructions, a third of their issue slots went to instruction fetch), not a single result bit.
+AKR_HD BsdfEval general_eval(const Material &m, const float *table, f3 wo, f3 wi) {
+    const float EPS = 1e-4f;  // BsdfMixture::EPS
+    const uint32_t type = m.type;
+    const bool is_p = type == MAT_PRINCIPLED;
+    const float mt = m.metallic, tr = m.transmission;
+    const bool base = is_p && mt < 1.0f - EPS;  // bsdf1 takes part in Mix(bsdf1, metal, metallic)   (principled.rs:131-142,170-175)
+    BsdfEval e_diff = zero_eval(), e_diel = zero_eval(), e_metal = zero_eval();
+    if (type == MAT_LAMBERT || (base && tr < 1.0f - EPS)) e_diff = diffuse_eval(ld3(m.diffuse), wo, wi);
+    if (type == MAT_GLASS || (base && tr > EPS)) e_diel = dielectric_eval(ld3(m.color), ld3(m.trans_color), m.eta, m.roughness_raw, wo, wi);
+    if (type == MAT_CONDUCTOR || (is_p && mt > EPS))
+        e_metal = mf_reflection_eval<1>(splat3(1.0f), 0.0f, m.metal_n, m.metal_k, tr_from_roughness(m.roughness), wo, wi);
+    if (type == MAT_LAMBERT) return e_diff;
+    if (type == MAT_CONDUCTOR) return e_metal;
+    if (type == MAT_GLASS) return e_diel;
+    if (!is_p) return zero_eval();
+    // bsdf0 = Mix(diffuse, dielectric, transmission)   (principled.rs:143-148; mod.rs:606-619)
+    BsdfEval ea = zero_eval();
+    if (base) {
+        ea = BsdfEval{lerp3(e_diff.f, e_diel.f, tr), lerpf(e_diff.pdf, e_diel.pdf, tr)};
+        if (m.lobes & LOBE_SPECULAR) {  // bsdf1 = Coated(top = specular GGX, bottom = bsdf0, e_top)   (principled.rs:55-80,151-168; mod.rs:486-503)
+            TR a = tr_from_roughness(m.roughness);
+            BsdfEval top = mf_reflection_eval<0>(ld3(m.spec_tint) * m.f0, m.eta_s, nullptr, nullptr, a, wo, wi);
+            f3 tint = ld3(m.spec_tint);
+            f3 eo = tint * ggx_dielectric_albedo(table, m.roughness, abs_cos_theta(wo), m.eta_s) * m.f0;
+            f3 ei = tint * ggx_dielectric_albedo(table, m.roughness, abs_cos_theta(wi), m.eta_s) * m.f0;
+            float p_top = avg3(eo);
+            float pdf = top.pdf * p_top + ea.pdf * (1.0f - p_top);
+            f3 f = top.f + ea.f * min3(splat3(1.0f) - eo, splat3(1.0f) - ei);
+            ea = BsdfEval{f, pdf};
+        }
+    }
+    // bsdf2 = Mix(bsdf1, metal, metallic); EmissiveSurface: pass-through; ScaledBsdf(lerp(1, coat_tint, coat_weight))  (principled.rs:178-193)
+    BsdfEval e2 = BsdfEval{lerp3(ea.f, e_metal.f, mt), lerpf(ea.pdf, e_metal.pdf, mt)};
+    BsdfEval scaled = BsdfEval{e2.f * ld3(m.coat_scale), e2.pdf};
+    if (!(m.lobes & LOBE_COAT)) return scaled;
+    // bsdf4 = Coated(top = clearcoat GGX, bottom = scaled, e_top)   (principled.rs:81-98,183-199)
+    TR a = tr_from_roughness(m.coat_roughness);
+    BsdfEval top = mf_reflection_eval<0>(splat3(1.0f) * m.coat_weight, m.coat_ior, nullptr, nullptr, a, wo, wi);
+    f3 eo = splat3(1.0f) * m.coat_weight * ggx_dielectric_albedo(table, m.coat_roughness, abs_cos_theta(wo), m.coat_ior);
+    f3 ei = splat3(1.0f) * m.coat_weight * ggx_dielectric_albedo(table, m.coat_roughness, abs_cos_theta(wi), m.coat_ior);
+    float p_top = avg3(eo);
+    float pdf = top.pdf * p_top + scaled.pdf * (1.0f - p_top);
+    f3 f = top.f + scaled.f * min3(splat3(1.0f) - eo, splat3(1.0f) - ei);
+    return BsdfEval{f, pdf};
+}
+// sample_wi of any material: walk the tree to ONE lobe (the choose2 sequence of BsdfMixture / CoatedBsdf::sample_wi,
+// mod.rs:504-535,620-640), then run one copy of the visible-normal sampling for whichever GGX lobe was picked.
+AKR_HD BsdfDir general_sample(const Material &m, const float *table, f3 wo, float u_select, f2 u) {
+    enum { PICK_NONE, PICK_DIFFUSE, PICK_REFLECT, PICK_DIELECTRIC };
+    int pick = PICK_NONE;
+    float rough = 0.0f;
+    switch (m.type) {
+    case MAT_LAMBERT: pick = PICK_DIFFUSE; break;
+    case MAT_CONDUCTOR: pick = PICK_REFLECT; rough = m.roughness; break;
+    case MAT_GLASS: pick = PICK_DIELECTRIC; break;
+    case MAT_PRINCIPLED: {
+        if (m.lobes & LOBE_COAT) {
+            f3 eo = splat3(1.0f) * m.coat_weight * ggx_dielectric_albedo(table, m.coat_roughness, abs_cos_theta(wo), m.coat_ior);
+            if (choose2(avg3(eo), u_select)) { pick = PICK_REFLECT; rough = m.coat_roughness; break; }
+        }
+        // Mix(bsdf1, metal, metallic): choice(frac, 1, 0) -> first = metal
+        if (choose2(m.metallic, u_select)) { pick = PICK_REFLECT; rough = m.roughness; break; }
+        if (m.lobes & LOBE_SPECULAR) {
+            f3 eo = ld3(m.spec_tint) * ggx_dielectric_albedo(table, m.roughness, abs_cos_theta(wo), m.eta_s) * m.f0;
+            if (choose2(avg3(eo), u_select)) { pick = PICK_REFLECT; rough = m.roughness; break; }
+        }  // else: choice with weight 0 never picks the top lobe and remaps u to (u - 0) / (1 - 0) == u
+        // Mix(diffuse, dielectric, transmission): choice(frac, 1, 0) -> first = bsdf_b (dielectric)
+        pick = choose2(m.transmission, u_select) ? PICK_DIELECTRIC : PICK_DIFFUSE;
+        break;
+    }
+    default: break;
+    }
+    if (pick == PICK_NONE) return BsdfDir{splat3(0.0f), false};
+    if (pick == PICK_DIFFUSE) return diffuse_sample(wo, u);
+    bool refract = false;
+    if (pick == PICK_DIELECTRIC) {  // dielectric_sample: choice(frac, 1, 0): first -> reflection
+        rough = m.roughness_raw;
+        float frac = fr_dielectric(cos_theta(wo), m.eta);
+        refract = !choose2(frac, u_select);
+    }
+    f3 wh = tr_sample_wh(tr_from_roughness(rough), wo, u);
+    if (refract) return mf_refract_about(m.eta, wh, wo);
+    f3 wi = reflect(wo, wh);
+    return BsdfDir{wi, same_hemisphere(wo, wi)};
+}
 template <int CLS> AKR_HD BsdfEval material_eval(const Material &m, const float *table, f3 wo, f3 wi) {
     if (CLS == CLS_LAMBERT) return diffuse_eval(ld3(m.diffuse), wo, wi);
     if (CLS == CLS_CONDUCTOR) return mf_reflection_eval<1>(splat3(1.0f), 0.0f, m.metal_n, m.metal_k, tr_from_roughness(m.roughness), wo, wi);
-    switch (m.type) {
-    case MAT_LAMBERT: return diffuse_eval(ld3(m.diffuse), wo, wi);
-    case MAT_CONDUCTOR: return mf_reflection_eval<1>(splat3(1.0f), 0.0f, m.metal_n, m.metal_k, tr_from_roughness(m.roughness), wo, wi);
-    case MAT_PRINCIPLED: return principled_eval(m, table, wo, wi);
-    case MAT_GLASS: return dielectric_eval(ld3(m.color), ld3(m.trans_color), m.eta, m.roughness_raw, wo, wi);
-    default: return zero_eval();
-    }
+    return general_eval(m, table, wo, wi);
 }
 template <int CLS> AKR_HD BsdfDir material_sample(const Material &m, const float *table, f3 wo, float u_select, f2 u) {
     if (CLS == CLS_LAMBERT) return diffuse_sample(wo, u);
     if (CLS == CLS_CONDUCTOR) return mf_reflection_sample(tr_from_roughness(m.roughness), wo, u);
-    switch (m.type) {
-    case MAT_LAMBERT: return diffuse_sample(wo, u);
-    case MAT_CONDUCTOR: return mf_reflection_sample(tr_from_roughness(m.roughness), wo, u);
-    case MAT_PRINCIPLED: return principled_sample(m, table, wo, u_select, u);
-    case MAT_GLASS: return dielectric_sample(m.eta, m.roughness_raw, wo, u_select, u);
-    default: return BsdfDir{splat3(0.0f), false};
-    }
+    return general_sample(m, table, wo, u_select, u);
 }
 
 // The two nested SurfaceClosures the reference wraps around a surface shader:

@@ -14,9 +14,13 @@
 #if defined(__CUDACC__)
 #define AKR_HD __host__ __device__ __forceinline__
 #define AKR_D __device__ __forceinline__
+#define AKR_HD_NOINLINE __host__ __device__ __noinline__   // big cold bodies called from several places of a hot loop
+#define AKR_NO_UNROLL _Pragma("unroll 1")
 #else
 #define AKR_HD inline
 #define AKR_D inline
+#define AKR_HD_NOINLINE inline
+#define AKR_NO_UNROLL
 #endif
 
 // Read-only scene / table data.  Routing these through __ldg (LDG.E.CONSTANT) was measured on B200 and LOST 4 % in the

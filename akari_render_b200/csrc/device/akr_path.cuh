@@ -420,22 +420,49 @@ AKR_HD ShadeOut shade_body(const SceneView &sc, const CornerAttribs &ca, const S
     }
     ClosureFrames cf = make_closure_frames(*m, si.frame, si.ng);
     f3 direct = splat3(0.0f);
-    if (dl_valid) {
-        BsdfEval e = closure_eval<CLS>(*m, sc.albedo_table, cf, wo, dl_wi);
-        float w = mis_weight(dl_pdf, e.pdf);
-        direct = dl_li * e.f * w / dl_pdf;
-    }
-    // SurfaceClosure::sample (mod.rs:795-815)
-    BsdfDir sd = closure_sample_wi<CLS>(*m, sc.albedo_table, cf, wo, ub0, ub12);
     f3 bs_wi = splat3(0.0f), bs_color = splat3(0.0f);
     float bs_pdf = 0.0f;
     bool bs_valid = false;
-    if (sd.valid) {
-        BsdfEval e = closure_eval<CLS>(*m, sc.albedo_table, cf, wo, sd.wi);
-        bs_wi = sd.wi;
-        bs_color = e.f;
-        bs_pdf = e.pdf;
-        bs_valid = e.pdf > 0.0f;
+    if (CLS == CLS_GENERAL || CLS == CLS_ANY) {
+        // The full tree is evaluated twice per bounce, for the light direction and for the sampled direction.  Both go
+        // through ONE copy of the evaluation code (a two-trip loop that is not unrolled); the direction is sampled
+        // first, it does not depend on the light evaluation.
+        BsdfDir sd = closure_sample_wi<CLS>(*m, sc.albedo_table, cf, wo, ub0, ub12);  // SurfaceClosure::sample (mod.rs:795-815)
+        BsdfEval e_dl = zero_eval(), e_bs = zero_eval();
+        AKR_NO_UNROLL
+        for (int k = 0; k < 2; ++k) {
+            const bool want = k == 0 ? dl_valid : sd.valid;
+            const f3 wi = k == 0 ? dl_wi : sd.wi;
+            BsdfEval e = zero_eval();
+            if (want) e = closure_eval<CLS>(*m, sc.albedo_table, cf, wo, wi);
+            if (k == 0) e_dl = e;
+            else e_bs = e;
+        }
+        if (dl_valid) {
+            float w = mis_weight(dl_pdf, e_dl.pdf);
+            direct = dl_li * e_dl.f * w / dl_pdf;
+        }
+        if (sd.valid) {
+            bs_wi = sd.wi;
+            bs_color = e_bs.f;
+            bs_pdf = e_bs.pdf;
+            bs_valid = e_bs.pdf > 0.0f;
+        }
+    } else {
+        if (dl_valid) {
+            BsdfEval e = closure_eval<CLS>(*m, sc.albedo_table, cf, wo, dl_wi);
+            float w = mis_weight(dl_pdf, e.pdf);
+            direct = dl_li * e.f * w / dl_pdf;
+        }
+        // SurfaceClosure::sample (mod.rs:795-815)
+        BsdfDir sd = closure_sample_wi<CLS>(*m, sc.albedo_table, cf, wo, ub0, ub12);
+        if (sd.valid) {
+            BsdfEval e = closure_eval<CLS>(*m, sc.albedo_table, cf, wo, sd.wi);
+            bs_wi = sd.wi;
+            bs_color = e.f;
+            bs_pdf = e.pdf;
+            bs_valid = e.pdf > 0.0f;
+        }
     }
     if (dl_valid) {  // the occlusion test and add_radiance(direct) happen in the shadow stage (pt.rs:504-513)
         out.has_shadow = true;

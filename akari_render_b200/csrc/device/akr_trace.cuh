@@ -62,16 +62,19 @@ AKR_HD f2 hit_uv(const SceneView &sc, uint32_t gid, float u, float v, bool for_a
     return f2{w * a[0] + u * b[0] + v * c[0], w * a[1] + u * b[1] + v * c[1]};
 }
 // scene.rs:49-86: pass if alpha >= 1 or alpha > hash / 2^32; alpha = Surface::alpha() of the material in SvmEvalMode::Alpha
+// texture-driven alpha: ONE out-of-line copy of the shader interpreter per kernel (inlined at every candidate-hit site it
+// made the alpha variants of the traversal kernels 26 K instructions long, 25x the opaque ones)
+AKR_HD_NOINLINE float alpha_of_dynamic(const SceneView &sc, const Material &mat, uint32_t gid, float u, float v) {
+    Material tmp;
+    svm_eval<true, false>(sc.svm, mat.shader_kind, mat.data_offset, hit_uv(sc, gid, u, v, true), tmp, nullptr);
+    return tmp.alpha;
+}
 AKR_HD bool alpha_test(const SceneView &sc, uint32_t gid, float u, float v) {
     const TriShade &ts = sc.shade[gid];
     if (!(ts.flags & TRI_ALPHA)) return true;
     const Material &mat = sc.materials[ts.mat];
     float alpha = mat.alpha;
-    if (mat.dynamic) {
-        Material tmp;
-        svm_eval<true, false>(sc.svm, mat.shader_kind, mat.data_offset, hit_uv(sc, gid, u, v, true), tmp, nullptr);
-        alpha = tmp.alpha;
-    }
+    if (mat.alpha_dynamic) alpha = alpha_of_dynamic(sc, mat, gid, u, v);
     uint32_t h = xxhash32_4(ts.inst, ts.prim, f2u(u), f2u(v));
     float hf = (float)h * (float)(1.0 / 4294967295.0);
     return (alpha >= 1.0f) || (alpha > hf);

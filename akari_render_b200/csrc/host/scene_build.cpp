@@ -18,6 +18,42 @@ namespace {
 // SVM: every material's node program is evaluated once here with the evaluator the kernels use (akr_svm.cuh).  A
 // program without hit-dependent nodes folds to constants; a texture-driven one keeps its ShaderRef for per-hit evaluation.
 // ---------------------------------------------------------------------------------------------
+// Can the alpha of shader (kind, data_offset) differ from hit to hit?  Alpha is the fourth component of the colour that
+// feeds a Diffuse / Principled closure (diffuse.rs:85-92, principled.rs:15-22); it is carried by image textures
+// (eval.rs:137-157) through spectral uplift (eval.rs:158-180) and the checkerboard.  A texture contributes a varying alpha
+// when one of its texels has alpha != 1 or when its address mode returns zeros outside [0, 1)^2 (bilinear weights
+// (1 - t) + t of an all-ones alpha round to exactly 1, so opaque textures stay exactly opaque).  Everything else has a
+// constant alpha of exactly 1 and the material's triangles need no stochastic alpha test at all.
+// Called after svm_eval<., true> has validated the program; `svm.textures` are the host copies.
+bool alpha_varies(const SvmView &svm, AkrShaderRef ref) {
+    const uint32_t first = svm.kind_first[ref.shader_kind], n_nodes = svm.kind_first[ref.shader_kind + 1u] - first;
+    bool av[kSvmMaxNodes] = {};
+    bool varies = false;
+    for (uint32_t i = 0; i < n_nodes; ++i) {
+        const AkrSvmNode &n = svm.nodes[first + i];
+        switch (n.op) {
+        case AKR_SVM_RGB_IMAGE_TEX: {
+            uint32_t tex;
+            std::memcpy(&tex, svm.data + ref.data_offset + n.a[0], 4);
+            const TextureRec &t = svm.textures[tex];
+            bool v = t.address != AKR_ADDRESS_REPEAT && t.address != AKR_ADDRESS_MIRROR && t.address != AKR_ADDRESS_EDGE;
+            const size_t n_texels = static_cast<size_t>(t.width) * t.height;
+            for (size_t k = 0; k < n_texels && !v; ++k)
+                v = t.texel_format == AKR_TEXEL_RGBA8 ? static_cast<const uint8_t *>(t.texels)[4 * k + 3] != 255u
+                                                      : static_cast<const float *>(t.texels)[4 * k + 3] != 1.0f;
+            av[i] = v;
+            break;
+        }
+        case AKR_SVM_SPECTRAL_UPLIFT: av[i] = av[n.a[0]]; break;
+        case AKR_SVM_CHECKERBOARD: av[i] = av[n.a[2]] || av[n.a[3]]; break;
+        case AKR_SVM_DIFFUSE_BSDF: varies |= av[n.a[0]]; break;
+        case AKR_SVM_PRINCIPLED_BSDF: varies |= av[n.a[AKR_P_BASE_COLOR]]; break;
+        default: break;  // scalars, vectors, rgb constants (alpha 1), glass and emission (alpha stays 1)
+        }
+    }
+    return varies;
+}
+
 int fold_material(const SvmView &svm, AkrShaderRef ref, Material &m, std::string &err) {
     std::memset(&m, 0, sizeof(m));
     bool dynamic = false;
@@ -31,6 +67,7 @@ int fold_material(const SvmView &svm, AkrShaderRef ref, Material &m, std::string
         return AKR_ERR_UNSUPPORTED;
     }
     m.dynamic = dynamic ? 1u : 0u;
+    m.alpha_dynamic = (dynamic && alpha_varies(svm, ref)) ? 1u : 0u;
     m.shader_kind = ref.shader_kind;
     m.data_offset = ref.data_offset;
     return AKR_OK;
@@ -451,7 +488,7 @@ int build_scene_blob(const AkrSceneDesc &d, HostSceneBlob &out, std::string &err
             if (g.normals) flags |= TRI_HAS_NORMALS;
             if (g.tangents) flags |= TRI_HAS_TANGENTS;
             if (g.uvs) flags |= TRI_HAS_UVS;
-            if (!(out.materials[ts.mat].alpha >= 1.0f) || out.materials[ts.mat].dynamic) {  // (a texture-driven alpha is only known per hit)
+            if (!(out.materials[ts.mat].alpha >= 1.0f) || out.materials[ts.mat].alpha_dynamic) {  // (a texture-driven alpha is only known per hit)
                 flags |= TRI_ALPHA;
                 out.any_alpha = 1;
             }

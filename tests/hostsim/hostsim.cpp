@@ -60,6 +60,7 @@ struct HostsimStats {
     uint32_t n_prims, n_pairs;
     uint32_t flat_blocks, flat_occluder_blocks;  // flat trace mode: 2-primitive blocks of the complete / occluder-only list
     uint32_t n_nodes4, bvh4_depth;
+    uint32_t any_alpha, any_dynamic;  // some triangle needs the stochastic alpha test / some material is texture-driven
 };
 
 // 0: Moeller-Trumbore triangles over the binary BVH (bit-exact twin of the oracle); 1: the CUDA kernels' primitive
@@ -241,6 +242,8 @@ int hostsim_render(const AkrSceneDesc *desc, const AkrPtConfig *cfg, const AkrSa
         stats->n_lights = (uint32_t)blob.lights.size();
         stats->bvh_depth = blob.bvh_depth;
         for (const Material &m : blob.materials) stats->material_types[m.type & 7u]++;
+        stats->any_alpha = blob.any_alpha;
+        stats->any_dynamic = blob.any_dynamic;
     }
     return AKR_OK;
 }

@@ -16,7 +16,8 @@ class HostsimStats(C.Structure):
     _fields_ = [("samples", C.c_uint64), ("segments", C.c_uint64), ("shadow_rays", C.c_uint64), ("n_nodes", C.c_uint32),
                 ("n_tris", C.c_uint32), ("n_materials", C.c_uint32), ("n_lights", C.c_uint32), ("bvh_depth", C.c_uint32),
                 ("material_types", C.c_uint32 * 8), ("n_prims", C.c_uint32), ("n_pairs", C.c_uint32),
-                ("flat_blocks", C.c_uint32), ("flat_occluder_blocks", C.c_uint32), ("n_nodes4", C.c_uint32), ("bvh4_depth", C.c_uint32)]
+                ("flat_blocks", C.c_uint32), ("flat_occluder_blocks", C.c_uint32), ("n_nodes4", C.c_uint32), ("bvh4_depth", C.c_uint32),
+                ("any_alpha", C.c_uint32), ("any_dynamic", C.c_uint32)]
 
 
 @pytest.fixture(scope="module", params=["queued", "fused"])

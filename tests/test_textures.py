@@ -96,6 +96,9 @@ def test_textured_scene_hostsim_bitwise(akr, oracle, tables, cbox_task, tmp_path
         assert np.array_equal(fh, ofh)
         assert (st.segments, st.shadow_rays) == (ost.segments, ost.shadow_rays)
         assert np.array_equal(film, ofilm)
+        # opaque textures (every texel alpha 1, no zero address mode) need no alpha test at all: the scene keeps the plain
+        # traversal and, being flat, the fused pipeline (scene_build.cpp alpha_varies)
+        assert st.any_dynamic == 1 and st.any_alpha == (1 if alpha else 0)
         # the primitive intersector (what the kernels run).  Opaque variant: the usual per-pixel gate.  Alpha cutout: the
         # alpha test hashes the BITS of the barycentrics (scene.rs:57-63), which differ in the last place between two
         # intersectors (as between the reference's own OptiX and Embree back ends), so every stochastic decision is
