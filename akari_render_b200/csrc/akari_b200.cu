@@ -810,12 +810,62 @@ constexpr int kShadeWarps = kShadeBlock / 32;
 #ifndef AKR_GENERAL_BLOCK
 #define AKR_GENERAL_BLOCK 256
 #endif
+#ifndef AKR_GENERAL_SORT
+#define AKR_GENERAL_SORT 1
+#endif
 constexpr int kGeneralBlock = AKR_GENERAL_BLOCK;  // block size of the kernels that carry the full Principled tree
 constexpr int shade_block_of(int cls) { return cls == CLS_GENERAL ? kGeneralBlock : kShadeBlock; }
 template <int CLS> struct ShadeLaunch {
     static constexpr int kThreads = shade_block_of(CLS);
     static constexpr int kMinBlocks = CLS == CLS_LAMBERT ? AKR_SHADE_MINB_LAMBERT : (CLS == CLS_CONDUCTOR ? AKR_SHADE_MINB_CONDUCTOR : AKR_SHADE_MINB_GENERAL);
 };
+
+// General class: the records of one CTA tile (2 per thread) are ordered by the material's sort key in shared memory
+// before they are shaded.  The queue order is the order in which paths happened to land on general materials, so a warp
+// of the plain tile feed evaluates the UNION of its lanes' trees (ncu on the all-Principled box: 14.9 of 32 lanes active);
+// after the counting sort a warp holds a run of one signature.  Keys are numbered by increasing cost and every warp takes
+// one run from the front of the sorted tile and one from the back, which evens out the time per warp between the two
+// __syncthreads of a tile.  The result does not depend on the record order (one path per record, own accumulator slots).
+struct SortScratch {
+    uint32_t hist[32];
+    uint32_t first[32];
+    uint16_t order[2 * kGeneralBlock];
+};
+// Counting sort of a CTA tile's 2 x THREADS slot indices by key (slot idx = threadIdx.x + j * THREADS carries key[j]; slots at
+// or past `cnt` must carry TRI_SORT_KEY_MASK and come out flagged 0x8000 at the back): per-warp aggregated histogram,
+// exclusive scan by warp 0, scatter.  Every thread of the CTA calls it; ss.order is complete when it returns.
+template <int THREADS> __device__ __forceinline__ void sort_tile_by_key(SortScratch &ss, const uint32_t (&key)[2], uint32_t cnt) {
+    const uint32_t lane = threadIdx.x & 31u, below = (1u << lane) - 1u;
+    if (threadIdx.x < 32) ss.hist[threadIdx.x] = 0u;
+    __syncthreads();
+    uint32_t rank[2];
+#pragma unroll
+    for (uint32_t j = 0; j < 2u; ++j) {
+        const uint32_t peers = __match_any_sync(0xffffffffu, key[j]);
+        const int leader = __ffs(peers) - 1;
+        uint32_t b = 0u;
+        if ((int)lane == leader) b = atomicAdd(&ss.hist[key[j]], (uint32_t)__popc(peers));
+        rank[j] = __shfl_sync(0xffffffffu, b, leader) + (uint32_t)__popc(peers & below);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const uint32_t v = ss.hist[lane];
+        uint32_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)lane >= o) incl += t;
+        }
+        ss.first[lane] = incl - v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (uint32_t j = 0; j < 2u; ++j) {
+        const uint32_t idx = threadIdx.x + j * THREADS;
+        ss.order[ss.first[key[j]] + rank[j]] = (uint16_t)(idx | (idx < cnt ? 0u : 0x8000u));
+    }
+    __syncthreads();
+}
 
 // Queued pipeline: one shade kernel per material class over the (slot, path id) list the trace stage binned.
 template <int CLS> __global__ void __launch_bounds__(ShadeLaunch<CLS>::kThreads, ShadeLaunch<CLS>::kMinBlocks) k_shade(const __grid_constant__ LaunchParams P, uint32_t depth) {
@@ -825,16 +875,19 @@ template <int CLS> __global__ void __launch_bounds__(ShadeLaunch<CLS>::kThreads,
     const PathQueue &qin = P.q[depth & 1u];
     const PathQueue &qout = P.q[(depth + 1u) & 1u];
     uint32_t *out_pair = ctr + kCtrStride;  // [0] next-depth paths, [1] shadow rays: reserved together
-    const uint32_t stride = gridDim.x * blockDim.x;
-    // warp-uniform trip count so that every lane takes part in the ballots; the (slot, path_id) entry of the
-    // next trip is fetched one trip ahead so that its latency is off the dependent chain
-    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    uint2 ent = make_uint2(k, 0u);
-    if (k < n) ent = slots[k];
-    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride, k += stride) {
-        const bool active = k < n;
-        const uint2 cur = ent;
-        if (k + stride < n) ent = slots[k + stride];
+    auto emit = [&](const ShadeOut &o) {  // warp-collective: append the continuation and the shadow ray
+        uint32_t ns, ss;
+        warp_append2(out_pair, o.has_next, o.has_shadow, ns, ss);
+        if (o.has_next) store_path(qout, ns, o.next);
+        if (o.has_shadow) {
+            const ShadowQueue &s = P.shadow;
+            stq(s.a + ss, f4{o.shadow.o.x, o.shadow.o.y, o.shadow.o.z, o.shadow.t_max});
+            stq(s.b + ss, f4{o.shadow.d.x, o.shadow.d.y, o.shadow.d.z, u2f(o.shadow.ex0)});
+            stq(s.c + ss, f4{o.shadow.contrib.x, o.shadow.contrib.y, o.shadow.contrib.z, u2f(o.shadow.path_id)});
+            s.ex1[ss] = o.shadow.ex1;
+        }
+    };
+    auto shade_one = [&](bool active, uint2 cur) {
         ShadeOut o;
         o.has_shadow = false;
         o.has_next = false;
@@ -851,16 +904,51 @@ template <int CLS> __global__ void __launch_bounds__(ShadeLaunch<CLS>::kThreads,
                 P.first_hits[2u * pix + 1u] = P.scene.shade[h.gid].prim;
             }
         }
-        uint32_t ns, ss;
-        warp_append2(out_pair, o.has_next, o.has_shadow, ns, ss);
-        if (o.has_next) store_path(qout, ns, o.next);
-        if (o.has_shadow) {
-            const ShadowQueue &s = P.shadow;
-            stq(s.a + ss, f4{o.shadow.o.x, o.shadow.o.y, o.shadow.o.z, o.shadow.t_max});
-            stq(s.b + ss, f4{o.shadow.d.x, o.shadow.d.y, o.shadow.d.z, u2f(o.shadow.ex0)});
-            stq(s.c + ss, f4{o.shadow.contrib.x, o.shadow.contrib.y, o.shadow.contrib.z, u2f(o.shadow.path_id)});
-            s.ex1[ss] = o.shadow.ex1;
+        emit(o);
+    };
+    if (CLS == CLS_GENERAL && AKR_GENERAL_SORT) {
+        // CTA tiles of 2 entries per thread, ordered by the material's sort key (see SortScratch): a warp then shades a run
+        // of one material signature; it takes one run from the cheap end of the tile and one from the expensive end
+        constexpr uint32_t THREADS = ShadeLaunch<CLS>::kThreads, T = 2u * THREADS;
+        __shared__ SortScratch ss;
+        __shared__ uint2 ents[T];
+        const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+        for (uint32_t first = blockIdx.x * T; first < n; first += gridDim.x * T) {
+            const uint32_t cnt = min(T, n - first);
+            uint32_t key[2];
+#pragma unroll
+            for (uint32_t j = 0; j < 2u; ++j) {
+                const uint32_t idx = threadIdx.x + j * THREADS;
+                key[j] = TRI_SORT_KEY_MASK;
+                if (idx < cnt) {
+                    const uint2 e = slots[first + idx];
+                    ents[idx] = e;
+                    const uint32_t gid = f2u(reinterpret_cast<const float *>(P.hits.h + e.x)[0]);
+                    key[j] = (P.scene.shade[gid].flags >> TRI_SORT_KEY_SHIFT) & TRI_SORT_KEY_MASK;
+                }
+            }
+            sort_tile_by_key<(int)THREADS>(ss, key, cnt);  // (its barriers also publish `ents`)
+#pragma unroll 1
+            for (uint32_t j = 0; j < 2u; ++j) {
+                const uint32_t e = ss.order[(j == 0u ? warp * 32u : T - (warp + 1u) * 32u) + lane];
+                const bool active = !(e & 0x8000u);
+                shade_one(active, active ? ents[e & 0x7fffu] : make_uint2(0u, 0u));
+            }
+            __syncthreads();  // before `ents` and the scratch are rewritten
         }
+        return;
+    }
+    const uint32_t stride = gridDim.x * blockDim.x;
+    // warp-uniform trip count so that every lane takes part in the ballots; the (slot, path_id) entry of the
+    // next trip is fetched one trip ahead so that its latency is off the dependent chain
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    uint2 ent = make_uint2(k, 0u);
+    if (k < n) ent = slots[k];
+    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride, k += stride) {
+        const bool active = k < n;
+        const uint2 cur = ent;
+        if (k + stride < n) ent = slots[k + stride];
+        shade_one(active, cur);
     }
 }
 
@@ -996,11 +1084,78 @@ __device__ __forceinline__ void bounce_phase(const LaunchParams &P, uint32_t dep
     if (lane == 0u && (n_traced | n_shadow))
         atomicAdd(reinterpret_cast<unsigned long long *>(P.counters + (depth + 1u) * kCtrStride), (unsigned long long)n_traced | ((unsigned long long)n_shadow << 32));
 }
+template <int THREADS>
+__device__ __forceinline__ void bounce_phase_sorted(const LaunchParams &P, uint32_t depth, const DevTracer &tr, uint32_t tiles, uint64_t *bar2, SortScratch &ss) {
+    constexpr uint32_t T = 2u * THREADS, kArray = T * 16u;  // records per CTA tile; bytes of one of its four SoA arrays
+    const uint32_t n = P.counters[depth * kCtrStride + 2u + CLS_GENERAL];
+    const uint32_t n_tiles = (n + T - 1u) / T;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t bar0 = smem_u32(bar2);
+    const RecQueue &qin = P.cq[depth & 1u][CLS_GENERAL];
+    const uint64_t pol = l2_evict_first_policy();
+    auto issue = [&](uint32_t tile, uint32_t buf) {
+        const uint32_t first = tile * T;
+        const uint32_t bytes = min(T, n - first) * 16u;
+        const uint32_t b = bar0 + buf * 8u, dst = tiles + buf * 4u * kArray;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(4u * bytes) : "memory");
+#pragma unroll
+        for (uint32_t j = 0; j < 4u; ++j) tma_bulk_g2s_hint(dst + j * kArray, qin.r[j] + first, bytes, b, pol);
+    };
+    uint32_t tile = blockIdx.x, it = 0u;
+    if (tile < n_tiles && threadIdx.x == 0) issue(tile, 0u);
+    uint32_t n_traced = 0u, n_shadow = 0u;  // warp-uniform
+    for (; tile < n_tiles; tile += gridDim.x, ++it) {
+        const uint32_t buf = it & 1u;
+        if (tile + gridDim.x < n_tiles && threadIdx.x == 0) issue(tile + gridDim.x, buf ^ 1u);  // (the other buffer was released by the barrier that ended the last trip)
+        mbar_wait(bar2 + buf, (it >> 1) & 1u);
+        const uint32_t cnt = min(T, n - tile * T), base = tiles + buf * 4u * kArray;
+        uint32_t key[2];
+#pragma unroll
+        for (uint32_t j = 0; j < 2u; ++j) {
+            const uint32_t idx = threadIdx.x + j * THREADS;
+            key[j] = TRI_SORT_KEY_MASK;  // slots past the end of the queue sort to the back
+            if (idx < cnt) {
+                uint32_t gid;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(gid) : "r"(base + idx * 16u + 12u));
+                key[j] = (P.scene.shade[gid].flags >> TRI_SORT_KEY_SHIFT) & TRI_SORT_KEY_MASK;
+            }
+        }
+        sort_tile_by_key<THREADS>(ss, key, cnt);
+#pragma unroll 1
+        for (uint32_t j = 0; j < 2u; ++j) {
+            const uint32_t pos = (j == 0u ? warp * 32u : T - (warp + 1u) * 32u) + lane;
+            const uint32_t e = ss.order[pos];
+            const bool active = !(e & 0x8000u);
+            const uint32_t src = base + (e & 0x7fffu) * 16u;
+            const float4 r0 = lds128(src), r1 = lds128(src + kArray), r2 = lds128(src + 2u * kArray), r3 = lds128(src + 3u * kArray);
+            BounceRec in;
+            in.d = mk3(r0.x, r0.y, r0.z);
+            in.gid = __float_as_uint(r0.w);
+            in.u = r1.x;
+            in.v = r1.y;
+            in.path_id = __float_as_uint(r1.z);
+            in.pxpy = __float_as_uint(r1.w);
+            in.beta = mk3(r2.x, r2.y, r2.z);
+            in.sample_index = __float_as_uint(r2.w);
+            in.L = mk3(r3.x, r3.y, r3.z);
+            const BounceOut r = bounce_fused<CLS_GENERAL>(P.scene, P.corners, P.tables, P.rp, P.wave, depth, active, in, tr, P.acc);
+            n_traced += (uint32_t)__popc(__ballot_sync(0xffffffffu, r.traced));
+            n_shadow += (uint32_t)__popc(__ballot_sync(0xffffffffu, r.shadow));
+            append_next(P, depth + 1u, r);
+        }
+        __syncthreads();  // every record of this buffer is in registers / done before the buffer is refilled and the scratch reused
+    }
+    if (lane == 0u && (n_traced | n_shadow))
+        atomicAdd(reinterpret_cast<unsigned long long *>(P.counters + (depth + 1u) * kCtrStride), (unsigned long long)n_traced | ((unsigned long long)n_shadow << 32));
+}
+
 // MASK = the shade classes this launch serves, one after the other in every CTA (bit c = class c).  Measured on B200:
 // serving Lambert + conductor in ONE launch per depth (half the launches, CTAs that run out of Lambert records start on
 // conductor records) is SLOWER than one launch per class — 31.0 vs 29.1 ms per pass on one GPU, 12.8 vs 13.8 G samples/s
 // on eight: the merged kernel's larger code and common register allocation cost more than the saved tails — so the
 // engine launches single-class masks; the template keeps the general form.
+// record buffers of the general bounce kernel: two CTA tiles of 2 records per thread (sorted feed) or two warp tiles per warp
+constexpr size_t kGeneralTileSmem = AKR_GENERAL_SORT ? (size_t)2 * (2 * kGeneralBlock) * 64 : (size_t)(kGeneralBlock / 32) * 2u * kTileBytes;
 template <uint32_t MASK> struct BounceLaunch {
     static constexpr int kThreads = (MASK & (1u << CLS_GENERAL)) ? kGeneralBlock : kShadeBlock;
     static constexpr int kWarps = kThreads / 32;
@@ -1026,6 +1181,11 @@ template <uint32_t MASK> __global__ void __launch_bounds__(BounceLaunch<MASK>::k
     }
     const DevTracer tr{P.scene, stage_scene(P, smem, &bar)};  // (inits `bar`, fences the barrier inits, __syncthreads)
     const uint32_t scene_bytes = (P.scene.n_pair_blocks + P.scene.n_single_blocks + P.scene.n_occ_pair_blocks + P.scene.n_occ_single_blocks) * (uint32_t)sizeof(PrimBlock2);
+    if (MASK == (1u << CLS_GENERAL) && AKR_GENERAL_SORT) {  // the general class alone: CTA tiles ordered by material signature
+        __shared__ SortScratch ss;
+        bounce_phase_sorted<BounceLaunch<MASK>::kThreads>(P, depth, tr, smem_u32(smem) + ((scene_bytes + 127u) & ~127u), &tile_bar[0][0], ss);
+        return;
+    }
     const uint32_t tiles = smem_u32(smem) + ((scene_bytes + 127u) & ~127u) + warp * 2u * kTileBytes;
     uint32_t it = 0u;
     if (MASK & (1u << CLS_LAMBERT)) bounce_phase<CLS_LAMBERT, kWarps>(P, depth, tr, tiles, &tile_bar[warp][0], it);
@@ -1490,7 +1650,7 @@ int akr_b200_upload_scene(AkrContext *ctx, const AkrSceneDesc *desc) {
         ctx->flat_bytes = (uint32_t)(blob.flat_blocks.size() * sizeof(PrimBlock2));
         const size_t smem_flat = (size_t)ctx->smem_nodes * sizeof(BvhNode) + ctx->flat_bytes;
         const size_t smem_bounce = ((ctx->flat_bytes + 127u) & ~127u) + (size_t)kShadeWarps * 2u * kTileBytes;
-        const size_t smem_bounce_general = ((ctx->flat_bytes + 127u) & ~127u) + (size_t)(kGeneralBlock / 32) * 2u * kTileBytes;
+        const size_t smem_bounce_general = ((ctx->flat_bytes + 127u) & ~127u) + kGeneralTileSmem;
         const bool all = ctx->smem_prims != 0;
         if (blob.any_alpha) {
             occ(ctx->occ_trace_flat, (const void *)k_trace_flat<true>, kBlock, smem_flat);
@@ -1651,7 +1811,7 @@ int akr_b200_render_pass(AkrContext *ctx, uint32_t n_spp, int blocking) {
     const size_t flat_smem = node_smem + ctx->flat_bytes;
     const size_t trace_smem = trace_mode == TRACE_FLAT ? flat_smem : ctx->smem_bytes + (size_t)P.stack_depth * kBlock * sizeof(int32_t);
     const size_t bounce_smem = ((ctx->flat_bytes + 127u) & ~127u) + (size_t)kShadeWarps * 2u * kTileBytes;
-    const size_t bounce_smem_general = ((ctx->flat_bytes + 127u) & ~127u) + (size_t)(kGeneralBlock / 32) * 2u * kTileBytes;
+    const size_t bounce_smem_general = ((ctx->flat_bytes + 127u) & ~127u) + kGeneralTileSmem;
     if (trace_smem > kSmemMax || bounce_smem > kSmemMax) return fail(ctx, AKR_ERR_UNSUPPORTED, "BVH too deep for the shared-memory traversal stack");
 
     const bool prof = ctx->opts.profile_stages != 0;

@@ -87,6 +87,11 @@ enum TriFlags : uint32_t {
     TRI_HAS_TANGENTS = 1u << 2,
     TRI_HAS_UVS = 1u << 3,
     TRI_ALPHA = 1u << 4,        // material alpha < 1: stochastic alpha test applies
+    // bits 8-12: sort key of the material's evaluation signature (type, lobe set, shader kind of texture-driven
+    // materials), numbered by increasing cost.  The general shade class orders each CTA tile of records by it so that
+    // a warp evaluates one kind of tree instead of the union of all of them (scene_build.cpp material_sort_keys).
+    TRI_SORT_KEY_SHIFT = 8,
+    TRI_SORT_KEY_MASK = 31u,
 };
 
 // Shading record per global triangle id: the bary-independent part of

@@ -54,6 +54,38 @@ bool alpha_varies(const SvmView &svm, AkrShaderRef ref) {
     return varies;
 }
 
+// Sort keys for the general shade class (akr_scene.cuh TRI_SORT_KEY_*): materials with the same evaluation signature —
+// closure type, lobe set, normal-map frame, and for texture-driven materials the shader kind (their lobe set is only
+// known per hit) — share a key; keys are numbered by increasing cost estimate so that a CTA can pair its cheapest run
+// of a sorted tile with its most expensive one.  More than 32 signatures fold onto the last keys (a warp then mixes
+// some neighbouring signatures: slower, not wrong).
+std::vector<uint32_t> material_sort_keys(const std::vector<Material> &mats) {
+    auto signature = [](const Material &m) -> uint64_t {
+        if (m.dynamic) return (1ull << 40) | m.shader_kind;
+        return (static_cast<uint64_t>(m.type) << 16) | (static_cast<uint64_t>(m.lobes & 0xffu) << 4) | (m.has_normal ? 2u : 0u) | (m.wrap_inner ? 1u : 0u);
+    };
+    auto cost = [](const Material &m) -> uint32_t {
+        if (m.dynamic) return 100u + m.shader_kind % 16u;  // shader interpretation on top of an unknown tree: the most expensive
+        uint32_t c = 0;
+        if (m.type == MAT_CONDUCTOR) c = 6;
+        else if (m.type == MAT_GLASS) c = 8;
+        else if (m.type == MAT_PRINCIPLED)
+            c = 1u * !!(m.lobes & LOBE_DIFFUSE) + 8u * !!(m.lobes & LOBE_TRANSMISSION) + 6u * !!(m.lobes & LOBE_METAL) + 5u * !!(m.lobes & LOBE_SPECULAR) +
+                5u * !!(m.lobes & LOBE_COAT);
+        return c;
+    };
+    std::map<uint64_t, uint32_t> cost_of;  // signature -> cost
+    for (const Material &m : mats) cost_of[signature(m)] = cost(m);
+    std::vector<std::pair<uint32_t, uint64_t>> order;
+    for (const auto &kv : cost_of) order.emplace_back(kv.second, kv.first);
+    std::sort(order.begin(), order.end());
+    std::map<uint64_t, uint32_t> key_of;
+    for (size_t i = 0; i < order.size(); ++i) key_of[order[i].second] = static_cast<uint32_t>(std::min<size_t>(i, TRI_SORT_KEY_MASK));
+    std::vector<uint32_t> keys(mats.size());
+    for (size_t i = 0; i < mats.size(); ++i) keys[i] = key_of[signature(mats[i])];
+    return keys;
+}
+
 int fold_material(const SvmView &svm, AkrShaderRef ref, Material &m, std::string &err) {
     std::memset(&m, 0, sizeof(m));
     bool dynamic = false;
@@ -379,6 +411,7 @@ int build_scene_blob(const AkrSceneDesc &d, HostSceneBlob &out, std::string &err
             if (rc != AKR_OK) return rc;
         }
     out.textures_host = host_textures;
+    const std::vector<uint32_t> sort_keys = material_sort_keys(out.materials);
     if (out.any_dynamic) out.corner_uvs.assign(static_cast<size_t>(total_tris) * 6, 0.0f);
     if (any_normals) out.corner_normals.assign(static_cast<size_t>(total_tris) * 9, 0.0f);
     if (any_tangents) out.corner_tangents.assign(static_cast<size_t>(total_tris) * 9, 0.0f);
@@ -492,7 +525,7 @@ int build_scene_blob(const AkrSceneDesc &d, HostSceneBlob &out, std::string &err
                 flags |= TRI_ALPHA;
                 out.any_alpha = 1;
             }
-            ts.flags = flags;
+            ts.flags = flags | (sort_keys[ts.mat] << TRI_SORT_KEY_SHIFT);
             if (!g.normals && !g.tangents) {
                 // flat triangle: ns = ng and the frame is constant (mesh.rs:629-633)
                 Frame f = (tt.x != 0.0f || tt.y != 0.0f || tt.z != 0.0f) ? frame_from_n_t(mk3(ng.x, ng.y, ng.z), mk3(tt.x, tt.y, tt.z))
