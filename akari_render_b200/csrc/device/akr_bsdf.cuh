@@ -200,10 +200,17 @@ AKR_HD float table_read_3d(const float *buf, float x, float y, float z) {
     float d1 = table_read_2d(buf, x, y, 256u * ni);
     return (1.0f - t) * d0 + t * d1;
 }
-AKR_HD float ggx_dielectric_albedo(const float *table, float roughness, float cos_i, float eta) {  // mod.rs:1145-1154
+AKR_HD float ggx_dielectric_albedo_inl(const float *table, float roughness, float cos_i, float eta) {  // mod.rs:1145-1154
     float z = sqrtf(fabsf((eta - 1.0f) / (eta + 1.0f)));
     cos_i = fabsf(clampf(cos_i, -0.999f, 0.999f));
     return table_read_3d(table, roughness, fabsf(cos_i), z);
+}
+
+// The general-class tree looks the table up six times per bounce (coat and specular layer, at wo and wi, in evaluate and in
+// sample_wi): one out-of-line copy (eight loads and a trilinear blend each; the general kernels are bound by instruction
+// fetch).
+AKR_HD_NOINLINE float ggx_dielectric_albedo(const float *table, float roughness, float cos_i, float eta) {
+    return ggx_dielectric_albedo_inl(table, roughness, cos_i, eta);
 }
 
 // ---- lobes -------------------------------------------------------------------------------------
@@ -221,7 +228,7 @@ AKR_HD BsdfDir diffuse_sample(f3 wo, f2 u) {  // diffuse.rs:41-52
     return BsdfDir{wi, true};
 }
 
-// MicrofacetReflection::evaluate (mod.rs:831-858). FRESNEL: 0 = dielectric(eta), 1 = complex(n,k)
+// MicrofacetReflection::evaluate (mod.rs:831-858). FRESNEL: 0 = dielectric(eta), 1 = complex(n,k), 2 = complex(n,k) compact
 template <int FRESNEL> AKR_HD BsdfEval mf_reflection_eval(f3 color, float eta, const float *n, const float *k, TR a, f3 wo, f3 wi) {
     f3 wh = wo + wi;
     float cos_o = cos_theta(wo), cos_i = cos_theta(wi);
@@ -232,12 +239,28 @@ template <int FRESNEL> AKR_HD BsdfEval mf_reflection_eval(f3 color, float eta, c
     float cf = dot(wi, face_forward(wh, mk3(0, 0, 1)));
     f3 fr;
     if (FRESNEL == 0) fr = splat3(1.0f) * fr_dielectric(cf, eta);
-    else fr = fr_complex_spec(cf, n, k);
+    else if (FRESNEL == 1) fr = fr_complex_spec(cf, n, k);
+    else {  // the same three fr_complex calls through one copy of the code (general class)
+        const float c = fabsf(cf);
+        fr = splat3(0.0f);
+        AKR_NO_UNROLL
+        for (int ch = 0; ch < 3; ++ch) {
+            const float v = fr_complex(c, Cx{n[ch], k[ch]});
+            if (ch == 0) fr.x = v;
+            else if (ch == 1) fr.y = v;
+            else fr.z = v;
+        }
+    }
     float d = tr_d(a, wh);
     float g = tr_g(a, wo, wi);
     f3 f = color * fr * fabsf(0.25f * d * g / (cos_i * cos_o)) * fabsf(cos_i);
     float pdf = tr_pdf(a, wo, wh) / (4.0f * fabsf(dot(wo, wh)));
     return BsdfEval{f, pdf};
+}
+// GGX reflection with dielectric Fresnel: dielectric mixture, specular layer and clearcoat of the general tree share one
+// out-of-line copy
+AKR_HD_NOINLINE BsdfEval mf_reflection_eval_dielectric(f3 color, float eta, float rough, f3 wo, f3 wi) {
+    return mf_reflection_eval<0>(color, eta, nullptr, nullptr, tr_from_roughness(rough), wo, wi);
 }
 AKR_HD BsdfDir mf_reflection_sample(TR a, f3 wo, f2 u) {  // mod.rs:861-873
     f3 wh = tr_sample_wh(a, wo, u);
@@ -358,9 +381,14 @@ AKR_HD BsdfEval general_eval(const Material &m, const float *table, f3 wo, f3 wi
     const bool base = is_p && mt < 1.0f - EPS;  // bsdf1 takes part in Mix(bsdf1, metal, metallic)   (principled.rs:131-142,170-175)
     BsdfEval e_diff = zero_eval(), e_diel = zero_eval(), e_metal = zero_eval();
     if (type == MAT_LAMBERT || (base && tr < 1.0f - EPS)) e_diff = diffuse_eval(ld3(m.diffuse), wo, wi);
-    if (type == MAT_GLASS || (base && tr > EPS)) e_diel = dielectric_eval(ld3(m.color), ld3(m.trans_color), m.eta, m.roughness_raw, wo, wi);
+    if (type == MAT_GLASS || (base && tr > EPS)) {  // dielectric_eval with the shared reflection lobe
+        const float frac = fr_dielectric(cos_theta(wo), m.eta);
+        const BsdfEval et = mf_transmission_eval(ld3(m.trans_color), m.eta, tr_from_roughness(m.roughness_raw), wo, wi);
+        const BsdfEval er = mf_reflection_eval_dielectric(ld3(m.color), m.eta, m.roughness_raw, wo, wi);
+        e_diel = BsdfEval{et.f + er.f, lerpf(et.pdf, er.pdf, frac)};
+    }
     if (type == MAT_CONDUCTOR || (is_p && mt > EPS))
-        e_metal = mf_reflection_eval<1>(splat3(1.0f), 0.0f, m.metal_n, m.metal_k, tr_from_roughness(m.roughness), wo, wi);
+        e_metal = mf_reflection_eval<2>(splat3(1.0f), 0.0f, m.metal_n, m.metal_k, tr_from_roughness(m.roughness), wo, wi);
     if (type == MAT_LAMBERT) return e_diff;
     if (type == MAT_CONDUCTOR) return e_metal;
     if (type == MAT_GLASS) return e_diel;
@@ -370,8 +398,7 @@ AKR_HD BsdfEval general_eval(const Material &m, const float *table, f3 wo, f3 wi
     if (base) {
         ea = BsdfEval{lerp3(e_diff.f, e_diel.f, tr), lerpf(e_diff.pdf, e_diel.pdf, tr)};
         if (m.lobes & LOBE_SPECULAR) {  // bsdf1 = Coated(top = specular GGX, bottom = bsdf0, e_top)   (principled.rs:55-80,151-168; mod.rs:486-503)
-            TR a = tr_from_roughness(m.roughness);
-            BsdfEval top = mf_reflection_eval<0>(ld3(m.spec_tint) * m.f0, m.eta_s, nullptr, nullptr, a, wo, wi);
+            BsdfEval top = mf_reflection_eval_dielectric(ld3(m.spec_tint) * m.f0, m.eta_s, m.roughness, wo, wi);
             f3 tint = ld3(m.spec_tint);
             f3 eo = tint * ggx_dielectric_albedo(table, m.roughness, abs_cos_theta(wo), m.eta_s) * m.f0;
             f3 ei = tint * ggx_dielectric_albedo(table, m.roughness, abs_cos_theta(wi), m.eta_s) * m.f0;
@@ -386,8 +413,7 @@ AKR_HD BsdfEval general_eval(const Material &m, const float *table, f3 wo, f3 wi
     BsdfEval scaled = BsdfEval{e2.f * ld3(m.coat_scale), e2.pdf};
     if (!(m.lobes & LOBE_COAT)) return scaled;
     // bsdf4 = Coated(top = clearcoat GGX, bottom = scaled, e_top)   (principled.rs:81-98,183-199)
-    TR a = tr_from_roughness(m.coat_roughness);
-    BsdfEval top = mf_reflection_eval<0>(splat3(1.0f) * m.coat_weight, m.coat_ior, nullptr, nullptr, a, wo, wi);
+    BsdfEval top = mf_reflection_eval_dielectric(splat3(1.0f) * m.coat_weight, m.coat_ior, m.coat_roughness, wo, wi);
     f3 eo = splat3(1.0f) * m.coat_weight * ggx_dielectric_albedo(table, m.coat_roughness, abs_cos_theta(wo), m.coat_ior);
     f3 ei = splat3(1.0f) * m.coat_weight * ggx_dielectric_albedo(table, m.coat_roughness, abs_cos_theta(wi), m.coat_ior);
     float p_top = avg3(eo);

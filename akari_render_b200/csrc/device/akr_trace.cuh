@@ -50,6 +50,26 @@ AKR_HD bool box_test(const float *lo, const float *hi, f3 o, f3 inv_d, float t_m
     return tn <= tf;
 }
 
+// The same slab test in fused-multiply-add form (what the 4-wide walk below uses per child, box4_test): t = plane * inv_d + ood,
+// ood = -o * inv_d, with inv_d from capped_inv_dir.  With inv_d = inf (a direction component of exactly 0) the two infinities would cancel to
+// NaN on one plane of a slab, the min / max drop it and the slab collapses to (-inf, -inf): a false reject.  Capped at 2^96
+// every product stays finite and the slab keeps its meaning (origin inside: (-huge, +huge); outside: both ends on one
+// side).  The rounding difference to box_test is |o| * 2^-24 in space, far inside the build-time padding.
+constexpr float kInvDirCap = 7.9228163e28f;
+AKR_HD f3 capped_inv_dir(f3 d) {
+    return mk3(fminf(fmaxf(1.0f / d.x, -kInvDirCap), kInvDirCap), fminf(fmaxf(1.0f / d.y, -kInvDirCap), kInvDirCap),
+               fminf(fmaxf(1.0f / d.z, -kInvDirCap), kInvDirCap));
+}
+AKR_HD bool box_test_fma(const float *lo, const float *hi, f3 inv_d, f3 ood, float t_min, float t_max, float &t_near) {
+    float tx0 = fmaf(lo[0], inv_d.x, ood.x), tx1 = fmaf(hi[0], inv_d.x, ood.x);
+    float ty0 = fmaf(lo[1], inv_d.y, ood.y), ty1 = fmaf(hi[1], inv_d.y, ood.y);
+    float tz0 = fmaf(lo[2], inv_d.z, ood.z), tz1 = fmaf(hi[2], inv_d.z, ood.z);
+    float tn = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), t_min));
+    float tf = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fminf(fmaxf(tz0, tz1), t_max));
+    t_near = tn;
+    return tn <= tf;
+}
+
 // Texture coordinates of a hit (mesh.rs:534-546): interpolated per-corner uvs, or the default corners (0,0), (1,0), (1,0.1).
 // `for_alpha_test`: the default third corner is (0, 0.1) in surface_interaction_for_alpha_test (mesh.rs:456-467) — preserved.
 AKR_HD f2 hit_uv(const SceneView &sc, uint32_t gid, float u, float v, bool for_alpha_test) {
@@ -150,8 +170,7 @@ AKR_HD HitRec trace_ray(const SceneView &sc, const TraceData &td, f3 o, f3 d, fl
     return best;
 }
 
-// Slab test of child k of a 4-wide node in the form the kernel evaluates with packed FMAs: t = plane * inv_d + ood,
-// ood = -o * inv_d (boxes are padded at build time; NaNs drop out of fminf/fmaxf).
+// Slab test of child k of a 4-wide node: box_test_fma on the transposed planes (inv_d from capped_inv_dir).
 AKR_HD bool box4_test(const Bvh4Node &n, int k, f3 inv_d, f3 ood, float t_min, float t_max, float &t_near) {
     float tx0 = fmaf(n.lo[0][k], inv_d.x, ood.x), tx1 = fmaf(n.hi[0][k], inv_d.x, ood.x);
     float ty0 = fmaf(n.lo[1][k], inv_d.y, ood.y), ty1 = fmaf(n.hi[1][k], inv_d.y, ood.y);
@@ -184,7 +203,7 @@ AKR_HD HitRec trace_ray4(const SceneView &sc, f3 o, f3 d, float t_min, float t_m
     const TriGeom *tris = sc.tris;
     HitRec best{0xffffffffu, 0.0f, 0.0f};
     float best_t = t_max;
-    const f3 inv_d = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    const f3 inv_d = capped_inv_dir(d);  // finite: plane * inv_d + ood must never be inf - inf (see box_test_fma)
     const f3 ood = mk3(-o.x * inv_d.x, -o.y * inv_d.y, -o.z * inv_d.z);
     int32_t stack[3 * AKR_BVH_STACK];
     int sp = 0;

@@ -343,4 +343,66 @@ void hostsim_fastdiv(const uint32_t *n, uint32_t count, uint32_t d, uint32_t *q,
     for (uint32_t i = 0; i < count; ++i) q[i] = fastdiv(n[i], f, r[i]);
 }
 
+// Slab test agreement: box_test ((plane - o) * inv_d, what trace_ray and the oracle's tree walk use) against box_test_fma
+// (plane * inv_d + ood with the capped inverse direction, what the 4-wide walk evaluates per child) over every node of
+// the scene's BVH and `n_rays` seeded rays, a quarter of them with a direction component of exactly 0, a quarter with a
+// denormal-small one, a quarter starting exactly on a vertex coordinate (rays start on surfaces).  counts = {accepted by both, box_test only, fma only}.
+int hostsim_box_test_agreement(const AkrSceneDesc *desc, uint32_t n_rays, uint32_t seed, uint64_t counts[3]) {
+    HostSceneBlob blob;
+    std::string err;
+    int rc = build_scene_blob(*desc, blob, err);
+    if (rc != AKR_OK) {
+        g_err = err;
+        return rc;
+    }
+    counts[0] = counts[1] = counts[2] = 0;
+    uint64_t state = 0x9e3779b97f4a7c15ull ^ seed;
+    auto rnd = [&]() {  // splitmix64 -> [0, 1)
+        state += 0x9e3779b97f4a7c15ull;
+        uint64_t z = state;
+        z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+        z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+        z ^= z >> 31;
+        return (float)(z >> 40) * (1.0f / 16777216.0f);
+    };
+    const BvhNode &root = blob.nodes[0];
+    float lo[3], hi[3];
+    for (int a = 0; a < 3; ++a) {
+        lo[a] = fminf(root.lo0[a], root.lo1[a]);
+        hi[a] = fmaxf(root.hi0[a], root.hi1[a]);
+    }
+    for (uint32_t r = 0; r < n_rays; ++r) {
+        float o[3], d[3];
+        for (int a = 0; a < 3; ++a) {
+            o[a] = lo[a] + (hi[a] - lo[a]) * rnd();
+            d[a] = 2.0f * rnd() - 1.0f;
+        }
+        const uint32_t mode = r & 3u, ax = (uint32_t)(rnd() * 3.0f) % 3u;
+        const BvhNode &pick = blob.nodes[(size_t)(rnd() * (float)blob.nodes.size()) % blob.nodes.size()];
+        // (origins exactly on a PADDED box plane are left out on purpose: there the reference form yields t = 0 and the fma
+        // form +-1 ulp of o * inv_d, a touch-or-miss at a point the padding keeps every primitive away from; rays start on
+        // surfaces, i.e. on vertex coordinates)
+        if (mode == 0u) o[ax] = blob.shade[(size_t)(rnd() * (float)blob.shade.size()) % blob.shade.size()].v0[ax];
+        (void)pick;
+        const float len = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+        for (int a = 0; a < 3; ++a) d[a] /= len;
+        if (mode == 1u) d[ax] = rnd() < 0.5f ? 0.0f : -0.0f;
+        if (mode == 2u) d[ax] = 1e-41f * (rnd() - 0.5f);
+        const f3 of = mk3(o[0], o[1], o[2]), df = mk3(d[0], d[1], d[2]);
+        const f3 inv = mk3(1.0f / df.x, 1.0f / df.y, 1.0f / df.z), invc = capped_inv_dir(df);
+        const f3 ood = mk3(-of.x * invc.x, -of.y * invc.y, -of.z * invc.z);
+        const float t_max = (r & 4u) ? 1e20f : 4.0f * rnd();
+        for (const BvhNode &n : blob.nodes)
+            for (int c = 0; c < 2; ++c) {
+                float ta, tb;
+                const bool a = box_test(c ? n.lo1 : n.lo0, c ? n.hi1 : n.hi0, of, inv, 0.0f, t_max, ta);
+                const bool b = box_test_fma(c ? n.lo1 : n.lo0, c ? n.hi1 : n.hi0, invc, ood, 0.0f, t_max, tb);
+                counts[0] += a && b;
+                counts[1] += a && !b;
+                counts[2] += b && !a;
+            }
+    }
+    return AKR_OK;
+}
+
 }  // extern "C"
