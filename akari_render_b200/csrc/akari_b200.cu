@@ -632,18 +632,22 @@ template <bool ALPHA> __global__ void __launch_bounds__(kBlock) k_trace_flat(con
 }
 
 // ------------------------------------------------------------------------------------------------
-// BVH scenes: persistent warps with dynamic ray fetch (Aila & Laine's "persistent while-while")
+// BVH scenes: persistent warps with dynamic ray fetch and majority-vote rounds
 // ------------------------------------------------------------------------------------------------
 // Incoherent rays leave a BVH at very different times; with one fixed ray per lane the warp idles until its slowest
 // lane is done (ncu on the 8.5 K-triangle test scene: 8.5 of 32 lanes active).  Here a warp keeps per-lane traversal
-// state, advances all lanes by a bounded number of node visits, and whenever fewer than AKR_REFILL_BELOW lanes still
-// carry a live ray it retires the finished ones (hit record, class binning / shadow resolve, warp-aggregated) and
-// hands the free lanes new rays from a global counter (counter block words [5] closest-hit, [6] shadow).
+// state and advances it in warp-uniform rounds (below); whenever fewer than AKR_REFILL_BELOW lanes still carry a live
+// ray it retires the finished ones (hit record, class binning / shadow resolve, warp-aggregated) and hands the free
+// lanes new rays from a global counter (counter block words [5] closest-hit, [6] shadow).  Measured on the clutter scene
+// (trace stage of one 64-spp pass): while-while segments of 12 visits, refill below 24 lanes: 72.8 ms; vote rounds with
+// refill below 24 / 20 / 16 / 12 / 8 lanes: 75.7 / 70.3 / 66.9 / 65.2 / 66.1 ms (a refill costs a retire pass with
+// atomics and queue stores: with uniform rounds it pays to run the warp emptier); biasing the vote 2:1 either way or
+// testing one primitive per leaf round: 65.8-72.4 ms.
 #ifndef AKR_REFILL_BELOW
-#define AKR_REFILL_BELOW 24
+#define AKR_REFILL_BELOW 12
 #endif
 #ifndef AKR_SEGMENT_STEPS
-#define AKR_SEGMENT_STEPS 12
+#define AKR_SEGMENT_STEPS 32
 #endif
 
 template <bool ANY_HIT, bool SMEM_ALL, bool ALPHA>
@@ -732,12 +736,19 @@ __device__ __forceinline__ void bvh_phase(const LaunchParams &P, const TraceSmem
             }
             if (__ballot_sync(0xffffffffu, have) == 0u) break;
         }
-        // ---- advance every live lane by a bounded number of visits ----
-        if (have && !done) {
-            int budget = AKR_SEGMENT_STEPS;
-            while (true) {
-                while (node >= 0 && budget > 0) {
-                    --budget;
+        // ---- rounds: the warp does whichever of the two activities more of its lanes are waiting for ----
+        // A lane alternates between runs of inner-node visits and leaves.  In a while-while loop the lanes that reach a leaf
+        // early idle until the last one has (ncu r02q: 12.7 of 32 lanes in the box tests, 16.4 in the primitive tests).  Here
+        // every round is warp-uniform: one node visit for the lanes at inner nodes, or one leaf for the lanes at leaves,
+        // decided by majority; the minority waits one round and grows meanwhile.
+#pragma unroll 1
+        for (int round = 0; round < AKR_SEGMENT_STEPS; ++round) {
+            const bool live = have && !done;
+            const uint32_t mi = __ballot_sync(0xffffffffu, live && node >= 0), ml = __ballot_sync(0xffffffffu, live && node < 0);
+            if ((mi | ml) == 0u) break;
+            if (!exhausted && __popc(mi | ml) < AKR_REFILL_BELOW) break;
+            if (__popc(mi) >= __popc(ml)) {
+                if (live && node >= 0) {
                     BvhNode n;
                     if (SMEM_ALL || (uint32_t)node < n_fast) n = load_node<true>(ts.nodes, nullptr, (uint32_t)node);
                     else n = load_node<false>(0u, sc.nodes, (uint32_t)node);
@@ -754,27 +765,24 @@ __device__ __forceinline__ void bvh_phase(const LaunchParams &P, const TraceSmem
                         node = c0;
                     } else if (h1) {
                         node = c1;
+                    } else if (sp == ts.stack) {
+                        done = true;
                     } else {
-                        if (sp == ts.stack) {
-                            done = true;
-                            break;
-                        }
                         sp -= kStackStride;
                         node = lds32(sp);
                     }
                 }
-                if (done || node >= 0) break;  // finished, or out of budget in the middle of a descent
+            } else if (live && node < 0) {
                 const uint32_t leaf = (uint32_t)(~node);
                 const uint32_t first = leaf >> 3, count = leaf & 7u;
                 for (uint32_t k = 0; k < count; ++k)
                     prim_test<ALPHA>(sc, load_prim<SMEM_ALL>(ts.prims, sc.prims, first + k), first + k, o, d, 0.0f, ex0, ex1, best);
                 if ((ANY_HIT && best.k != 0xffffffffu) || sp == ts.stack) {
                     done = true;
-                    break;
+                } else {
+                    sp -= kStackStride;
+                    node = lds32(sp);
                 }
-                sp -= kStackStride;
-                node = lds32(sp);
-                if (--budget <= 0) break;
             }
         }
     }
