@@ -210,8 +210,9 @@ using ImageResolver = std::function<uint32_t(const akr::json::Value &image)>;
 
 // ---- image decoding (load.rs:550-610) ---------------------------------------------------------------------------------
 // raw float: width * height * channels f32, missing channels filled with 0 (alpha: 1), NOT flipped (load.rs:556-588);
-// png: decoded, flipped vertically, converted to RGBA8 (load.rs:590-603).  jpeg / tiff / dds / exr need decoders this host
-// does not carry (the Rust host uses the `image` crate): rejected with AKR_ERR_UNSUPPORTED.
+// png / tiff: decoded, flipped vertically, converted to RGBA8 (load.rs:590-603); exr: decoded, flipped, RGBA32F (decode_exr).
+// jpeg / tga / dds need decoders this host does not carry (the Rust host uses the `image` crate): AKR_ERR_UNSUPPORTED
+// (jpeg is lossy: only a bit-exact port of jpeg-decoder 0.3's IDCT and upsampling would keep parity).
 uint8_t paeth(uint8_t a, uint8_t b, uint8_t c) {
     int p = (int)a + (int)b - (int)c, pa = std::abs(p - a), pb = std::abs(p - b), pc = std::abs(p - c);
     return (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
@@ -290,7 +291,11 @@ void decode_png(const uint8_t *data, size_t len, uint32_t &width, uint32_t &heig
         const uint32_t fy = height - 1 - y;  // DynamicImage::flipv (load.rs:590)
         for (uint32_t x = 0; x < width; ++x) {
             const uint8_t *px = img.data() + y * stride + x * bpp;
-            auto sample = [&](uint32_t c) -> uint8_t { return bit_depth == 8 ? px[c] : px[2 * c]; };  // 16 -> 8 bit: high byte (to_rgba8)
+            // 16 -> 8 bit as DynamicImage::to_rgba8 does it: round(v * 255 / 65535) = (v + 128) / 257
+            // (image 0.24.7, color.rs `impl FromPrimitive<u16> for u8`; ASSUMED from the pinned crate version, Cargo.lock:1034)
+            auto sample = [&](uint32_t c) -> uint8_t {
+                return bit_depth == 8 ? px[c] : static_cast<uint8_t>(((((uint32_t)px[2 * c] << 8) | px[2 * c + 1]) + 128u) / 257u);
+            };
             uint8_t r, g, b, a = 255;
             if (color_type == 3) {
                 const uint32_t i = px[0];
@@ -313,6 +318,404 @@ void decode_png(const uint8_t *data, size_t len, uint32_t &width, uint32_t &heig
         }
     }
 }
+// ---- TIFF (the `tiff` 0.9 decoder behind image::ImageFormat::Tiff -> flipv -> to_rgba8, load.rs:590-603) ----------------
+// Baseline strips, chunky layout, 8 / 16 bits per sample, gray / gray + alpha / RGB / RGBA, compression none / LZW / Deflate /
+// PackBits, horizontal predictor, either byte order.  Tiles, planar layout, palettes, CMYK / YCbCr and fax codecs are rejected.
+void tiff_lzw(const uint8_t *src, size_t n, std::vector<uint8_t> &out, size_t expect) {
+    std::vector<uint32_t> prefix(4096), length(4096);
+    std::vector<uint8_t> suffix(4096), first(4096);
+    for (uint32_t i = 0; i < 256; ++i) {
+        prefix[i] = 0xffffu;
+        length[i] = 1;
+        suffix[i] = first[i] = (uint8_t)i;
+    }
+    uint32_t next = 258, bits = 9, old = 0xffffu;
+    uint64_t acc = 0;
+    int nacc = 0;
+    size_t pos = 0;
+    std::vector<uint8_t> tmp;
+    auto emit = [&](uint32_t code) {
+        const uint32_t len = length[code];
+        const size_t base = out.size();
+        out.resize(base + len);
+        uint32_t c = code;
+        for (uint32_t k = len; k-- > 0;) {
+            out[base + k] = suffix[c];
+            c = prefix[c];
+        }
+    };
+    while (out.size() < expect) {
+        while (nacc < (int)bits && pos < n) {
+            acc = (acc << 8) | src[pos++];
+            nacc += 8;
+        }
+        if (nacc < (int)bits) break;
+        const uint32_t code = (uint32_t)(acc >> (nacc - bits)) & ((1u << bits) - 1u);
+        nacc -= bits;
+        if (code == 257u) break;  // EOI
+        if (code == 256u) {       // clear
+            next = 258;
+            bits = 9;
+            old = 0xffffu;
+            continue;
+        }
+        if (old == 0xffffu) {
+            if (code >= 256u) throw std::runtime_error("tiff: bad LZW stream");
+            emit(code);
+        } else if (code < next) {
+            emit(code);
+            if (next < 4096u) {
+                prefix[next] = old;
+                length[next] = length[old] + 1;
+                suffix[next] = first[code];
+                first[next] = first[old];
+                ++next;
+            }
+        } else if (code == next && next < 4096u) {
+            prefix[next] = old;
+            length[next] = length[old] + 1;
+            suffix[next] = first[old];
+            first[next] = first[old];
+            ++next;
+            emit(code);
+        } else {
+            throw std::runtime_error("tiff: bad LZW code");
+        }
+        old = code;
+        if (next + 1 >= (1u << bits) && bits < 12) ++bits;  // TIFF's early change: widen one code early
+    }
+}
+void decode_tiff(const uint8_t *data, size_t len, uint32_t &width, uint32_t &height, std::vector<uint8_t> &rgba8) {
+    if (len < 8) throw std::runtime_error("tiff: truncated file");
+    const bool le = data[0] == 'I' && data[1] == 'I', be = data[0] == 'M' && data[1] == 'M';
+    if (!le && !be) throw std::runtime_error("tiff: bad byte-order mark");
+    auto need = [&](size_t pos, size_t n) {
+        if (pos + n > len) throw std::runtime_error("tiff: truncated file");
+    };
+    auto r16 = [&](size_t p) -> uint32_t {
+        need(p, 2);
+        return le ? (uint32_t)data[p] | ((uint32_t)data[p + 1] << 8) : ((uint32_t)data[p] << 8) | data[p + 1];
+    };
+    auto r32 = [&](size_t p) -> uint32_t {
+        need(p, 4);
+        return le ? (uint32_t)data[p] | ((uint32_t)data[p + 1] << 8) | ((uint32_t)data[p + 2] << 16) | ((uint32_t)data[p + 3] << 24)
+                  : ((uint32_t)data[p] << 24) | ((uint32_t)data[p + 1] << 16) | ((uint32_t)data[p + 2] << 8) | data[p + 3];
+    };
+    if (r16(2) != 42u) throw std::runtime_error("tiff: bad magic number (BigTIFF is not supported)");
+    const size_t ifd = r32(4);
+    const uint32_t n_entries = r16(ifd);
+    uint32_t compression = 1, photometric = 1, spp = 1, rows_per_strip = 0xffffffffu, planar = 1, predictor = 1, extra = 0;
+    std::vector<uint32_t> bits, strip_offsets, strip_counts;
+    width = height = 0;
+    auto values = [&](size_t entry, std::vector<uint32_t> &out) {  // SHORT / LONG arrays, inline when they fit in 4 bytes
+        const uint32_t type = r16(entry + 2), count = r32(entry + 4);
+        const uint32_t size = type == 3 ? 2 : (type == 4 ? 4 : (type == 1 ? 1 : 0));
+        if (!size) throw std::runtime_error("tiff: unexpected field type");
+        size_t p = (size_t)size * count <= 4 ? entry + 8 : r32(entry + 8);
+        out.resize(count);
+        for (uint32_t i = 0; i < count; ++i, p += size) out[i] = size == 2 ? r16(p) : (size == 4 ? r32(p) : (need(p, 1), data[p]));
+    };
+    for (uint32_t e = 0; e < n_entries; ++e) {
+        const size_t entry = ifd + 2 + (size_t)e * 12;
+        need(entry, 12);
+        std::vector<uint32_t> v;
+        switch (r16(entry)) {
+        case 256: values(entry, v); width = v.at(0); break;
+        case 257: values(entry, v); height = v.at(0); break;
+        case 258: values(entry, bits); break;
+        case 259: values(entry, v); compression = v.at(0); break;
+        case 262: values(entry, v); photometric = v.at(0); break;
+        case 273: values(entry, strip_offsets); break;
+        case 277: values(entry, v); spp = v.at(0); break;
+        case 278: values(entry, v); rows_per_strip = v.at(0); break;
+        case 279: values(entry, strip_counts); break;
+        case 284: values(entry, v); planar = v.at(0); break;
+        case 317: values(entry, v); predictor = v.at(0); break;
+        case 338: values(entry, v); extra = (uint32_t)v.size(); break;
+        case 322: case 323: case 324: case 325: throw std::runtime_error("tiff: tiled files are not supported");
+        default: break;
+        }
+    }
+    if (!width || !height || strip_offsets.empty() || strip_offsets.size() != strip_counts.size()) throw std::runtime_error("tiff: missing size or strips");
+    if (bits.empty()) bits.assign(1, 1);
+    const uint32_t bps = bits[0];
+    for (uint32_t b : bits)
+        if (b != bps) throw std::runtime_error("tiff: mixed bits per sample");
+    if (bps != 8 && bps != 16) throw std::runtime_error("tiff: only 8 / 16 bits per sample are supported");
+    if (planar != 1 && spp > 1) throw std::runtime_error("tiff: planar layout is not supported");
+    if (photometric > 2 || (photometric == 2 && spp < 3) || spp > 4 || spp == 0) throw std::runtime_error("tiff: unsupported photometric interpretation / sample count");
+    (void)extra;
+    const size_t bpp = (size_t)spp * bps / 8, stride = (size_t)width * bpp;
+    rows_per_strip = std::min(rows_per_strip, height);
+    std::vector<uint8_t> img;
+    img.reserve(stride * height);
+    for (size_t sidx = 0; sidx < strip_offsets.size() && img.size() < stride * height; ++sidx) {
+        const size_t rows = std::min<size_t>(rows_per_strip, height - sidx * rows_per_strip), expect = rows * stride;
+        need(strip_offsets[sidx], strip_counts[sidx]);
+        const uint8_t *src = data + strip_offsets[sidx];
+        const size_t n = strip_counts[sidx], base = img.size();
+        std::vector<uint8_t> strip;
+        if (compression == 1) {
+            if (n < expect) throw std::runtime_error("tiff: short strip");
+            strip.assign(src, src + expect);
+        } else if (compression == 5) {
+            tiff_lzw(src, n, strip, expect);
+        } else if (compression == 8 || compression == 32946) {
+            strip.resize(expect);
+            uLongf out_len = static_cast<uLongf>(expect);
+            if (uncompress(strip.data(), &out_len, src, static_cast<uLong>(n)) != Z_OK) throw std::runtime_error("tiff: inflate failed");
+            strip.resize(out_len);
+        } else if (compression == 32773) {  // PackBits
+            size_t i = 0;
+            while (i < n && strip.size() < expect) {
+                const int c = (int8_t)src[i++];
+                if (c >= 0) {
+                    if (i + (size_t)c + 1 > n) throw std::runtime_error("tiff: bad PackBits data");
+                    strip.insert(strip.end(), src + i, src + i + c + 1);
+                    i += (size_t)c + 1;
+                } else if (c != -128) {
+                    if (i >= n) throw std::runtime_error("tiff: bad PackBits data");
+                    strip.insert(strip.end(), (size_t)(1 - c), src[i++]);
+                }
+            }
+        } else {
+            throw std::runtime_error("tiff: compression " + std::to_string(compression) + " is not supported (none, LZW, Deflate, PackBits are)");
+        }
+        if (strip.size() < expect) throw std::runtime_error("tiff: strip decodes to too few bytes");
+        img.insert(img.end(), strip.begin(), strip.begin() + expect);
+        if (predictor == 2) {  // horizontal differencing, per sample, in the file's byte order for 16-bit samples
+            for (size_t r = 0; r < rows; ++r) {
+                uint8_t *row = img.data() + base + r * stride;
+                if (bps == 8) {
+                    for (size_t x = bpp; x < stride; ++x) row[x] = static_cast<uint8_t>(row[x] + row[x - bpp]);
+                } else {
+                    for (size_t x = bpp; x + 1 < stride + 1 && x < stride; x += 2) {
+                        const uint32_t a = le ? row[x - bpp] | (row[x - bpp + 1] << 8) : (row[x - bpp] << 8) | row[x - bpp + 1];
+                        const uint32_t b = le ? row[x] | (row[x + 1] << 8) : (row[x] << 8) | row[x + 1];
+                        const uint32_t v = (a + b) & 0xffffu;
+                        if (le) {
+                            row[x] = (uint8_t)v;
+                            row[x + 1] = (uint8_t)(v >> 8);
+                        } else {
+                            row[x] = (uint8_t)(v >> 8);
+                            row[x + 1] = (uint8_t)v;
+                        }
+                    }
+                }
+            }
+        } else if (predictor != 1) {
+            throw std::runtime_error("tiff: floating-point predictor is not supported");
+        }
+    }
+    if (img.size() < stride * height) throw std::runtime_error("tiff: image data ends early");
+    rgba8.resize((size_t)width * height * 4);
+    for (uint32_t y = 0; y < height; ++y) {
+        const uint32_t fy = height - 1 - y;  // DynamicImage::flipv
+        for (uint32_t x = 0; x < width; ++x) {
+            const uint8_t *px = img.data() + y * stride + x * bpp;
+            auto sample = [&](uint32_t c) -> uint8_t {
+                if (bps == 8) return px[c];
+                const uint32_t v = le ? px[2 * c] | (px[2 * c + 1] << 8) : (px[2 * c] << 8) | px[2 * c + 1];
+                return static_cast<uint8_t>((v + 128u) / 257u);  // to_rgba8 (see decode_png)
+            };
+            uint8_t r, g, b, a = 255;
+            if (photometric <= 1) {
+                uint8_t l = sample(0);
+                if (photometric == 0) l = static_cast<uint8_t>(255 - l);  // WhiteIsZero
+                r = g = b = l;
+                if (spp >= 2) a = sample(1);
+            } else {
+                r = sample(0);
+                g = sample(1);
+                b = sample(2);
+                if (spp == 4) a = sample(3);
+            }
+            uint8_t *o = rgba8.data() + ((size_t)fy * width + x) * 4;
+            o[0] = r; o[1] = g; o[2] = b; o[3] = a;
+        }
+    }
+}
+
+// ---- OpenEXR (the `image` crate's OpenExrDecoder -> to_rgba32f, load.rs:590-610) -----------------------------------------
+// Single-part scanline files with R, G, B (and optionally A) channels of type HALF or FLOAT, compression NONE / RLE / ZIPS /
+// ZIP (lossless, bit-exact by construction).  Tiled, multi-part and deep files and the PIZ / PXR24 / B44 / DWA codecs are
+// rejected.  Rows are flipped (DynamicImage::flipv); a missing alpha channel reads 1.
+float half_to_float(uint16_t h) {
+    const uint32_t sign = (uint32_t)(h & 0x8000u) << 16, exp = (h >> 10) & 0x1fu, man = h & 0x3ffu;
+    uint32_t bits;
+    if (exp == 0) {
+        if (man == 0) bits = sign;
+        else {  // subnormal half: normalise
+            int e = -1;
+            uint32_t m = man;
+            do {
+                ++e;
+                m <<= 1;
+            } while (!(m & 0x400u));
+            bits = sign | ((uint32_t)(127 - 15 - e) << 23) | ((m & 0x3ffu) << 13);
+        }
+    } else if (exp == 31) {
+        bits = sign | 0x7f800000u | (man << 13);
+    } else {
+        bits = sign | ((exp + (127 - 15)) << 23) | (man << 13);
+    }
+    float f;
+    std::memcpy(&f, &bits, 4);
+    return f;
+}
+void decode_exr(const uint8_t *data, size_t len, uint32_t &width, uint32_t &height, std::vector<float> &rgba) {
+    auto need = [&](size_t pos, size_t n) {
+        if (pos + n > len) throw std::runtime_error("exr: truncated file");
+    };
+    auto rd32 = [&](size_t pos) {
+        need(pos, 4);
+        uint32_t v;
+        std::memcpy(&v, data + pos, 4);
+        return v;
+    };
+    if (len < 8 || rd32(0) != 20000630u) throw std::runtime_error("exr: bad magic number");
+    const uint32_t version = rd32(4);
+    if ((version & 0xffu) != 2u) throw std::runtime_error("exr: unsupported file version");
+    if (version & 0x1a00u) throw std::runtime_error("exr: tiled, deep and multi-part files are not supported");
+    struct Channel {
+        std::string name;
+        uint32_t type;  // 0 UINT, 1 HALF, 2 FLOAT
+    };
+    std::vector<Channel> channels;
+    int32_t win[4] = {0, 0, -1, -1};
+    uint32_t compression = 0xffu;
+    size_t pos = 8;
+    while (true) {  // attributes: name\0 type\0 size data
+        need(pos, 1);
+        if (data[pos] == 0) {
+            ++pos;
+            break;
+        }
+        auto cstr = [&]() {
+            size_t e = pos;
+            while (e < len && data[e]) ++e;
+            if (e >= len) throw std::runtime_error("exr: truncated header");
+            std::string r(reinterpret_cast<const char *>(data + pos), e - pos);
+            pos = e + 1;
+            return r;
+        };
+        const std::string name = cstr(), type = cstr();
+        const uint32_t size = rd32(pos);
+        pos += 4;
+        need(pos, size);
+        if (name == "channels" && type == "chlist") {
+            size_t q = pos;
+            while (q < pos + size && data[q]) {
+                size_t e = q;
+                while (e < pos + size && data[e]) ++e;
+                Channel c;
+                c.name.assign(reinterpret_cast<const char *>(data + q), e - q);
+                q = e + 1;
+                if (q + 16 > pos + size) throw std::runtime_error("exr: truncated channel list");
+                c.type = rd32(q);
+                if (rd32(q + 8) != 1u || rd32(q + 12) != 1u) throw std::runtime_error("exr: subsampled channels are not supported");
+                q += 16;
+                channels.push_back(c);
+            }
+        } else if (name == "compression") {
+            compression = data[pos];
+        } else if (name == "dataWindow") {
+            if (size != 16) throw std::runtime_error("exr: bad dataWindow");
+            std::memcpy(win, data + pos, 16);
+        }
+        pos += size;
+    }
+    if (channels.empty() || win[2] < win[0] || win[3] < win[1]) throw std::runtime_error("exr: missing channels or dataWindow");
+    uint32_t lines_per_chunk;
+    switch (compression) {
+    case 0: case 1: case 2: lines_per_chunk = 1; break;  // NONE, RLE, ZIPS
+    case 3: lines_per_chunk = 16; break;                 // ZIP
+    default: throw std::runtime_error("exr: compression " + std::to_string(compression) + " is not supported (NONE, RLE, ZIPS, ZIP are)");
+    }
+    width = (uint32_t)(win[2] - win[0] + 1);
+    height = (uint32_t)(win[3] - win[1] + 1);
+    int slot[4] = {-1, -1, -1, -1};  // index into `channels` of R, G, B, A
+    size_t line_bytes = 0;
+    std::vector<size_t> ch_offset(channels.size());
+    for (size_t i = 0; i < channels.size(); ++i) {
+        if (channels[i].type != 1u && channels[i].type != 2u) throw std::runtime_error("exr: only HALF and FLOAT channels are supported");
+        ch_offset[i] = line_bytes;
+        line_bytes += (size_t)width * (channels[i].type == 1u ? 2 : 4);
+        static const char *names[4] = {"R", "G", "B", "A"};
+        for (int k = 0; k < 4; ++k)
+            if (channels[i].name == names[k]) slot[k] = (int)i;
+    }
+    if (slot[0] < 0 || slot[1] < 0 || slot[2] < 0) throw std::runtime_error("exr: image contains no R, G, B channels");
+    const uint32_t n_chunks = (height + lines_per_chunk - 1) / lines_per_chunk;
+    need(pos, (size_t)n_chunks * 8);
+    rgba.assign((size_t)width * height * 4, 1.0f);
+    std::vector<uint8_t> buf, tmp;
+    for (uint32_t c = 0; c < n_chunks; ++c) {
+        uint64_t off;
+        std::memcpy(&off, data + pos + (size_t)c * 8, 8);
+        need(off, 8);
+        const int32_t y0 = (int32_t)rd32(off) - win[1];
+        const uint32_t csize = rd32(off + 4);
+        need(off + 8, csize);
+        if (y0 < 0 || (uint32_t)y0 >= height) throw std::runtime_error("exr: chunk outside the data window");
+        const uint32_t lines = std::min(lines_per_chunk, height - (uint32_t)y0);
+        const size_t raw_size = line_bytes * lines;
+        const uint8_t *src = data + off + 8;
+        buf.resize(raw_size);
+        if (compression == 0 || csize == raw_size) {  // stored (a codec falls back to raw bytes when it does not shrink the chunk)
+            if (csize != raw_size) throw std::runtime_error("exr: bad chunk size");
+            std::memcpy(buf.data(), src, raw_size);
+        } else {
+            tmp.resize(raw_size);
+            if (compression == 1) {  // RLE: n >= 0: one byte repeated n + 1 times; n < 0: -n literal bytes
+                size_t i = 0, o = 0;
+                while (i < csize) {
+                    const int n = (int8_t)src[i++];
+                    if (n < 0) {
+                        const size_t k = (size_t)(-n);
+                        if (i + k > csize || o + k > raw_size) throw std::runtime_error("exr: bad RLE data");
+                        std::memcpy(tmp.data() + o, src + i, k);
+                        i += k;
+                        o += k;
+                    } else {
+                        const size_t k = (size_t)n + 1;
+                        if (i >= csize || o + k > raw_size) throw std::runtime_error("exr: bad RLE data");
+                        std::memset(tmp.data() + o, src[i++], k);
+                        o += k;
+                    }
+                }
+                if (o != raw_size) throw std::runtime_error("exr: bad RLE data");
+            } else {
+                uLongf out_len = static_cast<uLongf>(raw_size);
+                if (uncompress(tmp.data(), &out_len, src, csize) != Z_OK || out_len != raw_size) throw std::runtime_error("exr: inflate failed");
+            }
+            for (size_t i = 1; i < raw_size; ++i) tmp[i] = static_cast<uint8_t>(tmp[i - 1] + tmp[i] - 128);  // undo the byte predictor
+            const size_t half = (raw_size + 1) / 2;                                                          // then the even / odd byte split
+            for (size_t i = 0; i < raw_size; ++i) buf[i] = (i & 1) ? tmp[half + i / 2] : tmp[i / 2];
+        }
+        for (uint32_t l = 0; l < lines; ++l) {
+            const uint32_t fy = height - 1 - ((uint32_t)y0 + l);  // DynamicImage::flipv
+            const uint8_t *line = buf.data() + (size_t)l * line_bytes;
+            for (int k = 0; k < 4; ++k) {
+                if (slot[k] < 0) continue;
+                const uint8_t *chp = line + ch_offset[(size_t)slot[k]];
+                const bool is_half = channels[(size_t)slot[k]].type == 1u;
+                for (uint32_t x = 0; x < width; ++x) {
+                    float v;
+                    if (is_half) {
+                        uint16_t h;
+                        std::memcpy(&h, chp + 2 * x, 2);
+                        v = half_to_float(h);
+                    } else {
+                        std::memcpy(&v, chp + 4 * x, 4);
+                    }
+                    rgba[((size_t)fy * width + x) * 4 + (size_t)k] = v;
+                }
+            }
+        }
+    }
+}
+
 void decode_image(const std::string &format, const uint8_t *bytes, size_t len, uint32_t width, uint32_t height, uint32_t channels, AkrImage &img,
                   std::vector<uint8_t> &texels) {
     if (channels == 0 || channels > 4) throw std::runtime_error("Invalid number of channels: " + std::to_string(channels));
@@ -332,8 +735,17 @@ void decode_image(const std::string &format, const uint8_t *bytes, size_t len, u
     } else if (format == "png") {
         img.texel_format = AKR_TEXEL_RGBA8;
         decode_png(bytes, len, img.width, img.height, texels);
+    } else if (format == "tiff") {
+        img.texel_format = AKR_TEXEL_RGBA8;
+        decode_tiff(bytes, len, img.width, img.height, texels);
+    } else if (format == "exr") {
+        img.texel_format = AKR_TEXEL_RGBA32F;
+        std::vector<float> rgba;
+        decode_exr(bytes, len, img.width, img.height, rgba);
+        texels.resize(rgba.size() * 4);
+        std::memcpy(texels.data(), rgba.data(), texels.size());
     } else {
-        throw std::runtime_error("image format '" + format + "' needs a decoder this host does not carry (png and raw float are implemented)");
+        throw std::runtime_error("image format '" + format + "' needs a decoder this host does not carry (png, tiff, exr and raw float are implemented)");
     }
 }
 

@@ -398,3 +398,136 @@ def write_textured(tmp_path, alpha_cutout=True):
     path = os.path.join(d, "scene.json")
     json.dump(scene, open(path, "w"))
     return path
+
+
+# ---- OpenEXR fixtures (single-part scanline; what decode_exr in scene_loader.cpp reads) -----------------------------
+def _exr_bytes(arr, compression="zip", pixel_type="half", data_window_origin=(0, 0)):
+    """Minimal OpenEXR writer: arr [h, w, 3 or 4] -> R, G, B(, A) channels (stored alphabetically: A, B, G, R), pixel type
+    'half' / 'float', compression 'none' / 'rle' / 'zips' / 'zip', increasing-y line order."""
+    import struct
+    import zlib
+    import numpy as np
+    h, w, c = arr.shape
+    names = ["R", "G", "B", "A"][:c]
+    order = sorted(range(c), key=lambda k: names[k])
+    dt = np.float16 if pixel_type == "half" else np.float32
+    ptype = 1 if pixel_type == "half" else 2
+    comp = {"none": 0, "rle": 1, "zips": 2, "zip": 3}[compression]
+    lines_per_chunk = 16 if comp == 3 else 1
+    x0, y0 = data_window_origin
+
+    def attr(name, typ, data):
+        return name.encode() + b"\0" + typ.encode() + b"\0" + struct.pack("<I", len(data)) + data
+    chlist = b"".join(names[k].encode() + b"\0" + struct.pack("<IB3xII", ptype, 0, 1, 1) for k in order) + b"\0"
+    box = struct.pack("<4i", x0, y0, x0 + w - 1, y0 + h - 1)
+    header = (struct.pack("<II", 20000630, 2) + attr("channels", "chlist", chlist) + attr("compression", "compression", bytes([comp])) +
+              attr("dataWindow", "box2i", box) + attr("displayWindow", "box2i", box) + attr("lineOrder", "lineOrder", b"\0") +
+              attr("pixelAspectRatio", "float", struct.pack("<f", 1.0)) + attr("screenWindowCenter", "v2f", struct.pack("<2f", 0, 0)) +
+              attr("screenWindowWidth", "float", struct.pack("<f", 1.0)) + b"\0")
+
+    def rle(b):
+        out, i = bytearray(), 0
+        while i < len(b):
+            j = i
+            while j + 1 < len(b) and b[j + 1] == b[i] and j - i < 126:
+                j += 1
+            if j - i >= 2:
+                out += struct.pack("b", j - i) + bytes([b[i]])
+                i = j + 1
+            else:
+                k = i
+                while k < len(b) and k - i < 127 and not (k + 2 < len(b) and b[k] == b[k + 1] == b[k + 2]):
+                    k += 1
+                out += struct.pack("b", -(k - i)) + bytes(b[i:k])
+                i = k
+        return bytes(out)
+    chunks = []
+    for cy in range(0, h, lines_per_chunk):
+        raw = b"".join(np.ascontiguousarray(arr[y, :, k], dt).tobytes() for y in range(cy, min(h, cy + lines_per_chunk)) for k in order)
+        data = raw
+        if comp != 0:
+            t = np.frombuffer(raw, np.uint8)
+            split = np.concatenate([t[0::2], t[1::2]]).astype(np.int32)  # even bytes, then odd bytes
+            pred = split.copy()
+            pred[1:] = (split[1:] - split[:-1] + 128 + 256) % 256          # byte predictor
+            packed = rle(bytes(pred.astype(np.uint8))) if comp == 1 else zlib.compress(bytes(pred.astype(np.uint8)))
+            if len(packed) < len(raw):
+                data = packed
+        chunks.append((y0 + cy, data))
+    table_pos = len(header)
+    pos = table_pos + 8 * len(chunks)
+    offsets, body = [], b""
+    for y, data in chunks:
+        offsets.append(pos + len(body))
+        body += struct.pack("<iI", y, len(data)) + data
+    return header + b"".join(struct.pack("<Q", o) for o in offsets) + body
+
+
+def write_image_textured(tmp_path, name, items, colorspace="none"):
+    """cbox with planar uvs whose listed materials take their base colour from an encoded image:
+    items = [(material, encoded bytes, format, width, height, channels)]."""
+    import numpy as np
+    scene = json.load(open(os.path.join(CBOX_DIR, "scene.json")))
+    blob = bytearray(open(os.path.join(CBOX_DIR, "Scene.bin"), "rb").read())
+    scene["buffers"]["Scene"]["path"] = "Scene.bin"
+    nview = len(scene["buffer_views"])
+
+    def add_view(raw):
+        nonlocal nview
+        while len(blob) % 16:
+            blob.append(0)
+        view = f"buf_view_{nview}"
+        nview += 1
+        scene["buffer_views"][view] = {"buffer": {"id": "Scene"}, "offset": len(blob), "length": len(raw)}
+        blob.extend(raw)
+        return {"id": view}
+    for material, raw, fmt, w, h, c in items:
+        g = scene["materials"][material]["shader"]
+        nodes, p = g["nodes"], _principled_name(g)
+        nodes["tex"] = {"type": "image", "uv": None,
+                        "image": {"data": add_view(raw), "format": fmt, "colorspace": colorspace, "extension": "repeat", "interpolation": "linear",
+                                  "width": w, "height": h, "channels": c}}
+        nodes["tex_up"] = {"type": "spectral_uplift", "rgb": {"id": "tex"}}
+        nodes[p]["base_color"] = {"id": "tex_up"}
+    for gname, g in scene["geometries"].items():  # planar uvs as in write_textured
+        v = scene["buffer_views"][g["vertices"]["id"]]
+        verts = np.frombuffer(bytes(blob[v["offset"]:v["offset"] + v["length"]]), np.float32).reshape(-1, 3)
+        v = scene["buffer_views"][g["indices"]["id"]]
+        idx = np.frombuffer(bytes(blob[v["offset"]:v["offset"] + v["length"]]), np.uint32).reshape(-1, 3)
+        lo, ext = verts.min(axis=0), np.maximum(verts.max(axis=0) - verts.min(axis=0), 1e-6)
+        uvs = np.zeros((len(idx) * 3, 2), np.float32)
+        for t, tri in enumerate(idx):
+            n = np.abs(np.cross(verts[tri[1]] - verts[tri[0]], verts[tri[2]] - verts[tri[0]]))
+            keep = [a for a in range(3) if a != int(np.argmax(n))]
+            for k in range(3):
+                q = (verts[tri[k]] - lo) / ext
+                uvs[3 * t + k] = (q[keep[0]], q[keep[1]])
+        g["uvs"] = add_view(uvs.tobytes())
+    scene["buffers"]["Scene"]["length"] = len(blob)
+    d = os.path.join(str(tmp_path), name)
+    os.makedirs(d, exist_ok=True)
+    open(os.path.join(d, "Scene.bin"), "wb").write(bytes(blob))
+    path = os.path.join(d, "scene.json")
+    json.dump(scene, open(path, "w"))
+    return path
+
+
+def write_exr_textured(tmp_path):
+    """cbox whose floor / back wall / left wall / right wall / ceiling base colours are OpenEXR textures in the supported
+    encodings.  Returns (scene path, {material: source array})."""
+    import numpy as np
+    rng = np.random.default_rng(11)
+    sources, items = {}, []
+    specs = [("floor_001", (9, 7, 3), "zip", "half", (0, 0)), ("backWall_001", (20, 5, 4), "zip", "float", (3, -2)),
+             ("leftWall_001", (4, 6, 3), "none", "float", (0, 0)), ("rightWall_001", (6, 6, 4), "zips", "half", (0, 0)),
+             ("ceiling_001", (5, 8, 3), "rle", "half", (0, 0))]
+    for material, shape, compression, pixel_type, origin in specs:
+        arr = (0.1 + 0.8 * rng.random(shape)).astype(np.float16 if pixel_type == "half" else np.float32).astype(np.float32)
+        if material == "ceiling_001":
+            arr[:, :, :] = np.round(arr * 4) / 4  # long runs of equal bytes: the RLE path really compresses
+            arr[2:, :, 1] = 0.5
+        if shape[2] == 4:
+            arr[..., 3] = 1.0
+        sources[material] = arr
+        items.append((material, _exr_bytes(arr, compression, pixel_type, origin), "exr", shape[1], shape[0], shape[2]))
+    return write_image_textured(tmp_path, "exr_textured", items), sources

@@ -178,3 +178,94 @@ def test_alpha_cutout_gpu_statistical_parity(akr, oracle, tables, cbox_task, tmp
     ds = abs(int(st.segments) - int(ost.segments)) / ost.segments
     measured(f"alpha cutout: first hits on the cut-out box gpu/oracle {ga}/{oa} (within 10 %), segments rel diff {ds:.2e} (<= 1e-2)")
     assert abs(ga - oa) <= 0.1 * oa and ds <= 1e-2
+
+
+def test_loader_decodes_openexr_images(akr, oracle, tables, cbox_task, tmp_path):
+    """OpenEXR textures (load.rs:590-610: decode, flipv, to_rgba32f): HALF / FLOAT channels stored alphabetically, ZIP (16-line
+    chunks), ZIPS, RLE and uncompressed scanlines, a data window that does not start at the origin, RGB and RGBA.  All four
+    codecs are lossless, so the texels must equal the source arrays exactly (rows flipped, missing alpha = 1), and the
+    kernels' bodies still equal the oracle bit for bit on the scene.  Truncated files, a bad magic number and the PIZ
+    codec are rejected."""
+    path, sources = sv.write_exr_textured(tmp_path)
+    scene = akr.load_scene(path)
+    imgs = _images(scene)
+    assert len(imgs) == len(sources) == 5
+    for arr in sources.values():
+        h, w, c = arr.shape
+        match = [g for g in imgs if (g.width, g.height) == (w, h)]
+        assert len(match) == 1 and match[0].texel_format == 1
+        got = np.ctypeslib.as_array(C.cast(match[0].texels, C.POINTER(C.c_float)), (w * h * 4,)).reshape(h, w, 4)
+        assert np.array_equal(got[..., :c], arr[::-1]) and (got[..., 3] == 1.0).all()
+    # render parity on the scene (texture-driven materials on five surfaces)
+    lib = C.CDLL(os.path.join(HERE, "hostsim", "libhostsim.so"))
+    lib.hostsim_last_error.restype = C.c_char_p
+    w = h = 32
+    scene.set_resolution(w, h)
+    task = cbox_task(4)
+    pmj, bn = tables
+    ofilm, ost, ofh = oracle.render(scene.desc, w, h, task.pt, task.sampler, task.filter, pmj, bn, want_first_hits=True)
+    film, fh, st = run_hostsim(lib, scene, task, tables, oracle.albedo_table(), w, h)
+    assert np.array_equal(film, ofilm) and st.any_dynamic == 1 and st.any_alpha == 0
+    # malformed / unsupported files are rejected, not mis-read
+    raw = sv._exr_bytes(np.ones((4, 4, 3), np.float32), "zip", "half")
+    for bad, what in ((raw[:40], "truncated"), (b"\x00" + raw[1:], "magic"), (raw.replace(b"compression\0compression\0\x01\0\0\0\x03", b"compression\0compression\0\x01\0\0\0\x04"), "PIZ")):
+        sj = json.load(open(path))
+        blob = bytearray(open(os.path.join(os.path.dirname(path), "Scene.bin"), "rb").read())
+        v = sj["buffer_views"][sj["materials"]["floor_001"]["shader"]["nodes"]["tex"]["image"]["data"]["id"]]
+        v["offset"], v["length"] = len(blob), len(bad)
+        blob.extend(bad)
+        sj["buffers"]["Scene"]["length"] = len(blob)
+        d = os.path.join(str(tmp_path), "bad_" + what)
+        os.makedirs(d, exist_ok=True)
+        open(os.path.join(d, "Scene.bin"), "wb").write(bytes(blob))
+        json.dump(sj, open(os.path.join(d, "scene.json"), "w"))
+        with pytest.raises(akr.AkariError):
+            akr.load_scene(os.path.join(d, "scene.json"))
+
+
+def test_loader_decodes_tiff_images(akr, tmp_path):
+    """TIFF textures (load.rs:590-603: decode, flipv, to_rgba8) written by an independent encoder (OpenCV / libtiff):
+    uncompressed, LZW, Deflate and PackBits strips, 8-bit gray / RGB / RGBA and 16-bit RGBA (-> 8 bit by
+    round(v * 255 / 65535) like image 0.24's to_rgba8)."""
+    import cv2
+    rng = np.random.default_rng(5)
+    cases = [("floor_001", (rng.random((33, 21, 3)) * 255).astype(np.uint8), 5), ("backWall_001", (rng.random((8, 40, 4)) * 255).astype(np.uint8), 1),
+             ("leftWall_001", (rng.random((17, 9)) * 255).astype(np.uint8), 8), ("rightWall_001", (rng.random((12, 12, 3)) * 255).astype(np.uint8), 32773),
+             ("ceiling_001", (rng.random((10, 14, 4)) * 65535).astype(np.uint16), 5)]
+    cases[3][1][3:9, :, :] = 77  # runs for PackBits
+    items, expect = [], {}
+    for material, arr, compression in cases:
+        bgr = arr if arr.ndim == 2 else arr[..., [2, 1, 0] + ([3] if arr.shape[2] == 4 else [])]
+        ok, buf = cv2.imencode(".tiff", bgr, [cv2.IMWRITE_TIFF_COMPRESSION, compression])
+        assert ok
+        h, w = arr.shape[:2]
+        c = 1 if arr.ndim == 2 else arr.shape[2]
+        items.append((material, bytes(buf), "tiff", w, h, c))
+        a8 = arr if arr.dtype == np.uint8 else ((arr.astype(np.uint32) + 128) // 257).astype(np.uint8)
+        rgba = np.full((h, w, 4), 255, np.uint8)
+        if c == 1:
+            rgba[..., :3] = a8[..., None]
+        else:
+            rgba[..., :c] = a8
+        expect[(w, h)] = rgba[::-1]
+    scene = akr.load_scene(sv.write_image_textured(tmp_path, "tiff_textured", items, colorspace="srgb"))
+    imgs = _images(scene)
+    assert len(imgs) == 5
+    for g in imgs:
+        got = np.ctypeslib.as_array(C.cast(g.texels, C.POINTER(C.c_uint8)), (g.width * g.height * 4,)).reshape(g.height, g.width, 4)
+        assert g.texel_format == 0 and np.array_equal(got, expect[(g.width, g.height)])
+
+
+def test_16_bit_png_converts_like_to_rgba8(akr, tmp_path):
+    """16-bit PNG samples become 8-bit by round(v * 255 / 65535) = (v + 128) // 257 (image 0.24.7 `to_rgba8`), not by
+    dropping the low byte."""
+    import cv2
+    rng = np.random.default_rng(9)
+    arr = (rng.random((6, 5, 4)) * 65535).astype(np.uint16)
+    arr[0, 0] = (255, 256, 383, 65535)  # values on which truncation and rounding differ
+    ok, buf = cv2.imencode(".png", arr[..., [2, 1, 0, 3]])
+    assert ok
+    scene = akr.load_scene(sv.write_image_textured(tmp_path, "png16", [("floor_001", bytes(buf), "png", 5, 6, 4)], colorspace="srgb"))
+    g = _images(scene)[0]
+    got = np.ctypeslib.as_array(C.cast(g.texels, C.POINTER(C.c_uint8)), (6 * 5 * 4,)).reshape(6, 5, 4)
+    assert np.array_equal(got, (((arr.astype(np.uint32) + 128) // 257).astype(np.uint8))[::-1])
