@@ -1283,7 +1283,7 @@ struct AkrContext {
 
     // scene
     DeviceBuffer nodes, prims, flat_prims, shade, instances, materials, lights, alias_j, alias_t, alias_pdf, corner_n, corner_t, corner_uv;
-    DeviceBuffer svm_nodes, svm_kind_first, svm_data, textures, texels;
+    DeviceBuffer svm_nodes, svm_kind_first, svm_data, svm_kind_hit_mask, svm_static_vals, textures, texels;
     SceneView scene{};
     CornerAttribs corners{};
     bool scene_ready = false;
@@ -1507,7 +1507,7 @@ void akr_b200_destroy(AkrContext *ctx) {
     cudaDeviceSynchronize();
     for (DeviceBuffer *b : {&ctx->pmj, &ctx->bn, &ctx->albedo, &ctx->nodes, &ctx->prims, &ctx->flat_prims, &ctx->shade, &ctx->instances, &ctx->materials, &ctx->lights,
                             &ctx->alias_j, &ctx->alias_t, &ctx->alias_pdf, &ctx->corner_n, &ctx->corner_t, &ctx->corner_uv, &ctx->svm_nodes,
-                            &ctx->svm_kind_first, &ctx->svm_data, &ctx->textures, &ctx->texels, &ctx->film, &ctx->wave_mem, &ctx->counters,
+                            &ctx->svm_kind_first, &ctx->svm_data, &ctx->svm_kind_hit_mask, &ctx->svm_static_vals, &ctx->textures, &ctx->texels, &ctx->film, &ctx->wave_mem, &ctx->counters,
                             &ctx->totals, &ctx->first_hits})
         dev_free(*b);
     if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
@@ -1581,6 +1581,8 @@ int akr_b200_upload_scene(AkrContext *ctx, const AkrSceneDesc *desc) {
     if ((rc = upload_vec(ctx, ctx->svm_nodes, blob.svm_nodes)) != AKR_OK) return rc;
     if ((rc = upload_vec(ctx, ctx->svm_kind_first, blob.svm_kind_first)) != AKR_OK) return rc;
     if ((rc = upload_vec(ctx, ctx->svm_data, blob.svm_data)) != AKR_OK) return rc;
+    if ((rc = upload_vec(ctx, ctx->svm_kind_hit_mask, blob.svm_kind_hit_mask)) != AKR_OK) return rc;
+    if ((rc = upload_vec(ctx, ctx->svm_static_vals, blob.svm_static_vals)) != AKR_OK) return rc;
     if ((rc = upload_vec(ctx, ctx->texels, blob.texels)) != AKR_OK) return rc;
     {  // texture records: byte offsets into the texel blob become device pointers
         std::vector<TextureRec> recs = blob.textures;
@@ -1622,6 +1624,8 @@ int akr_b200_upload_scene(AkrContext *ctx, const AkrSceneDesc *desc) {
     v.svm.n_kinds = (uint32_t)blob.svm_kind_first.size() - 1u;
     v.svm.n_textures = (uint32_t)blob.textures.size();
     v.svm.data_size = (uint32_t)blob.svm_data.size();
+    v.svm.kind_hit_mask = static_cast<const uint64_t *>(ctx->svm_kind_hit_mask.ptr);
+    v.svm.static_vals = static_cast<const SvmVal *>(ctx->svm_static_vals.ptr);
     v.corner_uvs = blob.corner_uvs.empty() ? nullptr : static_cast<const float *>(ctx->corner_uv.ptr);
     ctx->corners.normals = blob.corner_normals.empty() ? nullptr : static_cast<const float *>(ctx->corner_n.ptr);
     ctx->corners.tangents = blob.corner_tangents.empty() ? nullptr : static_cast<const float *>(ctx->corner_t.ptr);

@@ -58,7 +58,8 @@ struct Material {  // 48 words
     uint32_t shader_kind, data_offset;  // ShaderRef (svm/mod.rs:213-219)
     uint32_t alpha_dynamic;  // `dynamic`, and alpha itself can differ from hit to hit (a texture with alpha != 1 texels or
                              // the zero address mode feeds the closure colour): only then traversal evaluates alpha per hit
-    uint32_t _pad[2];
+    uint32_t static_offset;  // `dynamic`: first entry of this material's table of hit-independent node values (akr_svm.cuh)
+    uint32_t _pad[1];
 };
 static_assert(sizeof(Material) == 192, "Material is 48 words");
 

@@ -345,7 +345,7 @@ AKR_HD ShadeOut shade_body(const SceneView &sc, const CornerAttribs &ca, const S
     Material dyn;
     if ((CLS == CLS_GENERAL || CLS == CLS_ANY) && matp->dynamic) {  // texture-driven inputs: the reference's per-dispatch evaluation (eval.rs:364-380)
         dyn = *matp;
-        svm_eval<false, false>(sc.svm, matp->shader_kind, matp->data_offset, hit_uv(sc, hit.gid, hit.u, hit.v, false), dyn, nullptr);
+        svm_eval<false, false>(sc.svm, matp->shader_kind, matp->data_offset, hit_uv(sc, hit.gid, hit.u, hit.v, false), dyn, nullptr, matp->static_offset);
         matp = &dyn;
     }
     const Material &mat = *matp;
@@ -618,7 +618,7 @@ AKR_HD f3 aov_body(const SceneView &sc, const CornerAttribs &ca, const SamplerTa
     Material dyn;
     if (matp->dynamic) {
         dyn = *matp;
-        svm_eval<false, false>(sc.svm, matp->shader_kind, matp->data_offset, hit_uv(sc, hit.gid, hit.u, hit.v, false), dyn, nullptr);
+        svm_eval<false, false>(sc.svm, matp->shader_kind, matp->data_offset, hit_uv(sc, hit.gid, hit.u, hit.v, false), dyn, nullptr, matp->static_offset);
         matp = &dyn;
     }
     const Material &mat = *matp;

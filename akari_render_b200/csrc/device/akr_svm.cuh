@@ -24,6 +24,12 @@ struct TextureRec {            // one (image, sampler) slot (load.rs:611-646)
     uint32_t address, filter;  // AKR_ADDRESS_*, AKR_FILTER_*
     uint32_t _pad;
 };
+constexpr uint32_t kSvmMaxNodes = 64;
+enum SvmKind : uint32_t { SV_NONE = 0, SV_F, SV_F2, SV_F3, SV_F4, SV_COLOR_ALPHA, SV_CLOSURE, SV_TEXCOORDS, SV_SEPARATE };
+struct SvmVal {
+    float v[4];
+    uint32_t kind;
+};
 struct SvmView {
     const AkrSvmNode *nodes;        // every shader kind's nodes, concatenated
     const uint32_t *kind_first;     // [n_kinds + 1] first node of kind k
@@ -31,13 +37,18 @@ struct SvmView {
     const TextureRec *textures;
     uint32_t n_kinds, n_textures;
     uint32_t data_size, _pad;
+    // Per-hit evaluation of a texture-driven material only runs the nodes that depend on the hit: bit i of
+    // kind_hit_mask[kind] marks node i as hit-dependent (an image texture, texture coordinates, a checkerboard on the mesh
+    // uvs, or anything downstream of one — a property of the node program, not of its constants); the values of the other
+    // nodes were computed once at upload and sit in static_vals[Material.static_offset + i] (scene_build.cpp
+    // fold_material).  The reference interprets the whole program per dispatch (eval.rs:364-380); the values are the same.
+    const uint64_t *kind_hit_mask;  // [n_kinds]
+    const SvmVal *static_vals;
 };
-
-constexpr uint32_t kSvmMaxNodes = 64;
-enum SvmKind : uint32_t { SV_NONE = 0, SV_F, SV_F2, SV_F3, SV_F4, SV_COLOR_ALPHA, SV_CLOSURE, SV_TEXCOORDS, SV_SEPARATE };
-struct SvmVal {
-    float v[4];
-    uint32_t kind;
+// what the validating evaluation at upload reports besides the folded Material
+struct SvmFoldInfo {
+    uint64_t hit_mask;            // see SvmView::kind_hit_mask
+    SvmVal vals[kSvmMaxNodes];    // value of every node at uv = (0, 0): exact for the nodes outside hit_mask
 };
 enum SvmStatus : int { SVM_OK = 0, SVM_BAD_PROGRAM = 1, SVM_UNSUPPORTED = 2 };
 
@@ -133,11 +144,24 @@ AKR_HD float f0_from_ior(float ior) {  // mod.rs:1095-1098
 // skips everything of the closure but Material.alpha.  VALIDATE adds the bounds / ordering / type checks the upload
 // runs once per material, so that the per-hit evaluation on the device can trust the program.
 template <bool ALPHA_ONLY, bool VALIDATE>
-AKR_HD int svm_eval(const SvmView &svm, uint32_t shader_kind, uint32_t data_offset, f2 uv, Material &m, bool *dynamic) {
+AKR_HD int svm_eval(const SvmView &svm, uint32_t shader_kind, uint32_t data_offset, f2 uv, Material &m, bool *dynamic, uint32_t static_offset = AKR_SVM_NONE,
+                    SvmFoldInfo *fold = nullptr) {
     if (VALIDATE && shader_kind >= svm.n_kinds) return SVM_BAD_PROGRAM;
     const uint32_t first = svm.kind_first[shader_kind], n_nodes = svm.kind_first[shader_kind + 1u] - first;
     if (VALIDATE && (n_nodes == 0u || n_nodes > kSvmMaxNodes)) return SVM_UNSUPPORTED;
-    SvmVal vals[kSvmMaxNodes];
+    // `static_offset` given (per-hit evaluation of a texture-driven material): only hit-dependent nodes are interpreted,
+    // into `local`; every other node's value is read from the table computed at upload.  Otherwise all nodes run.
+    const bool partial = !VALIDATE && static_offset != AKR_SVM_NONE;
+    const uint64_t hit_mask = partial ? svm.kind_hit_mask[shader_kind] : ~0ull;
+    const SvmVal *table = partial ? svm.static_vals + static_offset : nullptr;
+    SvmVal local[kSvmMaxNodes];
+    uint64_t fold_mask = 0ull;  // VALIDATE: nodes found to depend on the hit
+    struct Vals {
+        SvmVal *local;
+        const SvmVal *table;
+        uint64_t hit_mask;
+        AKR_HD const SvmVal &operator[](uint32_t j) const { return (table && !((hit_mask >> j) & 1ull)) ? table[j] : local[j]; }
+    } vals{local, table, hit_mask};
     bool dyn = false, have_closure = false;
     m.alpha = 1.0f;
     m.type = MAT_EMISSION;
@@ -148,8 +172,10 @@ AKR_HD int svm_eval(const SvmView &svm, uint32_t shader_kind, uint32_t data_offs
         return f;
     };
     for (uint32_t i = 0; i < n_nodes; ++i) {
+        if (partial && !((hit_mask >> i) & 1ull)) continue;
         const AkrSvmNode &n = svm.nodes[first + i];
         if (VALIDATE) {
+            if (n.op == AKR_SVM_RGB_IMAGE_TEX || n.op == AKR_SVM_TEX_COORDS || (n.op == AKR_SVM_CHECKERBOARD && n.a[0] == AKR_SVM_NONE)) fold_mask |= 1ull << i;
             for (uint32_t k = 0; k < n.n_args; ++k) {
                 const bool is_const = (n.op == AKR_SVM_FLOAT || n.op == AKR_SVM_FLOAT3) || (n.op == AKR_SVM_RGB_TEX && k == 1u) ||
                                       (n.op == AKR_SVM_RGB_IMAGE_TEX && k <= 1u) || (n.op == AKR_SVM_MAPPING && k == 1u) ||
@@ -162,9 +188,10 @@ AKR_HD int svm_eval(const SvmView &svm, uint32_t shader_kind, uint32_t data_offs
                 }
                 if (n.a[k] == AKR_SVM_NONE && ((n.op == AKR_SVM_RGB_IMAGE_TEX && k == 2u) || (n.op == AKR_SVM_CHECKERBOARD && k == 0u))) continue;
                 if (n.a[k] >= i) return SVM_BAD_PROGRAM;  // refers to a later node
+                if ((fold_mask >> n.a[k]) & 1ull) fold_mask |= 1ull << i;  // downstream of a hit-dependent node
             }
         }
-        SvmVal &r = vals[i];
+        SvmVal &r = local[i];
         r.v[0] = r.v[1] = r.v[2] = r.v[3] = 0.0f;
         r.kind = SV_NONE;
         switch (n.op) {
@@ -391,6 +418,10 @@ AKR_HD int svm_eval(const SvmView &svm, uint32_t shader_kind, uint32_t data_offs
     }
     if (dynamic) *dynamic = dyn;
     if (VALIDATE && !have_closure) return SVM_BAD_PROGRAM;
+    if (VALIDATE && fold) {
+        fold->hit_mask = fold_mask;
+        for (uint32_t i = 0; i < n_nodes; ++i) fold->vals[i] = local[i];
+    }
     return SVM_OK;
 }
 

@@ -86,7 +86,7 @@ AKR_HD f2 hit_uv(const SceneView &sc, uint32_t gid, float u, float v, bool for_a
 // made the alpha variants of the traversal kernels 26 K instructions long, 25x the opaque ones)
 AKR_HD_NOINLINE float alpha_of_dynamic(const SceneView &sc, const Material &mat, uint32_t gid, float u, float v) {
     Material tmp;
-    svm_eval<true, false>(sc.svm, mat.shader_kind, mat.data_offset, hit_uv(sc, gid, u, v, true), tmp, nullptr);
+    svm_eval<true, false>(sc.svm, mat.shader_kind, mat.data_offset, hit_uv(sc, gid, u, v, true), tmp, nullptr, mat.static_offset);
     return tmp.alpha;
 }
 AKR_HD bool alpha_test(const SceneView &sc, uint32_t gid, float u, float v) {

@@ -86,10 +86,11 @@ std::vector<uint32_t> material_sort_keys(const std::vector<Material> &mats) {
     return keys;
 }
 
-int fold_material(const SvmView &svm, AkrShaderRef ref, Material &m, std::string &err) {
+int fold_material(const SvmView &svm, AkrShaderRef ref, Material &m, std::vector<uint64_t> &kind_hit_mask, std::vector<SvmVal> &static_vals, std::string &err) {
     std::memset(&m, 0, sizeof(m));
     bool dynamic = false;
-    int rc = svm_eval<false, true>(svm, ref.shader_kind, ref.data_offset, f2{0.0f, 0.0f}, m, &dynamic);
+    SvmFoldInfo fold;
+    int rc = svm_eval<false, true>(svm, ref.shader_kind, ref.data_offset, f2{0.0f, 0.0f}, m, &dynamic, AKR_SVM_NONE, &fold);
     if (rc == SVM_BAD_PROGRAM) {
         err = "malformed shader program (kind / constant offset / node reference / input type out of range)";
         return AKR_ERR_INVALID_ARGUMENT;
@@ -100,6 +101,13 @@ int fold_material(const SvmView &svm, AkrShaderRef ref, Material &m, std::string
     }
     m.dynamic = dynamic ? 1u : 0u;
     m.alpha_dynamic = (dynamic && alpha_varies(svm, ref)) ? 1u : 0u;
+    m.static_offset = AKR_SVM_NONE;
+    kind_hit_mask[ref.shader_kind] = fold.hit_mask;  // a property of the program: the same for every material of the kind
+    if (dynamic) {  // the per-hit evaluation reads the hit-independent nodes' values from here
+        const uint32_t n_nodes = svm.kind_first[ref.shader_kind + 1u] - svm.kind_first[ref.shader_kind];
+        m.static_offset = static_cast<uint32_t>(static_vals.size());
+        static_vals.insert(static_vals.end(), fold.vals, fold.vals + n_nodes);
+    }
     m.shader_kind = ref.shader_kind;
     m.data_offset = ref.data_offset;
     return AKR_OK;
@@ -367,6 +375,9 @@ int build_scene_blob(const AkrSceneDesc &d, HostSceneBlob &out, std::string &err
     svm.n_kinds = d.n_shader_kinds;
     svm.n_textures = d.n_images;
     svm.data_size = static_cast<uint32_t>(out.svm_data.size());
+    svm.kind_hit_mask = nullptr;  // (the validating evaluation interprets every node)
+    svm.static_vals = nullptr;
+    out.svm_kind_hit_mask.assign(d.n_shader_kinds, 0ull);
     // ---- materials: one record per distinct ShaderRef ----
     std::map<std::pair<uint32_t, uint32_t>, uint32_t> mat_index;
     auto material_of = [&](AkrShaderRef ref, uint32_t &idx) -> int {
@@ -377,7 +388,7 @@ int build_scene_blob(const AkrSceneDesc &d, HostSceneBlob &out, std::string &err
             return AKR_OK;
         }
         Material m;
-        int rc = fold_material(svm, ref, m, err);
+        int rc = fold_material(svm, ref, m, out.svm_kind_hit_mask, out.svm_static_vals, err);
         if (rc == AKR_OK && m.dynamic) out.any_dynamic = 1;
         if (rc != AKR_OK) return rc;
         idx = static_cast<uint32_t>(out.materials.size());
@@ -1044,6 +1055,8 @@ SceneView host_scene_view(const HostSceneBlob &b, const float *albedo_table) {
     v.svm.n_kinds = static_cast<uint32_t>(b.svm_kind_first.size() - 1);
     v.svm.n_textures = static_cast<uint32_t>(b.textures_host.size());
     v.svm.data_size = static_cast<uint32_t>(b.svm_data.size());
+    v.svm.kind_hit_mask = b.svm_kind_hit_mask.data();
+    v.svm.static_vals = b.svm_static_vals.empty() ? nullptr : b.svm_static_vals.data();
     v.corner_uvs = b.corner_uvs.empty() ? nullptr : b.corner_uvs.data();
     v.n_nodes = static_cast<uint32_t>(b.nodes.size());
     v.n_prims = static_cast<uint32_t>(b.prims.size());

@@ -40,6 +40,8 @@ struct HostSceneBlob {
     std::vector<AkrSvmNode> svm_nodes;
     std::vector<uint32_t> svm_kind_first;
     std::vector<uint8_t> svm_data;
+    std::vector<uint64_t> svm_kind_hit_mask;  // [n_kinds] hit-dependent nodes of each program (SvmView::kind_hit_mask)
+    std::vector<SvmVal> svm_static_vals;      // per texture-driven material: value of every node at upload (Material.static_offset)
     std::vector<TextureRec> textures;    // .texels = byte offset into `texels` (patched to a pointer by whoever owns the copy)
     std::vector<uint8_t> texels;
     std::vector<TextureRec> textures_host;  // the same records with .texels pointing into `texels` (host-side evaluation)
