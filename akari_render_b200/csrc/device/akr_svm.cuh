@@ -78,11 +78,9 @@ AKR_HD int wrap_texel(int i, int n, uint32_t address, bool &zero) {
     zero = true;
     return 0;
 }
-AKR_HD void fetch_texel(const TextureRec &t, int x, int y, float out[4]) {
-    bool zx, zy;
-    int ix = wrap_texel(x, (int)t.width, t.address, zx);
-    int iy = wrap_texel(y, (int)t.height, t.address, zy);
-    if (zx || zy) {
+// texel (ix, iy) of an image, coordinates already wrapped; `zero`: outside under the zero address mode
+AKR_HD void load_texel(const TextureRec &t, int ix, int iy, bool zero, float out[4]) {
+    if (zero) {
         out[0] = out[1] = out[2] = out[3] = 0.0f;
         return;
     }
@@ -95,6 +93,12 @@ AKR_HD void fetch_texel(const TextureRec &t, int x, int y, float out[4]) {
         for (int c = 0; c < 4; ++c) out[c] = p[c];
     }
 }
+AKR_HD void fetch_texel(const TextureRec &t, int x, int y, float out[4]) {
+    bool zx, zy;
+    int ix = wrap_texel(x, (int)t.width, t.address, zx);
+    int iy = wrap_texel(y, (int)t.height, t.address, zy);
+    load_texel(t, ix, iy, zx || zy, out);
+}
 AKR_HD void sample_texture(const TextureRec &t, f2 uv, float out[4]) {
     float fx = uv.x * (float)t.width, fy = uv.y * (float)t.height;
     if (t.filter == AKR_FILTER_POINT) {
@@ -105,11 +109,15 @@ AKR_HD void sample_texture(const TextureRec &t, f2 uv, float out[4]) {
     float x0 = floorf(x), y0 = floorf(y);
     float tx = x - x0, ty = y - y0;
     int ix = (int)x0, iy = (int)y0;
+    // the four texels share two columns and two rows: four coordinate wraps (integer modulo) instead of eight
+    bool zx0, zx1, zy0, zy1;
+    const int wx0 = wrap_texel(ix, (int)t.width, t.address, zx0), wx1 = wrap_texel(ix + 1, (int)t.width, t.address, zx1);
+    const int wy0 = wrap_texel(iy, (int)t.height, t.address, zy0), wy1 = wrap_texel(iy + 1, (int)t.height, t.address, zy1);
     float c00[4], c10[4], c01[4], c11[4];
-    fetch_texel(t, ix, iy, c00);
-    fetch_texel(t, ix + 1, iy, c10);
-    fetch_texel(t, ix, iy + 1, c01);
-    fetch_texel(t, ix + 1, iy + 1, c11);
+    load_texel(t, wx0, wy0, zx0 || zy0, c00);
+    load_texel(t, wx1, wy0, zx1 || zy0, c10);
+    load_texel(t, wx0, wy1, zx0 || zy1, c01);
+    load_texel(t, wx1, wy1, zx1 || zy1, c11);
     for (int c = 0; c < 4; ++c) {
         float a = c00[c] * (1.0f - tx) + c10[c] * tx;
         float b = c01[c] * (1.0f - tx) + c11[c] * tx;
@@ -160,7 +168,7 @@ AKR_HD int svm_eval(const SvmView &svm, uint32_t shader_kind, uint32_t data_offs
         SvmVal *local;
         const SvmVal *table;
         uint64_t hit_mask;
-        AKR_HD const SvmVal &operator[](uint32_t j) const { return (table && !((hit_mask >> j) & 1ull)) ? table[j] : local[j]; }
+        AKR_HD const SvmVal &operator[](uint32_t j) const { return ((hit_mask >> j) & 1ull) ? local[j] : table[j]; }  // (full evaluation: hit_mask = ~0)
     } vals{local, table, hit_mask};
     bool dyn = false, have_closure = false;
     m.alpha = 1.0f;
@@ -219,8 +227,10 @@ AKR_HD int svm_eval(const SvmView &svm, uint32_t shader_kind, uint32_t data_offs
             if (VALIDATE && tex >= svm.n_textures) return SVM_BAD_PROGRAM;
             const f2 tuv = n.a[2] != AKR_SVM_NONE ? sv_float2_auto(vals[n.a[2]]) : uv;
             sample_texture(svm.textures[tex], tuv, r.v);
-            if (n.a[1] != 0u)
-                for (int c = 0; c < 3; ++c) r.v[c] = srgb_to_linear1(r.v[c]);
+            if (n.a[1] != 0u) {
+                AKR_NO_UNROLL
+                for (int c = 0; c < 3; ++c) r.v[c] = srgb_to_linear1(r.v[c]);  // (one copy of powf)
+            }
             r.kind = SV_F4;
             dyn = true;
             break;
