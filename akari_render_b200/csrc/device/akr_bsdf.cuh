@@ -110,18 +110,18 @@ AKR_HD float tr_lambda(TR a, f3 w) {  // :59-65
 }
 AKR_HD float tr_g1(TR a, f3 w) { return 1.0f / (1.0f + tr_lambda(a, w)); }
 AKR_HD float tr_g(TR a, f3 wo, f3 wi) { return 1.0f / (1.0f + tr_lambda(a, wo) + tr_lambda(a, wi)); }
-AKR_HD f3 tr_sample_wh(TR a, f3 w, f2 u) {  // VNDF, :118-138
+AKR_HD f3 tr_sample_wh_disk(TR a, f3 w, f2 p) {  // VNDF, :118-138, from the disk point p = uniform_sample_disk(u)
     f3 wh = normalize(mk3(a.ax * w.x, a.ay * w.y, w.z));
     if (wh.z < 0.0f) wh = -wh;
     f3 t1 = (wh.z < 0.99999f) ? normalize(cross(mk3(0, 0, 1), wh)) : mk3(1, 0, 0);
     f3 t2 = normalize(cross(wh, t1));
-    f2 p = uniform_sample_disk(u);
     float h = sqrtf(1.0f - sqr(p.x));
     p.y = lerpf(h, p.y, (1.0f + wh.z) * 0.5f);
     float pz = sqrtf(fmaxf(1.0f - (p.x * p.x + p.y * p.y), 0.0f));
     f3 nh = p.x * t1 + p.y * t2 + pz * wh;
     return normalize(mk3(a.ax * nh.x, a.ay * nh.y, fmaxf(nh.z, 1e-6f)));
 }
+AKR_HD f3 tr_sample_wh(TR a, f3 w, f2 u) { return tr_sample_wh_disk(a, w, uniform_sample_disk(u)); }
 AKR_HD float tr_pdf(TR a, f3 wo, f3 wh) {  // :196-206 (sample_visible)
     return tr_d(a, wh) * tr_g1(a, wo) * fabsf(dot(wo, wh)) / abs_cos_theta(wo);
 }
@@ -450,14 +450,18 @@ AKR_HD BsdfDir general_sample(const Material &m, const float *table, f3 wo, floa
     default: break;
     }
     if (pick == PICK_NONE) return BsdfDir{splat3(0.0f), false};
-    if (pick == PICK_DIFFUSE) return diffuse_sample(wo, u);
+    const f2 disk = uniform_sample_disk(u);  // the cosine-hemisphere and the visible-normal sampling both start from it: one sincos
+    if (pick == PICK_DIFFUSE) {  // diffuse_sample
+        f3 wi = cos_hemisphere_from_disk(disk);
+        return BsdfDir{same_hemisphere(wo, wi) ? wi : -wi, true};
+    }
     bool refract = false;
     if (pick == PICK_DIELECTRIC) {  // dielectric_sample: choice(frac, 1, 0): first -> reflection
         rough = m.roughness_raw;
         float frac = fr_dielectric(cos_theta(wo), m.eta);
         refract = !choose2(frac, u_select);
     }
-    f3 wh = tr_sample_wh(tr_from_roughness(rough), wo, u);
+    f3 wh = tr_sample_wh_disk(tr_from_roughness(rough), wo, disk);
     if (refract) return mf_refract_about(m.eta, wh, wo);
     f3 wi = reflect(wo, wh);
     return BsdfDir{wi, same_hemisphere(wo, wi)};

@@ -242,11 +242,11 @@ AKR_HD f2 uniform_sample_disk(f2 u) {  // :5-9
 #endif
     return f2{r * c, r * s};
 }
-AKR_HD f3 cos_sample_hemisphere(f2 u) {  // :17-21
-    f2 d = uniform_sample_disk(u);
+AKR_HD f3 cos_hemisphere_from_disk(f2 d) {
     float z = sqrtf(fmaxf(1.0f - d.x * d.x - d.y * d.y, 0.0f));
     return mk3(d.x, d.y, z);
 }
+AKR_HD f3 cos_sample_hemisphere(f2 u) { return cos_hemisphere_from_disk(uniform_sample_disk(u)); }  // :17-21
 AKR_HD f2 uniform_sample_triangle(f2 u) {  // :32-44
     if (u.x < u.y) {
         float b0 = u.x / 2.0f;

@@ -411,7 +411,7 @@ AKR_HD ShadeOut shade_body(const SceneView &sc, const CornerAttribs &ca, const S
     // sample_surface_and_shade_direct (pt.rs:297-323)
     Material fd;
     const Material *m = &mat;
-    if (rp.force_diffuse) {  // pt.rs:268-279
+    if ((CLS == CLS_LAMBERT || CLS == CLS_ANY) && rp.force_diffuse) {  // pt.rs:268-279 (every hit is binned into the Lambert class then)
         fd = mat;
         fd.type = MAT_LAMBERT;
         fd.wrap_inner = 0u;
@@ -423,7 +423,7 @@ AKR_HD ShadeOut shade_body(const SceneView &sc, const CornerAttribs &ca, const S
     f3 bs_wi = splat3(0.0f), bs_color = splat3(0.0f);
     float bs_pdf = 0.0f;
     bool bs_valid = false;
-    if (CLS == CLS_GENERAL || CLS == CLS_ANY) {
+    if (CLS == CLS_GENERAL || CLS == CLS_ANY) {  // (measured for the conductor class too: 6.82 vs 6.58 ms per pass, its two inlined copies stay)
         // The full tree is evaluated twice per bounce, for the light direction and for the sampled direction.  Both go
         // through ONE copy of the evaluation code (a two-trip loop that is not unrolled); the direction is sampled
         // first, it does not depend on the light evaluation.
