@@ -405,4 +405,26 @@ int hostsim_box_test_agreement(const AkrSceneDesc *desc, uint32_t n_rays, uint32
     return AKR_OK;
 }
 
+// Per material (up to `cap`): the sort key the general shade class orders its CTA tiles by (TriShade.flags bits 8-12, read
+// back from a triangle that uses the material), closure type, lobe set, `dynamic`.  Returns the number of materials.
+int hostsim_material_keys(const AkrSceneDesc *desc, uint32_t cap, uint32_t *keys, uint32_t *types, uint32_t *lobes, uint32_t *dynamic) {
+    HostSceneBlob blob;
+    std::string err;
+    int rc = build_scene_blob(*desc, blob, err);
+    if (rc != AKR_OK) {
+        g_err = err;
+        return -1;
+    }
+    const uint32_t n = (uint32_t)std::min<size_t>(cap, blob.materials.size());
+    for (uint32_t m = 0; m < n; ++m) {
+        keys[m] = 0xffffffffu;
+        types[m] = blob.materials[m].type;
+        lobes[m] = blob.materials[m].lobes;
+        dynamic[m] = blob.materials[m].dynamic;
+    }
+    for (const TriShade &ts : blob.shade)
+        if (ts.mat < n) keys[ts.mat] = (ts.flags >> TRI_SORT_KEY_SHIFT) & TRI_SORT_KEY_MASK;
+    return (int)blob.materials.size();
+}
+
 }  // extern "C"

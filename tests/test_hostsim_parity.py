@@ -332,3 +332,26 @@ def test_fma_slab_test_agrees_with_the_reference_form(cbox, tmp_path):
         assert rc == 0, lib.hostsim_last_error()
         both, ref_only, fma_only = list(cnt)
         assert both > n_rays and ref_only == 0 and fma_only == 0, (name, list(cnt))
+
+
+def test_material_sort_keys_group_equal_trees_and_order_them_by_cost(cbox, tmp_path):
+    """The general shade class sorts each CTA tile of records by a 5-bit key (scene_build.cpp material_sort_keys): materials
+    whose closure tree is the same (type, lobe set) share a key, different trees get different keys, and the numbering
+    follows the cost estimate (a Lambert reduction first, the coated / transmissive / metallic mixes last)."""
+    import akari_render_b200 as akr
+    lib = C.CDLL(os.path.join(HERE, "hostsim", "libhostsim.so"))
+    cap = 64
+    arrs = [(C.c_uint32 * cap)() for _ in range(4)]
+
+    def keys_of(scene):
+        n = lib.hostsim_material_keys(scene.desc, cap, *arrs)
+        assert 0 < n <= cap
+        return [(arrs[0][i], arrs[1][i], arrs[2][i], arrs[3][i]) for i in range(n)]
+    base = keys_of(cbox(16, 16))
+    assert len({k for k, t, l, d in base if (t, l) == (base[0][1], base[0][2])}) == 1  # the white Lambert walls share one key
+    sig_to_key = {}
+    for k, t, l, d in keys_of(akr.load_scene(sv.write_variant(tmp_path, "pm", sv.variant_principled_mix))):
+        assert sig_to_key.setdefault((t, l, d), k) == k       # same tree -> same key
+    assert len(set(sig_to_key.values())) == len(sig_to_key)   # different trees -> different keys
+    n_lobes = sorted((k, bin(l).count("1")) for (t, l, d), k in sig_to_key.items())
+    assert n_lobes[0][1] <= n_lobes[-1][1] and n_lobes[0][1] < max(c for _, c in n_lobes)  # cheapest first

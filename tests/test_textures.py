@@ -269,3 +269,43 @@ def test_16_bit_png_converts_like_to_rgba8(akr, tmp_path):
     g = _images(scene)[0]
     got = np.ctypeslib.as_array(C.cast(g.texels, C.POINTER(C.c_uint8)), (6 * 5 * 4,)).reshape(6, 5, 4)
     assert np.array_equal(got, (((arr.astype(np.uint32) + 128) // 257).astype(np.uint8))[::-1])
+
+
+def test_clip_address_mode_keeps_the_alpha_test_on_an_opaque_texture(akr, oracle, tables, cbox_task, tmp_path):
+    """An image whose texels are all opaque still yields alpha 0 outside [0, 1)^2 under the `clip` (zero) address mode
+    (the sampler returns (0, 0, 0, 0) there), so a surface that samples it beyond the unit square must keep the stochastic
+    alpha test: rays pass through those parts.  `alpha_varies` (scene_build.cpp) has to flag it; the kernels' bodies then
+    equal the oracle — which alpha-tests every texture-driven material — bit for bit, with hits seen behind the wall."""
+    import cv2
+    rng = np.random.default_rng(3)
+    png = (rng.random((8, 8, 3)) * 255).astype(np.uint8)  # three channels: decoded alpha is 255 everywhere
+    ok, buf = cv2.imencode(".png", png)
+    assert ok
+    path = sv.write_image_textured(tmp_path, "clip_opaque", [("backWall_001", bytes(buf), "png", 8, 8, 3)], colorspace="srgb")
+    sj = json.load(open(path))
+    nodes = sj["materials"]["backWall_001"]["shader"]["nodes"]
+    nodes["tex"]["image"]["extension"] = "clip"
+    nodes["tc"] = {"type": "texcoords"}
+    nodes["uv"] = {"type": "extract", "node": {"id": "tc"}, "field": "uv"}
+    nodes["m_loc"] = {"type": "float3", "value": [-0.5, -0.5, 0.0]}
+    nodes["m_rot"] = {"type": "float3", "value": [0.0, 0.0, 0.0]}
+    nodes["m_scale"] = {"type": "float3", "value": [2.0, 2.0, 1.0]}
+    nodes["map"] = {"type": "mapping", "vector": {"id": "uv"}, "mapping": "point", "location": {"id": "m_loc"}, "rotation": {"id": "m_rot"},
+                    "scale": {"id": "m_scale"}}
+    nodes["tex"]["uv"] = {"id": "map"}  # uv * 2 - 0.5: the texture covers the middle of the wall, the rim samples outside
+    json.dump(sj, open(path, "w"))
+    lib = C.CDLL(os.path.join(HERE, "hostsim", "libhostsim.so"))
+    lib.hostsim_last_error.restype = C.c_char_p
+    w = h = 40
+    scene = akr.load_scene(path).set_resolution(w, h)
+    task = cbox_task(8)
+    pmj, bn = tables
+    ofilm, ost, ofh = oracle.render(scene.desc, w, h, task.pt, task.sampler, task.filter, pmj, bn, want_first_hits=True)
+    film, fh, st = run_hostsim(lib, scene, task, tables, oracle.albedo_table(), w, h)
+    assert st.any_alpha == 1
+    assert np.array_equal(fh, ofh) and np.array_equal(film, ofilm)
+    back_wall = 3  # instance id (SURVEY A.1)
+    plain = akr.load_scene(os.path.join(sv.CBOX_DIR, "scene.json")).set_resolution(w, h)
+    _, _, pfh = oracle.render(plain.desc, w, h, task.pt, task.sampler, task.filter, pmj, bn, want_first_hits=True)
+    n_clip, n_plain = int((ofh[:, 0] == back_wall).sum()), int((pfh[:, 0] == back_wall).sum())
+    assert 0 < n_clip < 0.8 * n_plain, (n_clip, n_plain)  # the rim of the wall lets camera rays through
