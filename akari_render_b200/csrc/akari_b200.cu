@@ -97,6 +97,8 @@ struct LaunchParams {
     uint32_t stage_flat;        // stage the pairs-first flat list instead of the BVH-ordered primitives
     uint32_t aov, aov_remap;    // k_aov: which AKR_AOV_* quantity, v -> v * 0.5 + 0.5
     uint32_t *first_hits;       // optional AOV (engine option aov_mask bit 0): [n_film_pixels][2] (inst, prim) of sample 0
+    uint32_t *sort_order;       // general class, global sort: record indices of a depth ordered by material sort key
+    uint32_t *sort_hist;        // [kMaxDepthSlots][64]: per key the record count [0, 32) and the scatter cursor [32, 64)
 };
 
 // Queue records are written once and read once, gigabytes later: stream them past L2 residency (evict-first) so that
@@ -818,62 +820,12 @@ constexpr int kShadeWarps = kShadeBlock / 32;
 #ifndef AKR_GENERAL_BLOCK
 #define AKR_GENERAL_BLOCK 256
 #endif
-#ifndef AKR_GENERAL_SORT
-#define AKR_GENERAL_SORT 1
-#endif
 constexpr int kGeneralBlock = AKR_GENERAL_BLOCK;  // block size of the kernels that carry the full Principled tree
 constexpr int shade_block_of(int cls) { return cls == CLS_GENERAL ? kGeneralBlock : kShadeBlock; }
 template <int CLS> struct ShadeLaunch {
     static constexpr int kThreads = shade_block_of(CLS);
     static constexpr int kMinBlocks = CLS == CLS_LAMBERT ? AKR_SHADE_MINB_LAMBERT : (CLS == CLS_CONDUCTOR ? AKR_SHADE_MINB_CONDUCTOR : AKR_SHADE_MINB_GENERAL);
 };
-
-// General class: the records of one CTA tile (2 per thread) are ordered by the material's sort key in shared memory
-// before they are shaded.  The queue order is the order in which paths happened to land on general materials, so a warp
-// of the plain tile feed evaluates the UNION of its lanes' trees (ncu on the all-Principled box: 14.9 of 32 lanes active);
-// after the counting sort a warp holds a run of one signature.  Keys are numbered by increasing cost and every warp takes
-// one run from the front of the sorted tile and one from the back, which evens out the time per warp between the two
-// __syncthreads of a tile.  The result does not depend on the record order (one path per record, own accumulator slots).
-struct SortScratch {
-    uint32_t hist[32];
-    uint32_t first[32];
-    uint16_t order[2 * kGeneralBlock];
-};
-// Counting sort of a CTA tile's 2 x THREADS slot indices by key (slot idx = threadIdx.x + j * THREADS carries key[j]; slots at
-// or past `cnt` must carry TRI_SORT_KEY_MASK and come out flagged 0x8000 at the back): per-warp aggregated histogram,
-// exclusive scan by warp 0, scatter.  Every thread of the CTA calls it; ss.order is complete when it returns.
-template <int THREADS> __device__ __forceinline__ void sort_tile_by_key(SortScratch &ss, const uint32_t (&key)[2], uint32_t cnt) {
-    const uint32_t lane = threadIdx.x & 31u, below = (1u << lane) - 1u;
-    if (threadIdx.x < 32) ss.hist[threadIdx.x] = 0u;
-    __syncthreads();
-    uint32_t rank[2];
-#pragma unroll
-    for (uint32_t j = 0; j < 2u; ++j) {
-        const uint32_t peers = __match_any_sync(0xffffffffu, key[j]);
-        const int leader = __ffs(peers) - 1;
-        uint32_t b = 0u;
-        if ((int)lane == leader) b = atomicAdd(&ss.hist[key[j]], (uint32_t)__popc(peers));
-        rank[j] = __shfl_sync(0xffffffffu, b, leader) + (uint32_t)__popc(peers & below);
-    }
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        const uint32_t v = ss.hist[lane];
-        uint32_t incl = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-            if ((int)lane >= o) incl += t;
-        }
-        ss.first[lane] = incl - v;
-    }
-    __syncthreads();
-#pragma unroll
-    for (uint32_t j = 0; j < 2u; ++j) {
-        const uint32_t idx = threadIdx.x + j * THREADS;
-        ss.order[ss.first[key[j]] + rank[j]] = (uint16_t)(idx | (idx < cnt ? 0u : 0x8000u));
-    }
-    __syncthreads();
-}
 
 // Queued pipeline: one shade kernel per material class over the (slot, path id) list the trace stage binned.
 template <int CLS> __global__ void __launch_bounds__(ShadeLaunch<CLS>::kThreads, ShadeLaunch<CLS>::kMinBlocks) k_shade(const __grid_constant__ LaunchParams P, uint32_t depth) {
@@ -914,48 +866,18 @@ template <int CLS> __global__ void __launch_bounds__(ShadeLaunch<CLS>::kThreads,
         }
         emit(o);
     };
-    if (CLS == CLS_GENERAL && AKR_GENERAL_SORT) {
-        // CTA tiles of 2 entries per thread, ordered by the material's sort key (see SortScratch): a warp then shades a run
-        // of one material signature; it takes one run from the cheap end of the tile and one from the expensive end
-        constexpr uint32_t THREADS = ShadeLaunch<CLS>::kThreads, T = 2u * THREADS;
-        __shared__ SortScratch ss;
-        __shared__ uint2 ents[T];
-        const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-        for (uint32_t first = blockIdx.x * T; first < n; first += gridDim.x * T) {
-            const uint32_t cnt = min(T, n - first);
-            uint32_t key[2];
-#pragma unroll
-            for (uint32_t j = 0; j < 2u; ++j) {
-                const uint32_t idx = threadIdx.x + j * THREADS;
-                key[j] = TRI_SORT_KEY_MASK;
-                if (idx < cnt) {
-                    const uint2 e = slots[first + idx];
-                    ents[idx] = e;
-                    const uint32_t gid = f2u(reinterpret_cast<const float *>(P.hits.h + e.x)[0]);
-                    key[j] = (P.scene.shade[gid].flags >> TRI_SORT_KEY_SHIFT) & TRI_SORT_KEY_MASK;
-                }
-            }
-            sort_tile_by_key<(int)THREADS>(ss, key, cnt);  // (its barriers also publish `ents`)
-#pragma unroll 1
-            for (uint32_t j = 0; j < 2u; ++j) {
-                const uint32_t e = ss.order[(j == 0u ? warp * 32u : T - (warp + 1u) * 32u) + lane];
-                const bool active = !(e & 0x8000u);
-                shade_one(active, active ? ents[e & 0x7fffu] : make_uint2(0u, 0u));
-            }
-            __syncthreads();  // before `ents` and the scratch are rewritten
-        }
-        return;
-    }
     const uint32_t stride = gridDim.x * blockDim.x;
     // warp-uniform trip count so that every lane takes part in the ballots; the (slot, path_id) entry of the
     // next trip is fetched one trip ahead so that its latency is off the dependent chain
+    // general class: entry k is slots[sort_order[k]] — the class list ordered by material sort key (k_sort_hist / k_sort_scatter)
+    auto entry = [&](uint32_t k) { return CLS == CLS_GENERAL ? slots[P.sort_order[k]] : slots[k]; };
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     uint2 ent = make_uint2(k, 0u);
-    if (k < n) ent = slots[k];
+    if (k < n) ent = entry(k);
     for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride, k += stride) {
         const bool active = k < n;
         const uint2 cur = ent;
-        if (k + stride < n) ent = slots[k + stride];
+        if (k + stride < n) ent = entry(k + stride);
         shade_one(active, cur);
     }
 }
@@ -1092,66 +1014,92 @@ __device__ __forceinline__ void bounce_phase(const LaunchParams &P, uint32_t dep
     if (lane == 0u && (n_traced | n_shadow))
         atomicAdd(reinterpret_cast<unsigned long long *>(P.counters + (depth + 1u) * kCtrStride), (unsigned long long)n_traced | ((unsigned long long)n_shadow << 32));
 }
-template <int THREADS>
-__device__ __forceinline__ void bounce_phase_sorted(const LaunchParams &P, uint32_t depth, const DevTracer &tr, uint32_t tiles, uint64_t *bar2, SortScratch &ss) {
-    constexpr uint32_t T = 2u * THREADS, kArray = T * 16u;  // records per CTA tile; bytes of one of its four SoA arrays
+// ---- general class: the records of a depth ordered by material signature -------------------------------------------------
+// The general class holds every closure tree there is (Principled lobe sets, glass, texture-driven programs).  In queue
+// order — the order in which paths happened to land on such materials — a warp evaluates the UNION of its lanes' trees
+// (ncu on the all-Principled box: 14.9 of 32 lanes active) and the warps of an SM run through different regions of an
+// 8 K-instruction body at the same time (47 % of the stalls were instruction fetch).  So before a depth is shaded, two
+// small kernels order its records by the 5-bit sort key scene_build.cpp stores in TriShade.flags (same closure type, lobe
+// set, normal-map frame, shader kind of a texture-driven material => same key; numbered by increasing cost): a counting
+// sort of the record INDICES (histogram, then a scatter behind per-key cursors) into `sort_order`.  The shade / bounce
+// kernel takes 32 consecutive entries per warp and gathers their records: full lanes, and the whole machine works on one
+// signature for long stretches.  The result does not depend on the order (one path per record, own accumulator slots).
+// Measured (general kernel of one 64-spp pass, incl. the two sort kernels): all-Principled box 127 ms unsorted, 110 ms with
+// a per-CTA sort of 512-record tiles in shared memory, 60 ms with this global order (at equal code otherwise 82 -> 60).
+template <bool QUEUED> __device__ __forceinline__ uint32_t general_key_of(const LaunchParams &P, uint32_t depth, uint32_t i) {
+    uint32_t gid;
+    if (QUEUED) gid = __float_as_uint(reinterpret_cast<const float *>(P.hits.h + P.cls.idx[CLS_GENERAL][i].x)[0]);  // the hit of the entry's slot
+    else gid = __float_as_uint(reinterpret_cast<const float *>(P.cq[depth & 1u][CLS_GENERAL].r[0] + i)[3]);     // the record's own hit
+    return (P.scene.shade[gid].flags >> TRI_SORT_KEY_SHIFT) & TRI_SORT_KEY_MASK;
+}
+template <bool QUEUED> __global__ void __launch_bounds__(256) k_sort_hist(const __grid_constant__ LaunchParams P, uint32_t depth) {
+    __shared__ uint32_t h[32];
     const uint32_t n = P.counters[depth * kCtrStride + 2u + CLS_GENERAL];
-    const uint32_t n_tiles = (n + T - 1u) / T;
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    const uint32_t bar0 = smem_u32(bar2);
+    if (blockIdx.x * blockDim.x >= n) return;
+    if (threadIdx.x < 32) h[threadIdx.x] = 0u;
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31u;
+    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += gridDim.x * blockDim.x) {
+        const uint32_t i = base + lane;
+        const uint32_t key = i < n ? general_key_of<QUEUED>(P, depth, i) : 0xffffffffu;
+        const uint32_t peers = __match_any_sync(0xffffffffu, key);
+        if (i < n && (int)lane == __ffs(peers) - 1) atomicAdd(&h[key], (uint32_t)__popc(peers));
+    }
+    __syncthreads();
+    if (threadIdx.x < 32 && h[threadIdx.x]) atomicAdd(P.sort_hist + depth * 64u + threadIdx.x, h[threadIdx.x]);
+}
+template <bool QUEUED> __global__ void __launch_bounds__(256) k_sort_scatter(const __grid_constant__ LaunchParams P, uint32_t depth) {
+    __shared__ uint32_t first[32];
+    const uint32_t n = P.counters[depth * kCtrStride + 2u + CLS_GENERAL];
+    if (blockIdx.x * blockDim.x >= n) return;
+    uint32_t *hist = P.sort_hist + depth * 64u, *cursor = hist + 32u;
+    const uint32_t lane = threadIdx.x & 31u, below = (1u << lane) - 1u;
+    if (threadIdx.x < 32) {  // exclusive scan of the key counts
+        const uint32_t v = hist[lane];
+        uint32_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)lane >= o) incl += t;
+        }
+        first[lane] = incl - v;
+    }
+    __syncthreads();
+    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += gridDim.x * blockDim.x) {
+        const uint32_t i = base + lane;
+        const uint32_t key = i < n ? general_key_of<QUEUED>(P, depth, i) : 0xffffffffu;
+        const uint32_t peers = __match_any_sync(0xffffffffu, key);
+        const int leader = __ffs(peers) - 1;
+        uint32_t b = 0u;
+        if (i < n && (int)lane == leader) b = atomicAdd(&cursor[key], (uint32_t)__popc(peers));
+        b = __shfl_sync(0xffffffffu, b, leader);
+        if (i < n) P.sort_order[first[key] + b + (uint32_t)__popc(peers & below)] = i;
+    }
+}
+__device__ __forceinline__ void bounce_phase_ordered(const LaunchParams &P, uint32_t depth, const DevTracer &tr) {
+    const uint32_t n = P.counters[depth * kCtrStride + 2u + CLS_GENERAL];
+    const uint32_t lane = threadIdx.x & 31u, n_tiles = (n + 31u) >> 5, wstride = gridDim.x * (blockDim.x >> 5);
     const RecQueue &qin = P.cq[depth & 1u][CLS_GENERAL];
-    const uint64_t pol = l2_evict_first_policy();
-    auto issue = [&](uint32_t tile, uint32_t buf) {
-        const uint32_t first = tile * T;
-        const uint32_t bytes = min(T, n - first) * 16u;
-        const uint32_t b = bar0 + buf * 8u, dst = tiles + buf * 4u * kArray;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(4u * bytes) : "memory");
-#pragma unroll
-        for (uint32_t j = 0; j < 4u; ++j) tma_bulk_g2s_hint(dst + j * kArray, qin.r[j] + first, bytes, b, pol);
-    };
-    uint32_t tile = blockIdx.x, it = 0u;
-    if (tile < n_tiles && threadIdx.x == 0) issue(tile, 0u);
-    uint32_t n_traced = 0u, n_shadow = 0u;  // warp-uniform
-    for (; tile < n_tiles; tile += gridDim.x, ++it) {
-        const uint32_t buf = it & 1u;
-        if (tile + gridDim.x < n_tiles && threadIdx.x == 0) issue(tile + gridDim.x, buf ^ 1u);  // (the other buffer was released by the barrier that ended the last trip)
-        mbar_wait(bar2 + buf, (it >> 1) & 1u);
-        const uint32_t cnt = min(T, n - tile * T), base = tiles + buf * 4u * kArray;
-        uint32_t key[2];
-#pragma unroll
-        for (uint32_t j = 0; j < 2u; ++j) {
-            const uint32_t idx = threadIdx.x + j * THREADS;
-            key[j] = TRI_SORT_KEY_MASK;  // slots past the end of the queue sort to the back
-            if (idx < cnt) {
-                uint32_t gid;
-                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(gid) : "r"(base + idx * 16u + 12u));
-                key[j] = (P.scene.shade[gid].flags >> TRI_SORT_KEY_SHIFT) & TRI_SORT_KEY_MASK;
-            }
-        }
-        sort_tile_by_key<THREADS>(ss, key, cnt);
-#pragma unroll 1
-        for (uint32_t j = 0; j < 2u; ++j) {
-            const uint32_t pos = (j == 0u ? warp * 32u : T - (warp + 1u) * 32u) + lane;
-            const uint32_t e = ss.order[pos];
-            const bool active = !(e & 0x8000u);
-            const uint32_t src = base + (e & 0x7fffu) * 16u;
-            const float4 r0 = lds128(src), r1 = lds128(src + kArray), r2 = lds128(src + 2u * kArray), r3 = lds128(src + 3u * kArray);
-            BounceRec in;
-            in.d = mk3(r0.x, r0.y, r0.z);
-            in.gid = __float_as_uint(r0.w);
-            in.u = r1.x;
-            in.v = r1.y;
-            in.path_id = __float_as_uint(r1.z);
-            in.pxpy = __float_as_uint(r1.w);
-            in.beta = mk3(r2.x, r2.y, r2.z);
-            in.sample_index = __float_as_uint(r2.w);
-            in.L = mk3(r3.x, r3.y, r3.z);
-            const BounceOut r = bounce_fused<CLS_GENERAL>(P.scene, P.corners, P.tables, P.rp, P.wave, depth, active, in, tr, P.acc);
-            n_traced += (uint32_t)__popc(__ballot_sync(0xffffffffu, r.traced));
-            n_shadow += (uint32_t)__popc(__ballot_sync(0xffffffffu, r.shadow));
-            append_next(P, depth + 1u, r);
-        }
-        __syncthreads();  // every record of this buffer is in registers / done before the buffer is refilled and the scratch reused
+    uint32_t n_traced = 0u, n_shadow = 0u;
+    for (uint32_t tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); tile < n_tiles; tile += wstride) {
+        const uint32_t k = tile * 32u + lane;
+        const bool active = k < n;
+        const uint32_t i = active ? P.sort_order[k] : 0u;
+        const f4 r0 = ldq(qin.r[0] + i), r1 = ldq(qin.r[1] + i), r2 = ldq(qin.r[2] + i), r3 = ldq(qin.r[3] + i);
+        BounceRec in;
+        in.d = mk3(r0.x, r0.y, r0.z);
+        in.gid = f2u(r0.w);
+        in.u = r1.x;
+        in.v = r1.y;
+        in.path_id = f2u(r1.z);
+        in.pxpy = f2u(r1.w);
+        in.beta = mk3(r2.x, r2.y, r2.z);
+        in.sample_index = f2u(r2.w);
+        in.L = mk3(r3.x, r3.y, r3.z);
+        const BounceOut r = bounce_fused<CLS_GENERAL>(P.scene, P.corners, P.tables, P.rp, P.wave, depth, active, in, tr, P.acc);
+        n_traced += (uint32_t)__popc(__ballot_sync(0xffffffffu, r.traced));
+        n_shadow += (uint32_t)__popc(__ballot_sync(0xffffffffu, r.shadow));
+        append_next(P, depth + 1u, r);
     }
     if (lane == 0u && (n_traced | n_shadow))
         atomicAdd(reinterpret_cast<unsigned long long *>(P.counters + (depth + 1u) * kCtrStride), (unsigned long long)n_traced | ((unsigned long long)n_shadow << 32));
@@ -1162,8 +1110,7 @@ __device__ __forceinline__ void bounce_phase_sorted(const LaunchParams &P, uint3
 // conductor records) is SLOWER than one launch per class — 31.0 vs 29.1 ms per pass on one GPU, 12.8 vs 13.8 G samples/s
 // on eight: the merged kernel's larger code and common register allocation cost more than the saved tails — so the
 // engine launches single-class masks; the template keeps the general form.
-// record buffers of the general bounce kernel: two CTA tiles of 2 records per thread (sorted feed) or two warp tiles per warp
-constexpr size_t kGeneralTileSmem = AKR_GENERAL_SORT ? (size_t)2 * (2 * kGeneralBlock) * 64 : (size_t)(kGeneralBlock / 32) * 2u * kTileBytes;
+constexpr size_t kGeneralTileSmem = 0;  // the general bounce kernel gathers its records through sort_order: no tile buffers
 template <uint32_t MASK> struct BounceLaunch {
     static constexpr int kThreads = (MASK & (1u << CLS_GENERAL)) ? kGeneralBlock : kShadeBlock;
     static constexpr int kWarps = kThreads / 32;
@@ -1189,9 +1136,8 @@ template <uint32_t MASK> __global__ void __launch_bounds__(BounceLaunch<MASK>::k
     }
     const DevTracer tr{P.scene, stage_scene(P, smem, &bar)};  // (inits `bar`, fences the barrier inits, __syncthreads)
     const uint32_t scene_bytes = (P.scene.n_pair_blocks + P.scene.n_single_blocks + P.scene.n_occ_pair_blocks + P.scene.n_occ_single_blocks) * (uint32_t)sizeof(PrimBlock2);
-    if (MASK == (1u << CLS_GENERAL) && AKR_GENERAL_SORT) {  // the general class alone: CTA tiles ordered by material signature
-        __shared__ SortScratch ss;
-        bounce_phase_sorted<BounceLaunch<MASK>::kThreads>(P, depth, tr, smem_u32(smem) + ((scene_bytes + 127u) & ~127u), &tile_bar[0][0], ss);
+    if (MASK == (1u << CLS_GENERAL)) {  // the general class alone: records in the order k_sort_hist / k_sort_scatter left in sort_order
+        bounce_phase_ordered(P, depth, tr);
         return;
     }
     const uint32_t tiles = smem_u32(smem) + ((scene_bytes + 127u) & ~127u) + warp * 2u * kTileBytes;
@@ -1223,7 +1169,7 @@ __global__ void __launch_bounds__(kBlock) k_accumulate(const __grid_constant__ L
 }
 
 // folds the per-depth counters of one wave into the 64-bit totals and clears them for the next wave
-__global__ void k_fold_counters(uint32_t *counters, unsigned long long *totals, uint32_t n_depth) {
+__global__ void k_fold_counters(uint32_t *counters, unsigned long long *totals, uint32_t n_depth, uint32_t *sort_hist) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         unsigned long long seg = 0, sh = 0, hits = 0;
         for (uint32_t d = 0; d < n_depth; ++d) {
@@ -1237,6 +1183,7 @@ __global__ void k_fold_counters(uint32_t *counters, unsigned long long *totals, 
     }
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < n_depth * kCtrStride; i += blockDim.x) counters[i] = 0u;
+    for (uint32_t i = threadIdx.x; i < n_depth * 64u; i += blockDim.x) sort_hist[i] = 0u;
 }
 
 // Film::copy_to_rgba_image(hdr = true) (film.rs:120-148), splat_scale = 1
@@ -1283,7 +1230,7 @@ struct AkrContext {
 
     // scene
     DeviceBuffer nodes, prims, flat_prims, shade, instances, materials, lights, alias_j, alias_t, alias_pdf, corner_n, corner_t, corner_uv;
-    DeviceBuffer svm_nodes, svm_kind_first, svm_data, svm_kind_hit_mask, svm_static_vals, textures, texels;
+    DeviceBuffer svm_nodes, svm_kind_first, svm_data, svm_kind_hit_mask, svm_static_vals, textures, texels, sort_order;
     SceneView scene{};
     CornerAttribs corners{};
     bool scene_ready = false;
@@ -1383,13 +1330,18 @@ int grid_for(const AkrContext *ctx, uint32_t n, int ctas_per_sm) {
 // queues (4 + 4 records of 16 B: one per depth parity) and the accumulators (2).
 int ensure_wave_buffers(AkrContext *ctx, uint32_t capacity, bool fused, uint32_t class_mask) {
     const uint32_t layout = fused ? (2u | (class_mask << 8)) : 1u;
-    if (ctx->wave_capacity >= capacity && ctx->wave_mem.ptr && ctx->wave_layout == layout) return AKR_OK;
     const size_t cap = ((size_t)capacity + 31u) & ~(size_t)31u;
+    if ((class_mask & (1u << CLS_GENERAL)) && ctx->sort_order.bytes < cap * sizeof(uint32_t)) {  // index order of the general class (k_sort_*)
+        int rc = dev_alloc(ctx, ctx->sort_order, cap * sizeof(uint32_t));
+        if (rc != AKR_OK) return rc;
+    }
+    if (ctx->wave_capacity >= capacity && ctx->wave_mem.ptr && ctx->wave_layout == layout) return AKR_OK;
     size_t n_classes = 0;
     for (uint32_t c = 0; c < (uint32_t)CLS_COUNT; ++c) n_classes += (class_mask >> c) & 1u;
     const size_t n_vec = fused ? 8 * n_classes + 2 : 3 + 3 + 1 + 3 + 2, n_word = fused ? 0 : 2 + 2 * (size_t)CLS_COUNT;
     int rc = dev_alloc(ctx, ctx->wave_mem, cap * (n_vec * 16 + n_word * 4));
     if (rc != AKR_OK) return rc;
+
     f4 *vbase = static_cast<f4 *>(ctx->wave_mem.ptr);
     size_t voff = 0;
     auto take_v = [&]() {
@@ -1491,7 +1443,8 @@ int akr_b200_create(int device_ordinal, AkrContext **out_ctx) {
             return AKR_ERR_CUDA;
         }
     }
-    if (dev_alloc(ctx, ctx->counters, kMaxDepthSlots * kCtrStride * sizeof(uint32_t)) != AKR_OK || dev_alloc(ctx, ctx->totals, 4 * sizeof(unsigned long long)) != AKR_OK) {
+    if (dev_alloc(ctx, ctx->counters, kMaxDepthSlots * (kCtrStride + 64u) * sizeof(uint32_t)) != AKR_OK ||  // (+ the sort histograms)
+        dev_alloc(ctx, ctx->totals, 4 * sizeof(unsigned long long)) != AKR_OK) {
         delete ctx;
         return AKR_ERR_CUDA;
     }
@@ -1507,7 +1460,7 @@ void akr_b200_destroy(AkrContext *ctx) {
     cudaDeviceSynchronize();
     for (DeviceBuffer *b : {&ctx->pmj, &ctx->bn, &ctx->albedo, &ctx->nodes, &ctx->prims, &ctx->flat_prims, &ctx->shade, &ctx->instances, &ctx->materials, &ctx->lights,
                             &ctx->alias_j, &ctx->alias_t, &ctx->alias_pdf, &ctx->corner_n, &ctx->corner_t, &ctx->corner_uv, &ctx->svm_nodes,
-                            &ctx->svm_kind_first, &ctx->svm_data, &ctx->svm_kind_hit_mask, &ctx->svm_static_vals, &ctx->textures, &ctx->texels, &ctx->film, &ctx->wave_mem, &ctx->counters,
+                            &ctx->svm_kind_first, &ctx->svm_data, &ctx->svm_kind_hit_mask, &ctx->svm_static_vals, &ctx->textures, &ctx->texels, &ctx->sort_order, &ctx->film, &ctx->wave_mem, &ctx->counters,
                             &ctx->totals, &ctx->first_hits})
         dev_free(*b);
     if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
@@ -1809,6 +1762,8 @@ int akr_b200_render_pass(AkrContext *ctx, uint32_t n_spp, int blocking) {
     std::memcpy(P.cq, ctx->cq, sizeof(P.cq));
     P.acc = ctx->acc;
     P.counters = static_cast<uint32_t *>(ctx->counters.ptr);
+    P.sort_hist = P.counters + kMaxDepthSlots * kCtrStride;
+    P.sort_order = static_cast<uint32_t *>(ctx->sort_order.ptr);
     P.film = static_cast<float *>(ctx->film.ptr);
     P.n_film_pixels = ctx->n_pixels;
     P.scene_smem_nodes = fused ? 0u : ctx->smem_nodes;  // the fused kernels stage the flat list only
@@ -1894,6 +1849,18 @@ int akr_b200_render_pass(AkrContext *ctx, uint32_t n_spp, int blocking) {
                         }
                     }
                     if (class_mask & 4u) {
+                        {  // order the depth's general records by material sort key
+                            const int sg = grid_for(ctx, n_paths, 8);
+                            if (prof) {
+                                AKR_LAUNCH_B(6, k_sort_hist<false>, sg, 256, 0, P, depth);
+                                AKR_LAUNCH_B(6, k_sort_scatter<false>, sg, 256, 0, P, depth);
+                            } else {
+                                k_sort_hist<false><<<sg, 256, 0, side>>>(P, depth);
+                                k_sort_scatter<false><<<sg, 256, 0, side>>>(P, depth);
+                                count_launch(6);
+                                count_launch(6);
+                            }
+                        }
                         if (prof) AKR_LAUNCH_B(6, (k_bounce<4u>), shade_grid(ctx->occ_bounce[2], kGeneralBlock), kGeneralBlock, bounce_smem_general, P, depth);
                         else {
                             k_bounce<4u><<<shade_grid(ctx->occ_bounce[2], kGeneralBlock), kGeneralBlock, bounce_smem_general, side>>>(P, depth);
@@ -1928,11 +1895,16 @@ int akr_b200_render_pass(AkrContext *ctx, uint32_t n_spp, int blocking) {
                     }
                     if (class_mask & (1u << CLS_LAMBERT)) AKR_LAUNCH_B(2, (k_shade<CLS_LAMBERT>), shade_grid(ctx->occ_shade[0]), kShadeBlock, 0, P, depth);
                     if (class_mask & (1u << CLS_CONDUCTOR)) AKR_LAUNCH_B(3, (k_shade<CLS_CONDUCTOR>), shade_grid(ctx->occ_shade[1]), kShadeBlock, 0, P, depth);
+                    if (class_mask & (1u << CLS_GENERAL)) {
+                        const int sg = grid_for(ctx, n_paths, 8);
+                        AKR_LAUNCH_B(6, k_sort_hist<true>, sg, 256, 0, P, depth);
+                        AKR_LAUNCH_B(6, k_sort_scatter<true>, sg, 256, 0, P, depth);
+                    }
                     if (class_mask & (1u << CLS_GENERAL)) AKR_LAUNCH_B(6, (k_shade<CLS_GENERAL>), shade_grid(ctx->occ_shade[2], kGeneralBlock), kGeneralBlock, 0, P, depth);
                 }
             }
             AKR_LAUNCH(4, k_accumulate, grid_for(ctx, n_pix, 8), 0, P);
-            AKR_LAUNCH_B(5, k_fold_counters, 1, 128, 0, P.counters, static_cast<unsigned long long *>(ctx->totals.ptr), ctx->rp.max_depth + 2u);
+            AKR_LAUNCH_B(5, k_fold_counters, 1, 128, 0, P.counters, static_cast<unsigned long long *>(ctx->totals.ptr), ctx->rp.max_depth + 2u, P.sort_hist);
             ctx->stats.samples += n_paths;
         }
     }
