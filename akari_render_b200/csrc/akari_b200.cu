@@ -11,11 +11,14 @@
 //   into shared memory with 1-D TMA bulk copies (cp.async.bulk + mbarrier, double buffered) while it works on the
 //   current ones, and appends survivors to the queue of the class of the NEXT hit with warp-aggregated atomics.
 //   There is no hit queue, no shadow queue, no (slot, path id) indirection and no accumulator read-modify-write.
+//   The general class (full Principled tree, glass, texture-driven materials) is fed differently: k_sort_hist /
+//   k_sort_scatter order a depth's records by material signature and the warps gather through that order, so that a
+//   warp — and the SM — runs one closure tree at a time.
 //
 // QUEUED (BVH scenes, and flat scenes with alpha-tested materials):
 //   k_raygen -> [ trace(d) -> k_shade<class>(d) ] for d = 0 .. max_depth -> k_accumulate
-//   trace(d) = k_trace_bvh: persistent warps with dynamic ray fetch over a BVH2 (top of the tree in shared memory),
-//   closest-hit rays of depth d and the shadow rays shade(d - 1) queued (k_trace<TRACE_FLAT> on flat scenes).
+//   trace(d) = k_trace_bvh: persistent warps with dynamic ray fetch and majority-vote rounds over a BVH2 (top of the tree
+//   in shared memory), closest-hit rays of depth d and the shadow rays shade(d - 1) queued (k_trace_flat on flat scenes).
 //   Hits are binned by the shade class of their material and one shade kernel is compiled per class.
 //
 // Every kernel is a persistent grid-stride kernel sized SM count x resident CTAs; queue lengths live in device memory,
@@ -1049,7 +1052,7 @@ template <bool QUEUED> __global__ void __launch_bounds__(256) k_sort_hist(const 
     if (threadIdx.x < 32 && h[threadIdx.x]) atomicAdd(P.sort_hist + depth * 64u + threadIdx.x, h[threadIdx.x]);
 }
 template <bool QUEUED> __global__ void __launch_bounds__(256) k_sort_scatter(const __grid_constant__ LaunchParams P, uint32_t depth) {
-    __shared__ uint32_t first[32];
+    __shared__ uint32_t first[32], h[32], base[32];
     const uint32_t n = P.counters[depth * kCtrStride + 2u + CLS_GENERAL];
     if (blockIdx.x * blockDim.x >= n) return;
     uint32_t *hist = P.sort_hist + depth * 64u, *cursor = hist + 32u;
@@ -1064,16 +1067,23 @@ template <bool QUEUED> __global__ void __launch_bounds__(256) k_sort_scatter(con
         }
         first[lane] = incl - v;
     }
-    __syncthreads();
-    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += gridDim.x * blockDim.x) {
-        const uint32_t i = base + lane;
+    // per chunk of 256 records: ranks within the CTA from shared-memory atomics (one per warp and key), then ONE global
+    // atomic per key reserves the CTA's range behind that key's cursor (per-warp global atomics on the handful of hot
+    // cursors made this kernel 0.74 ms per depth, ncu r02zz)
+    for (uint32_t chunk = blockIdx.x * blockDim.x; chunk < n; chunk += gridDim.x * blockDim.x) {
+        if (threadIdx.x < 32) h[threadIdx.x] = 0u;
+        __syncthreads();
+        const uint32_t i = chunk + threadIdx.x;
         const uint32_t key = i < n ? general_key_of<QUEUED>(P, depth, i) : 0xffffffffu;
         const uint32_t peers = __match_any_sync(0xffffffffu, key);
         const int leader = __ffs(peers) - 1;
-        uint32_t b = 0u;
-        if (i < n && (int)lane == leader) b = atomicAdd(&cursor[key], (uint32_t)__popc(peers));
-        b = __shfl_sync(0xffffffffu, b, leader);
-        if (i < n) P.sort_order[first[key] + b + (uint32_t)__popc(peers & below)] = i;
+        uint32_t r = 0u;
+        if (i < n && (int)lane == leader) r = atomicAdd(&h[key], (uint32_t)__popc(peers));
+        r = __shfl_sync(0xffffffffu, r, leader) + (uint32_t)__popc(peers & below);
+        __syncthreads();
+        if (threadIdx.x < 32 && h[threadIdx.x]) base[threadIdx.x] = atomicAdd(&cursor[threadIdx.x], h[threadIdx.x]);
+        __syncthreads();
+        if (i < n) P.sort_order[first[key] + base[key] + r] = i;
     }
 }
 __device__ __forceinline__ void bounce_phase_ordered(const LaunchParams &P, uint32_t depth, const DevTracer &tr) {

@@ -351,7 +351,7 @@ def main():
             ks = [v for k, v in tj.items() if k.startswith(pref)]
             if ks:
                 traffic = sum(v["dram_read"] + v["dram_write"] for v in ks) / sum(v["launches"] for v in ks)
-                traffic_src = "profiles/launches_current.json (ncu launch list of tools/quick_stage_bench.py cbox, one 64-spp pass, cold-cache, per launch)"
+                traffic_src = "profiles/launches_current.json (ncu launch list of `bench.py --steps 1 --warmup 1 --spp 64`: five 64-spp passes, cold-cache, per launch)"
         except Exception:
             pass
     achieved = (dom_bytes / 1e9) / (dom_ms * 1e-3) if dom_ms > 0 else 0.0
