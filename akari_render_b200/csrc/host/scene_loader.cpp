@@ -211,8 +211,8 @@ using ImageResolver = std::function<uint32_t(const akr::json::Value &image)>;
 // ---- image decoding (load.rs:550-610) ---------------------------------------------------------------------------------
 // raw float: width * height * channels f32, missing channels filled with 0 (alpha: 1), NOT flipped (load.rs:556-588);
 // png / tiff: decoded, flipped vertically, converted to RGBA8 (load.rs:590-603); exr: decoded, flipped, RGBA32F (decode_exr).
-// jpeg / tga / dds need decoders this host does not carry (the Rust host uses the `image` crate): AKR_ERR_UNSUPPORTED
-// (jpeg is lossy: only a bit-exact port of jpeg-decoder 0.3's IDCT and upsampling would keep parity).
+// jpeg: decode_jpeg below (lossy format: texel-exactness against jpeg-decoder 0.3 is ASSUMED).  dds needs a decoder this host
+// does not carry: AKR_ERR_UNSUPPORTED; tga / bmp are not loadable by the reference either (load.rs:597 `unreachable!()`).
 uint8_t paeth(uint8_t a, uint8_t b, uint8_t c) {
     int p = (int)a + (int)b - (int)c, pa = std::abs(p - a), pb = std::abs(p - b), pc = std::abs(p - c);
     return (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
@@ -318,6 +318,477 @@ void decode_png(const uint8_t *data, size_t len, uint32_t &width, uint32_t &heig
         }
     }
 }
+// ---- JPEG (jpeg-decoder 0.3 behind image::ImageFormat::Jpeg -> flipv -> to_rgba8, load.rs:590-603) ---------------------
+// Sequential and progressive Huffman JPEG (any scan structure), 8 bit, 1 (gray) or 3 (YCbCr) components, sampling factors
+// 1 or 2, restart intervals.  JPEG is lossy and the decoded bytes depend on the decoder's arithmetic: this one follows the published
+// structure of jpeg-decoder 0.3 — the integer IDCT it took from stb_image (12-bit constants, 512 / 65536 + 128 << 17
+// rounding), its triangle-filter ("fancy") chroma upsampling for h2v1 / h1v2 / h2v2, and the 20-bit fixed-point BT.601
+// conversion — from memory of that crate, which is not vendored here: texel-exact agreement with the reference is
+// ASSUMED, not verified (the test bounds the distance to libjpeg-turbo instead).  Arithmetic-coded, lossless, 12-bit and
+// CMYK files are rejected.
+struct JpegHuff {
+    uint8_t bits[17] = {0};
+    uint8_t vals[256] = {0};
+    int mincode[17] = {0}, maxcode[18] = {0}, valptr[17] = {0};
+    bool present = false;
+    void build() {
+        int code = 0, k = 0;
+        for (int l = 1; l <= 16; ++l) {
+            valptr[l] = k;
+            mincode[l] = code;
+            code += bits[l];
+            k += bits[l];
+            maxcode[l] = bits[l] ? code - 1 : -1;
+            code <<= 1;
+        }
+        maxcode[17] = 0x7fffffff;
+        present = true;
+    }
+};
+struct JpegBits {
+    const uint8_t *p, *end;
+    uint32_t acc = 0;
+    int n = 0;
+    bool marker = false;
+    int bit() {
+        if (n == 0) {
+            uint8_t b = 0;
+            if (!marker && p < end) {
+                b = *p++;
+                if (b == 0xff) {
+                    if (p < end && *p == 0x00) ++p;  // stuffed zero
+                    else {                            // a marker: feed zeros from here on
+                        marker = true;
+                        --p;
+                        b = 0;
+                    }
+                }
+            }
+            acc = b;
+            n = 8;
+        }
+        --n;
+        return (acc >> n) & 1;
+    }
+    int receive(int s) {
+        int v = 0;
+        for (int i = 0; i < s; ++i) v = (v << 1) | bit();
+        return v;
+    }
+    int decode(const JpegHuff &h) {
+        int code = 0;
+        for (int l = 1; l <= 16; ++l) {
+            code = (code << 1) | bit();
+            if (h.maxcode[l] >= 0 && code <= h.maxcode[l] && code >= h.mincode[l]) return h.vals[h.valptr[l] + code - h.mincode[l]];
+        }
+        throw std::runtime_error("jpeg: bad Huffman code");
+    }
+    void reset() {
+        n = 0;
+        acc = 0;
+        marker = false;
+    }
+};
+inline int jpeg_extend(int v, int s) { return s && v < (1 << (s - 1)) ? v - (1 << s) + 1 : v; }
+inline uint8_t jpeg_clamp(int x) { return (uint8_t)(x < 0 ? 0 : (x > 255 ? 255 : x)); }
+// stb_image's stbi__idct_block (the IDCT jpeg-decoder's idct.rs is a port of): coefficients already dequantised
+void jpeg_idct(const int *d, uint8_t *out, size_t stride) {
+    auto f2f = [](double x) { return (int)(x * 4096 + 0.5); };
+    int val[64];
+#define AKR_IDCT_1D(s0, s1, s2, s3, s4, s5, s6, s7)                                                            \
+    int t0, t1, t2, t3, p1, p2, p3, p4, p5, x0, x1, x2, x3;                                                    \
+    p2 = s2; p3 = s6;                                                                                          \
+    p1 = (p2 + p3) * f2f(0.5411961);                                                                           \
+    t2 = p1 + p3 * f2f(-1.847759065);                                                                          \
+    t3 = p1 + p2 * f2f(0.765366865);                                                                           \
+    p2 = s0; p3 = s4;                                                                                          \
+    t0 = (p2 + p3) * 4096; t1 = (p2 - p3) * 4096;                                                              \
+    x0 = t0 + t3; x3 = t0 - t3; x1 = t1 + t2; x2 = t1 - t2;                                                    \
+    t0 = s7; t1 = s5; t2 = s3; t3 = s1;                                                                        \
+    p3 = t0 + t2; p4 = t1 + t3; p1 = t0 + t3; p2 = t1 + t2;                                                    \
+    p5 = (p3 + p4) * f2f(1.175875602);                                                                         \
+    t0 = t0 * f2f(0.298631336); t1 = t1 * f2f(2.053119869); t2 = t2 * f2f(3.072711026); t3 = t3 * f2f(1.501321110); \
+    p1 = p5 + p1 * f2f(-0.899976223); p2 = p5 + p2 * f2f(-2.562915447);                                        \
+    p3 = p3 * f2f(-1.961570560); p4 = p4 * f2f(-0.390180644);                                                  \
+    t3 += p1 + p4; t2 += p2 + p3; t1 += p2 + p4; t0 += p1 + p3;
+    for (int i = 0; i < 8; ++i) {  // columns
+        const int *c = d + i;
+        int *v = val + i;
+        if (c[8] == 0 && c[16] == 0 && c[24] == 0 && c[32] == 0 && c[40] == 0 && c[48] == 0 && c[56] == 0) {
+            const int dc = c[0] * 4;
+            v[0] = v[8] = v[16] = v[24] = v[32] = v[40] = v[48] = v[56] = dc;
+        } else {
+            AKR_IDCT_1D(c[0], c[8], c[16], c[24], c[32], c[40], c[48], c[56])
+            x0 += 512; x1 += 512; x2 += 512; x3 += 512;
+            v[0] = (x0 + t3) >> 10; v[56] = (x0 - t3) >> 10;
+            v[8] = (x1 + t2) >> 10; v[48] = (x1 - t2) >> 10;
+            v[16] = (x2 + t1) >> 10; v[40] = (x2 - t1) >> 10;
+            v[24] = (x3 + t0) >> 10; v[32] = (x3 - t0) >> 10;
+        }
+    }
+    for (int i = 0; i < 8; ++i) {  // rows
+        const int *v = val + i * 8;
+        uint8_t *o = out + (size_t)i * stride;
+        AKR_IDCT_1D(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7])
+        x0 += 65536 + (128 << 17); x1 += 65536 + (128 << 17); x2 += 65536 + (128 << 17); x3 += 65536 + (128 << 17);
+        o[0] = jpeg_clamp((x0 + t3) >> 17); o[7] = jpeg_clamp((x0 - t3) >> 17);
+        o[1] = jpeg_clamp((x1 + t2) >> 17); o[6] = jpeg_clamp((x1 - t2) >> 17);
+        o[2] = jpeg_clamp((x2 + t1) >> 17); o[5] = jpeg_clamp((x2 - t1) >> 17);
+        o[3] = jpeg_clamp((x3 + t0) >> 17); o[4] = jpeg_clamp((x3 - t0) >> 17);
+    }
+#undef AKR_IDCT_1D
+}
+void decode_jpeg(const uint8_t *data, size_t len, uint32_t &width, uint32_t &height, std::vector<uint8_t> &rgba8) {
+    static const uint8_t zigzag[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
+                                       41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
+                                       30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+    if (len < 4 || data[0] != 0xff || data[1] != 0xd8) throw std::runtime_error("jpeg: missing SOI");
+    struct Comp {
+        int id = 0, h = 1, v = 1, tq = 0, td = 0, ta = 0, pred = 0;
+        uint32_t bw = 0, bh = 0;    // blocks per line / column, padded to whole MCUs (the layout of `coef` and `plane`)
+        uint32_t rbw = 0, rbh = 0;  // blocks that carry image samples (what a non-interleaved scan visits)
+        std::vector<int16_t> coef;  // quantised coefficients, natural order, 64 per block: scans accumulate here
+        std::vector<uint8_t> plane;
+    };
+    std::vector<Comp> comps;
+    uint16_t qt[4][64] = {{0}};
+    bool have_qt[4] = {false, false, false, false};
+    JpegHuff dc[4], ac[4];
+    uint32_t restart = 0;
+    int hmax = 1, vmax = 1;
+    bool have_frame = false, progressive = false, decoded = false;
+    size_t pos = 2;
+    auto be16 = [&](size_t p) -> uint32_t {
+        if (p + 2 > len) throw std::runtime_error("jpeg: truncated file");
+        return ((uint32_t)data[p] << 8) | data[p + 1];
+    };
+    while (pos + 4 <= len) {
+        if (data[pos] != 0xff) {  // entropy-coded bytes left over by a scan that ended on a marker: skip to the next marker
+            ++pos;
+            continue;
+        }
+        const uint8_t m = data[pos + 1];
+        pos += 2;
+        if (m == 0xff) {  // fill byte
+            --pos;
+            continue;
+        }
+        if (m == 0xd9) break;
+        if (m == 0x00 || m == 0x01 || (m >= 0xd0 && m <= 0xd7)) continue;
+        const uint32_t seglen = be16(pos);
+        if (seglen < 2 || pos + seglen > len) throw std::runtime_error("jpeg: bad segment length");
+        const uint8_t *seg = data + pos + 2;
+        const size_t n = seglen - 2;
+        if (m == 0xdb) {  // DQT
+            size_t i = 0;
+            while (i < n) {
+                const int pq = seg[i] >> 4, tq = seg[i] & 15;
+                ++i;
+                if (tq > 3 || i + (pq ? 128 : 64) > n) throw std::runtime_error("jpeg: bad DQT");
+                for (int k = 0; k < 64; ++k) {
+                    qt[tq][zigzag[k]] = pq ? (uint16_t)((seg[i] << 8) | seg[i + 1]) : seg[i];
+                    i += pq ? 2 : 1;
+                }
+                have_qt[tq] = true;
+            }
+        } else if (m == 0xc4) {  // DHT
+            size_t i = 0;
+            while (i < n) {
+                const int tc = seg[i] >> 4, th = seg[i] & 15;
+                ++i;
+                if (tc > 1 || th > 3 || i + 16 > n) throw std::runtime_error("jpeg: bad DHT");
+                JpegHuff &h = tc ? ac[th] : dc[th];
+                int total = 0;
+                for (int l = 1; l <= 16; ++l) {
+                    h.bits[l] = seg[i + l - 1];
+                    total += h.bits[l];
+                }
+                i += 16;
+                if (total > 256 || i + total > n) throw std::runtime_error("jpeg: bad DHT");
+                std::memcpy(h.vals, seg + i, total);
+                i += total;
+                h.build();
+            }
+        } else if (m == 0xc0 || m == 0xc1 || m == 0xc2) {  // SOF0 / SOF1 (sequential), SOF2 (progressive)
+            if (have_frame) throw std::runtime_error("jpeg: more than one frame");
+            if (n < 6 || seg[0] != 8) throw std::runtime_error("jpeg: only 8-bit samples are supported");
+            progressive = m == 0xc2;
+            height = (seg[1] << 8) | seg[2];
+            width = (seg[3] << 8) | seg[4];
+            const int nc = seg[5];
+            if ((nc != 1 && nc != 3) || n < (size_t)(6 + 3 * nc) || !width || !height) throw std::runtime_error("jpeg: unsupported component count / size");
+            comps.resize(nc);
+            for (int c = 0; c < nc; ++c) {
+                comps[c].id = seg[6 + 3 * c];
+                comps[c].h = seg[7 + 3 * c] >> 4;
+                comps[c].v = seg[7 + 3 * c] & 15;
+                comps[c].tq = seg[8 + 3 * c];
+                if (comps[c].h < 1 || comps[c].h > 2 || comps[c].v < 1 || comps[c].v > 2 || comps[c].tq > 3) throw std::runtime_error("jpeg: unsupported sampling factors");
+                hmax = std::max(hmax, comps[c].h);
+                vmax = std::max(vmax, comps[c].v);
+            }
+            if (nc == 1) comps[0].h = comps[0].v = hmax = vmax = 1;  // a single component is never interleaved
+            const uint32_t mcux = (width + 8 * hmax - 1) / (8 * hmax), mcuy = (height + 8 * vmax - 1) / (8 * vmax);
+            for (Comp &c : comps) {
+                c.bw = mcux * c.h;
+                c.bh = mcuy * c.v;
+                c.rbw = ((width * c.h + hmax - 1) / hmax + 7) / 8;
+                c.rbh = ((height * c.v + vmax - 1) / vmax + 7) / 8;
+                c.coef.assign((size_t)c.bw * c.bh * 64, 0);
+            }
+            have_frame = true;
+        } else if (m >= 0xc3 && m <= 0xcf && m != 0xc4 && m != 0xc8 && m != 0xcc) {
+            throw std::runtime_error("jpeg: lossless, hierarchical and arithmetic-coded files are not supported");
+        } else if (m == 0xdd) {
+            if (n < 2) throw std::runtime_error("jpeg: bad DRI");
+            restart = (seg[0] << 8) | seg[1];
+        } else if (m == 0xda) {  // SOS
+            if (!have_frame) throw std::runtime_error("jpeg: SOS before SOF");
+            const int ns = seg[0];
+            if (ns < 1 || ns > (int)comps.size() || n < (size_t)(1 + 2 * ns + 3)) throw std::runtime_error("jpeg: bad SOS");
+            std::vector<Comp *> sc;
+            for (int k = 0; k < ns; ++k) {
+                Comp *c = nullptr;
+                for (Comp &cc : comps)
+                    if (cc.id == seg[1 + 2 * k]) c = &cc;
+                if (!c) throw std::runtime_error("jpeg: scan names an unknown component");
+                c->td = seg[2 + 2 * k] >> 4;
+                c->ta = seg[2 + 2 * k] & 15;
+                if (c->td > 3 || c->ta > 3) throw std::runtime_error("jpeg: bad table selector");
+                c->pred = 0;
+                sc.push_back(c);
+            }
+            const int ss = seg[1 + 2 * ns], se = seg[2 + 2 * ns], ah = seg[3 + 2 * ns] >> 4, al = seg[3 + 2 * ns] & 15;
+            if (progressive) {
+                if (ss > se || se > 63 || (ss == 0 && se != 0) || (ss != 0 && ns != 1) || al > 13) throw std::runtime_error("jpeg: bad progressive scan parameters");
+            } else if (ss != 0 || se != 63 || ah != 0 || al != 0) {
+                throw std::runtime_error("jpeg: bad sequential scan parameters");
+            }
+            for (Comp *c : sc) {
+                const bool need_dc = !progressive || ss == 0, need_ac = !progressive || ss != 0;
+                if ((need_dc && !(progressive && ah) && !dc[c->td].present) || (need_ac && !ac[c->ta].present)) throw std::runtime_error("jpeg: missing Huffman table");
+            }
+            JpegBits br{data + pos + seglen, data + len};
+            uint32_t until_restart = restart, eobrun = 0;
+            auto decode_block = [&](Comp &c, int16_t *blk) {
+                if (!progressive) {
+                    const int t = br.decode(dc[c.td]);
+                    if (t > 11) throw std::runtime_error("jpeg: bad DC size");
+                    c.pred += jpeg_extend(br.receive(t), t);
+                    blk[0] = (int16_t)c.pred;
+                    for (int k = 1; k < 64;) {
+                        const int rs = br.decode(ac[c.ta]), r = rs >> 4, sz = rs & 15;
+                        if (sz == 0) {
+                            if (r != 15) break;
+                            k += 16;
+                            continue;
+                        }
+                        k += r;
+                        if (k > 63) throw std::runtime_error("jpeg: bad AC run");
+                        blk[zigzag[k]] = (int16_t)jpeg_extend(br.receive(sz), sz);
+                        ++k;
+                    }
+                } else if (ss == 0) {  // DC: first pass or one more bit
+                    if (ah == 0) {
+                        const int t = br.decode(dc[c.td]);
+                        if (t > 11) throw std::runtime_error("jpeg: bad DC size");
+                        c.pred += jpeg_extend(br.receive(t), t);
+                        blk[0] = (int16_t)(c.pred * (1 << al));
+                    } else if (br.bit()) {
+                        blk[0] = (int16_t)(blk[0] + (1 << al));
+                    }
+                } else if (ah == 0) {  // AC band, first pass
+                    if (eobrun) {
+                        --eobrun;
+                        return;
+                    }
+                    for (int k = ss; k <= se;) {
+                        const int rs = br.decode(ac[c.ta]), r = rs >> 4, sz = rs & 15;
+                        if (sz == 0) {
+                            if (r < 15) {
+                                eobrun = (1u << r) - 1u;
+                                if (r) eobrun += (uint32_t)br.receive(r);
+                                break;
+                            }
+                            k += 16;
+                        } else {
+                            k += r;
+                            if (k > 63) throw std::runtime_error("jpeg: bad AC run");
+                            blk[zigzag[k]] = (int16_t)(jpeg_extend(br.receive(sz), sz) * (1 << al));
+                            ++k;
+                        }
+                    }
+                } else {  // AC band, refinement: one more bit for the non-zero coefficients, new +-1 coefficients in between
+                    const int bit = 1 << al;
+                    auto refine = [&](int16_t &p) {
+                        if (br.bit() && (p & bit) == 0) p = (int16_t)(p > 0 ? p + bit : p - bit);
+                    };
+                    if (eobrun) {
+                        --eobrun;
+                        for (int k = ss; k <= se; ++k)
+                            if (blk[zigzag[k]]) refine(blk[zigzag[k]]);
+                        return;
+                    }
+                    for (int k = ss; k <= se;) {
+                        const int rs = br.decode(ac[c.ta]), sz = rs & 15;
+                        int r = rs >> 4, value = 0;
+                        if (sz == 0) {
+                            if (r < 15) {
+                                eobrun = (1u << r) - 1u;
+                                if (r) eobrun += (uint32_t)br.receive(r);
+                                r = 64;  // run to the end of the band, refining on the way
+                            }
+                        } else {
+                            if (sz != 1) throw std::runtime_error("jpeg: bad refinement code");
+                            value = br.bit() ? bit : -bit;
+                        }
+                        while (k <= se) {
+                            int16_t &p = blk[zigzag[k++]];
+                            if (p) {
+                                refine(p);
+                            } else {
+                                if (r == 0) {
+                                    p = (int16_t)value;
+                                    break;
+                                }
+                                --r;
+                            }
+                        }
+                    }
+                }
+            };
+            auto maybe_restart = [&]() {
+                if (restart && until_restart == 0) {  // RSTn: byte-align, skip the marker, reset predictors and the EOB run
+                    br.reset();
+                    while (br.p + 1 < br.end && !(br.p[0] == 0xff && br.p[1] >= 0xd0 && br.p[1] <= 0xd7)) ++br.p;
+                    if (br.p + 1 < br.end) br.p += 2;
+                    for (Comp *c : sc) c->pred = 0;
+                    eobrun = 0;
+                    until_restart = restart;
+                }
+            };
+            if (ns == 1) {  // non-interleaved: the component's own blocks, row by row
+                Comp &c = *sc[0];
+                for (uint32_t by = 0; by < c.rbh; ++by)
+                    for (uint32_t bx = 0; bx < c.rbw; ++bx) {
+                        maybe_restart();
+                        decode_block(c, c.coef.data() + ((size_t)by * c.bw + bx) * 64);
+                        if (restart) --until_restart;
+                    }
+            } else {
+                const uint32_t mcux = comps[0].bw / comps[0].h, mcuy = comps[0].bh / comps[0].v;
+                for (uint32_t my = 0; my < mcuy; ++my)
+                    for (uint32_t mx = 0; mx < mcux; ++mx) {
+                        maybe_restart();
+                        for (Comp *c : sc)
+                            for (int by = 0; by < c->v; ++by)
+                                for (int bx = 0; bx < c->h; ++bx)
+                                    decode_block(*c, c->coef.data() + ((size_t)(my * c->v + by) * c->bw + (mx * c->h + bx)) * 64);
+                        if (restart) --until_restart;
+                    }
+            }
+            decoded = true;
+            pos = (size_t)(br.p - data);  // continue the marker search behind the entropy-coded segment
+            continue;
+        }
+        pos += seglen;
+    }
+    if (decoded) {  // dequantise + IDCT every block
+        int deq[64];
+        for (Comp &c : comps) {
+            if (!have_qt[c.tq]) throw std::runtime_error("jpeg: missing quantisation table");
+            const size_t stride = (size_t)c.bw * 8;
+            c.plane.assign(stride * c.bh * 8, 0);
+            for (uint32_t by = 0; by < c.bh; ++by)
+                for (uint32_t bx = 0; bx < c.bw; ++bx) {
+                    const int16_t *blk = c.coef.data() + ((size_t)by * c.bw + bx) * 64;
+                    for (int k = 0; k < 64; ++k) deq[k] = blk[k] * qt[c.tq][k];
+                    jpeg_idct(deq, c.plane.data() + (size_t)by * 8 * stride + (size_t)bx * 8, stride);
+                }
+        }
+    }
+    if (!decoded) throw std::runtime_error("jpeg: no image data");
+    // upsample the chroma planes to full resolution (jpeg-decoder's upsampler.rs: triangle filters for the factor-2 cases)
+    auto upsample = [&](const Comp &c, std::vector<uint8_t> &out) {
+        const uint32_t cw = (width * c.h + hmax - 1) / hmax, chh = (height * c.v + vmax - 1) / vmax;  // the component's own size
+        const size_t stride = (size_t)c.bw * 8;
+        const bool h2 = hmax == 2 && c.h == 1, v2 = vmax == 2 && c.v == 1;
+        out.assign((size_t)width * height, 0);
+        std::vector<uint8_t> line((size_t)cw * 2 + 2);
+        for (uint32_t y = 0; y < height; ++y) {
+            const uint8_t *near_row, *far_row;
+            if (v2) {
+                const uint32_t rn = std::min(y / 2, chh - 1);
+                const uint32_t rf = (y & 1) ? std::min(rn + 1, chh - 1) : (rn ? rn - 1 : 0);
+                near_row = c.plane.data() + (size_t)rn * stride;
+                far_row = c.plane.data() + (size_t)rf * stride;
+            } else {
+                near_row = far_row = c.plane.data() + (size_t)std::min(y, chh - 1) * stride;
+            }
+            uint8_t *o = out.data() + (size_t)y * width;
+            if (!h2 && !v2) {
+                std::memcpy(o, near_row, width);
+            } else if (!h2) {  // h1v2
+                for (uint32_t x = 0; x < width; ++x) o[x] = (uint8_t)((3 * near_row[x] + far_row[x] + 2) >> 2);
+            } else if (!v2) {  // h2v1
+                if (cw == 1) {
+                    line[0] = line[1] = near_row[0];
+                } else {
+                    line[0] = near_row[0];
+                    line[1] = (uint8_t)((near_row[0] * 3 + near_row[1] + 2) >> 2);
+                    for (uint32_t i = 1; i + 1 < cw; ++i) {
+                        const int s3 = 3 * near_row[i] + 2;
+                        line[2 * i] = (uint8_t)((s3 + near_row[i - 1]) >> 2);
+                        line[2 * i + 1] = (uint8_t)((s3 + near_row[i + 1]) >> 2);
+                    }
+                    line[2 * (cw - 1)] = (uint8_t)((near_row[cw - 1] * 3 + near_row[cw - 2] + 2) >> 2);
+                    line[2 * (cw - 1) + 1] = near_row[cw - 1];
+                }
+                std::memcpy(o, line.data(), width);
+            } else {  // h2v2
+                if (cw == 1) {
+                    line[0] = line[1] = (uint8_t)((3 * near_row[0] + far_row[0] + 2) >> 2);
+                } else {
+                    int t0 = 3 * near_row[0] + far_row[0], t1 = 3 * near_row[1] + far_row[1];
+                    line[0] = (uint8_t)((t0 * 4 + 8) >> 4);
+                    line[1] = (uint8_t)((3 * t0 + t1 + 8) >> 4);
+                    for (uint32_t i = 2; i < cw; ++i) {
+                        const int t2 = 3 * near_row[i] + far_row[i];
+                        line[2 * i - 2] = (uint8_t)((3 * t1 + t0 + 8) >> 4);
+                        line[2 * i - 1] = (uint8_t)((3 * t1 + t2 + 8) >> 4);
+                        t0 = t1;
+                        t1 = t2;
+                    }
+                    line[2 * cw - 2] = (uint8_t)((3 * t1 + t0 + 8) >> 4);
+                    line[2 * cw - 1] = (uint8_t)((t1 * 4 + 8) >> 4);
+                }
+                std::memcpy(o, line.data(), width);
+            }
+        }
+    };
+    std::vector<uint8_t> full[3];
+    for (size_t c = 0; c < comps.size(); ++c) upsample(comps[c], full[c]);
+    rgba8.resize((size_t)width * height * 4);
+    auto f2f20 = [](float x) { return (int)(x * (float)(1 << 20) + 0.5f); };
+    for (uint32_t y = 0; y < height; ++y) {
+        const uint32_t fy = height - 1 - y;  // DynamicImage::flipv
+        for (uint32_t x = 0; x < width; ++x) {
+            const size_t i = (size_t)y * width + x;
+            uint8_t r, g, b;
+            if (comps.size() == 1) {
+                r = g = b = full[0][i];
+            } else {  // BT.601, 20-bit fixed point
+                const int yy = ((int)full[0][i] << 20) + (1 << 19), cb = (int)full[1][i] - 128, cr = (int)full[2][i] - 128;
+                r = jpeg_clamp((yy + f2f20(1.40200f) * cr) >> 20);
+                g = jpeg_clamp((yy - f2f20(0.34414f) * cb - f2f20(0.71414f) * cr) >> 20);
+                b = jpeg_clamp((yy + f2f20(1.77200f) * cb) >> 20);
+            }
+            uint8_t *o = rgba8.data() + ((size_t)fy * width + x) * 4;
+            o[0] = r; o[1] = g; o[2] = b; o[3] = 255;
+        }
+    }
+}
+
 // ---- TIFF (the `tiff` 0.9 decoder behind image::ImageFormat::Tiff -> flipv -> to_rgba8, load.rs:590-603) ----------------
 // Baseline strips, chunky layout, 8 / 16 bits per sample, gray / gray + alpha / RGB / RGBA, compression none / LZW / Deflate /
 // PackBits, horizontal predictor, either byte order.  Tiles, planar layout, palettes, CMYK / YCbCr and fax codecs are rejected.
@@ -735,6 +1206,9 @@ void decode_image(const std::string &format, const uint8_t *bytes, size_t len, u
     } else if (format == "png") {
         img.texel_format = AKR_TEXEL_RGBA8;
         decode_png(bytes, len, img.width, img.height, texels);
+    } else if (format == "jpeg") {
+        img.texel_format = AKR_TEXEL_RGBA8;
+        decode_jpeg(bytes, len, img.width, img.height, texels);
     } else if (format == "tiff") {
         img.texel_format = AKR_TEXEL_RGBA8;
         decode_tiff(bytes, len, img.width, img.height, texels);
@@ -745,7 +1219,7 @@ void decode_image(const std::string &format, const uint8_t *bytes, size_t len, u
         texels.resize(rgba.size() * 4);
         std::memcpy(texels.data(), rgba.data(), texels.size());
     } else {
-        throw std::runtime_error("image format '" + format + "' needs a decoder this host does not carry (png, tiff, exr and raw float are implemented)");
+        throw std::runtime_error("image format '" + format + "' needs a decoder this host does not carry (png, jpeg, tiff, exr and raw float are implemented)");
     }
 }
 

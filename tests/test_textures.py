@@ -67,7 +67,7 @@ def test_unsupported_nodes_and_formats_are_rejected(akr, tmp_path):
     path = sv.write_textured(tmp_path)
     sj = json.load(open(path))
     bad = json.loads(json.dumps(sj))
-    bad["materials"]["floor_001"]["shader"]["nodes"]["tex"]["image"]["format"] = "jpeg"
+    bad["materials"]["floor_001"]["shader"]["nodes"]["tex"]["image"]["format"] = "dds"
     p2 = os.path.join(os.path.dirname(path), "bad.json")
     json.dump(bad, open(p2, "w"))
     with pytest.raises(akr.AkariError):
@@ -309,3 +309,68 @@ def test_clip_address_mode_keeps_the_alpha_test_on_an_opaque_texture(akr, oracle
     _, _, pfh = oracle.render(plain.desc, w, h, task.pt, task.sampler, task.filter, pmj, bn, want_first_hits=True)
     n_clip, n_plain = int((ofh[:, 0] == back_wall).sum()), int((pfh[:, 0] == back_wall).sum())
     assert 0 < n_clip < 0.8 * n_plain, (n_clip, n_plain)  # the rim of the wall lets camera rays through
+
+
+def test_loader_decodes_jpeg_images(akr, tmp_path):
+    """JPEG textures (load.rs:590-603).  JPEG is lossy and decoders differ in their last bit (IDCT, chroma upsampling,
+    colour conversion); decode_jpeg follows jpeg-decoder 0.3's published structure (exactness ASSUMED), so
+    the test bounds its distance to an independent decoder (OpenCV / libjpeg-turbo): 4:4:4 and gray within 2 / 255 per
+    texel, subsampled chroma (4:2:2, 4:2:0, odd sizes: MCU padding, edge replication) within 1 / 255 on average, with
+    restart intervals; sequential and progressive scan structures."""
+    import cv2
+    rng = np.random.default_rng(21)
+
+    def smooth(h, w, c):  # band-limited content (what textures are): sums of low-frequency waves + mild noise
+        yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+        img = np.zeros((h, w, c), np.float32)
+        for k in range(c):
+            for _ in range(4):
+                fx, fy, ph = rng.random() * 0.25, rng.random() * 0.25, rng.random() * 6.28
+                img[..., k] += np.sin(xx * fx + yy * fy + ph)
+        img = (img - img.min()) / (img.max() - img.min())
+        return (img * 235 + 10 + rng.random((h, w, c)) * 6).clip(0, 255).astype(np.uint8)
+    S = cv2.IMWRITE_JPEG_SAMPLING_FACTOR
+    cases = [("floor_001", smooth(40, 56, 3), [S, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444, cv2.IMWRITE_JPEG_QUALITY, 92], 2.0, 0.6),
+             ("backWall_001", smooth(33, 47, 3), [S, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420, cv2.IMWRITE_JPEG_QUALITY, 90], 8.0, 1.0),
+             ("leftWall_001", smooth(24, 31, 3), [S, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422, cv2.IMWRITE_JPEG_QUALITY, 85, cv2.IMWRITE_JPEG_RST_INTERVAL, 3], 8.0, 1.0),
+             ("rightWall_001", smooth(19, 26, 1)[..., 0], [cv2.IMWRITE_JPEG_QUALITY, 80], 2.0, 0.6),
+             ("ceiling_001", smooth(16, 16, 3), [S, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_440, cv2.IMWRITE_JPEG_QUALITY, 95], 8.0, 1.0)]
+    items, expect = [], {}
+    for material, arr, params, max_err, mean_err in cases:
+        ok, buf = cv2.imencode(".jpg", arr if arr.ndim == 2 else arr[..., ::-1], params)
+        assert ok
+        h, w = arr.shape[:2]
+        items.append((material, bytes(buf), "jpeg", w, h, 1 if arr.ndim == 2 else 3))
+        ref = cv2.imdecode(buf, cv2.IMREAD_UNCHANGED)
+        ref = np.repeat(ref[..., None], 3, axis=2) if ref.ndim == 2 else ref[..., ::-1]
+        expect[(w, h)] = (ref[::-1].astype(np.int32), max_err, mean_err)
+    scene = akr.load_scene(sv.write_image_textured(tmp_path, "jpeg_textured", items, colorspace="srgb"))
+    imgs = _images(scene)
+    assert len(imgs) == 5
+    for g in imgs:
+        got = np.ctypeslib.as_array(C.cast(g.texels, C.POINTER(C.c_uint8)), (g.width * g.height * 4,)).reshape(g.height, g.width, 4).astype(np.int32)
+        ref, max_err, mean_err = expect[(g.width, g.height)]
+        d = np.abs(got[..., :3] - ref)
+        assert g.texel_format == 0 and (got[..., 3] == 255).all()
+        assert d.max() <= max_err and d.mean() <= mean_err, ((g.width, g.height), int(d.max()), float(d.mean()))
+    # progressive files (spectral selection + successive approximation, DC interleaved / AC per component, EOB runs)
+    for k, (shape, params) in enumerate([((45, 38, 3), [cv2.IMWRITE_JPEG_PROGRESSIVE, 1, cv2.IMWRITE_JPEG_QUALITY, 88]),
+                                         ((24, 40, 3), [cv2.IMWRITE_JPEG_PROGRESSIVE, 1, S, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444, cv2.IMWRITE_JPEG_RST_INTERVAL, 2]),
+                                         ((30, 30, 1), [cv2.IMWRITE_JPEG_PROGRESSIVE, 1, cv2.IMWRITE_JPEG_QUALITY, 60])]):
+        arr = smooth(*shape)
+        arr = arr[..., 0] if shape[2] == 1 else arr
+        ok, buf = cv2.imencode(".jpg", arr if arr.ndim == 2 else arr[..., ::-1], params)
+        assert ok and b"\xff\xc2" in bytes(buf)
+        ref = cv2.imdecode(buf, cv2.IMREAD_UNCHANGED)
+        ref = (np.repeat(ref[..., None], 3, axis=2) if ref.ndim == 2 else ref[..., ::-1])[::-1].astype(np.int32)
+        h, w = shape[:2]
+        scene = akr.load_scene(sv.write_image_textured(tmp_path, f"jpeg_progressive{k}", [("floor_001", bytes(buf), "jpeg", w, h, shape[2])]))
+        g = _images(scene)[0]  # (texels live as long as `scene`)
+        got = np.ctypeslib.as_array(C.cast(g.texels, C.POINTER(C.c_uint8)), (w * h * 4,)).reshape(h, w, 4).astype(np.int32)
+        d = np.abs(got[..., :3] - ref)
+        assert d.max() <= 8 and d.mean() <= 1.0, (k, int(d.max()), float(d.mean()))
+    # arithmetic-coded / truncated files are rejected
+    ok, buf = cv2.imencode(".jpg", smooth(16, 16, 3))
+    for bad in (bytes(buf)[:60], bytes(buf).replace(b"\xff\xc0", b"\xff\xc9", 1)):
+        with pytest.raises(akr.AkariError):
+            akr.load_scene(sv.write_image_textured(tmp_path, "jpeg_bad", [("floor_001", bad, "jpeg", 16, 16, 3)]))
