@@ -319,7 +319,7 @@ typedef struct AkrEngineOptions {
                                      * and shade class), 2 = off (always trace stage + shade stage + queues),
                                      * 3 = fused, every kernel on the context stream (no side stream; A/B runs) */
     uint32_t smem_node_kb;          /* BVH scenes that do not fit in shared memory: KiB of top-of-tree nodes each
-                                     * CTA stages (0 = default 16); read by akr_b200_upload_scene              */
+                                     * CTA stages (0 = default 4); read by akr_b200_upload_scene               */
     uint32_t aov_mask;              /* AKR_AOV_* outputs to record; read by akr_b200_begin                    */
     uint32_t _reserved[1];
 } AkrEngineOptions;
