@@ -9,6 +9,7 @@
 #include "../../akari_render_b200/csrc/host/scene_build.h"
 #include "../../oracle/chi2_tables.h"
 
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -18,6 +19,7 @@ using namespace akr;
 
 static thread_local int g_use_prims = 0;
 static thread_local int g_fused = 0;
+static thread_local int g_general_order = 0;
 static thread_local uint32_t g_tile_block = 1, g_tile_shards = 1, g_tile_shard = 0;  // interleaved tile (AkrTile semantics)
 
 namespace {
@@ -48,6 +50,18 @@ struct HostTracer {  // the Tracer of akr_path.cuh's fused bodies, one ray at a 
 };
 }  // namespace
 
+// permutation of [0, n) that orders items by key(i) as hostsim_set_general_order asks
+template <class KeyFn> static std::vector<uint32_t> general_order(size_t n, KeyFn key) {
+    std::vector<uint32_t> idx(n);
+    for (size_t i = 0; i < n; ++i) idx[i] = (uint32_t)i;
+    if (g_general_order == 1) std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return key(a) < key(b); });
+    if (g_general_order == 2) {
+        std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return key(a) < key(b); });
+        std::reverse(idx.begin(), idx.end());
+    }
+    return idx;
+}
+
 extern "C" {
 
 static thread_local std::string g_err;
@@ -71,6 +85,10 @@ void hostsim_set_intersector(int use_prims) { g_use_prims = use_prims; }
 // depth and shade class does shade + shadow ray + next ray on records that carry hit and radiance: akr_path.cuh
 // bounce_fused, what flat scenes run)
 void hostsim_set_pipeline(int fused) { g_fused = fused; }
+// Order in which the records of the general shade class are processed at every depth: 0 = arrival order; 1 = by material
+// sort key, ascending (what k_sort_hist / k_sort_scatter produce on the device, up to the order within a key); 2 = by key
+// descending with each key's records reversed.  The film must not depend on it (one path per record, own accumulators).
+void hostsim_set_general_order(int mode) { g_general_order = mode; }
 // rows [y0, y1) of hostsim_render are then the rows of shard `shard` of `n_shards` interleaved sets of `block_rows`-row blocks
 void hostsim_set_tile_interleave(uint32_t block_rows, uint32_t n_shards, uint32_t shard) {
     g_tile_block = block_rows ? block_rows : 1u;
@@ -156,7 +174,11 @@ int hostsim_render(const AkrSceneDesc *desc, const AkrPtConfig *cfg, const AkrSa
             }
             for (uint32_t depth = 0; depth < rp.max_depth; ++depth) {
                 for (uint32_t c = 0; c < (uint32_t)CLS_COUNT; ++c) {
-                    for (const BounceRec &rec : cur[c]) {
+                    const std::vector<BounceRec> &recs = cur[c];
+                    auto key_of = [&](uint32_t i) { return (sc.shade[recs[i].gid].flags >> TRI_SORT_KEY_SHIFT) & TRI_SORT_KEY_MASK; };
+                    const std::vector<uint32_t> order = c == CLS_GENERAL ? general_order(recs.size(), key_of) : general_order(0, key_of);
+                    for (size_t oi = 0; oi < recs.size(); ++oi) {
+                        const BounceRec &rec = recs[c == CLS_GENERAL ? order[oi] : oi];
                         BounceOut r = c == CLS_LAMBERT     ? bounce_fused<CLS_LAMBERT>(sc, ca, tab, rp, wave, depth, true, rec, tr, av)
                                       : c == CLS_CONDUCTOR ? bounce_fused<CLS_CONDUCTOR>(sc, ca, tab, rp, wave, depth, true, rec, tr, av)
                                                            : bounce_fused<CLS_GENERAL>(sc, ca, tab, rp, wave, depth, true, rec, tr, av);
@@ -200,13 +222,22 @@ int hostsim_render(const AkrSceneDesc *desc, const AkrPtConfig *cfg, const AkrSa
                 }
             next.clear();
             std::vector<ShadowItem> shq;
+            // the trace stage bins hits by shade class; the general class list is then shaded in the order of its sort keys
+            std::vector<uint32_t> general_items, visit;
+            auto class_of = [&](size_t i) { return rp.force_diffuse ? (uint32_t)CLS_LAMBERT : shade_class_of(sc.materials[sc.shade[hits[i].gid].mat]); };
             for (size_t i = 0; i < cur.size(); ++i) {
                 if (hits[i].gid == 0xffffffffu) {  // the trace stage ends missed paths itself
                     miss_body(rp, depth, cur[i].beta, cur[i].path_id, av);
                     continue;
                 }
-                // bin by shade class like the trace kernel does; each class runs its own specialisation
-                uint32_t cls = rp.force_diffuse ? (uint32_t)CLS_LAMBERT : shade_class_of(sc.materials[sc.shade[hits[i].gid].mat]);
+                if (g_general_order != 0 && class_of(i) == CLS_GENERAL) general_items.push_back((uint32_t)i);
+                else visit.push_back((uint32_t)i);
+            }
+            for (uint32_t k : general_order(general_items.size(), [&](uint32_t j) { return (sc.shade[hits[general_items[j]].gid].flags >> TRI_SORT_KEY_SHIFT) & TRI_SORT_KEY_MASK; }))
+                visit.push_back(general_items[k]);
+            for (uint32_t i : visit) {
+                // each class runs its own specialisation
+                uint32_t cls = class_of(i);
                 ShadeOut o = cls == CLS_LAMBERT     ? shade_body<CLS_LAMBERT>(sc, ca, tab, rp, wave, depth, cur[i], hits[i], av)
                              : cls == CLS_CONDUCTOR ? shade_body<CLS_CONDUCTOR>(sc, ca, tab, rp, wave, depth, cur[i], hits[i], av)
                                                     : shade_body<CLS_GENERAL>(sc, ca, tab, rp, wave, depth, cur[i], hits[i], av);

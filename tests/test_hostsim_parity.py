@@ -355,3 +355,29 @@ def test_material_sort_keys_group_equal_trees_and_order_them_by_cost(cbox, tmp_p
     assert len(set(sig_to_key.values())) == len(sig_to_key)   # different trees -> different keys
     n_lobes = sorted((k, bin(l).count("1")) for (t, l, d), k in sig_to_key.items())
     assert n_lobes[0][1] <= n_lobes[-1][1] and n_lobes[0][1] < max(c for _, c in n_lobes)  # cheapest first
+
+
+@pytest.mark.parametrize("pipeline", [0, 1], ids=["queued", "fused"])
+def test_general_class_order_does_not_change_the_film(oracle, tables, cbox_task, tmp_path, pipeline):
+    """On the device the general shade class is processed in the order of the materials' sort keys (k_sort_hist /
+    k_sort_scatter), not in arrival order.  One path per record and own accumulator slots make the film independent of that
+    order: the kernels' bodies run over the all-Principled box in arrival order, ascending key order and reversed descending
+    order give the same bits — the oracle's."""
+    import akari_render_b200 as akr
+    lib = C.CDLL(os.path.join(HERE, "hostsim", "libhostsim.so"))
+    lib.hostsim_last_error.restype = C.c_char_p
+    w = h = 40
+    scene = akr.load_scene(sv.write_variant(tmp_path, "pm", sv.variant_principled_mix)).set_resolution(w, h)
+    task = cbox_task(8)
+    pmj, bn = tables
+    ofilm, ost, _ = oracle.render(scene.desc, w, h, task.pt, task.sampler, task.filter, pmj, bn, want_first_hits=True)
+    lib.hostsim_set_pipeline(pipeline)
+    try:
+        for mode in (0, 1, 2):
+            lib.hostsim_set_general_order(mode)
+            film, fh, st = run_hostsim(lib, scene, task, tables, oracle.albedo_table(), w, h)
+            assert np.array_equal(film, ofilm), mode
+            assert (st.segments, st.shadow_rays) == (ost.segments, ost.shadow_rays)
+    finally:
+        lib.hostsim_set_general_order(0)
+        lib.hostsim_set_pipeline(0)
