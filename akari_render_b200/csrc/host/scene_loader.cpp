@@ -1543,8 +1543,12 @@ void load_scene_impl(const std::string &path, AkrHostScene &hs) {
         else if (extension == "mirror") img.address = AKR_ADDRESS_MIRROR;
         else if (extension == "extend") img.address = AKR_ADDRESS_EDGE;
         else throw std::runtime_error("image: unknown extension '" + extension + "'");
-        if (interp == "nearest") img.filter = AKR_FILTER_POINT;  // load.rs:690-699 (cubic falls back to linear)
-        else if (interp == "linear" || interp == "cubic") img.filter = AKR_FILTER_LINEAR;
+        // load.rs:690-699: Linear -> SamplerFilter::LinearLinear, Nearest -> SamplerFilter::LinearPoint, Cubic -> LinearLinear with
+        // a warning.  In LuisaCompute's sampler LINEAR_POINT means "linear filtering inside a level, nearest level" (the D3D
+        // MIN_MAG_LINEAR_MIP_POINT naming; only Filter::POINT fetches the nearest texel) and these textures have one level, so
+        // ALL THREE modes sample bilinearly in the reference — reproduced here (third-party semantics, not vendored: ASSUMED).
+        // AKR_FILTER_POINT stays in the ABI for hosts that bind a Filter::POINT sampler.
+        if (interp == "nearest" || interp == "linear" || interp == "cubic") img.filter = AKR_FILTER_LINEAR;
         else throw std::runtime_error("image: unknown interpolation '" + interp + "'");
         auto [bytes, len] = view_bytes(image.at("data"), 1, "image data");
         std::vector<uint8_t> texels;
