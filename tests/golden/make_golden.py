@@ -38,3 +38,24 @@ json.dump({"segments": int(st.segments), "shadow_rays": int(st.shadow_rays), "sa
            "n_seg": st.segments / st.samples, "shadow_per_seg": st.shadow_rays / st.segments},
           open(os.path.join(HERE, "cbox_256x256_16spp.json"), "w"))
 print("golden fixtures written")
+
+# ---- digests of the oracle's film on the scene variants the round-2 features are tested on (32 x 32 @ 8 spp) -------------
+# (a digest, not an array: these scenes exist to pin the oracle against accidental edits; the arrays above serve the GPU tests)
+import hashlib  # noqa: E402
+import tempfile  # noqa: E402
+
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import scene_variants as sv  # noqa: E402
+
+task.pt.spp = 8
+digests = {}
+tmp = tempfile.mkdtemp()
+for name, path in (("principled_mix", sv.write_variant(tmp, "pm", sv.variant_principled_mix)), ("nodes", sv.write_variant(tmp, "nodes", sv.variant_nodes)),
+                   ("textured", sv.write_textured(tmp, alpha_cutout=False)), ("textured_alpha", sv.write_textured(tmp, alpha_cutout=True)),
+                   ("clutter", sv.write_clutter(tmp, n_lon=8, n_lat=6)), ("exr_textured", sv.write_exr_textured(tmp)[0])):
+    scene = akr.load_scene(path).set_resolution(32, 32)
+    film, st, fh = oracle.render(scene.desc, 32, 32, task.pt, task.sampler, task.filter, pmj, bn, want_first_hits=True)
+    digests[name] = {"film_sha256": hashlib.sha256(np.ascontiguousarray(film).tobytes()).hexdigest(), "segments": int(st.segments),
+                     "shadow_rays": int(st.shadow_rays)}
+json.dump(digests, open(os.path.join(HERE, "variant_digests.json"), "w"), indent=1)
+print("variant digests written")

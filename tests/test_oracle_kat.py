@@ -219,3 +219,24 @@ def test_golden_image_regression(oracle, tables, cbox, cbox_task):
     assert st.segments == meta["segments"] and st.shadow_rays == meta["shadow_rays"]
     assert np.array_equal(film, gold)
     assert np.array_equal(fh, np.load(os.path.join(GOLDEN, "cbox_64x64_first_hits.npy")))
+
+
+def test_variant_digests_pin_the_oracle(oracle, tables, cbox_task, tmp_path):
+    """Round-2 features (full Principled tree, closure nodes, texture-driven graphs, alpha cut-outs, BVH scene, OpenEXR
+    textures): SHA-256 of the oracle's 32x32 @ 8 spp film per scene variant, committed by tests/golden/make_golden.py —
+    an accidental edit of the oracle, the loader, an image decoder or the scene build shows up here."""
+    import hashlib
+    import akari_render_b200 as akr
+    import scene_variants as sv
+    want = json.load(open(os.path.join(GOLDEN, "variant_digests.json")))
+    paths = {"principled_mix": lambda: sv.write_variant(tmp_path, "pm", sv.variant_principled_mix), "nodes": lambda: sv.write_variant(tmp_path, "nodes", sv.variant_nodes),
+             "textured": lambda: sv.write_textured(tmp_path, alpha_cutout=False), "textured_alpha": lambda: sv.write_textured(tmp_path, alpha_cutout=True),
+             "clutter": lambda: sv.write_clutter(tmp_path, n_lon=8, n_lat=6), "exr_textured": lambda: sv.write_exr_textured(tmp_path)[0]}
+    assert set(want) == set(paths)
+    pmj, bn = tables
+    task = cbox_task(8)
+    for name, make in paths.items():
+        scene = akr.load_scene(make()).set_resolution(32, 32)
+        film, st, _ = oracle.render(scene.desc, 32, 32, task.pt, task.sampler, task.filter, pmj, bn, want_first_hits=True)
+        got = {"film_sha256": hashlib.sha256(np.ascontiguousarray(film).tobytes()).hexdigest(), "segments": int(st.segments), "shadow_rays": int(st.shadow_rays)}
+        assert got == want[name], name
