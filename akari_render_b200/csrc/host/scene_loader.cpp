@@ -1865,13 +1865,61 @@ int akr_host_parse_method_file(const char *method_json_path, AkrRenderTask *out_
     }
 }
 
+// util::write_image_ldr (util/mod.rs:64-94): linear -> sRGB (color.rs:565-571), (x * 255).clamp(0, 255) as u8 (truncation; NaN -> 0),
+// 8-bit RGB.  Only the png container is written here (the reference hands the extension to image::RgbImage::save).
+void write_png_ldr(const std::string &path, const float *rgb, uint32_t w, uint32_t h) {
+    std::vector<uint8_t> raw((size_t)h * (1 + (size_t)w * 3));
+    for (uint32_t y = 0; y < h; ++y) {
+        uint8_t *row = raw.data() + (size_t)y * (1 + (size_t)w * 3);
+        row[0] = 0;  // filter type None
+        for (uint32_t x = 0; x < w; ++x)
+            for (int c = 0; c < 3; ++c) {
+                const float l = rgb[((size_t)y * w + x) * 3 + c];
+                const float s = l <= 0.0031308f ? l * 12.92f : std::pow(l, 1.0f / 2.4f) * 1.055f - 0.055f;
+                float v = s * 255.0f;
+                v = v != v ? 0.0f : (v < 0.0f ? 0.0f : (v > 255.0f ? 255.0f : v));
+                row[1 + (size_t)x * 3 + c] = (uint8_t)v;
+            }
+    }
+    uLongf zlen = compressBound(static_cast<uLong>(raw.size()));
+    std::vector<uint8_t> z(zlen);
+    if (compress2(z.data(), &zlen, raw.data(), static_cast<uLong>(raw.size()), 6) != Z_OK) throw std::runtime_error("png: deflate failed");
+    std::ofstream f(path, std::ios::binary);
+    if (!f) throw std::runtime_error("cannot open '" + path + "' for writing");
+    auto put32 = [](uint8_t *p, uint32_t v) {
+        p[0] = (uint8_t)(v >> 24); p[1] = (uint8_t)(v >> 16); p[2] = (uint8_t)(v >> 8); p[3] = (uint8_t)v;
+    };
+    auto chunk = [&](const char *type, const uint8_t *data, uint32_t n) {
+        uint8_t hdr[8];
+        put32(hdr, n);
+        std::memcpy(hdr + 4, type, 4);
+        f.write(reinterpret_cast<const char *>(hdr), 8);
+        if (n) f.write(reinterpret_cast<const char *>(data), n);
+        uLong crc = crc32(0L, reinterpret_cast<const Bytef *>(type), 4);
+        if (n) crc = crc32(crc, data, n);
+        uint8_t c[4];
+        put32(c, (uint32_t)crc);
+        f.write(reinterpret_cast<const char *>(c), 4);
+    };
+    static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+    f.write(reinterpret_cast<const char *>(sig), 8);
+    uint8_t ihdr[13];
+    put32(ihdr, w);
+    put32(ihdr + 4, h);
+    ihdr[8] = 8; ihdr[9] = 2; ihdr[10] = 0; ihdr[11] = 0; ihdr[12] = 0;  // 8 bit, RGB, deflate, adaptive filtering, no interlace
+    chunk("IHDR", ihdr, 13);
+    chunk("IDAT", z.data(), (uint32_t)zlen);
+    chunk("IEND", nullptr, 0);
+}
+
 int akr_host_write_image(const char *path, const float *rgb, uint32_t width, uint32_t height) {
     if (!path || !rgb || width == 0 || height == 0) return set_error(AKR_ERR_INVALID_ARGUMENT, "null argument");
     try {
         std::string p = path;
         if (p.size() >= 4 && p.substr(p.size() - 4) == ".exr") write_exr(p, rgb, width, height);
         else if (p.size() >= 4 && p.substr(p.size() - 4) == ".pfm") write_pfm(p, rgb, width, height);
-        else return set_error(AKR_ERR_UNSUPPORTED, "only .exr and .pfm outputs are implemented");
+        else if (p.size() >= 4 && p.substr(p.size() - 4) == ".png") write_png_ldr(p, rgb, width, height);
+        else return set_error(AKR_ERR_UNSUPPORTED, "only .exr, .pfm and .png outputs are implemented");
         return AKR_OK;
     } catch (const std::exception &e) {
         return set_error(AKR_ERR_INVALID_ARGUMENT, std::string("akr_host_write_image: ") + e.what());

@@ -49,8 +49,9 @@ int akr_host_parse_method_file(const char *method_json_path, AkrRenderTask *out_
 int akr_host_parse_method_string(const char *method_json, AkrRenderTask *out_task);
 void akr_host_default_task(AkrRenderTask *out_task);   /* pt::Config::default, pt.rs:929-944 */
 
-/* util::write_image for `.exr` (util/mod.rs:95-127): linear RGB f32, uncompressed scanlines.
- * `.pfm` is also accepted. rgb = [height][width][3]. */
+/* util::write_image (util/mod.rs:57-127): `.exr` = linear RGB f32, uncompressed scanlines (write_image_hdr); `.png` =
+ * write_image_ldr: linear -> sRGB, (x * 255).clamp(0, 255) as u8, 8-bit RGB.  `.pfm` is also accepted.
+ * rgb = [height][width][3]. */
 int akr_host_write_image(const char *path, const float *rgb, uint32_t width, uint32_t height);
 
 const char *akr_host_last_error(void);

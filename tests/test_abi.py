@@ -68,3 +68,29 @@ def test_write_image_exr_and_pfm_round_trip(akr, tmp_path):
             __import__("pytest").skip("this OpenCV build has no OpenEXR reader")
         assert back is not None and back.dtype == np.float32 and back.shape == rgb.shape
         assert np.array_equal(back[..., ::-1], rgb)  # OpenCV returns BGR
+
+
+def test_write_image_png_is_the_reference_ldr_conversion(akr, tmp_path):
+    """util::write_image for non-`.exr` paths (util/mod.rs:64-94): linear -> sRGB (color.rs:565-571), then
+    `(x * 255.0).clamp(0.0, 255.0) as u8` (truncation, NaN -> 0), 8-bit RGB; read back with OpenCV's png decoder."""
+    import numpy as np
+    cv2 = __import__("pytest").importorskip("cv2")
+    rng = np.random.default_rng(8)
+    rgb = (rng.random((17, 23, 3)) ** 3 * 1.4).astype(np.float32)
+    rgb[0, 0] = (0.0, 0.0031308, 0.0031309)
+    rgb[0, 1] = (-1.0, 1.0, 50.0)
+    rgb[0, 2] = (np.nan, 0.5, 0.25)
+    path = str(tmp_path / "img.png")
+    akr.write_image(path, rgb)
+    back = cv2.imread(path, cv2.IMREAD_UNCHANGED)
+    assert back is not None and back.dtype == np.uint8 and back.shape == rgb.shape
+    lin = rgb.astype(np.float32)
+    with np.errstate(invalid="ignore"):
+        srgb = np.where(lin <= np.float32(0.0031308), lin * np.float32(12.92), np.power(lin, np.float32(1.0 / 2.4)) * np.float32(1.055) - np.float32(0.055))
+        want = np.nan_to_num(np.clip(srgb * np.float32(255.0), 0.0, 255.0), nan=0.0).astype(np.uint8)
+    d = np.abs(back[..., ::-1].astype(np.int32) - want.astype(np.int32))
+    assert d.max() <= 1 and (d == 0).mean() > 0.995, (int(d.max()), float((d == 0).mean()))  # (powf of numpy vs libm: last-ulp ties)
+    # -1 -> 0; 50 -> 255; NaN -> 0; and linear 1.0 -> 254: 1.0 * 1.055f - 0.055f = 0.99999994f, * 255 = 254.99998, truncated (as the reference does)
+    assert tuple(int(v) for v in back[0, 1, ::-1]) == (0, 254, 255) and back[0, 2, 2] == 0
+    with __import__("pytest").raises(akr.AkariError):
+        akr.write_image(str(tmp_path / "img.bmp"), rgb)
