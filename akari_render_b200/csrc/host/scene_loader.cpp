@@ -213,6 +213,15 @@ using ImageResolver = std::function<uint32_t(const akr::json::Value &image)>;
 // png / tiff: decoded, flipped vertically, converted to RGBA8 (load.rs:590-603); exr: decoded, flipped, RGBA32F (decode_exr).
 // jpeg: decode_jpeg below (lossy format: texel-exactness against jpeg-decoder 0.3 is ASSUMED).  dds needs a decoder this host
 // does not carry: AKR_ERR_UNSUPPORTED; tga / bmp are not loadable by the reference either (load.rs:597 `unreachable!()`).
+// header sanity before any allocation: a corrupt size field must not turn into a multi-gigabyte request
+// (no codec here packs more than ~2 K texels into a byte — deflate tops out at 1032 : 1, a DC-only JPEG block spends 2 bits on
+// 64 samples — so the file length bounds the plausible size)
+void check_image_size(uint32_t width, uint32_t height, size_t file_bytes, const char *what) {
+    const uint64_t texels = (uint64_t)width * height;
+    if (width == 0 || height == 0 || width > 65535u || height > 65535u || texels > (1ull << 28) || texels > (uint64_t)file_bytes * 2048u + 4096u)
+        throw std::runtime_error(std::string(what) + ": image size " + std::to_string(width) + " x " + std::to_string(height) + " is out of range for a file of " +
+                                 std::to_string(file_bytes) + " bytes");
+}
 uint8_t paeth(uint8_t a, uint8_t b, uint8_t c) {
     int p = (int)a + (int)b - (int)c, pa = std::abs(p - a), pb = std::abs(p - b), pc = std::abs(p - c);
     return (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
@@ -249,6 +258,7 @@ void decode_png(const uint8_t *data, size_t len, uint32_t &width, uint32_t &heig
         pos += 12 + clen;
     }
     if (!have_ihdr || width == 0 || height == 0) throw std::runtime_error("png: no IHDR");
+    check_image_size(width, height, len, "png");
     if (interlace != 0) throw std::runtime_error("png: interlaced images are not supported");
     if (bit_depth != 8 && bit_depth != 16) throw std::runtime_error("png: only 8 / 16 bits per channel are supported");
     uint32_t ch;
@@ -390,13 +400,15 @@ struct JpegBits {
     }
 };
 inline int jpeg_extend(int v, int s) { return s && v < (1 << (s - 1)) ? v - (1 << s) + 1 : v; }
-inline uint8_t jpeg_clamp(int x) { return (uint8_t)(x < 0 ? 0 : (x > 255 ? 255 : x)); }
+inline uint8_t jpeg_clamp(int64_t x) { return (uint8_t)(x < 0 ? 0 : (x > 255 ? 255 : x)); }
 // stb_image's stbi__idct_block (the IDCT jpeg-decoder's idct.rs is a port of): coefficients already dequantised
+// (64-bit intermediates: the same values as the 32-bit original on every real image, and no signed overflow on corrupt
+// files whose 16-bit quantisation entries blow the coefficients up — found by fuzzing under UBSan)
 void jpeg_idct(const int *d, uint8_t *out, size_t stride) {
-    auto f2f = [](double x) { return (int)(x * 4096 + 0.5); };
-    int val[64];
+    auto f2f = [](double x) { return (int64_t)(x * 4096 + 0.5); };
+    int64_t val[64];
 #define AKR_IDCT_1D(s0, s1, s2, s3, s4, s5, s6, s7)                                                            \
-    int t0, t1, t2, t3, p1, p2, p3, p4, p5, x0, x1, x2, x3;                                                    \
+    int64_t t0, t1, t2, t3, p1, p2, p3, p4, p5, x0, x1, x2, x3;                                                \
     p2 = s2; p3 = s6;                                                                                          \
     p1 = (p2 + p3) * f2f(0.5411961);                                                                           \
     t2 = p1 + p3 * f2f(-1.847759065);                                                                          \
@@ -413,9 +425,9 @@ void jpeg_idct(const int *d, uint8_t *out, size_t stride) {
     t3 += p1 + p4; t2 += p2 + p3; t1 += p2 + p4; t0 += p1 + p3;
     for (int i = 0; i < 8; ++i) {  // columns
         const int *c = d + i;
-        int *v = val + i;
+        int64_t *v = val + i;
         if (c[8] == 0 && c[16] == 0 && c[24] == 0 && c[32] == 0 && c[40] == 0 && c[48] == 0 && c[56] == 0) {
-            const int dc = c[0] * 4;
+            const int64_t dc = (int64_t)c[0] * 4;
             v[0] = v[8] = v[16] = v[24] = v[32] = v[40] = v[48] = v[56] = dc;
         } else {
             AKR_IDCT_1D(c[0], c[8], c[16], c[24], c[32], c[40], c[48], c[56])
@@ -427,7 +439,7 @@ void jpeg_idct(const int *d, uint8_t *out, size_t stride) {
         }
     }
     for (int i = 0; i < 8; ++i) {  // rows
-        const int *v = val + i * 8;
+        const int64_t *v = val + i * 8;
         uint8_t *o = out + (size_t)i * stride;
         AKR_IDCT_1D(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7])
         x0 += 65536 + (128 << 17); x1 += 65536 + (128 << 17); x2 += 65536 + (128 << 17); x3 += 65536 + (128 << 17);
@@ -444,7 +456,8 @@ void decode_jpeg(const uint8_t *data, size_t len, uint32_t &width, uint32_t &hei
                                        30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
     if (len < 4 || data[0] != 0xff || data[1] != 0xd8) throw std::runtime_error("jpeg: missing SOI");
     struct Comp {
-        int id = 0, h = 1, v = 1, tq = 0, td = 0, ta = 0, pred = 0;
+        int id = 0, h = 1, v = 1, tq = 0, td = 0, ta = 0;
+        int64_t pred = 0;           // DC predictor (64 bit: cannot overflow on a corrupt stream)
         uint32_t bw = 0, bh = 0;    // blocks per line / column, padded to whole MCUs (the layout of `coef` and `plane`)
         uint32_t rbw = 0, rbh = 0;  // blocks that carry image samples (what a non-interleaved scan visits)
         std::vector<int16_t> coef;  // quantised coefficients, natural order, 64 per block: scans accumulate here
@@ -517,6 +530,7 @@ void decode_jpeg(const uint8_t *data, size_t len, uint32_t &width, uint32_t &hei
             width = (seg[3] << 8) | seg[4];
             const int nc = seg[5];
             if ((nc != 1 && nc != 3) || n < (size_t)(6 + 3 * nc) || !width || !height) throw std::runtime_error("jpeg: unsupported component count / size");
+            check_image_size(width, height, len, "jpeg");
             comps.resize(nc);
             for (int c = 0; c < nc; ++c) {
                 comps[c].id = seg[6 + 3 * c];
@@ -702,7 +716,10 @@ void decode_jpeg(const uint8_t *data, size_t len, uint32_t &width, uint32_t &hei
             for (uint32_t by = 0; by < c.bh; ++by)
                 for (uint32_t bx = 0; bx < c.bw; ++bx) {
                     const int16_t *blk = c.coef.data() + ((size_t)by * c.bw + bx) * 64;
-                    for (int k = 0; k < 64; ++k) deq[k] = blk[k] * qt[c.tq][k];
+                    for (int k = 0; k < 64; ++k) {  // (a real coefficient stays below 2^19; the clamp only tames corrupt tables)
+                        const int64_t v = (int64_t)blk[k] * qt[c.tq][k];
+                        deq[k] = (int)(v < -(1 << 24) ? -(1 << 24) : (v > (1 << 24) ? (1 << 24) : v));
+                    }
                     jpeg_idct(deq, c.plane.data() + (size_t)by * 8 * stride + (size_t)bx * 8, stride);
                 }
         }
@@ -882,6 +899,7 @@ void decode_tiff(const uint8_t *data, size_t len, uint32_t &width, uint32_t &hei
         const uint32_t type = r16(entry + 2), count = r32(entry + 4);
         const uint32_t size = type == 3 ? 2 : (type == 4 ? 4 : (type == 1 ? 1 : 0));
         if (!size) throw std::runtime_error("tiff: unexpected field type");
+        if ((uint64_t)size * count > len) throw std::runtime_error("tiff: field longer than the file");
         size_t p = (size_t)size * count <= 4 ? entry + 8 : r32(entry + 8);
         out.resize(count);
         for (uint32_t i = 0; i < count; ++i, p += size) out[i] = size == 2 ? r16(p) : (size == 4 ? r32(p) : (need(p, 1), data[p]));
@@ -908,6 +926,7 @@ void decode_tiff(const uint8_t *data, size_t len, uint32_t &width, uint32_t &hei
         }
     }
     if (!width || !height || strip_offsets.empty() || strip_offsets.size() != strip_counts.size()) throw std::runtime_error("tiff: missing size or strips");
+    check_image_size(width, height, len, "tiff");
     if (bits.empty()) bits.assign(1, 1);
     const uint32_t bps = bits[0];
     for (uint32_t b : bits)
@@ -1103,8 +1122,10 @@ void decode_exr(const uint8_t *data, size_t len, uint32_t &width, uint32_t &heig
     case 3: lines_per_chunk = 16; break;                 // ZIP
     default: throw std::runtime_error("exr: compression " + std::to_string(compression) + " is not supported (NONE, RLE, ZIPS, ZIP are)");
     }
+    if ((int64_t)win[2] - win[0] >= 65535 || (int64_t)win[3] - win[1] >= 65535) throw std::runtime_error("exr: data window out of range");
     width = (uint32_t)(win[2] - win[0] + 1);
     height = (uint32_t)(win[3] - win[1] + 1);
+    check_image_size(width, height, len, "exr");
     int slot[4] = {-1, -1, -1, -1};  // index into `channels` of R, G, B, A
     size_t line_bytes = 0;
     std::vector<size_t> ch_offset(channels.size());
