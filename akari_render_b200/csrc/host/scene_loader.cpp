@@ -1501,7 +1501,7 @@ void load_scene_impl(const std::string &path, AkrHostScene &hs) {
         const std::vector<uint8_t> &buf = hs.buffers.at(v.at("buffer").at("id").string());
         size_t off = static_cast<size_t>(v.at("offset").u64());
         size_t len = static_cast<size_t>(v.at("length").u64());
-        if (off + len > buf.size()) throw std::runtime_error(std::string("buffer view out of range for ") + what);
+        if (off > buf.size() || len > buf.size() - off) throw std::runtime_error(std::string("buffer view out of range for ") + what);  // (no off + len: it can wrap)
         if (len % elem != 0) throw std::runtime_error(std::string("Invalid slice length for ") + what);
         return {buf.data() + off, len};
     };
@@ -1514,12 +1514,12 @@ void load_scene_impl(const std::string &path, AkrHostScene &hs) {
         auto copy_f = [&](const Value &ref, size_t elem, std::vector<float> &dst, const char *what) {
             auto [p, len] = view_bytes(ref, elem, what);
             dst.resize(len / 4);
-            std::memcpy(dst.data(), p, len);
+            if (len) std::memcpy(dst.data(), p, len);
         };
         auto copy_u = [&](const Value &ref, size_t elem, std::vector<uint32_t> &dst, const char *what) {
             auto [p, len] = view_bytes(ref, elem, what);
             dst.resize(len / 4);
-            std::memcpy(dst.data(), p, len);
+            if (len) std::memcpy(dst.data(), p, len);
         };
         copy_f(g.at("vertices"), 12, m.vertices, "vertices");
         copy_u(g.at("indices"), 12, m.indices, "indices");
