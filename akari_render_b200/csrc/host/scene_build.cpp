@@ -346,6 +346,10 @@ int build_scene_blob(const AkrSceneDesc &d, HostSceneBlob &out, std::string &err
         out.svm_kind_first.push_back(static_cast<uint32_t>(out.svm_nodes.size()));
     }
     out.svm_data.assign(d.shader_data, d.shader_data + d.shader_data_size);
+    if (d.n_images && !d.images) {
+        err = "n_images > 0 without an image array";
+        return AKR_ERR_INVALID_ARGUMENT;
+    }
     for (uint32_t t = 0; t < d.n_images; ++t) {
         const AkrImage &img = d.images[t];
         if (!img.texels || img.width == 0 || img.height == 0 || img.texel_format > AKR_TEXEL_RGBA32F || img.address > AKR_ADDRESS_EDGE || img.filter > AKR_FILTER_LINEAR) {
