@@ -84,6 +84,14 @@ class Parser {
   private:
     const char *s_;
     size_t n_, i_ = 0;
+    int depth_ = 0;  // nesting of arrays / objects: bounded like serde_json's recursion limit (128), the parser is recursive
+    struct Nest {
+        Parser &p;
+        explicit Nest(Parser &parser) : p(parser) {
+            if (++p.depth_ > 128) p.fail("recursion limit exceeded");
+        }
+        ~Nest() { --p.depth_; }
+    };
     [[noreturn]] void fail(const char *msg) {
         throw std::runtime_error(std::string("json: ") + msg + " at byte " + std::to_string(i_));
     }
@@ -177,6 +185,7 @@ class Parser {
         return out;
     }
     Value array() {
+        Nest nest(*this);
         ++i_;
         Value v;
         v.type = Value::ArrayT;
@@ -203,6 +212,7 @@ class Parser {
         return v;
     }
     Value object() {
+        Nest nest(*this);
         ++i_;
         Value v;
         v.type = Value::ObjectT;

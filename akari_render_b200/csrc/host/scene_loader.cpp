@@ -18,6 +18,7 @@
 #include <cstring>
 #include <fstream>
 #include <map>
+#include <set>
 #include <sstream>
 #include <string>
 #include <vector>
@@ -1262,6 +1263,7 @@ class ShaderCompiler {
     const akr::json::Value &nodes_;
     ImageResolver images_;
     std::map<std::string, uint32_t> env_;
+    std::set<std::string> in_progress_;  // nodes on the current compile_node recursion path
     std::vector<AkrSvmNode> bytecode_;
     std::vector<uint8_t> data_;
 
@@ -1298,6 +1300,14 @@ class ShaderCompiler {
     uint32_t compile_node(const std::string &id) {
         auto it = env_.find(id);
         if (it != env_.end()) return it->second;
+        // a node that (transitively) feeds itself: the reference's compiler recurses until its stack overflows
+        // (compiler.rs:116-337 has no visited set either); rejected here
+        if (!in_progress_.insert(id).second) throw std::runtime_error("shader graph has a cycle through node '" + id + "'");
+        struct Done {
+            std::set<std::string> &s;
+            const std::string &id;
+            ~Done() { s.erase(id); }
+        } done{in_progress_, id};
         const akr::json::Value &node = nodes_.at(id);
         const std::string &type = node.at("type").string();
         uint32_t idx;

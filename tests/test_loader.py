@@ -120,3 +120,34 @@ def test_base64_and_binary_buffers_load_the_same_bytes(akr, tmp_path):
         assert len(got) == len(want)
         for (v, t), (v0, t0) in zip(got, want):
             assert np.array_equal(v, v0) and np.array_equal(t, t0), kind
+
+
+def test_deeply_nested_json_and_cyclic_shader_graphs_are_rejected(akr, tmp_path):
+    """Both used to overflow the stack of the (recursive) JSON parser / shader compiler: nesting beyond 128 levels is refused
+    like serde_json's recursion limit does; a shader node that transitively feeds itself is refused (the reference's
+    compiler has no visited set and would recurse until it crashes, compiler.rs:116-337)."""
+    d = tmp_path / "deep"
+    d.mkdir()
+    for text in ("[" * 2_000_000, '{"a":' * 500_000, "[" * 129 + "]" * 129):
+        (d / "scene.json").write_text(text)
+        with pytest.raises(akr.AkariError, match="recursion limit"):
+            akr.load_scene(str(d / "scene.json"))
+    scene = json.load(open(os.path.join(sv.CBOX_DIR, "scene.json")))
+    g = scene["materials"]["floor_001"]["shader"]
+    p = sv._principled_name(g)
+    g["nodes"]["a"] = {"type": "spectral_uplift", "rgb": {"id": "b"}}
+    g["nodes"]["b"] = {"type": "spectral_uplift", "rgb": {"id": "a"}}
+    g["nodes"][p]["base_color"] = {"id": "a"}
+    with pytest.raises(akr.AkariError, match="cycle"):
+        akr.load_scene(_write(tmp_path, "cyclic", scene))
+    scene = json.load(open(os.path.join(sv.CBOX_DIR, "scene.json")))
+    g = scene["materials"]["floor_001"]["shader"]
+    g["nodes"][sv._principled_name(g)]["normal"] = {"id": sv._principled_name(g)}
+    with pytest.raises(akr.AkariError, match="cycle"):
+        akr.load_scene(_write(tmp_path, "self_cycle", scene))
+    # a diamond (one node feeding two inputs) is not a cycle
+    scene = json.load(open(os.path.join(sv.CBOX_DIR, "scene.json")))
+    g = scene["materials"]["floor_001"]["shader"]
+    p = sv._principled_name(g)
+    g["nodes"][p]["coat_roughness"] = dict(g["nodes"][p]["roughness"])
+    akr.load_scene(_write(tmp_path, "diamond", scene))
