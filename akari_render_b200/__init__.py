@@ -46,7 +46,7 @@ def host_lib():
 
 def _host_check(rc):
     if rc != 0:
-        raise AkariError(rc, host_lib().akr_host_last_error().decode())
+        raise AkariError(rc, host_lib().akr_host_last_error().decode("utf-8", "replace"))
 
 
 _tables = None
@@ -132,7 +132,7 @@ class RenderTask:
 
     @property
     def out(self):
-        return self.raw.out.decode()
+        return self.raw.out.decode("utf-8", "replace")
 
     @property
     def method(self):
@@ -187,7 +187,7 @@ class PathTracer:
 
     def _check(self, rc):
         if rc != 0:
-            raise AkariError(rc, self._lib.akr_b200_last_error(self._ctx).decode())
+            raise AkariError(rc, self._lib.akr_b200_last_error(self._ctx).decode("utf-8", "replace"))
 
     def close(self):
         if self._ctx:

@@ -151,3 +151,14 @@ def test_deeply_nested_json_and_cyclic_shader_graphs_are_rejected(akr, tmp_path)
     p = sv._principled_name(g)
     g["nodes"][p]["coat_roughness"] = dict(g["nodes"][p]["roughness"])
     akr.load_scene(_write(tmp_path, "diamond", scene))
+
+
+def test_error_messages_with_non_utf8_bytes_still_raise_akari_error(akr, tmp_path):
+    """A corrupt file can put arbitrary bytes into the loader's error text; the binding must still raise AkariError."""
+    scene = open(os.path.join(sv.CBOX_DIR, "scene.json"), "rb").read().replace(b'"perspective"', b'"persp\xff\xfective"')
+    d = tmp_path / "bad_utf8"
+    d.mkdir()
+    (d / "scene.json").write_bytes(scene)
+    shutil.copy(os.path.join(sv.CBOX_DIR, "Scene.bin"), str(d / "Scene.bin"))
+    with pytest.raises(akr.AkariError):
+        akr.load_scene(str(d / "scene.json"))
