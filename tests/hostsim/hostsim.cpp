@@ -112,6 +112,10 @@ int hostsim_render(const AkrSceneDesc *desc, const AkrPtConfig *cfg, const AkrSa
         g_err = "scene too large for the flat trace mode";
         return AKR_ERR_UNSUPPORTED;
     }
+    if (blob.bvh_depth + 2u > (uint32_t)AKR_BVH_STACK) {  // the host walks use a fixed stack and would silently drop subtrees beyond it
+        g_err = "BVH deeper than the host walk's stack (the CUDA kernels size theirs from the tree)";
+        return AKR_ERR_UNSUPPORTED;
+    }
     if (scfg->type != AKR_SAMPLER_PMJ02BN) {
         g_err = "pmj02bn only";
         return AKR_ERR_UNSUPPORTED;
