@@ -471,6 +471,7 @@ void decode_jpeg(const uint8_t *data, size_t len, uint32_t &width, uint32_t &hei
     uint32_t restart = 0;
     int hmax = 1, vmax = 1;
     bool have_frame = false, progressive = false, decoded = false;
+    int adobe_transform = -1;  // no APP14 marker: three components are YCbCr (JFIF)
     size_t pos = 2;
     auto be16 = [&](size_t p) -> uint32_t {
         if (p + 2 > len) throw std::runtime_error("jpeg: truncated file");
@@ -554,6 +555,8 @@ void decode_jpeg(const uint8_t *data, size_t len, uint32_t &width, uint32_t &hei
             have_frame = true;
         } else if (m >= 0xc3 && m <= 0xcf && m != 0xc4 && m != 0xc8 && m != 0xcc) {
             throw std::runtime_error("jpeg: lossless, hierarchical and arithmetic-coded files are not supported");
+        } else if (m == 0xee) {  // APP14 "Adobe": colour transform flag (0 = components are R, G, B as they stand; 1 = YCbCr)
+            if (n >= 12 && std::memcmp(seg, "Adobe", 5) == 0) adobe_transform = seg[11];
         } else if (m == 0xdd) {
             if (n < 2) throw std::runtime_error("jpeg: bad DRI");
             restart = (seg[0] << 8) | seg[1];
@@ -795,6 +798,10 @@ void decode_jpeg(const uint8_t *data, size_t len, uint32_t &width, uint32_t &hei
             uint8_t r, g, b;
             if (comps.size() == 1) {
                 r = g = b = full[0][i];
+            } else if (adobe_transform == 0) {  // Adobe RGB JPEG: no colour transform
+                r = full[0][i];
+                g = full[1][i];
+                b = full[2][i];
             } else {  // BT.601, 20-bit fixed point
                 const int yy = ((int)full[0][i] << 20) + (1 << 19), cb = (int)full[1][i] - 128, cr = (int)full[2][i] - 128;
                 r = jpeg_clamp((yy + f2f20(1.40200f) * cr) >> 20);

@@ -374,6 +374,17 @@ def test_loader_decodes_jpeg_images(akr, tmp_path):
         got = np.ctypeslib.as_array(C.cast(g.texels, C.POINTER(C.c_uint8)), (w * h * 4,)).reshape(h, w, 4).astype(np.int32)
         d = np.abs(got[..., :3] - ref)
         assert d.max() <= 8 and d.mean() <= 1.0, (k, int(d.max()), float(d.mean()))
+    # an Adobe APP14 marker with transform 0 says the three components are R, G, B as they stand (no YCbCr conversion)
+    ok, buf = cv2.imencode(".jpg", smooth(16, 24, 3), [S, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444])
+    raw = bytes(buf)
+    adobe = b"\xff\xee\x00\x0eAdobe\x00\x64\x00\x00\x00\x00\x00"  # version 100, flags 0 / 0, transform 0
+    assert raw[2:4] == b"\xff\xe0"  # the JFIF APP0 segment: dropped, libjpeg lets JFIF win over Adobe (jpeg-decoder 0.3 does not look at it)
+    patched = raw[:2] + adobe + raw[4 + ((raw[4] << 8) | raw[5]):]
+    ref = cv2.imdecode(np.frombuffer(patched, np.uint8), cv2.IMREAD_UNCHANGED)[..., ::-1][::-1].astype(np.int32)
+    scene = akr.load_scene(sv.write_image_textured(tmp_path, "jpeg_adobe_rgb", [("floor_001", patched, "jpeg", 24, 16, 3)]))
+    g = _images(scene)[0]
+    got = np.ctypeslib.as_array(C.cast(g.texels, C.POINTER(C.c_uint8)), (24 * 16 * 4,)).reshape(16, 24, 4).astype(np.int32)
+    assert np.abs(got[..., :3] - ref).max() <= 2
     # arithmetic-coded / truncated files are rejected
     ok, buf = cv2.imencode(".jpg", smooth(16, 16, 3))
     for bad in (bytes(buf)[:60], bytes(buf).replace(b"\xff\xc0", b"\xff\xc9", 1)):
