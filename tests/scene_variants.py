@@ -193,7 +193,7 @@ def write_clutter(tmp_path, n_lon=32, n_lat=24):
 
 
 # ---- white furnace: a closed, uniformly emitting Lambert cube around the camera ----------------------------------------
-def write_furnace(tmp_path, albedo=0.5, emission=1.0, half=2.0):
+def write_furnace(tmp_path, albedo=0.5, emission=1.0, half=2.0, textured=False):
     """Closed cube (inward-facing normals) centred on the cbox camera: every surface point emits `emission` and reflects
     Lambert `albedo`.  Radiance seen along any path of at most D bounces is emission * sum_{k=0..D} albedo^k."""
     import numpy as np
@@ -231,10 +231,19 @@ def write_furnace(tmp_path, albedo=0.5, emission=1.0, half=2.0):
     scene["instances"] = {"furnace": {"geometry": {"id": "furnace_mesh"},
                                       "transform": {"type": "matrix", "data": [[1.0, 0, 0, 0], [0, 1.0, 0, 0], [0, 0, 1.0, 0], [0, 0, 0, 1.0]]},
                                       "materials": [{"id": "furnace"}]}}
+    if textured:  # the same albedo from a constant-valued float image: a texture-driven material with the same analytic answer
+        g = scene["materials"]["furnace"]["shader"]
+        nodes, p = g["nodes"], _principled_name(g)
+        tex = np.full((4, 4, 3), albedo, np.float32)
+        nodes["tex"] = {"type": "image", "uv": None,
+                        "image": {"data": add_view(tex), "format": "float", "colorspace": "none", "extension": "repeat", "interpolation": "linear",
+                                  "width": 4, "height": 4, "channels": 3}}
+        nodes["tex_up"] = {"type": "spectral_uplift", "rgb": {"id": "tex"}}
+        nodes[p]["base_color"] = {"id": "tex_up"}
     scene["lights"] = {}
     scene["buffer_views"] = views
     scene["buffers"] = {"Scene": {"type": "path", "path": "Scene.bin", "length": len(blob)}}
-    d = os.path.join(str(tmp_path), "furnace")
+    d = os.path.join(str(tmp_path), "furnace_textured" if textured else "furnace")
     os.makedirs(d, exist_ok=True)
     open(os.path.join(d, "Scene.bin"), "wb").write(bytes(blob))
     path = os.path.join(d, "scene.json")

@@ -89,6 +89,31 @@ def test_white_furnace_hostsim_bitwise(akr, oracle, tables, tmp_path, fused):
         lib.hostsim_set_pipeline(0)
 
 
+@pytest.mark.parametrize("fused", [0, 1], ids=["queued", "fused"])
+def test_textured_white_furnace_pins_the_texture_driven_path(akr, oracle, tables, tmp_path, fused):
+    """The furnace again, with the albedo read from a constant-valued image texture: the material is texture-driven (shader
+    interpreted per hit, general shade class, bilinear fetches whose weights (1 - t) + t must sum to exactly 1), and the
+    answer is the same closed form — exact in the oracle, and the kernels' bodies reproduce the oracle bit for bit."""
+    from test_hostsim_parity import run_hostsim
+    lib = C.CDLL(os.path.join(HERE, "hostsim", "libhostsim.so"))
+    lib.hostsim_last_error.restype = C.c_char_p
+    w = h = 24
+    scene = akr.load_scene(sv.write_furnace(tmp_path, RHO, EMIT, textured=True)).set_resolution(w, h)
+    pmj, bn = tables
+    task = _furnace_task(akr, 8, use_nee=0, rr_depth=100)
+    ofilm, ost, _ = oracle.render(scene.desc, w, h, task.pt, task.sampler, task.filter, pmj, bn)
+    err = float(np.abs(oracle.resolve(ofilm, w * h) - FURNACE).max())
+    measured(f"textured white furnace (oracle) 24x24@8: max |pixel - {FURNACE}| = {err:.2e} (<= 1e-5)")
+    assert err <= 1e-5 and ost.segments == w * h * 8 * (DEPTH + 1)
+    lib.hostsim_set_pipeline(fused)
+    try:
+        film, _, st = run_hostsim(lib, scene, task, tables, oracle.albedo_table(), w, h)
+        assert st.any_dynamic == 1 and st.any_alpha == 0
+        assert np.array_equal(film, ofilm) and st.segments == ost.segments
+    finally:
+        lib.hostsim_set_pipeline(0)
+
+
 def test_nee_on_off_equal_means_oracle(oracle, tables, cbox, cbox_task):
     w = h = 48
     scene = cbox(w, h)
